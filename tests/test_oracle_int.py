@@ -1,0 +1,68 @@
+"""The integer-path oracle is pinned before anything is compared against it.
+
+(a) golden vectors: logits + density produced by the reference's serialize.py +
+    C++ engine in the build container (tests/golden/make_golden.py);
+(b) the reference engine itself (oracle/_ref), when that build is present, on
+    randomized .nnue files that use the format's full integer ranges.
+Bit-exact in both cases.
+"""
+import numpy as np
+import pytest
+
+from util import GOLDEN, GOLDEN_CASES, INT_ARCHS, load_golden, write_random_nnue
+
+
+def chw_bytes_as_hwc(images_chw):
+    """evaluate.py:154-168 dumps CHW floats and the engine reads them as HWC: a reinterpretation."""
+    B, C, H, W = images_chw.shape
+    return np.ascontiguousarray(images_chw).reshape(B, H, W, C)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_c_oracle_matches_reference_golden(oracle_built, name):
+    rec = load_golden(name)
+    n = int(rec["int.n_images"])
+    orc = oracle_built.IntOracle(GOLDEN / f"{name}.nnue")
+    logits, dens = orc.eval_batch(chw_bytes_as_hwc(rec["images"][:n]))
+    assert logits.dtype == np.float32
+    np.testing.assert_array_equal(logits, rec["int.logits"])
+    np.testing.assert_array_equal(dens, rec["int.density"])
+
+
+def test_c_oracle_header_fields(oracle_built):
+    rec = load_golden("default_cfg")
+    orc = oracle_built.IntOracle(GOLDEN / "default_cfg.nnue")
+    c = rec["cfg"]
+    assert (orc.F, orc.L1, orc.L2, orc.L3, orc.NC, orc.OC, orc.G, orc.n_buckets) == (
+        c["grid"] ** 2 * c["C"], c["L1"], c["L2"], c["L3"], c["NC"], c["C"], c["grid"], 1)
+    # engine stride rule ceil((H-1)/(G-1)) (nnue_engine.cpp:710-718), not the Python floor rule
+    assert orc.stride(32) == 4 and orc.stride(96) == 11 and orc.stride(10) == 1
+
+
+def test_c_oracle_rejects_malformed(oracle_built, tmp_path):
+    good = (GOLDEN / "parity_small.nnue").read_bytes()
+    for bad in (b"XXXX" + good[4:], good[:4] + b"\x03\x00\x00\x00" + good[8:], good[:200], good[:-3]):
+        p = tmp_path / "bad.nnue"
+        p.write_bytes(bad)
+        with pytest.raises(ValueError):
+            oracle_built.IntOracle(p)
+
+
+@pytest.mark.parametrize("arch", INT_ARCHS[:7], ids=lambda a: "x".join(map(str, a)))
+@pytest.mark.parametrize("wild", [False, True])
+def test_c_oracle_matches_reference_engine(oracle_built, tmp_path, arch, wild):
+    if not oracle_built.RefEngine.available():
+        pytest.skip("oracle/_ref not built (reference sources absent)")
+    G, C, L1, L2, L3, NC, H = arch
+    rng = np.random.default_rng(hash(arch) % (2**32) + wild)
+    path = tmp_path / "m.nnue"
+    write_random_nnue(path, rng, G, C, L1, L2, L3, NC, wild=wild)
+    imgs = (rng.standard_normal((6, H, H, 3)) * (3.0 if wild else 1.0)).astype(np.float32)
+    imgs[0] = 0.0
+    ref = oracle_built.RefEngine(path)
+    orc = oracle_built.IntOracle(path)
+    rl, rd = ref.eval_batch(imgs, threads=2)
+    ol, od = orc.eval_batch(imgs, threads=2)
+    np.testing.assert_array_equal(ol, rl)
+    np.testing.assert_array_equal(od, rd)
+    assert (ref.F, ref.L1, ref.L2, ref.L3, ref.OC, ref.G) == (orc.F, orc.L1, orc.L2, orc.L3, orc.OC, orc.G)
