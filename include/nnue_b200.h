@@ -1,0 +1,238 @@
+/*
+ * nnue_b200.h -- C ABI of the B200-native NNUE hot path (libnnue_b200.so).
+ *
+ * The reference (marict/nnue-vision) has no C plugin ABI for this path: its
+ * boundary is the Python module surface of nnue.py plus the .nnue file format
+ * and the C++ NNUEEvaluator class.  Every entry point below names the
+ * reference interface it stands in for (file:line relative to the reference
+ * checkout); INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - pointers named *_d are DEVICE pointers owned by the caller and must stay
+ *     valid until the work queued on `stream` has run; *_h are host pointers;
+ *   - launches are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *     the float-path calls never allocate and never synchronise -- scratch is
+ *     passed in (`workspace_d`, sized by nnue_workspace_bytes);
+ *   - return value: 0 = NNUE_OK, negative = error code (nnue_error_string).
+ */
+#ifndef NNUE_B200_H
+#define NNUE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNUE_B200_ABI_VERSION 1
+
+enum {
+    NNUE_OK = 0,
+    NNUE_ERR_INVALID_ARG = -1,   /* null pointer, non-positive size, inconsistent shape */
+    NNUE_ERR_UNSUPPORTED = -2,   /* shape outside what the kernels are built for */
+    NNUE_ERR_CUDA = -3,          /* a CUDA runtime call or launch failed (see nnue_last_cuda_error) */
+    NNUE_ERR_IO = -4,            /* cannot open / short read of a .nnue file */
+    NNUE_ERR_FORMAT = -5,        /* .nnue magic / version / architecture check failed */
+    NNUE_ERR_WORKSPACE = -6,     /* workspace too small */
+    NNUE_ERR_RASTER = -7         /* conv raster does not fit the feature buffer (engine would overrun) */
+};
+
+/*
+ * Shape of one float-path problem.  Mirrors the constructor arguments of
+ * nnue.NNUE (nnue.py:454-464) plus the per-call image size; derived fields are
+ * filled by nnue_shape_init and must not be edited afterwards.
+ */
+typedef struct nnue_shape {
+    int32_t B, H, W;          /* batch, image height, image width (images are [B,3,H,W] fp32) */
+    int32_t C, G;             /* num_features_per_square, grid_size (GridFeatureSet, nnue.py:81-90) */
+    int32_t L1, L2, L3, NC;   /* l1_size, l2_size, l3_size, num_classes */
+    int32_t stride;           /* conv stride (model attribute; nnue.py:519 computes it from input_size) */
+    /* ---- derived ---- */
+    int32_t F;                /* G*G*C rows of the feature-transformer table */
+    int32_t Gh, Gw;           /* conv output raster: (H-1)/stride+1, (W-1)/stride+1 */
+    int32_t P;                /* C*Gh*Gw flat CHW positions (may exceed F: clamp at nnue.py:701) */
+    int32_t CW;               /* ceil(Gh*Gw/32): 32-bit words per channel in the sample-major bitmask */
+    int32_t NW;               /* C*CW words per sample in bits_s */
+    int32_t PP;               /* NW*32 padded positions (rows of bits_t, columns of dval) */
+    int32_t BW;               /* ceil(B/32) words per padded position in bits_t */
+} nnue_shape;
+
+int nnue_b200_abi_version(void);
+const char *nnue_error_string(int code);
+/* text of the last CUDA error seen by this library on the calling thread ("" if none) */
+const char *nnue_last_cuda_error(void);
+
+/*
+ * Tuning knobs (process-wide; defaults work).  Keys:
+ *   "ft_fwd_staging"  0 = gather table rows from global/L2, 1 = auto (default), 2 = stage the
+ *                     whole table in shared memory with bulk TMA copies whenever it fits.
+ */
+int nnue_set_option(const char *key, int value);
+
+/* Fill the derived fields; returns NNUE_ERR_INVALID_ARG on non-positive sizes. */
+int nnue_shape_init(nnue_shape *s, int B, int H, int W, int C, int G, int L1, int L2, int L3, int NC,
+                    int stride);
+/* Bytes of scratch the float-path calls may use for this shape (max over all of them). */
+size_t nnue_workspace_bytes(const nnue_shape *s);
+
+/* ------------------------------------------------------------------------- *
+ *  Float training path                                                       *
+ * ------------------------------------------------------------------------- */
+
+/*
+ * Grid-feature extraction: 3x3 conv (pad 1, stride s, no bias) + per-channel hard
+ * threshold -> active-feature bitmask.  Replaces `self.conv(images)` +
+ * StraightThroughBinary.forward + NNUE._to_sparse_features
+ * (nnue.py:640, 18-25, 590-635).
+ *   images_d [B,3,H,W] f32; conv_w_d [C,3,3,3] f32; thr_d [C] f32
+ *   bits_s_d [B][NW] u32   bit k of word (c*CW+j) = position (c, cell 32j+k) active
+ *   bits_t_d [PP][BW] u32  transposed (position-major) copy, or NULL to skip
+ *   conv_out_d [B,C,Gh,Gw] f32 pre-threshold activations, or NULL
+ *   nnz_d [B] i32 active positions per sample, or NULL
+ */
+int nnue_extract_fwd(const nnue_shape *s, const float *images_d, const float *conv_w_d,
+                     const float *thr_d, uint32_t *bits_s_d, uint32_t *bits_t_d, float *conv_out_d,
+                     int32_t *nnz_d, void *stream);
+
+/*
+ * bits -> the padded (indices, values) pair NNUE._to_sparse_features returns
+ * (nnue.py:590-635): ascending CHW flat indices, -1 / 0.0 padding.
+ *   idx_d [B,K] i64, val_d [B,K] f32, K >= max(1, max nnz)
+ */
+int nnue_sparse_from_bits(const nnue_shape *s, const uint32_t *bits_s_d, int K, int64_t *idx_d,
+                          float *val_d, void *stream);
+
+/*
+ * Feature-transformer forward on the bitmask (values are all 1.0 on this path):
+ * out[b] = bias + sum over active p of W[min(p, F-1)].  Replaces
+ * FeatureTransformer.forward as called from NNUE.forward (nnue.py:653, 686-710).
+ *   ft_w_d [F,L1] f32; ft_b_d [L1] f32; ft_out_d [B,L1] f32
+ */
+int nnue_ft_fwd(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w_d,
+                const float *ft_b_d, float *ft_out_d, void *stream);
+
+/*
+ * General FeatureTransformer.forward(feature_indices, feature_values) (nnue.py:686-710) for
+ * callers that use `model.input(idx, val)` directly (tests/test_model.py:1026-1064):
+ * arbitrary repeated / unsorted / out-of-range indices, -1 = skip, arbitrary values.
+ *   idx_d [B,K] i64; val_d [B,K] f32
+ */
+int nnue_ft_fwd_indexed(int B, int K, int F, int L1, const int64_t *idx_d, const float *val_d,
+                        const float *ft_w_d, const float *ft_b_d, float *ft_out_d, void *stream);
+/*
+ * Backward of the indexed form.  The weight gradient is a SORTED SEGMENT REDUCTION: the
+ * caller passes the (row, sample, value) triples sorted by row (rows already clamped,
+ * -1 entries removed); one warp sums each row's segment, no atomics.
+ *   n_pairs triples: row_d i32 ascending, sample_d i32, pval_d f32
+ *   g_out_d [B,L1]; g_w_d [F,L1] (fully written, zeros for untouched rows); g_b_d [L1];
+ *   g_val_d [B,K] (d out / d val, 0 at idx<0), may be NULL
+ */
+int nnue_ft_bwd_indexed(int B, int K, int F, int L1, const int64_t *idx_d, const float *ft_w_d,
+                        const float *g_out_d, int n_pairs, const int32_t *row_d,
+                        const int32_t *sample_d, const float *pval_d, float *g_w_d, float *g_b_d,
+                        float *g_val_d, void *stream);
+
+/*
+ * Pairwise product + 3-layer head, ReLU fused in the epilogues.  Replaces
+ * nnue.py:660-669 + SimpleClassifier.forward (nnue.py:728-738).
+ *   w1 [L2,L1] b1 [L2]; w2 [L3,L2] b2 [L3]; w3 [NC,L3] b3 [NC]
+ *   act1_d [B,L2], act2_d [B,L3]: post-ReLU activations kept for the backward
+ *   logits_d [B,NC]
+ */
+int nnue_head_fwd(const nnue_shape *s, const float *ft_out_d, const float *w1_d, const float *b1_d,
+                  const float *w2_d, const float *b2_d, const float *w3_d, const float *b3_d,
+                  float *act1_d, float *act2_d, float *logits_d, void *stream);
+
+/*
+ * Mean cross-entropy (train.py:250-254) fused with its gradient.
+ *   labels_d [B] i64
+ *   loss_d [1] f32 = sum_b CE_b * inv_count            (may be NULL: gradient only)
+ *   g_logits_d [B,NC] = (softmax - onehot) * inv_count * g  (may be NULL: loss only), where
+ *   g = *g_scale_d, a DEVICE scalar (the upstream gradient of the loss), or 1 when NULL.
+ *   inv_count is 1/B on one GPU and 1/(global B) under data parallelism;
+ *   per_sample_d [B] (may be NULL) receives the unscaled CE_b.
+ */
+int nnue_ce_fwd_bwd(int B, int NC, const float *logits_d, const int64_t *labels_d, float inv_count,
+                    const float *g_scale_d, float *loss_d, float *per_sample_d, float *g_logits_d,
+                    void *workspace_d, size_t workspace_bytes, void *stream);
+
+/*
+ * Backward of nnue_head_fwd: parameter gradients of the three Linear layers and the
+ * gradient w.r.t. the feature-transformer output (pairwise backward fused).
+ *   g_logits_d [B,NC] -> g_w{1,2,3}, g_b{1,2,3}, g_ft_d [B,L1]
+ */
+int nnue_head_bwd(const nnue_shape *s, const float *g_logits_d, const float *ft_out_d,
+                  const float *act1_d, const float *act2_d, const float *w1_d, const float *w2_d,
+                  const float *w3_d, float *g_w1_d, float *g_b1_d, float *g_w2_d, float *g_b2_d,
+                  float *g_w3_d, float *g_b3_d, float *g_ft_d, void *workspace_d,
+                  size_t workspace_bytes, void *stream);
+
+/*
+ * Feature-transformer weight/bias gradient on the transposed bitmask: a segment
+ * reduction over (feature, sample) pairs already sorted by feature (the bit-matrix
+ * transpose is the sort), no atomics, deterministic.  Rows p >= F fold onto row F-1.
+ * Replaces the B IndexBackward / index_put nodes autograd builds for nnue.py:702-708.
+ *   bits_t_d [PP][BW]; g_ft_d [B,L1]; g_w_d [F,L1] fully written; g_b_d [L1]
+ */
+int nnue_ft_bwd_dw(const nnue_shape *s, const uint32_t *bits_t_d, const float *g_ft_d, float *g_w_d,
+                   float *g_b_d, void *workspace_d, size_t workspace_bytes, void *stream);
+
+/*
+ * Gradient w.r.t. the feature values at ACTIVE positions: dval[b,p] = <W[min(p,F-1)], g_ft[b]>
+ * (the autograd edge that reaches conv / threshold, nnue.py:602-603, 705).
+ *   dval_d [B][PP] f32, padded-position layout, written only where the bit is set
+ */
+int nnue_ft_bwd_dval(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w_d,
+                     const float *g_ft_d, float *dval_d, void *stream);
+
+/*
+ * Backward of the extraction: straight-through to the conv (nnue.py:28-33), sigmoid
+ * surrogate for the threshold (nnue.py:36-52, k = 10), conv weight gradient.
+ *   g_conv_w_d [C,3,3,3]; g_thr_d [C]
+ */
+int nnue_extract_bwd(const nnue_shape *s, const float *images_d, const float *conv_w_d,
+                     const float *thr_d, const uint32_t *bits_s_d, const float *dval_d,
+                     float *g_conv_w_d, float *g_thr_d, void *workspace_d, size_t workspace_bytes,
+                     void *stream);
+
+/* ------------------------------------------------------------------------- *
+ *  Quantized integer inference path (bit-exact vs serialize.py + engine)     *
+ * ------------------------------------------------------------------------- */
+
+typedef struct nnue_qmodel nnue_qmodel; /* opaque: parsed .nnue + device-resident blobs */
+
+/*
+ * Parse a .nnue v2 file (format: serialize.py:30-63, 103-136, 394-491) and upload it.
+ * Replaces NNUEEvaluator::load_model (engine/src/nnue_engine.cpp:544-657) incl. its
+ * validation.  Allocates device memory on the current device; synchronous.
+ */
+int nnue_q_load(const char *path, nnue_qmodel **out);
+int nnue_q_load_memory(const void *bytes_h, size_t n_bytes, nnue_qmodel **out);
+void nnue_q_free(nnue_qmodel *m);
+/* dims[8] = F, L1, L2, L3, NC, OC (channels per square), G, n_buckets; thr = header threshold */
+int nnue_q_dims(const nnue_qmodel *m, int32_t *dims, float *visual_threshold);
+
+/*
+ * Batched NNUEEvaluator::evaluate_logits (nnue_engine.cpp:704-734) + the density line of
+ * nnue_inference.cpp:50-54: conv -> threshold -> int16-wrap accumulate -> clipped ReLU ->
+ * pairwise -> layer stack, one fused kernel.
+ *   images_d [B][H*W*3] f32: the raw buffer the engine is handed, read as HWC
+ *   logits_d [B,NC] f32 (multiples of 1/64); density_d [B] f32 (may be NULL)
+ *   bucket: layer-stack index (the engine ignores it, nnue_engine.cpp:480-481; values
+ *           >= n_buckets fall back to 0 as nnue_engine.cpp:705-707 does)
+ */
+int nnue_q_infer(const nnue_qmodel *m, const float *images_d, int B, int H, int W, int bucket,
+                 float *logits_d, float *density_d, void *stream);
+/*
+ * Same through HOST buffers (the call evaluate.py:126-173 would make instead of one
+ * subprocess per sample): H2D, kernel, D2H and a stream synchronise inside the call.
+ */
+int nnue_q_infer_host(const nnue_qmodel *m, const float *images_h, int B, int H, int W, int bucket,
+                      float *logits_h, float *density_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNUE_B200_H */

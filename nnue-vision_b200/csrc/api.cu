@@ -1,0 +1,71 @@
+// api.cu -- error reporting, shape derivation and workspace sizing for libnnue_b200.
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "plan.cuh"
+
+namespace nnue {
+static thread_local char g_cuda_err[256] = "";
+void note_cuda_error(cudaError_t e, const char *what) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+static int g_options[kNumOptions] = {/*ft_fwd_staging=*/1};
+int get_option(int which) { return which >= 0 && which < kNumOptions ? g_options[which] : 0; }
+}  // namespace nnue
+
+extern "C" {
+
+int nnue_set_option(const char *key, int value) {
+    if (!key) return NNUE_ERR_INVALID_ARG;
+    if (!strcmp(key, "ft_fwd_staging")) { nnue::g_options[nnue::kOptFtFwdStaging] = value; return NNUE_OK; }
+    return NNUE_ERR_INVALID_ARG;
+}
+
+int nnue_b200_abi_version(void) { return NNUE_B200_ABI_VERSION; }
+
+const char *nnue_error_string(int code) {
+    switch (code) {
+        case NNUE_OK: return "ok";
+        case NNUE_ERR_INVALID_ARG: return "invalid argument";
+        case NNUE_ERR_UNSUPPORTED: return "shape not supported by the sm_100a kernels";
+        case NNUE_ERR_CUDA: return "CUDA error (see nnue_last_cuda_error)";
+        case NNUE_ERR_IO: return "cannot read .nnue file";
+        case NNUE_ERR_FORMAT: return "malformed .nnue file";
+        case NNUE_ERR_WORKSPACE: return "workspace too small";
+        case NNUE_ERR_RASTER: return "conv raster exceeds the feature buffer";
+        default: return "unknown error";
+    }
+}
+
+const char *nnue_last_cuda_error(void) { return nnue::g_cuda_err; }
+
+int nnue_shape_init(nnue_shape *s, int B, int H, int W, int C, int G, int L1, int L2, int L3, int NC, int stride) {
+    if (!s || B < 1 || H < 1 || W < 1 || C < 1 || G < 1 || L1 < 2 || L2 < 1 || L3 < 1 || NC < 1 || stride < 1)
+        return NNUE_ERR_INVALID_ARG;
+    if (L1 % 2) return NNUE_ERR_UNSUPPORTED;  // torch.split(l0, L1//2) must give exactly two halves (nnue.py:660)
+    memset(s, 0, sizeof(*s));
+    s->B = B; s->H = H; s->W = W; s->C = C; s->G = G;
+    s->L1 = L1; s->L2 = L2; s->L3 = L3; s->NC = NC; s->stride = stride;
+    const long long F = 1LL * G * G * C;
+    s->Gh = (H - 1) / stride + 1;  // (H + 2*1 - 3)/stride + 1
+    s->Gw = (W - 1) / stride + 1;
+    const long long P = 1LL * C * s->Gh * s->Gw;
+    s->CW = nnue::ceil_div(s->Gh * s->Gw, 32);
+    const long long NW = 1LL * C * s->CW;
+    if (F > (1LL << 30) || P > (1LL << 30) || NW * 32 > (1LL << 30)) return NNUE_ERR_UNSUPPORTED;
+    s->F = (int)F; s->P = (int)P; s->NW = (int)NW; s->PP = (int)(NW * 32);
+    s->BW = nnue::ceil_div(B, 32);
+    return NNUE_OK;
+}
+
+size_t nnue_workspace_bytes(const nnue_shape *s) {
+    if (!s) return 0;
+    size_t m = nnue::ws_head_bwd(*s);
+    size_t v = nnue::ws_ft_bwd_dw(*s); if (v > m) m = v;
+    v = nnue::ws_extract_bwd(*s); if (v > m) m = v;
+    v = nnue::ws_ce(s->B); if (v > m) m = v;
+    return m + 256;
+}
+
+}  // extern "C"

@@ -1,0 +1,294 @@
+// extract.cu -- grid-feature extraction (conv 3x3 + threshold -> bitmasks) and its backward.
+//
+// Work decomposition: one warp owns a "unit" = (sample b, cell word j): 32 consecutive cells
+// of the conv raster, one cell per lane.  A lane keeps its 3x3x3 input patch in registers and
+// produces every channel for that cell, so __ballot_sync over the warp yields one 32-bit word
+// of the sample-major bitmask per channel with no shared-memory traffic.
+#include "common.cuh"
+#include "plan.cuh"
+
+namespace nnue {
+
+constexpr int kExtThreads = 256;
+constexpr float kSteSharpness = 10.0f;  // nnue.py:41
+
+// conv weights are staged in shared memory padded to 28 floats per channel so that a channel's
+// 27 taps are read with 7 broadcast LDS.128
+__device__ __forceinline__ void stage_conv_weights(float *sw, float *sthr, const float *conv_w, const float *thr,
+                                                   int c0, int cn) {
+    for (int i = threadIdx.x; i < cn * 28; i += blockDim.x) {
+        const int c = i / 28, t = i % 28;
+        sw[i] = t < 27 ? conv_w[(c0 + c) * 27 + t] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < cn; i += blockDim.x) sthr[i] = thr[c0 + i];
+}
+
+// patch[ic*9 + kh*3 + kw] (PyTorch OIHW tap order), zero outside the image (padding = 1)
+__device__ __forceinline__ void load_patch(float (&patch)[28], const float *img, int H, int W, int oy, int ox,
+                                           int stride, bool valid) {
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        const int iy = oy * stride + kh - 1;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int ix = ox * stride + kw - 1;
+            const bool in = valid && iy >= 0 && iy < H && ix >= 0 && ix < W;
+#pragma unroll
+            for (int ic = 0; ic < 3; ++ic)
+                patch[ic * 9 + kh * 3 + kw] = in ? __ldg(img + ((size_t)ic * H + iy) * W + ix) : 0.0f;
+        }
+    }
+    patch[27] = 0.0f;
+}
+
+// patch carries a 28th element fixed at 0 so the 7 x float4 weight reads need no tail case
+__device__ __forceinline__ float conv_tap_sum(const float (&patch)[28], const float *w28) {
+    const float4 *w4 = reinterpret_cast<const float4 *>(w28);
+    float acc = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+        const float4 w = w4[q];
+        acc = fmaf(patch[q * 4 + 0], w.x, acc);
+        acc = fmaf(patch[q * 4 + 1], w.y, acc);
+        acc = fmaf(patch[q * 4 + 2], w.z, acc);
+        acc = fmaf(patch[q * 4 + 3], w.w, acc);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(kExtThreads)
+extract_fwd_kernel(const nnue_shape s, const float *__restrict__ images, const float *__restrict__ conv_w,
+                   const float *__restrict__ thr, uint32_t *__restrict__ bits_s, float *__restrict__ conv_out) {
+    extern __shared__ __align__(16) float smem[];
+    float *sw = smem;                 // [C][28]
+    float *sthr = smem + s.C * 28;    // [C]
+    stage_conv_weights(sw, sthr, conv_w, thr, 0, s.C);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int cells = s.Gh * s.Gw;
+    const long long units = 1LL * s.B * s.CW;
+    for (long long u = 1LL * blockIdx.x * wpb + warp; u < units; u += 1LL * gridDim.x * wpb) {
+        const int b = (int)(u / s.CW), j = (int)(u % s.CW);
+        const int cell = j * 32 + lane;
+        const bool valid = cell < cells;
+        const int oy = valid ? cell / s.Gw : 0, ox = valid ? cell % s.Gw : 0;
+        float patch[28];
+        load_patch(patch, images + (size_t)b * 3 * s.H * s.W, s.H, s.W, oy, ox, s.stride, valid);
+        for (int c = 0; c < s.C; ++c) {
+            const float x = conv_tap_sum(patch, sw + c * 28);
+            const unsigned word = __ballot_sync(kFull, valid && x > sthr[c]);
+            if (lane == 0) bits_s[(size_t)b * s.NW + c * s.CW + j] = word;
+            if (conv_out && valid) conv_out[((size_t)b * s.C + c) * cells + cell] = x;
+        }
+    }
+}
+
+// Position-major copy of the bitmask: bits_t[pp][bw] holds, for padded position pp, one bit per
+// sample of the 32-sample group bw.  This transpose IS the sort by feature that the weight
+// gradient's segment reduction consumes.  One CTA transposes 8 sample groups x 32 words.
+constexpr int kTrGroups = 8;
+__global__ void __launch_bounds__(1024)
+bits_transpose_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, uint32_t *__restrict__ bits_t) {
+    __shared__ uint32_t tile[kTrGroups][32][33];
+    const int k = threadIdx.x, wi = threadIdx.y;  // blockDim = (32, 32)
+    const int w0 = blockIdx.x * 32, g0 = blockIdx.y * kTrGroups;
+    // load: thread (k, wi) -> sample row wi of each group, word column k (coalesced over k)
+    for (int g = 0; g < kTrGroups; ++g) {
+        const int b = (g0 + g) * 32 + wi, w = w0 + k;
+        tile[g][wi][k] = (b < s.B && w < s.NW) ? bits_s[(size_t)b * s.NW + w] : 0u;
+    }
+    __syncthreads();
+    const int w = w0 + wi;
+    if (w >= s.NW) return;
+    for (int g = 0; g < kTrGroups; ++g) {
+        if (g0 + g >= s.BW) break;
+        unsigned out = 0;
+#pragma unroll
+        for (int sidx = 0; sidx < 32; ++sidx) out |= ((tile[g][sidx][wi] >> k) & 1u) << sidx;
+        bits_t[((size_t)w * 32 + k) * s.BW + g0 + g] = out;
+    }
+}
+
+__global__ void bits_count_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, int32_t *__restrict__ nnz) {
+    const int lane = threadIdx.x & 31;
+    const int b = (int)((1LL * blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (b >= s.B) return;
+    int n = 0;
+    for (int w = lane; w < s.NW; w += 32) n += __popc(bits_s[(size_t)b * s.NW + w]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(kFull, n, o);
+    if (lane == 0) nnz[b] = n;
+}
+
+// bits -> padded (indices, values) as NNUE._to_sparse_features lays them out (nnue.py:590-635)
+__global__ void sparse_from_bits_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, int K,
+                                        int64_t *__restrict__ idx, float *__restrict__ val) {
+    const int lane = threadIdx.x & 31;
+    const int b = (int)((1LL * blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (b >= s.B) return;
+    const int cells = s.Gh * s.Gw;
+    int off = 0;
+    for (int w = 0; w < s.NW; ++w) {
+        const unsigned word = bits_s[(size_t)b * s.NW + w];
+        if (!word) continue;
+        const int c = w / s.CW, j = w % s.CW;
+        if ((word >> lane) & 1u) {
+            const int pos = off + __popc(word & ((1u << lane) - 1u));
+            if (pos < K) {
+                idx[(size_t)b * K + pos] = (int64_t)c * cells + j * 32 + lane;
+                val[(size_t)b * K + pos] = 1.0f;
+            }
+        }
+        off += __popc(word);
+    }
+    for (int p = off + lane; p < K; p += 32) {
+        idx[(size_t)b * K + p] = -1;
+        val[(size_t)b * K + p] = 0.0f;
+    }
+}
+
+// ---- backward ----------------------------------------------------------------------------
+// g_x = g_bin (straight-through), g_thr[c] = -sum g_bin * k * sig * (1 - sig), g_conv_w =
+// conv2d_weight(images, g_x).  g_bin is non-zero only at active positions, so both sums run over
+// set bits.  The pre-threshold activation is recomputed with the forward's exact tap order.
+// grid = (units share, channel chunk of kExbCCH); each thread keeps kExbCCH x 27 tap accumulators.
+__global__ void __launch_bounds__(kExbThreads)
+extract_bwd_kernel(const nnue_shape s, const float *__restrict__ images, const float *__restrict__ conv_w,
+                   const float *__restrict__ thr, const uint32_t *__restrict__ bits_s,
+                   const float *__restrict__ dval, float *__restrict__ partial) {
+    __shared__ __align__(16) float sw[kExbCCH * 28];
+    __shared__ float sthr[kExbCCH];
+    __shared__ float red[kExbThreads / 32][kExbCCH * 28];
+    const int c0 = blockIdx.y * kExbCCH;
+    const int cn = min(kExbCCH, s.C - c0);
+    stage_conv_weights(sw, sthr, conv_w, thr, c0, cn);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int cells = s.Gh * s.Gw;
+    float acc[kExbCCH][27];
+    float dth[kExbCCH];
+#pragma unroll
+    for (int cc = 0; cc < kExbCCH; ++cc) {
+        dth[cc] = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 27; ++t) acc[cc][t] = 0.0f;
+    }
+    const long long units = 1LL * s.B * s.CW;
+    for (long long u = 1LL * blockIdx.x * wpb + warp; u < units; u += 1LL * gridDim.x * wpb) {
+        const int b = (int)(u / s.CW), j = (int)(u % s.CW);
+        unsigned words[kExbCCH];
+        unsigned any = 0;
+#pragma unroll
+        for (int cc = 0; cc < kExbCCH; ++cc) {
+            words[cc] = cc < cn ? __ldg(bits_s + (size_t)b * s.NW + (c0 + cc) * s.CW + j) : 0u;
+            any |= words[cc];
+        }
+        if (!any) continue;  // warp-uniform
+        const int cell = j * 32 + lane;
+        const bool valid = cell < cells;
+        const int oy = valid ? cell / s.Gw : 0, ox = valid ? cell % s.Gw : 0;
+        float patch[28];
+        load_patch(patch, images + (size_t)b * 3 * s.H * s.W, s.H, s.W, oy, ox, s.stride, valid);
+#pragma unroll
+        for (int cc = 0; cc < kExbCCH; ++cc) {
+            if (!words[cc]) continue;  // warp-uniform
+            const bool on = (words[cc] >> lane) & 1u;
+            const float g = on ? __ldg(dval + (size_t)b * s.PP + ((size_t)(c0 + cc) * s.CW + j) * 32 + lane) : 0.0f;
+            const float x = conv_tap_sum(patch, sw + cc * 28);
+            const float sg = 1.0f / (1.0f + expf(-kSteSharpness * (x - sthr[cc])));
+            dth[cc] -= g * (kSteSharpness * sg * (1.0f - sg));
+#pragma unroll
+            for (int t = 0; t < 27; ++t) acc[cc][t] = fmaf(g, patch[t], acc[cc][t]);
+        }
+    }
+    // block reduction: warp shuffle, then across warps through shared memory (fixed order)
+#pragma unroll
+    for (int cc = 0; cc < kExbCCH; ++cc) {
+#pragma unroll
+        for (int t = 0; t < 27; ++t) {
+            const float v = warp_sum(acc[cc][t]);
+            if (lane == 0) red[warp][cc * 28 + t] = v;
+        }
+        const float v = warp_sum(dth[cc]);
+        if (lane == 0) red[warp][cc * 28 + 27] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cn * 28; i += blockDim.x) {
+        float v = 0.0f;
+        for (int w = 0; w < wpb; ++w) v += red[w][i];
+        partial[((size_t)blockIdx.x * s.C + c0) * 28 + i] = v;
+    }
+}
+
+// out: g_conv_w[c*27 + t], g_thr[c]; partial [nblk][C][28] summed in block order
+__global__ void extract_bwd_finish_kernel(int C, int nblk, const float *__restrict__ partial,
+                                          float *__restrict__ g_conv_w, float *__restrict__ g_thr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C * 28) return;
+    float v = 0.0f;
+    for (int k = 0; k < nblk; ++k) v += partial[(size_t)k * C * 28 + i];
+    const int c = i / 28, t = i % 28;
+    if (t < 27) g_conv_w[c * 27 + t] = v;
+    else g_thr[c] = v;
+}
+
+}  // namespace nnue
+
+using namespace nnue;
+
+extern "C" {
+
+int nnue_extract_fwd(const nnue_shape *s, const float *images_d, const float *conv_w_d, const float *thr_d,
+                     uint32_t *bits_s_d, uint32_t *bits_t_d, float *conv_out_d, int32_t *nnz_d, void *stream) {
+    if (!s || !images_d || !conv_w_d || !thr_d || !bits_s_d) return NNUE_ERR_INVALID_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem = (size_t)s->C * 29 * sizeof(float);
+    if (smem > 48 * 1024) return NNUE_ERR_UNSUPPORTED;  // C <= 423 channels
+    const long long units = 1LL * s->B * s->CW;
+    const int wpb = kExtThreads / 32;
+    long long grid = (units + wpb - 1) / wpb;
+    const long long cap = 32LL * kNumSMs;
+    if (grid > cap) grid = cap;
+    extract_fwd_kernel<<<(int)grid, kExtThreads, smem, st>>>(*s, images_d, conv_w_d, thr_d, bits_s_d, conv_out_d);
+    NNUE_CHECK_LAUNCH("extract_fwd_kernel");
+    if (bits_t_d) {
+        dim3 g(ceil_div(s->NW, 32), ceil_div(s->BW, kTrGroups)), blk(32, 32);
+        bits_transpose_kernel<<<g, blk, 0, st>>>(*s, bits_s_d, bits_t_d);
+        NNUE_CHECK_LAUNCH("bits_transpose_kernel");
+    }
+    if (nnz_d) {
+        bits_count_kernel<<<ceil_div(s->B, 8), 256, 0, st>>>(*s, bits_s_d, nnz_d);
+        NNUE_CHECK_LAUNCH("bits_count_kernel");
+    }
+    return NNUE_OK;
+}
+
+int nnue_sparse_from_bits(const nnue_shape *s, const uint32_t *bits_s_d, int K, int64_t *idx_d, float *val_d,
+                          void *stream) {
+    if (!s || !bits_s_d || !idx_d || !val_d || K < 1) return NNUE_ERR_INVALID_ARG;
+    sparse_from_bits_kernel<<<ceil_div(s->B, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(*s, bits_s_d, K, idx_d,
+                                                                                                val_d);
+    NNUE_CHECK_LAUNCH("sparse_from_bits_kernel");
+    return NNUE_OK;
+}
+
+int nnue_extract_bwd(const nnue_shape *s, const float *images_d, const float *conv_w_d, const float *thr_d,
+                     const uint32_t *bits_s_d, const float *dval_d, float *g_conv_w_d, float *g_thr_d,
+                     void *workspace_d, size_t workspace_bytes, void *stream) {
+    if (!s || !images_d || !conv_w_d || !thr_d || !bits_s_d || !dval_d || !g_conv_w_d || !g_thr_d || !workspace_d)
+        return NNUE_ERR_INVALID_ARG;
+    if (workspace_bytes < ws_extract_bwd(*s)) return NNUE_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float *partial = static_cast<float *>(workspace_d);
+    const int gx = exb_grid_x(*s);
+    dim3 grid(gx, ceil_div(s->C, kExbCCH));
+    extract_bwd_kernel<<<grid, kExbThreads, 0, st>>>(*s, images_d, conv_w_d, thr_d, bits_s_d, dval_d, partial);
+    NNUE_CHECK_LAUNCH("extract_bwd_kernel");
+    extract_bwd_finish_kernel<<<ceil_div(s->C * 28, 128), 128, 0, st>>>(s->C, gx, partial, g_conv_w_d, g_thr_d);
+    NNUE_CHECK_LAUNCH("extract_bwd_finish_kernel");
+    return NNUE_OK;
+}
+
+}  // extern "C"

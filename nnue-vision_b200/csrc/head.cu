@@ -1,0 +1,329 @@
+// head.cu -- pairwise product + the three dense layers (forward and backward) and the fused
+// mean cross-entropy.  The layers are small (L1 <= 1024 inputs, <= 1000 outputs) next to the batch,
+// so they run as fp32 register-tiled FMA kernels (exact fp32 accumulation keeps the 1e-5 parity
+// bar; a bf16/tf32 tensor-core path would not) with bias, ReLU, ReLU-mask and the pairwise
+// transform fused into the tile loaders and epilogues.
+#include "common.cuh"
+#include "plan.cuh"
+
+namespace nnue {
+
+// C[m, n] = epilogue( sum_k A(m,k) * B(k,n) ), operands addressed through element strides so
+// that one kernel serves X*W^T (forward), dY*W (input gradient) and dY^T*X (weight gradient).
+struct GemmArgs {
+    const float *A; long long sam, sak;
+    const float *Bm; long long sbk, sbn;
+    float *C; long long scm;            // C[m*scm + n]
+    int M, N, K;
+    const float *bias;                  // [N] added before the activation, or null
+    const float *mask; long long smm;   // C *= (mask[m*smm + n] > 0): ReLU backward, or null
+    int relu;                           // max(0, .) in the epilogue
+    int a_pair_half;                    // > 0: A is ft[m, 2h]; A(m,k) = k < h ? ft[m,k]*ft[m,k+h] : ft[m,k-h]
+    int b_pair_half;                    // > 0: same transform on B(k, n) = l0[k, n] rows of ft
+    int b_ones_col;                     // >= 0: B(k, n == b_ones_col) = 1 (bias-gradient column)
+    int ksplit;                         // K elements per blockIdx.z slice (split-K partials)
+    long long c_split_stride;           // elements between consecutive split-K partials of C
+};
+
+__device__ __forceinline__ float gemm_load_a(const GemmArgs &g, int m, int k) {
+    if (g.a_pair_half > 0) {
+        const int h = g.a_pair_half;
+        const float *row = g.A + (size_t)m * g.sam;
+        return k < h ? __ldg(row + k) * __ldg(row + k + h) : __ldg(row + k - h);
+    }
+    return __ldg(g.A + (size_t)m * g.sam + (size_t)k * g.sak);
+}
+__device__ __forceinline__ float gemm_load_b(const GemmArgs &g, int k, int n) {
+    if (n == g.b_ones_col) return 1.0f;
+    if (g.b_pair_half > 0) {
+        const int h = g.b_pair_half;
+        const float *row = g.Bm + (size_t)k * g.sbk;
+        return n < h ? __ldg(row + n) * __ldg(row + n + h) : __ldg(row + n - h);
+    }
+    return __ldg(g.Bm + (size_t)k * g.sbk + (size_t)n * g.sbn);
+}
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+gemm_kernel(const GemmArgs g) {
+    constexpr int BK = kGemmBK;
+    constexpr int NT = (BM / TM) * (BN / TN);
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int k_begin = blockIdx.z * g.ksplit;
+    const int k_end = min(g.K, k_begin + g.ksplit);
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+
+    const bool a_k_contig = (g.sak == 1) || g.a_pair_half > 0;
+    const bool b_k_contig = (g.sbk == 1) && g.b_pair_half == 0;
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+        for (int i = tid; i < BM * BK; i += NT) {
+            int m, k;
+            if (a_k_contig) { m = i / BK; k = i % BK; } else { k = i / BM; m = i % BM; }
+            const int gm = m0 + m, gk = k0 + k;
+            As[k][m] = (gm < g.M && gk < k_end) ? gemm_load_a(g, gm, gk) : 0.0f;
+        }
+        for (int i = tid; i < BN * BK; i += NT) {
+            int n, k;
+            if (b_k_contig) { n = i / BK; k = i % BK; } else { k = i / BN; n = i % BN; }
+            const int gn = n0 + n, gk = k0 + k;
+            Bs[k][n] = (gn < g.N && gk < k_end) ? gemm_load_b(g, gk, gn) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float *C = g.C + (size_t)blockIdx.z * g.c_split_stride;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + ty * TM + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx * TN + j;
+            if (n >= g.N) continue;
+            float v = acc[i][j];
+            if (g.bias) v += __ldg(g.bias + n);
+            if (g.relu) v = fmaxf(v, 0.0f);
+            if (g.mask) v = __ldg(g.mask + (size_t)m * g.smm + n) > 0.0f ? v : 0.0f;
+            C[(size_t)m * g.scm + n] = v;
+        }
+    }
+}
+
+static int launch_gemm(GemmArgs g, int splits, cudaStream_t st) {
+    g.ksplit = ceil_div(ceil_div(g.K, splits), kGemmBK) * kGemmBK;
+    const int nz = ceil_div(g.K, g.ksplit);
+    if (g.N <= 8) {
+        gemm_kernel<128, 8, 4, 1><<<dim3(ceil_div(g.M, 128), 1, nz), 256, 0, st>>>(g);
+    } else if (g.N <= 16) {
+        gemm_kernel<128, 16, 4, 2><<<dim3(ceil_div(g.M, 128), 1, nz), 256, 0, st>>>(g);
+    } else if (g.N <= 32) {
+        gemm_kernel<128, 32, 8, 2><<<dim3(ceil_div(g.M, 128), 1, nz), 256, 0, st>>>(g);
+    } else {
+        gemm_kernel<64, 64, 4, 4><<<dim3(ceil_div(g.M, 64), ceil_div(g.N, 64), nz), 256, 0, st>>>(g);
+    }
+    NNUE_CHECK_LAUNCH("gemm_kernel");
+    return nz;
+}
+
+// Weight(+bias) gradient: dWb[N_out, K_in + 1] = dY^T [N_out, B] * [X | 1] [B, K_in + 1], split over
+// the batch into partials, then folded in slice order into g_w [N_out, K_in] and g_b [N_out].
+__global__ void fold_wgrad_kernel(int n_out, int k_in, int nparts, const float *__restrict__ partial,
+                                  float *__restrict__ g_w, float *__restrict__ g_b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cols = k_in + 1;
+    if (i >= n_out * cols) return;
+    float acc = 0.0f;
+    for (int k = 0; k < nparts; ++k) acc += partial[(size_t)k * n_out * cols + i];
+    const int r = i / cols, c = i % cols;
+    if (c < k_in) g_w[(size_t)r * k_in + c] = acc;
+    else g_b[r] = acc;
+}
+
+static int wgrad(const float *dY, int n_out, const float *X, int k_in, int pair_half, int B, float *partial,
+                 float *g_w, float *g_b, cudaStream_t st) {
+    GemmArgs g{};
+    g.A = dY; g.sam = 1; g.sak = n_out;       // A(m = out, k = b) = dY[b, out]
+    g.Bm = X; g.sbk = pair_half > 0 ? 2 * pair_half : k_in; g.sbn = 1;  // B(k = b, n) = X[b, n]
+    g.b_pair_half = pair_half;
+    g.b_ones_col = k_in;
+    g.M = n_out; g.N = k_in + 1; g.K = B;
+    g.C = partial; g.scm = k_in + 1;
+    g.c_split_stride = (long long)n_out * (k_in + 1);
+    const int splits = gemm_splits(n_out, k_in + 1, B, 64, 64);
+    // always the 64x64 tile here: M and N are layer widths, K is the batch
+    g.ksplit = ceil_div(ceil_div(g.K, splits), kGemmBK) * kGemmBK;
+    const int nz = ceil_div(g.K, g.ksplit);
+    gemm_kernel<64, 64, 4, 4><<<dim3(ceil_div(g.M, 64), ceil_div(g.N, 64), nz), 256, 0, st>>>(g);
+    NNUE_CHECK_LAUNCH("gemm_kernel(wgrad)");
+    const int n = n_out * (k_in + 1);
+    fold_wgrad_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n_out, k_in, nz, partial, g_w, g_b);
+    NNUE_CHECK_LAUNCH("fold_wgrad_kernel");
+    return NNUE_OK;
+}
+
+// pairwise backward: g_ft[:, i] = g_l0[:, i] * ft[:, i+h] + g_l0[:, i+h];  g_ft[:, i+h] = g_l0[:, i] * ft[:, i]
+__global__ void pairwise_bwd_kernel(long long n, int h, const float *__restrict__ g_l0, const float *__restrict__ ft,
+                                    float *__restrict__ g_ft) {
+    const long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long b = i / h;
+    const int c = (int)(i % h);
+    const size_t o = (size_t)b * 2 * h + c;
+    const float gp = g_l0[o], ga = g_l0[o + h];
+    g_ft[o] = fmaf(gp, ft[o + h], ga);
+    g_ft[o + h] = gp * ft[o];
+}
+
+// mean cross-entropy + gradient; one warp per sample
+__global__ void __launch_bounds__(256)
+ce_kernel(int B, int NC, const float *__restrict__ logits, const int64_t *__restrict__ labels, float inv_count,
+          const float *__restrict__ g_scale, float *__restrict__ per_sample, float *__restrict__ g_logits) {
+    const int lane = threadIdx.x & 31;
+    const int b = (int)((1LL * blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (b >= B) return;
+    const float *row = logits + (size_t)b * NC;
+    float mx = -INFINITY;
+    for (int c = lane; c < NC; c += 32) mx = fmaxf(mx, row[c]);
+    mx = warp_max(mx);
+    float se = 0.0f;
+    for (int c = lane; c < NC; c += 32) se += expf(row[c] - mx);
+    se = warp_sum(se);
+    const int y = (int)labels[b];
+    const float lse = mx + logf(se);
+    if (per_sample && lane == 0) per_sample[b] = lse - row[y];
+    if (g_logits) {
+        const float g_mul = g_scale ? inv_count * __ldg(g_scale) : inv_count;
+        const float inv = 1.0f / se;
+        for (int c = lane; c < NC; c += 32) {
+            const float p = expf(row[c] - mx) * inv;
+            g_logits[(size_t)b * NC + c] = (p - (c == y ? 1.0f : 0.0f)) * g_mul;
+        }
+    }
+}
+// fixed-order tree sum of n values by one CTA
+__global__ void __launch_bounds__(1024)
+sum_scale_kernel(int n, const float *__restrict__ x, float scale, float *__restrict__ out) {
+    __shared__ float red[32];
+    float acc = 0.0f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += x[i];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) out[0] = v * scale;
+    }
+}
+
+}  // namespace nnue
+
+using namespace nnue;
+
+extern "C" {
+
+int nnue_head_fwd(const nnue_shape *s, const float *ft_out_d, const float *w1_d, const float *b1_d, const float *w2_d,
+                  const float *b2_d, const float *w3_d, const float *b3_d, float *act1_d, float *act2_d,
+                  float *logits_d, void *stream) {
+    if (!s || !ft_out_d || !w1_d || !b1_d || !w2_d || !b2_d || !w3_d || !b3_d || !act1_d || !act2_d || !logits_d)
+        return NNUE_ERR_INVALID_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GemmArgs g{};
+    g.b_ones_col = -1;
+    // layer 1: act1 = relu(l0 * W1^T + b1), l0 built on the fly from ft_out
+    g.A = ft_out_d; g.sam = s->L1; g.sak = 1; g.a_pair_half = s->L1 / 2;
+    g.Bm = w1_d; g.sbk = 1; g.sbn = s->L1;
+    g.M = s->B; g.N = s->L2; g.K = s->L1;
+    g.C = act1_d; g.scm = s->L2; g.bias = b1_d; g.relu = 1;
+    int rc = launch_gemm(g, 1, st);
+    if (rc < 0) return rc;
+    // layer 2
+    g.A = act1_d; g.sam = s->L2; g.a_pair_half = 0;
+    g.Bm = w2_d; g.sbn = s->L2;
+    g.N = s->L3; g.K = s->L2;
+    g.C = act2_d; g.scm = s->L3; g.bias = b2_d;
+    rc = launch_gemm(g, 1, st);
+    if (rc < 0) return rc;
+    // output layer
+    g.A = act2_d; g.sam = s->L3;
+    g.Bm = w3_d; g.sbn = s->L3;
+    g.N = s->NC; g.K = s->L3;
+    g.C = logits_d; g.scm = s->NC; g.bias = b3_d; g.relu = 0;
+    rc = launch_gemm(g, 1, st);
+    return rc < 0 ? rc : NNUE_OK;
+}
+
+int nnue_ce_fwd_bwd(int B, int NC, const float *logits_d, const int64_t *labels_d, float inv_count,
+                    const float *g_scale_d, float *loss_d, float *per_sample_d, float *g_logits_d, void *workspace_d,
+                    size_t workspace_bytes, void *stream) {
+    if (B < 1 || NC < 1 || !logits_d || !labels_d || (!loss_d && !g_logits_d)) return NNUE_ERR_INVALID_ARG;
+    float *per = per_sample_d;
+    if (!per && loss_d) {
+        if (!workspace_d || workspace_bytes < ws_ce(B)) return NNUE_ERR_WORKSPACE;
+        per = static_cast<float *>(workspace_d);
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ce_kernel<<<ceil_div(B, 8), 256, 0, st>>>(B, NC, logits_d, labels_d, inv_count, g_scale_d, per, g_logits_d);
+    NNUE_CHECK_LAUNCH("ce_kernel");
+    if (loss_d) {
+        sum_scale_kernel<<<1, 1024, 0, st>>>(B, per, inv_count, loss_d);
+        NNUE_CHECK_LAUNCH("sum_scale_kernel");
+    }
+    return NNUE_OK;
+}
+
+int nnue_head_bwd(const nnue_shape *s, const float *g_logits_d, const float *ft_out_d, const float *act1_d,
+                  const float *act2_d, const float *w1_d, const float *w2_d, const float *w3_d, float *g_w1_d,
+                  float *g_b1_d, float *g_w2_d, float *g_b2_d, float *g_w3_d, float *g_b3_d, float *g_ft_d,
+                  void *workspace_d, size_t workspace_bytes, void *stream) {
+    if (!s || !g_logits_d || !ft_out_d || !act1_d || !act2_d || !w1_d || !w2_d || !w3_d || !g_w1_d || !g_b1_d ||
+        !g_w2_d || !g_b2_d || !g_w3_d || !g_b3_d || !g_ft_d || !workspace_d)
+        return NNUE_ERR_INVALID_ARG;
+    if (workspace_bytes < ws_head_bwd(*s)) return NNUE_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int B = s->B, L1 = s->L1, L2 = s->L2, L3 = s->L3, NC = s->NC;
+    char *ws = static_cast<char *>(workspace_d);
+    auto carve = [&](size_t bytes) { float *p = reinterpret_cast<float *>(ws); ws += align_up(bytes, 256); return p; };
+    float *p3 = carve((size_t)gemm_splits(NC, L3 + 1, B, 64, 64) * NC * (L3 + 1) * 4);
+    float *p2 = carve((size_t)gemm_splits(L3, L2 + 1, B, 64, 64) * L3 * (L2 + 1) * 4);
+    float *p1 = carve((size_t)gemm_splits(L2, L1 + 1, B, 64, 64) * L2 * (L1 + 1) * 4);
+    float *g_act2 = carve((size_t)B * L3 * 4);
+    float *g_act1 = carve((size_t)B * L2 * 4);
+    float *g_l0 = carve((size_t)B * L1 * 4);
+
+    int rc = wgrad(g_logits_d, NC, act2_d, L3, 0, B, p3, g_w3_d, g_b3_d, st);
+    if (rc < 0) return rc;
+    GemmArgs g{};
+    g.b_ones_col = -1;
+    // g_z2 = (g_logits * W3) masked by act2 > 0
+    g.A = g_logits_d; g.sam = NC; g.sak = 1;
+    g.Bm = w3_d; g.sbk = L3; g.sbn = 1;
+    g.M = B; g.N = L3; g.K = NC;
+    g.C = g_act2; g.scm = L3; g.mask = act2_d; g.smm = L3;
+    rc = launch_gemm(g, 1, st);
+    if (rc < 0) return rc;
+    rc = wgrad(g_act2, L3, act1_d, L2, 0, B, p2, g_w2_d, g_b2_d, st);
+    if (rc < 0) return rc;
+    // g_z1 = (g_z2 * W2) masked by act1 > 0
+    g.A = g_act2; g.sam = L3;
+    g.Bm = w2_d; g.sbk = L2;
+    g.N = L2; g.K = L3;
+    g.C = g_act1; g.scm = L2; g.mask = act1_d; g.smm = L2;
+    rc = launch_gemm(g, 1, st);
+    if (rc < 0) return rc;
+    rc = wgrad(g_act1, L2, ft_out_d, L1, L1 / 2, B, p1, g_w1_d, g_b1_d, st);
+    if (rc < 0) return rc;
+    // g_l0 = g_z1 * W1, then the pairwise backward
+    g.A = g_act1; g.sam = L2;
+    g.Bm = w1_d; g.sbk = L1;
+    g.N = L1; g.K = L2;
+    g.C = g_l0; g.scm = L1; g.mask = nullptr;
+    rc = launch_gemm(g, 1, st);
+    if (rc < 0) return rc;
+    const long long n = 1LL * B * (L1 / 2);
+    pairwise_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(n, L1 / 2, g_l0, ft_out_d, g_ft_d);
+    NNUE_CHECK_LAUNCH("pairwise_bwd_kernel");
+    return NNUE_OK;
+}
+
+}  // extern "C"

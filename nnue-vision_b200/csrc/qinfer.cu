@@ -1,0 +1,461 @@
+// qinfer.cu -- quantized integer inference, bit-exact against serialize.py + engine/ of the
+// reference: .nnue v2 loader (host) and one fused kernel per batch:
+//   conv (int32) -> int8 clamp -> threshold -> int16 wrap-around accumulate -> clipped ReLU ->
+//   pairwise -> L1 (float divide, truncate) -> L2 (integer divide) -> output / 64.
+// One warp owns a sample; the active set never leaves registers (ballot words), the accumulator
+// is packed int16x2 (__vadd2 wraps exactly like the engine's int16 adds), the dense layers are
+// __dp4a over weights repacked at load time (all activations are in [0,127] by construction).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+struct nnue_qmodel {
+    int F, L1, L2, L3, NC, OC, G, n_buckets;
+    float nnue2score, quantized_one, threshold;
+    float conv_scale, ft_scale;
+    int L1p;   // L1 rounded up to 8 (table rows are 16-byte aligned)
+    int K1, K2, K3;  // dp4a depth (groups of 4 inputs) of the three dense layers
+    // device blobs
+    int32_t *conv_w;   // [OC][28] taps in the engine's [kh][kw][ic] order, widened to int32
+    int32_t *conv_b;   // [OC]
+    int16_t *ft_w;     // [F][L1p]
+    int16_t *ft_b;     // [L1p]  bias truncated to int16 (simd_scalar.cpp:82-84)
+    struct Stack {
+        float l1_scale, l2_scale, out_scale;
+        int32_t *w1, *b1;  // w1 [K1][L2] dp4a words: inputs 4k..4k+3 of output o
+        int32_t *w2, *b2;  // w2 [K2][L3]
+        int32_t *wo, *bo;  // wo [K3][NC]
+    };
+    std::vector<Stack> stacks;
+    std::vector<void *> allocs;
+    // scratch for nnue_q_infer_host (one instance per host thread, like NNUEEvaluator)
+    mutable float *h_img = nullptr, *h_logits = nullptr, *h_density = nullptr;
+    mutable size_t h_cap_img = 0, h_cap_b = 0;
+    mutable cudaStream_t h_stream = nullptr;
+};
+
+namespace nnue {
+
+struct Reader {
+    const unsigned char *p, *end;
+    bool ok = true;
+    bool take(void *dst, size_t n) {
+        if (!ok || (size_t)(end - p) < n) { ok = false; return false; }
+        memcpy(dst, p, n);
+        p += n;
+        return true;
+    }
+    bool skip(size_t n) {
+        if (!ok || (size_t)(end - p) < n) { ok = false; return false; }
+        p += n;
+        return true;
+    }
+    uint32_t u32() { uint32_t v = 0; take(&v, 4); return v; }
+    float f32() { float v = 0; take(&v, 4); return v; }
+};
+
+template <typename T>
+static int upload(nnue_qmodel *m, const std::vector<T> &h, T **out) {
+    void *d = nullptr;
+    NNUE_CUDA_TRY(cudaMalloc(&d, h.size() * sizeof(T) + 16));
+    m->allocs.push_back(d);
+    NNUE_CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<T *>(d);
+    return NNUE_OK;
+}
+
+// repack int8 [n_out][row_stride] (first k_in columns used) into dp4a words [ceil(k_in/4)][n_out]
+static std::vector<int32_t> pack_dp4a(const std::vector<int8_t> &w, int n_out, int k_in, int row_stride) {
+    const int K4 = (k_in + 3) / 4;
+    std::vector<int32_t> out((size_t)K4 * n_out, 0);
+    for (int o = 0; o < n_out; ++o)
+        for (int k = 0; k < k_in; ++k) {
+            const uint32_t byte = (uint8_t)w[(size_t)o * row_stride + k];
+            out[(size_t)(k / 4) * n_out + o] |= (int32_t)(byte << (8 * (k % 4)));
+        }
+    return out;
+}
+
+// Format: serialize.py:30-63 (header), 103-136 (conv), 394-420 (FT), 423-491 (stack).  Checks
+// mirror NNUEEvaluator::load_model / LayerStack::load_from_stream (nnue_engine.cpp:544-657, 283-380).
+static int parse_and_upload(const unsigned char *bytes, size_t n, nnue_qmodel *m) {
+    Reader r{bytes, bytes + n};
+    char magic[4];
+    if (!r.take(magic, 4) || memcmp(magic, "NNUE", 4) != 0) return NNUE_ERR_FORMAT;
+    if (r.u32() != 2 || !r.ok) return NNUE_ERR_FORMAT;
+    const uint32_t F = r.u32(), L1 = r.u32(), L2 = r.u32(), L3 = r.u32(), nb = r.u32();
+    m->nnue2score = r.f32(); m->quantized_one = r.f32(); m->threshold = r.f32();
+    (void)r.u32();  // conv layer type
+    m->conv_scale = r.f32();
+    const uint32_t OC = r.u32(), IC = r.u32(), KH = r.u32(), KW = r.u32();
+    if (!r.ok || IC != 3 || KH != 3 || KW != 3 || OC == 0 || OC > (1u << 20)) return NNUE_ERR_FORMAT;
+    std::vector<int8_t> cw((size_t)OC * 27);
+    if (!r.take(cw.data(), cw.size())) return NNUE_ERR_FORMAT;
+    if (r.u32() != OC) return NNUE_ERR_FORMAT;
+    std::vector<int32_t> cb(OC);
+    if (!r.take(cb.data(), (size_t)OC * 4)) return NNUE_ERR_FORMAT;
+    if (F == 0 || F % OC) return NNUE_ERR_FORMAT;
+    const int G = (int)sqrt((double)(F / OC));  // nnue_engine.cpp:599
+    if ((uint32_t)(G * G) * OC != F) return NNUE_ERR_FORMAT;
+    m->ft_scale = r.f32();
+    if (r.u32() != F || r.u32() != L1 || !r.ok || L1 == 0) return NNUE_ERR_FORMAT;
+    if ((uint64_t)F * L1 > (1ull << 31)) return NNUE_ERR_UNSUPPORTED;
+    std::vector<int16_t> fw((size_t)F * L1);
+    if (!r.take(fw.data(), fw.size() * 2)) return NNUE_ERR_FORMAT;
+    if (r.u32() != L1) return NNUE_ERR_FORMAT;
+    std::vector<int32_t> fb(L1);
+    if (!r.take(fb.data(), (size_t)L1 * 4)) return NNUE_ERR_FORMAT;
+    if (nb < 1 || nb > 4096) return NNUE_ERR_FORMAT;
+
+    m->F = (int)F; m->L1 = (int)L1; m->L2 = (int)L2; m->L3 = (int)L3; m->OC = (int)OC; m->G = G;
+    m->n_buckets = (int)nb;
+    m->L1p = (int)((L1 + 7) / 8 * 8);
+    m->K1 = (int)((L1 + 3) / 4); m->K2 = (int)((L2 + 3) / 4); m->K3 = (int)((L3 + 3) / 4);
+
+    // conv taps: the engine indexes the file's bytes as [oc][kh][kw][ic] (nnue_engine.cpp:69)
+    std::vector<int32_t> cw32((size_t)OC * 28, 0);
+    for (uint32_t oc = 0; oc < OC; ++oc)
+        for (int t = 0; t < 27; ++t) cw32[(size_t)oc * 28 + t] = cw[(size_t)oc * 27 + t];
+    std::vector<int16_t> fwp((size_t)F * m->L1p, 0), fbp((size_t)m->L1p, 0);
+    for (uint32_t f = 0; f < F; ++f) memcpy(&fwp[(size_t)f * m->L1p], &fw[(size_t)f * L1], (size_t)L1 * 2);
+    for (uint32_t i = 0; i < L1; ++i) fbp[i] = (int16_t)fb[i];
+    int rc;
+    if ((rc = upload(m, cw32, &m->conv_w)) || (rc = upload(m, cb, &m->conv_b)) || (rc = upload(m, fwp, &m->ft_w)) ||
+        (rc = upload(m, fbp, &m->ft_b)))
+        return rc;
+
+    for (uint32_t b = 0; b < nb; ++b) {
+        nnue_qmodel::Stack st{};
+        st.l1_scale = r.f32(); st.l2_scale = r.f32(); st.out_scale = r.f32();
+        (void)r.f32();  // l1_fact_scale
+        uint32_t rows = r.u32(), cols = r.u32();
+        if (!r.ok || rows != L2 + 1 || cols != L1 || L2 < 1 || L3 < 1) return NNUE_ERR_FORMAT;
+        std::vector<int8_t> w1((size_t)rows * cols);
+        if (!r.take(w1.data(), w1.size())) return NNUE_ERR_FORMAT;
+        uint32_t nbias = r.u32();
+        if (!r.ok || nbias < L2) return NNUE_ERR_FORMAT;
+        std::vector<int32_t> b1(nbias);
+        if (!r.take(b1.data(), (size_t)nbias * 4)) return NNUE_ERR_FORMAT;
+        rows = r.u32(); cols = r.u32();  // L1 factoriser: unused by the multiclass head
+        if (!r.ok || cols != L1 || rows <= L2) return NNUE_ERR_FORMAT;
+        if (!r.skip((size_t)rows * cols)) return NNUE_ERR_FORMAT;
+        nbias = r.u32();
+        if (!r.skip((size_t)nbias * 4)) return NNUE_ERR_FORMAT;
+        rows = r.u32(); cols = r.u32();
+        if (!r.ok || cols != 2 * L2 || rows != L3) return NNUE_ERR_FORMAT;
+        std::vector<int8_t> w2((size_t)rows * cols);
+        if (!r.take(w2.data(), w2.size())) return NNUE_ERR_FORMAT;
+        nbias = r.u32();
+        if (!r.ok || nbias < L3) return NNUE_ERR_FORMAT;
+        std::vector<int32_t> b2(nbias);
+        if (!r.take(b2.data(), (size_t)nbias * 4)) return NNUE_ERR_FORMAT;
+        rows = r.u32(); cols = r.u32();
+        if (!r.ok || cols != L3 || rows < 1 || rows > (1u << 24)) return NNUE_ERR_FORMAT;
+        if (b == 0) m->NC = (int)rows;
+        else if ((int)rows != m->NC) return NNUE_ERR_FORMAT;
+        std::vector<int8_t> wo((size_t)rows * cols);
+        if (!r.take(wo.data(), wo.size())) return NNUE_ERR_FORMAT;
+        nbias = r.u32();
+        if (!r.ok || nbias < rows) return NNUE_ERR_FORMAT;
+        std::vector<int32_t> bo(nbias);
+        if (!r.take(bo.data(), (size_t)nbias * 4)) return NNUE_ERR_FORMAT;
+        if ((rc = upload(m, pack_dp4a(w1, (int)L2, (int)L1, (int)L1), &st.w1)) || (rc = upload(m, b1, &st.b1)) ||
+            (rc = upload(m, pack_dp4a(w2, (int)L3, (int)L2, (int)(2 * L2)), &st.w2)) || (rc = upload(m, b2, &st.b2)) ||
+            (rc = upload(m, pack_dp4a(wo, m->NC, (int)L3, (int)L3), &st.wo)) || (rc = upload(m, bo, &st.bo)))
+            return rc;
+        m->stacks.push_back(st);
+    }
+    return NNUE_OK;
+}
+
+struct QParams {
+    int B, H, W, stride, oh, ow;
+    int F, L1, L2, L3, NC, OC, L1p, K1, K2, K3;
+    float threshold, conv_scale;
+    int conv_iscale, qone, l2_iscale;
+    float l1_scale, out_scale;
+    const int32_t *conv_w, *conv_b;
+    const int16_t *ft_w, *ft_b;
+    const int32_t *w1, *b1, *w2, *b2, *wo, *bo;
+    const float *images;
+    float *logits, *density;
+};
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return max(lo, min(hi, v)); }
+
+constexpr int kQWarps = 8;
+
+// MAXW: 32-bit accumulator words per lane (L1p/2 <= 32*MAXW)
+template <int MAXW>
+__global__ void __launch_bounds__(kQWarps * 32)
+q_infer_kernel(const QParams q) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t *s_cw = reinterpret_cast<int32_t *>(smem_raw);       // [OC][28]
+    int32_t *s_cb = s_cw + q.OC * 28;                             // [OC]
+    const int act_bytes = q.L1p * 2 + q.K1 * 4 + q.K2 * 4 + q.K3 * 4;
+    unsigned char *s_act = reinterpret_cast<unsigned char *>(s_cb + q.OC) + (threadIdx.x >> 5) * act_bytes;
+    for (int i = threadIdx.x; i < q.OC * 28; i += blockDim.x) s_cw[i] = q.conv_w[i];
+    for (int i = threadIdx.x; i < q.OC; i += blockDim.x) s_cb[i] = q.conv_b[i];
+    __syncthreads();
+
+    uint32_t *s_acc = reinterpret_cast<uint32_t *>(s_act);                  // int16x2 [L1p/2]
+    int8_t *s_pw = reinterpret_cast<int8_t *>(s_act + q.L1p * 2);           // [4*K1]
+    int8_t *s_h1 = s_pw + q.K1 * 4;                                         // [4*K2]
+    int8_t *s_h2 = s_h1 + q.K2 * 4;                                         // [4*K3]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwords = q.L1p / 2;
+    const int cells = q.oh * q.ow;
+    const uint32_t *ftw32 = reinterpret_cast<const uint32_t *>(q.ft_w);
+    const uint32_t *ftb32 = reinterpret_cast<const uint32_t *>(q.ft_b);
+
+    for (int b = blockIdx.x * kQWarps + warp; b < q.B; b += gridDim.x * kQWarps) {
+        const float *img = q.images + (size_t)b * q.H * q.W * 3;
+        uint32_t acc[MAXW];
+#pragma unroll
+        for (int i = 0; i < MAXW; ++i) acc[i] = (i * 32 + lane < nwords) ? __ldg(ftb32 + i * 32 + lane) : 0u;
+        int n_active = 0;
+
+        // Q1 + Q2 + Q3: conv cell per lane, ballot per channel, accumulate rows of set bits
+        for (int cell0 = 0; cell0 < cells; cell0 += 32) {
+            const int cell = cell0 + lane;
+            const bool valid = cell < cells;
+            const int oy = valid ? cell / q.ow : 0, ox = valid ? cell % q.ow : 0;
+            int xq[27];  // [kh][kw][ic], truncated (int32)(pixel * scale), 0 in the padding
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const int iy = oy * q.stride + kh - 1;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int ix = ox * q.stride + kw - 1;
+                    const bool in = valid && iy >= 0 && iy < q.H && ix >= 0 && ix < q.W;
+#pragma unroll
+                    for (int ic = 0; ic < 3; ++ic) {
+                        const float px = in ? __ldg(img + ((size_t)iy * q.W + ix) * 3 + ic) : 0.0f;
+                        xq[(kh * 3 + kw) * 3 + ic] = __float2int_rz(__fmul_rn(px, q.conv_scale));
+                    }
+                }
+            }
+            for (int oc = 0; oc < q.OC; ++oc) {
+                int a = s_cb[oc];
+                const int32_t *w = s_cw + oc * 28;
+#pragma unroll
+                for (int t = 0; t < 27; ++t) a += xq[t] * w[t];
+                const int v = clampi(a / q.conv_iscale, -127, 127);
+                const bool on = valid && oc < 64 && (float)v > q.threshold;
+                unsigned word = __ballot_sync(kFull, on);
+                n_active += __popc(word);
+                while (word) {
+                    const int k = __ffs(word) - 1;
+                    word &= word - 1;
+                    const uint32_t *row = ftw32 + ((size_t)(cell0 + k) * q.OC + oc) * nwords;
+#pragma unroll
+                    for (int i = 0; i < MAXW; ++i)
+                        if (i * 32 + lane < nwords) acc[i] = __vadd2(acc[i], __ldg(row + i * 32 + lane));
+                }
+            }
+        }
+        // buffer entries past the conv raster stay 0 (nnue_engine.cpp:720): active iff 0 > threshold
+        if (0.0f > q.threshold) {
+            for (int f = cells * q.OC; f < q.F; ++f) {
+                if (f % q.OC >= 64) continue;
+                ++n_active;
+                const uint32_t *row = ftw32 + (size_t)f * nwords;
+#pragma unroll
+                for (int i = 0; i < MAXW; ++i)
+                    if (i * 32 + lane < nwords) acc[i] = __vadd2(acc[i], __ldg(row + i * 32 + lane));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MAXW; ++i)
+            if (i * 32 + lane < nwords) s_acc[i * 32 + lane] = acc[i];
+        __syncwarp();
+
+        // Q4 clipped ReLU + Q5 pairwise (nnue_engine.cpp:726-729, 490-500)
+        const int16_t *a16 = reinterpret_cast<const int16_t *>(s_acc);
+        const int half = q.L1 / 2;
+        for (int i = lane; i < q.K1 * 4; i += 32) {
+            int v = 0;
+            if (i < half) {
+                const int x = clampi(a16[i], 0, q.qone), y = clampi(a16[i + half], 0, q.qone);
+                v = clampi((x * y) / 128, 0, 127);
+            } else if (i < 2 * half) {
+                v = clampi(clampi(a16[i - half], 0, q.qone), 0, 127);
+            }
+            s_pw[i] = (int8_t)v;
+        }
+        __syncwarp();
+        // L1: float divide then truncate (simd_scalar.cpp:131-133), clamp 0..127
+        const int32_t *pw4 = reinterpret_cast<const int32_t *>(s_pw);
+        for (int o = lane; o < q.K2 * 4; o += 32) {
+            int v = 0;
+            if (o < q.L2) {
+                int a = __ldg(q.b1 + o);
+                for (int k = 0; k < q.K1; ++k) a = __dp4a(pw4[k], __ldg(q.w1 + (size_t)k * q.L2 + o), a);
+                v = clampi(__float2int_rz(__fdiv_rn(__int2float_rn(a), q.l1_scale)), 0, 127);
+            }
+            s_h1[o] = (int8_t)v;
+        }
+        __syncwarp();
+        // L2: integer divide (truncating), clamp +-127, ReLU (nnue_engine.cpp:512-523)
+        const int32_t *h14 = reinterpret_cast<const int32_t *>(s_h1);
+        for (int o = lane; o < q.K3 * 4; o += 32) {
+            int v = 0;
+            if (o < q.L3) {
+                int a = __ldg(q.b2 + o);
+                for (int k = 0; k < q.K2; ++k) a = __dp4a(h14[k], __ldg(q.w2 + (size_t)k * q.L3 + o), a);
+                v = max(0, clampi(a / q.l2_iscale, -127, 127));
+            }
+            s_h2[o] = (int8_t)v;
+        }
+        __syncwarp();
+        // output: (float)acc / output_scale (nnue_engine.cpp:526-533)
+        const int32_t *h24 = reinterpret_cast<const int32_t *>(s_h2);
+        for (int c = lane; c < q.NC; c += 32) {
+            int a = __ldg(q.bo + c);
+            for (int k = 0; k < q.K3; ++k) a = __dp4a(h24[k], __ldg(q.wo + (size_t)k * q.NC + c), a);
+            q.logits[(size_t)b * q.NC + c] = __fdiv_rn(__int2float_rn(a), q.out_scale);
+        }
+        if (q.density && lane == 0)
+            q.density[b] = __fdiv_rn(__int2float_rn(n_active), __int2float_rn(q.F));  // nnue_inference.cpp:54
+        __syncwarp();
+    }
+}
+
+static int fill_params(const nnue_qmodel *m, int B, int H, int W, int bucket, QParams *q) {
+    if (!m || B < 1 || H < 1 || W < 1) return NNUE_ERR_INVALID_ARG;
+    if (bucket < 0) return NNUE_ERR_INVALID_ARG;
+    if (bucket >= m->n_buckets) bucket = 0;  // nnue_engine.cpp:705-707
+    // engine stride rule: ceil((H-1)/(G-1)), collapse to one cell when G == 1 (nnue_engine.cpp:710-718)
+    int stride = m->G > 1 ? (H - 1 + m->G - 2) / (m->G - 1) : (H > 1 ? H : 1);
+    if (stride < 1) stride = 1;
+    q->B = B; q->H = H; q->W = W; q->stride = stride;
+    q->oh = (H - 1) / stride + 1; q->ow = (W - 1) / stride + 1;
+    if (1LL * q->oh * q->ow * m->OC > m->F) return NNUE_ERR_RASTER;
+    q->F = m->F; q->L1 = m->L1; q->L2 = m->L2; q->L3 = m->L3; q->NC = m->NC; q->OC = m->OC;
+    q->L1p = m->L1p; q->K1 = m->K1; q->K2 = m->K2; q->K3 = m->K3;
+    q->threshold = m->threshold; q->conv_scale = m->conv_scale;
+    q->conv_iscale = (int)m->conv_scale;
+    q->qone = (int)(int16_t)m->quantized_one;
+    const nnue_qmodel::Stack &st = m->stacks[(size_t)bucket];
+    q->l2_iscale = (int)st.l2_scale; q->l1_scale = st.l1_scale; q->out_scale = st.out_scale;
+    if (q->conv_iscale == 0 || q->l2_iscale == 0) return NNUE_ERR_FORMAT;
+    q->conv_w = m->conv_w; q->conv_b = m->conv_b; q->ft_w = m->ft_w; q->ft_b = m->ft_b;
+    q->w1 = st.w1; q->b1 = st.b1; q->w2 = st.w2; q->b2 = st.b2; q->wo = st.wo; q->bo = st.bo;
+    return NNUE_OK;
+}
+
+static int launch_q_infer(const QParams &q, cudaStream_t st) {
+    const size_t act = (size_t)q.L1p * 2 + (size_t)(q.K1 + q.K2 + q.K3) * 4;
+    const size_t smem = (size_t)q.OC * 29 * 4 + kQWarps * act;
+    if (smem > 200 * 1024) return NNUE_ERR_UNSUPPORTED;
+    int grid = ceil_div(q.B, kQWarps);
+    if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
+    const int nwords = q.L1p / 2;
+#define NNUE_QLAUNCH(MAXW)                                                                                   \
+    do {                                                                                                     \
+        auto k = q_infer_kernel<MAXW>;                                                                       \
+        if (smem > 48 * 1024)                                                                                \
+            NNUE_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        k<<<grid, kQWarps * 32, smem, st>>>(q);                                                              \
+    } while (0)
+    if (nwords <= 32) NNUE_QLAUNCH(1);
+    else if (nwords <= 128) NNUE_QLAUNCH(4);
+    else if (nwords <= 512) NNUE_QLAUNCH(16);
+    else if (nwords <= 1024) NNUE_QLAUNCH(32);
+    else return NNUE_ERR_UNSUPPORTED;
+#undef NNUE_QLAUNCH
+    NNUE_CHECK_LAUNCH("q_infer_kernel");
+    return NNUE_OK;
+}
+
+}  // namespace nnue
+
+using namespace nnue;
+
+extern "C" {
+
+void nnue_q_free(nnue_qmodel *m) {
+    if (!m) return;
+    for (void *p : m->allocs) cudaFree(p);
+    if (m->h_img) cudaFree(m->h_img);
+    if (m->h_logits) cudaFree(m->h_logits);
+    if (m->h_density) cudaFree(m->h_density);
+    if (m->h_stream) cudaStreamDestroy(m->h_stream);
+    delete m;
+}
+
+int nnue_q_load_memory(const void *bytes_h, size_t n_bytes, nnue_qmodel **out) {
+    if (!bytes_h || !out) return NNUE_ERR_INVALID_ARG;
+    *out = nullptr;
+    nnue_qmodel *m = new nnue_qmodel();
+    const int rc = parse_and_upload(static_cast<const unsigned char *>(bytes_h), n_bytes, m);
+    if (rc != NNUE_OK) { nnue_q_free(m); return rc; }
+    *out = m;
+    return NNUE_OK;
+}
+
+int nnue_q_load(const char *path, nnue_qmodel **out) {
+    if (!path || !out) return NNUE_ERR_INVALID_ARG;
+    *out = nullptr;
+    FILE *f = fopen(path, "rb");
+    if (!f) return NNUE_ERR_IO;
+    std::vector<unsigned char> buf;
+    unsigned char chunk[1 << 16];
+    size_t got;
+    while ((got = fread(chunk, 1, sizeof(chunk), f)) > 0) buf.insert(buf.end(), chunk, chunk + got);
+    const bool err = ferror(f) != 0;
+    fclose(f);
+    if (err) return NNUE_ERR_IO;
+    return nnue_q_load_memory(buf.data(), buf.size(), out);
+}
+
+int nnue_q_dims(const nnue_qmodel *m, int32_t *dims, float *visual_threshold) {
+    if (!m || !dims) return NNUE_ERR_INVALID_ARG;
+    dims[0] = m->F; dims[1] = m->L1; dims[2] = m->L2; dims[3] = m->L3; dims[4] = m->NC; dims[5] = m->OC;
+    dims[6] = m->G; dims[7] = m->n_buckets;
+    if (visual_threshold) *visual_threshold = m->threshold;
+    return NNUE_OK;
+}
+
+int nnue_q_infer(const nnue_qmodel *m, const float *images_d, int B, int H, int W, int bucket, float *logits_d,
+                 float *density_d, void *stream) {
+    if (!images_d || !logits_d) return NNUE_ERR_INVALID_ARG;
+    QParams q{};
+    const int rc = fill_params(m, B, H, W, bucket, &q);
+    if (rc != NNUE_OK) return rc;
+    q.images = images_d; q.logits = logits_d; q.density = density_d;
+    return launch_q_infer(q, static_cast<cudaStream_t>(stream));
+}
+
+int nnue_q_infer_host(const nnue_qmodel *m, const float *images_h, int B, int H, int W, int bucket, float *logits_h,
+                      float *density_h) {
+    if (!m || !images_h || !logits_h || B < 1 || H < 1 || W < 1) return NNUE_ERR_INVALID_ARG;
+    const size_t img_bytes = (size_t)B * H * W * 3 * 4;
+    if (!m->h_stream) NNUE_CUDA_TRY(cudaStreamCreateWithFlags(&m->h_stream, cudaStreamNonBlocking));
+    if (img_bytes > m->h_cap_img) {
+        if (m->h_img) { cudaFree(m->h_img); m->h_img = nullptr; m->h_cap_img = 0; }
+        NNUE_CUDA_TRY(cudaMalloc(&m->h_img, img_bytes));
+        m->h_cap_img = img_bytes;
+    }
+    if ((size_t)B > m->h_cap_b) {
+        if (m->h_logits) { cudaFree(m->h_logits); cudaFree(m->h_density); m->h_logits = nullptr; m->h_cap_b = 0; }
+        NNUE_CUDA_TRY(cudaMalloc(&m->h_logits, (size_t)B * m->NC * 4));
+        NNUE_CUDA_TRY(cudaMalloc(&m->h_density, (size_t)B * 4));
+        m->h_cap_b = (size_t)B;
+    }
+    NNUE_CUDA_TRY(cudaMemcpyAsync(m->h_img, images_h, img_bytes, cudaMemcpyHostToDevice, m->h_stream));
+    const int rc = nnue_q_infer(m, m->h_img, B, H, W, bucket, m->h_logits, m->h_density, m->h_stream);
+    if (rc != NNUE_OK) return rc;
+    NNUE_CUDA_TRY(cudaMemcpyAsync(logits_h, m->h_logits, (size_t)B * m->NC * 4, cudaMemcpyDeviceToHost, m->h_stream));
+    if (density_h)
+        NNUE_CUDA_TRY(cudaMemcpyAsync(density_h, m->h_density, (size_t)B * 4, cudaMemcpyDeviceToHost, m->h_stream));
+    NNUE_CUDA_TRY(cudaStreamSynchronize(m->h_stream));
+    return NNUE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+"""-m gpu: the quantized integer inference path must be BIT-EXACT against the reference's
+serialize.py + C++ engine (golden vectors), against the C oracle, and -- where oracle/_ref was
+built -- against the reference engine itself, through both the device and the host entry points."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from util import GOLDEN, GOLDEN_CASES, INT_ARCHS, load_golden, write_random_nnue
+
+
+def _engine():
+    from nnue_vision_b200 import engine
+    return engine
+
+
+def chw_bytes_as_hwc(images_chw):
+    B, C, H, W = images_chw.shape
+    return np.ascontiguousarray(images_chw).reshape(B, H, W, C)
+
+
+def gpu_eval(ev, imgs_bhwc):
+    logits, dens = ev.evaluate_logits(torch.as_tensor(imgs_bhwc).cuda().contiguous())
+    torch.cuda.synchronize()
+    return logits.cpu().numpy(), dens.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_matches_reference_engine_golden(name):
+    rec = load_golden(name)
+    n = int(rec["int.n_images"])
+    ev = _engine().NNUEEvaluator(GOLDEN / f"{name}.nnue")
+    c = rec["cfg"]
+    assert (ev.num_features, ev.l1_size, ev.l2_size, ev.l3_size, ev.num_classes, ev.grid_size) == (
+        c["grid"] ** 2 * c["C"], c["L1"], c["L2"], c["L3"], c["NC"], c["grid"])
+    imgs = chw_bytes_as_hwc(rec["images"][:n])
+    logits, dens = gpu_eval(ev, imgs)
+    np.testing.assert_array_equal(logits, rec["int.logits"])
+    np.testing.assert_array_equal(dens, rec["int.density"])
+    hl, hd = ev.evaluate_logits_host(imgs)
+    np.testing.assert_array_equal(hl, rec["int.logits"])
+    np.testing.assert_array_equal(hd, rec["int.density"])
+
+
+@pytest.mark.parametrize("arch", INT_ARCHS, ids=lambda a: "x".join(map(str, a)))
+@pytest.mark.parametrize("wild", [False, True])
+def test_random_models_match_oracle(oracle_built, tmp_path, arch, wild):
+    """Random .nnue payloads over the format's full integer ranges: int16 wraparound, every clamp,
+    negative thresholds (zero-filled tail of the conv buffer becomes active), > 64 channels."""
+    G, C, L1, L2, L3, NC, H = arch
+    rng = np.random.default_rng(abs(hash(arch)) % (2**32) + 17 * wild)
+    path = tmp_path / "m.nnue"
+    write_random_nnue(path, rng, G, C, L1, L2, L3, NC, wild=wild)
+    B = 5 if H > 100 else 37
+    imgs = (rng.standard_normal((B, H, H, 3)) * (3.0 if wild else 1.0)).astype(np.float32)
+    imgs[0] = 0.0
+    orc = oracle_built.IntOracle(path)
+    ol, od = orc.eval_batch(imgs, threads=4)
+    ev = _engine().NNUEEvaluator(path)
+    gl, gd = gpu_eval(ev, imgs)
+    np.testing.assert_array_equal(gl, ol)
+    np.testing.assert_array_equal(gd, od)
+    if oracle_built.RefEngine.available():
+        rl, rd = oracle_built.RefEngine(path).eval_batch(imgs, threads=4)
+        np.testing.assert_array_equal(gl, rl)
+        np.testing.assert_array_equal(gd, rd)
+
+
+@pytest.mark.parametrize("thr", [-0.5, 0.0, 126.5, 127.0])
+def test_threshold_edges(oracle_built, tmp_path, thr):
+    rng = np.random.default_rng(3)
+    path = tmp_path / "m.nnue"
+    write_random_nnue(path, rng, 6, 8, 64, 8, 8, 10, wild=True, threshold=thr)
+    imgs = (rng.standard_normal((16, 40, 40, 3)) * 4).astype(np.float32)
+    ol, od = oracle_built.IntOracle(path).eval_batch(imgs)
+    gl, gd = gpu_eval(_engine().NNUEEvaluator(path), imgs)
+    np.testing.assert_array_equal(gl, ol)
+    np.testing.assert_array_equal(gd, od)
+
+
+def test_batch_sweep_is_batch_invariant_and_exact(oracle_built):
+    """BASELINE config: batch sweep 1..65536 on the default model.  The oracle checks the first
+    2048 samples; beyond that, per-sample results must not depend on the batch they ran in."""
+    path = GOLDEN / "default_cfg.nnue"
+    rng = np.random.default_rng(11)
+    full = rng.standard_normal((65536, 32, 32, 3)).astype(np.float32)
+    ev = _engine().NNUEEvaluator(path)
+    big_l, big_d = gpu_eval(ev, full)
+    ol, od = oracle_built.IntOracle(path).eval_batch(full[:2048], threads=8)
+    np.testing.assert_array_equal(big_l[:2048], ol)
+    np.testing.assert_array_equal(big_d[:2048], od)
+    for B in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 4096, 16384):
+        l, d = gpu_eval(ev, full[:B])
+        np.testing.assert_array_equal(l, big_l[:B])
+        np.testing.assert_array_equal(d, big_d[:B])
+    # logits are multiples of 1/64 (nnue_engine.cpp:532)
+    assert np.all(big_l * 64 == np.round(big_l * 64))
+
+
+def test_serialized_model_round_trip(oracle_built, tmp_path):
+    """float model -> our serializer -> our GPU engine == C oracle on the same file."""
+    from nnue_vision_b200 import nnue, serialize
+    torch.manual_seed(5)
+    model = nnue.NNUE(nnue.GridFeatureSet(10, 8), 64, 32, 8, num_classes=10, input_size=32)
+    with torch.no_grad():
+        model.input.weight.mul_(3.0)
+        model.input.bias.normal_(0, 0.5)
+    path = tmp_path / "m.nnue"
+    serialize.serialize_model(model, path)
+    rng = np.random.default_rng(0)
+    chw = rng.standard_normal((64, 3, 32, 32)).astype(np.float32)
+    imgs = chw_bytes_as_hwc(chw)
+    ol, od = oracle_built.IntOracle(path).eval_batch(imgs)
+    gl, gd = gpu_eval(_engine().NNUEEvaluator(path), imgs)
+    np.testing.assert_array_equal(gl, ol)
+    np.testing.assert_array_equal(gd, od)
+
+
+def test_load_errors(tmp_path):
+    eng = _engine()
+    ev = eng.NNUEEvaluator()
+    assert ev.load_model(tmp_path / "missing.nnue") is False
+    good = (GOLDEN / "parity_small.nnue").read_bytes()
+    for bad in (b"XXXX" + good[4:], good[:4] + b"\x03\x00\x00\x00" + good[8:], good[:300], good[:-2]):
+        p = tmp_path / "bad.nnue"
+        p.write_bytes(bad)
+        assert ev.load_model(p) is False
+    assert ev.load_model(GOLDEN / "parity_small.nnue") is True
+    from nnue_vision_b200 import _lib
+    with pytest.raises(_lib.NnueError):  # 64x48 image: raster would overrun the feature buffer
+        ev.evaluate_logits(torch.zeros(1, 48, 200, 3).cuda())
