@@ -1,0 +1,432 @@
+#!/usr/bin/env python3
+"""bench.py -- NNUE train samples/s (fwd+bwd) on B200, with roofline, CPU baseline and e2e legs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (N=1 default)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W     # N > 1: one rank per GPU, NCCL
+    python bench.py --impl reference [...]                         # the reference's CPU path
+
+A "step" is one pass of the hot path (grid-feature extraction -> feature transformer ->
+pairwise + head -> mean CE -> full backward -> gradient all-reduce when N > 1) over one batch of
+synthetic CIFAR-shaped input, config `train_nnue_default.py` at batch 16384 per GPU (weak scaling).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+# config/train_nnue_default.py:16-35 of the reference (batch overridden to the BASELINE value)
+WORKLOADS = {
+    "default_cifar_b16384": dict(grid=10, C=8, L1=64, L2=32, L3=8, NC=10, input=32, image=32, batch=16384),
+    "test_cifar_b16": dict(grid=8, C=4, L1=64, L2=4, L3=8, NC=10, input=32, image=32, batch=16),
+    "real_cifar_l1_1024_b16384": dict(grid=10, C=8, L1=1024, L2=128, L3=32, NC=10, input=32, image=32, batch=16384),
+    "imagenet_small_b2048": dict(grid=16, C=32, L1=256, L2=16, L3=32, NC=1000, input=224, image=224, batch=2048),
+}
+METRIC = "nnue_train_samples_per_sec_fwd_bwd"
+UNIT = "samples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="default_cifar_b16384", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-int", action="store_true", help="skip the integer-inference side measurement")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(w, device, seed=42):
+    from nnue_vision_b200 import nnue
+    torch.manual_seed(seed)  # the reference's own initialisers, same RNG stream (tests/test_serialize.py)
+    model = nnue.NNUE(nnue.GridFeatureSet(w["grid"], w["C"]), w["L1"], w["L2"], w["L3"], num_classes=w["NC"],
+                      input_size=w["input"])
+    return model.to(device)
+
+
+def synthetic_batch(w, B, seed, device=None, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    images = torch.randn(B, 3, w["image"], w["image"], generator=g)
+    labels = torch.randint(0, w["NC"], (B,), generator=g)
+    if pin:
+        return images.pin_memory(), labels.pin_memory()
+    return images.to(device), labels.to(device)
+
+
+def max_over_ranks(ms, world, device):
+    if world == 1:
+        return ms
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+
+def cpu_baseline_training(w, seconds, threads=None):
+    """The oracle's reference-shaped step (per-sample nonzero / gather-sum loops under autograd --
+    the algorithm of nnue.py:601-606, 694-708) timed on the host cores: kind "port"."""
+    from oracle import float_oracle as fo
+    if threads:
+        torch.set_num_threads(threads)
+    B = min(256, w["batch"])
+    torch.manual_seed(42)
+    state = cpu_reference_state(w)
+    images, labels = synthetic_batch(w, B, seed=7, device="cpu")
+    stride = fo.python_stride(w["input"], w["grid"])
+    fo.reference_style_step(state, images, labels, stride)  # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        fo.reference_style_step(state, images, labels, stride)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > seconds or n >= 200:
+            break
+    return {"value": n * B / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} fwd+bwd passes of batch {B} of workload (oracle.float_oracle.reference_style_step), {dt:.1f} s"}
+
+
+def cpu_reference_state(w):
+    """Reference-initialised parameters as plain CPU tensors (no CUDA needed)."""
+    from nnue_vision_b200 import nnue
+    torch.manual_seed(42)
+    m = nnue.NNUE(nnue.GridFeatureSet(w["grid"], w["C"]), w["L1"], w["L2"], w["L3"], num_classes=w["NC"],
+                  input_size=w["input"])
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the training path on the host cores.
+    The reference's float path is Python (nnue.py) and cannot travel to the GPU box, so this arm
+    times the oracle's faithful restatement of it (kind "port") with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = dict(WORKLOADS[args.workload])
+    if args.batch:
+        w["batch"] = args.batch
+    from oracle import float_oracle as fo
+    from oracle.int_oracle import host_threads
+    threads = host_threads()
+    torch.set_num_threads(threads)
+    B = min(256, w["batch"])
+    state = cpu_reference_state(w)
+    images, labels = synthetic_batch(w, B, seed=7, device="cpu")
+    stride = fo.python_stride(w["input"], w["grid"])
+    for _ in range(max(1, min(args.warmup, 3))):
+        fo.reference_style_step(state, images, labels, stride)
+    steps = max(1, min(args.steps, 40))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fo.reference_style_step(state, images, labels, stride)
+    dt = time.perf_counter() - t0
+    value = steps * B / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "batch_per_step": B,
+                   "note": "CPU only; each step is a bounded sample (batch 256) of the workload; cost is linear in batch"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{steps} fwd+bwd passes of batch {B} (oracle.float_oracle.reference_style_step)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def stage_breakdown(dp, images, labels, reps=5):
+    """Average device time of each C-ABI stage, from CUDA events recorded on the launching stream."""
+    totals = {}
+    for _ in range(reps):
+        marks = []
+        dp.step(images, labels, marks=marks)
+        torch.cuda.synchronize()
+        for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+            totals[n1] = totals.get(n1, 0.0) + e0.elapsed_time(e1)
+    return {k: v / reps for k, v in totals.items()}
+
+
+def int_inference_leg(w, device, seconds):
+    """Side measurement: batched bit-exact integer inference (nnue_q_infer) vs the reference's C++ engine
+    (oracle/_ref, kind "reference") or the C oracle (kind "port") on the host cores."""
+    import tempfile
+    import numpy as np
+    from nnue_vision_b200 import engine, serialize
+    from oracle import int_oracle
+    model = build_model(w, "cpu")
+    B = w["batch"]
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        path = Path(td) / "m.nnue"
+        serialize.serialize_model(model, path)
+        ev = engine.NNUEEvaluator(path)
+        imgs = torch.randn(B, w["image"], w["image"], 3, generator=torch.Generator().manual_seed(3))
+        d_imgs = imgs.to(device)
+        for _ in range(3):
+            ev.evaluate_logits(d_imgs)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        e0.record()
+        for _ in range(reps):
+            logits, dens = ev.evaluate_logits(d_imgs)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out["device"] = {"value": B / (ms * 1e-3), "unit": "samples/s", "batch": B, "ms": ms}
+        # end to end through host buffers (pinned), copies inside the C call
+        pinned = imgs.pin_memory().numpy()
+        ev.evaluate_logits_host(pinned)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            hl, hd = ev.evaluate_logits_host(pinned)
+        dt = (time.perf_counter() - t0) / 5
+        out["e2e_host"] = {"value": B / dt, "unit": "samples/s", "h2d_bytes": int(pinned.nbytes),
+                           "d2h_bytes": int(hl.nbytes + hd.nbytes)}
+        # CPU: the reference engine on all host threads (bounded sample), checked bit-exact first
+        n = min(B, 4096)
+        threads = int_oracle.host_threads()
+        kind = "reference" if int_oracle.RefEngine.available() else "port"
+        cpu = int_oracle.RefEngine(path) if kind == "reference" else int_oracle.IntOracle(path)
+        sample = imgs[:n].numpy()
+        cl, cd = cpu.eval_batch(sample, threads=threads)
+        out["bit_exact_vs_cpu"] = bool(np.array_equal(cl, hl[:n]) and np.array_equal(cd, hd[:n]))
+        reps, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds / 3:
+            cpu.eval_batch(sample, threads=threads)
+            reps += 1
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": reps * n / dt, "unit": "samples/s", "cores": threads, "kind": kind,
+                               "sample": f"{reps} x {n} images through evaluate_logits, one evaluator per thread"}
+        t0 = time.perf_counter()
+        cpu.eval_batch(sample[:512], threads=1)
+        out["cpu_single_thread"] = {"value": 512 / (time.perf_counter() - t0), "unit": "samples/s", "cores": 1}
+    return out
+
+
+def run_b200(args):
+    from nnue_vision_b200 import _lib, train
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the NNUE hot path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=device)
+    w = dict(WORKLOADS[args.workload])
+    if args.batch:
+        w["batch"] = args.batch
+    B = w["batch"]
+    model = build_model(w, device)
+    dp = train.DataParallelStep(model)
+    if world > 1:  # identical replicas
+        for p in model.parameters():
+            torch.distributed.broadcast(p.data, src=0)
+
+    # three input sets (3 x B x 12 KB = 600 MB at CIFAR shape, far above the 126 MB L2), cycled
+    n_sets = 3
+    sets = [synthetic_batch(w, B, seed=1000 * rank + i, device=device) for i in range(n_sets)]
+    global_batch = B * world
+
+    for i in range(max(args.warmup, 3)):
+        dp.step(*sets[i % n_sets], global_batch=global_batch)
+    barrier(world)
+    _lib.lib().nnue_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for i in range(args.steps):
+            loss = dp.step(*sets[i % n_sets], global_batch=global_batch)
+        e1.record()
+        barrier(world)
+    launches = int(_lib.lib().nnue_launch_count(0))
+    ms_total = max_over_ranks(e0.elapsed_time(e1), world, device)
+    value = args.steps * global_batch / (ms_total * 1e-3)
+    final_loss = float(loss)
+
+    # ---- e2e: the user-facing call with HOST buffers; H2D of the step's inputs and D2H of the loss timed
+    host_sets = [synthetic_batch(w, B, seed=2000 * rank + i, pin=True) for i in range(2)]
+    dev_img = [torch.empty_like(sets[0][0]) for _ in range(2)]
+    dev_lab = [torch.empty_like(sets[0][1]) for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+
+    def e2e_steps(n):
+        # double-buffered: the copy of step i+1 overlaps the kernels of step i; every step still
+        # moves its own inputs host->device and reads its loss back
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        with torch.cuda.stream(copy_stream):
+            dev_img[0].copy_(host_sets[0][0], non_blocking=True)
+            dev_lab[0].copy_(host_sets[0][1], non_blocking=True)
+            ready[0].record()
+        losses = []
+        for i in range(n):
+            cur, nxt = i % 2, (i + 1) % 2
+            if i + 1 < n:
+                with torch.cuda.stream(copy_stream):
+                    if i >= 1:
+                        copy_stream.wait_event(done[nxt])
+                    dev_img[nxt].copy_(host_sets[nxt][0], non_blocking=True)
+                    dev_lab[nxt].copy_(host_sets[nxt][1], non_blocking=True)
+                    ready[nxt].record()
+            torch.cuda.current_stream().wait_event(ready[cur])
+            l = dp.step(dev_img[cur], dev_lab[cur], global_batch=global_batch)
+            done[cur].record()
+            losses.append(float(l))  # D2H read of the step's result
+        return losses
+
+    e2e_steps(3)
+    barrier(world)
+    t0 = time.perf_counter()
+    e2e_steps(args.steps)
+    barrier(world)
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, device)
+    e2e_value = args.steps * global_batch / (e2e_ms * 1e-3)
+    h2d = int(host_sets[0][0].numel() * 4 + host_sets[0][1].numel() * 8) * world
+
+    # ---- per-stage device times and the roofline of the dominant kernel
+    stages = stage_breakdown(dp, *sets[0])
+    shape, bits = model.extract_bits(sets[0][0])
+    nnz_total = int(sum(int(torch.bitwise_and(bits >> k, 1).sum()) for k in range(32)))
+    L1, F = w["L1"], shape.F
+    img_bytes = B * 3 * w["image"] * w["image"] * 4
+    algo = {  # algorithmic bytes per launch, SURVEY.md section 8(d)
+        "ft_fwd": nnz_total * L1 * 4 + B * L1 * 4 + nnz_total * 4,
+        "ft_bwd_dw": nnz_total * L1 * 4 + F * L1 * 4,
+        "ft_bwd_dval": nnz_total * L1 * 4 + B * L1 * 4 + nnz_total * 4,
+        "extract_fwd": img_bytes + B * shape.NW * 4 + shape.PP * shape.BW * 4,
+        "extract_bwd": img_bytes + nnz_total * 4 + B * shape.NW * 4,
+    }
+    peak, peak_src = peaks()
+    roofs = {}
+    for k, b in algo.items():
+        if k in stages and stages[k] > 0:
+            ach = b / (stages[k] * 1e-3) / 1e9
+            roofs[k] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "traffic": None, "ms": stages[k], "algorithmic_bytes": b}
+    dominant = max(roofs, key=lambda k: roofs[k]["ms"]) if roofs else None
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "per_gpu_batch": B, "global_batch": global_batch,
+                   "arch": {k: w[k] for k in ("grid", "C", "L1", "L2", "L3", "NC", "input", "image")},
+                   "parallelism": f"dp{world}", "nnz_per_sample": nnz_total / B,
+                   "l2_policy": "inputs larger than L2: 3 image sets x %.0f MB cycled" % (img_bytes / 1e6),
+                   "loss_after_timed_steps": final_loss},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * world,
+                "ms_per_step": e2e_ms / args.steps,
+                "note": "DataParallelStep.step on pinned host batches, H2D double-buffered against compute, loss read back every step"},
+        "gpu_launches": launches,
+        "stages_ms": stages,
+    }
+    if dominant:
+        line["roofline"] = dict(roofs[dominant], kernel=dominant, peak_source=peak_src,
+                                note="table (205 KB) is shared-memory/L2 resident at this config: algorithmic bytes are on-chip traffic and may exceed the HBM peak; see profiles/ for ncu dram bytes")
+        line["roofline_all"] = roofs
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_training(w, args.cpu_seconds)
+        if not args.no_int:
+            try:
+                line["int_inference"] = int_inference_leg(w, device, args.cpu_seconds)
+            except Exception as e:  # the side measurement must never lose the headline line
+                line["int_inference"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,9 @@ const char *nnue_error_string(int code);
 /* text of the last CUDA error seen by this library on the calling thread ("" if none) */
 const char *nnue_last_cuda_error(void);
 
+/* Kernels this library has launched in this process so far (optionally reset to 0). */
+unsigned long long nnue_launch_count(int reset);
+
 /*
  * Tuning knobs (process-wide; defaults work).  Keys:
  *   "ft_fwd_staging"  0 = gather table rows from global/L2, 1 = auto (default), 2 = stage the

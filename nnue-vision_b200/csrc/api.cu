@@ -10,6 +10,8 @@ static thread_local char g_cuda_err[256] = "";
 void note_cuda_error(cudaError_t e, const char *what) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
 }
+static unsigned long long g_launches = 0;
+void note_launch() { __atomic_fetch_add(&g_launches, 1ULL, __ATOMIC_RELAXED); }
 static int g_options[kNumOptions] = {/*ft_fwd_staging=*/1};
 int get_option(int which) { return which >= 0 && which < kNumOptions ? g_options[which] : 0; }
 }  // namespace nnue
@@ -20,6 +22,12 @@ int nnue_set_option(const char *key, int value) {
     if (!key) return NNUE_ERR_INVALID_ARG;
     if (!strcmp(key, "ft_fwd_staging")) { nnue::g_options[nnue::kOptFtFwdStaging] = value; return NNUE_OK; }
     return NNUE_ERR_INVALID_ARG;
+}
+
+unsigned long long nnue_launch_count(int reset) {
+    const unsigned long long v = __atomic_load_n(&nnue::g_launches, __ATOMIC_RELAXED);
+    if (reset) __atomic_store_n(&nnue::g_launches, 0ULL, __ATOMIC_RELAXED);
+    return v;
 }
 
 int nnue_b200_abi_version(void) { return NNUE_B200_ABI_VERSION; }

@@ -27,8 +27,11 @@ void note_cuda_error(cudaError_t e, const char *what);
         }                                                     \
     } while (0)
 
+// every kernel launch goes through this macro, which also feeds nnue_launch_count()
+void note_launch();
 #define NNUE_CHECK_LAUNCH(name)                               \
     do {                                                      \
+        ::nnue::note_launch();                                \
         cudaError_t _e = cudaGetLastError();                  \
         if (_e != cudaSuccess) {                              \
             ::nnue::note_cuda_error(_e, name);                \

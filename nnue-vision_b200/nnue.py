@@ -167,7 +167,15 @@ class _Saved:
     __slots__ = ("shape", "images", "bits_s", "bits_t", "ft_out", "act1", "act2", "params")
 
 
-def _run_forward(shape, images, params, need_backward):
+def _mark(marks, name):
+    """Stage boundary for bench.py's per-kernel timing: records a CUDA event on the current stream."""
+    if marks is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append((name, ev))
+
+
+def _run_forward(shape, images, params, need_backward, marks=None):
     """extract -> feature transformer -> head.  `params` = (thr, conv_w, ft_w, ft_b, w1, b1, w2, b2, w3, b3)."""
     L = _lib.lib()
     st = stream_ptr()
@@ -175,18 +183,22 @@ def _run_forward(shape, images, params, need_backward):
     sp = ctypes.byref(shape)
     bits_s = _empty((shape.B, shape.NW), torch.int32, images)
     bits_t = _empty((shape.PP, shape.BW), torch.int32, images) if need_backward else None
+    _mark(marks, "start")
     check(L.nnue_extract_fwd(sp, dptr(images), dptr(conv_w), dptr(thr), dptr(bits_s), dptr(bits_t), None, None, st))
+    _mark(marks, "extract_fwd")
     ft_out = _empty((shape.B, shape.L1), torch.float32, images)
     check(L.nnue_ft_fwd(sp, dptr(bits_s), dptr(ft_w), dptr(ft_b), dptr(ft_out), st))
+    _mark(marks, "ft_fwd")
     act1 = _empty((shape.B, shape.L2), torch.float32, images)
     act2 = _empty((shape.B, shape.L3), torch.float32, images)
     logits = _empty((shape.B, shape.NC), torch.float32, images)
     check(L.nnue_head_fwd(sp, dptr(ft_out), dptr(w1), dptr(b1), dptr(w2), dptr(b2), dptr(w3), dptr(b3), dptr(act1),
                           dptr(act2), dptr(logits), st))
+    _mark(marks, "head_fwd")
     return logits, bits_s, bits_t, ft_out, act1, act2
 
 
-def _run_backward(shape, images, params, bits_s, bits_t, ft_out, act1, act2, g_logits, grads=None):
+def _run_backward(shape, images, params, bits_s, bits_t, ft_out, act1, act2, g_logits, grads=None, marks=None):
     """All parameter gradients from g_logits.  `grads` (optional) are preallocated output tensors in
     parameter order (thr, conv_w, ft_w, ft_b, w1, b1, w2, b2, w3, b3) -- e.g. views of a flat
     data-parallel gradient buffer -- otherwise fresh tensors are returned."""
@@ -203,11 +215,15 @@ def _run_backward(shape, images, params, bits_s, bits_t, ft_out, act1, act2, g_l
     check(L.nnue_head_bwd(sp, dptr(g_logits), dptr(ft_out), dptr(act1), dptr(act2), dptr(w1), dptr(w2), dptr(w3),
                           dptr(g_w1), dptr(g_b1), dptr(g_w2), dptr(g_b2), dptr(g_w3), dptr(g_b3), dptr(g_ft),
                           dptr(ws), ws_bytes, st))
+    _mark(marks, "head_bwd")
     check(L.nnue_ft_bwd_dw(sp, dptr(bits_t), dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(ws), ws_bytes, st))
+    _mark(marks, "ft_bwd_dw")
     dval = _empty((shape.B, shape.PP), torch.float32, images)
     check(L.nnue_ft_bwd_dval(sp, dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(dval), st))
+    _mark(marks, "ft_bwd_dval")
     check(L.nnue_extract_bwd(sp, dptr(images), dptr(conv_w), dptr(thr), dptr(bits_s), dptr(dval), dptr(g_conv_w),
                              dptr(g_thr), dptr(ws), ws_bytes, st))
+    _mark(marks, "extract_bwd")
     return grads
 
 

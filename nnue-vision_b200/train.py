@@ -56,7 +56,7 @@ def _cuda_local_step(model):
     """The B200 hot path: forward, fused CE, backward -- every kernel through the C ABI."""
     from . import _lib, nnue as _nnue
 
-    def run(images, labels, inv_count, buf: FlatGradBuffer):
+    def run(images, labels, inv_count, buf: FlatGradBuffer, marks=None):
         images = model._check_images(images)
         labels = labels.to(device=images.device, dtype=torch.long).contiguous()
         fs = model.feature_set
@@ -64,12 +64,14 @@ def _cuda_local_step(model):
         params = tuple(p.detach().contiguous() for p in model._hot_params())
         shape = _lib.make_shape(B, H, W, fs.num_features_per_square, fs.grid_size, model.l1_size, model.l2_size,
                                 model.l3_size, model.num_classes, model.conv.stride[0])
-        logits, bits_s, bits_t, ft_out, act1, act2 = _nnue._run_forward(shape, images, params, True)
+        logits, bits_s, bits_t, ft_out, act1, act2 = _nnue._run_forward(shape, images, params, True, marks)
         g_logits = torch.empty_like(logits)
         _lib.check(_lib.lib().nnue_ce_fwd_bwd(B, shape.NC, _lib.dptr(logits), _lib.dptr(labels), inv_count, None,
                                               _lib.dptr(buf.loss), None, _lib.dptr(g_logits),
                                               _lib.dptr(run.ws(B, images)), B * 4 + 256, _lib.stream_ptr()))
-        _nnue._run_backward(shape, images, params, bits_s, bits_t, ft_out, act1, act2, g_logits, grads=buf.views)
+        _nnue._mark(marks, "ce")
+        _nnue._run_backward(shape, images, params, bits_s, bits_t, ft_out, act1, act2, g_logits, grads=buf.views,
+                            marks=marks)
 
     def ws(B, like):
         if run._ws is None or run._ws.numel() < B * 4 + 256 or run._ws.device != like.device:
@@ -102,10 +104,13 @@ class DataParallelStep:
         self.buf.attach()
         self._local = local_step if local_step is not None else _cuda_local_step(model)
 
-    def step(self, images, labels, global_batch: Optional[int] = None):
+    def step(self, images, labels, global_batch: Optional[int] = None, marks=None):
         if global_batch is None:
             global_batch = images.shape[0] * self.world  # equal shards
-        self._local(images, labels, 1.0 / float(global_batch), self.buf)
+        if marks is not None:
+            self._local(images, labels, 1.0 / float(global_batch), self.buf, marks)
+        else:
+            self._local(images, labels, 1.0 / float(global_batch), self.buf)
         if self.world > 1:
             dist.all_reduce(self.buf.flat, op=dist.ReduceOp.SUM, group=self.group)
         return self.buf.loss.reshape(())
