@@ -92,12 +92,14 @@ size_t nnue_workspace_bytes(const nnue_shape *s);
  *   images_d [B,3,H,W] f32; conv_w_d [C,3,3,3] f32; thr_d [C] f32
  *   bits_s_d [B][NW] u32   bit k of word (c*CW+j) = position (c, cell 32j+k) active
  *   bits_t_d [PP][BW] u32  transposed (position-major) copy, or NULL to skip
- *   conv_out_d [B,C,Gh,Gw] f32 pre-threshold activations, or NULL
+ *   xpad_d [B][PP] f32 pre-threshold activations in padded-position layout (kept for the
+ *          threshold gradient in nnue_ft_bwd_dval), or NULL when no backward will follow
+ *   conv_out_d [B,C,Gh,Gw] f32 the same activations in the reference's NCHW layout, or NULL
  *   nnz_d [B] i32 active positions per sample, or NULL
  */
 int nnue_extract_fwd(const nnue_shape *s, const float *images_d, const float *conv_w_d,
-                     const float *thr_d, uint32_t *bits_s_d, uint32_t *bits_t_d, float *conv_out_d,
-                     int32_t *nnz_d, void *stream);
+                     const float *thr_d, uint32_t *bits_s_d, uint32_t *bits_t_d, float *xpad_d,
+                     float *conv_out_d, int32_t *nnz_d, void *stream);
 
 /*
  * bits -> the padded (indices, values) pair NNUE._to_sparse_features returns
@@ -184,21 +186,24 @@ int nnue_ft_bwd_dw(const nnue_shape *s, const uint32_t *bits_t_d, const float *g
 
 /*
  * Gradient w.r.t. the feature values at ACTIVE positions: dval[b,p] = <W[min(p,F-1)], g_ft[b]>
- * (the autograd edge that reaches conv / threshold, nnue.py:602-603, 705).
- *   dval_d [B][PP] f32, padded-position layout, written only where the bit is set
+ * (the autograd edge that reaches conv / threshold, nnue.py:602-603, 705), fused with the
+ * straight-through threshold gradient (StraightThroughBinary.backward, nnue.py:36-52, k = 10):
+ *   g_thr[c] = -sum over active (b, p in channel c) of dval[b,p] * k * sig * (1 - sig),
+ *   sig = sigmoid(k * (x[b,p] - thr[c])).
+ *   xpad_d [B][PP] from nnue_extract_fwd; dval_d [B][PP] f32, written only where the bit is set
  */
 int nnue_ft_bwd_dval(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w_d,
-                     const float *g_ft_d, float *dval_d, void *stream);
+                     const float *g_ft_d, const float *xpad_d, const float *thr_d, float *dval_d,
+                     float *g_thr_d, void *workspace_d, size_t workspace_bytes, void *stream);
 
 /*
- * Backward of the extraction: straight-through to the conv (nnue.py:28-33), sigmoid
- * surrogate for the threshold (nnue.py:36-52, k = 10), conv weight gradient.
- *   g_conv_w_d [C,3,3,3]; g_thr_d [C]
+ * Conv weight gradient: g_x = g_bin (straight-through, nnue.py:28-33) so
+ * g_conv_w = conv2d_weight(images, g_bin) with g_bin = dval at active positions, 0 elsewhere.
+ *   g_conv_w_d [C,3,3,3]
  */
-int nnue_extract_bwd(const nnue_shape *s, const float *images_d, const float *conv_w_d,
-                     const float *thr_d, const uint32_t *bits_s_d, const float *dval_d,
-                     float *g_conv_w_d, float *g_thr_d, void *workspace_d, size_t workspace_bytes,
-                     void *stream);
+int nnue_extract_bwd(const nnue_shape *s, const float *images_d, const uint32_t *bits_s_d,
+                     const float *dval_d, float *g_conv_w_d, void *workspace_d,
+                     size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------- *
  *  Quantized integer inference path (bit-exact vs serialize.py + engine)     *

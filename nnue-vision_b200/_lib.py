@@ -33,7 +33,7 @@ SIGNATURES = {
     "nnue_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "nnue_shape_init": (ctypes.c_int, [SHAPE_P] + [ctypes.c_int] * 10),
     "nnue_workspace_bytes": (sz, [SHAPE_P]),
-    "nnue_extract_fwd": (ctypes.c_int, [SHAPE_P, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "nnue_extract_fwd": (ctypes.c_int, [SHAPE_P] + [vp] * 9),
     "nnue_sparse_from_bits": (ctypes.c_int, [SHAPE_P, vp, ctypes.c_int, vp, vp, vp]),
     "nnue_ft_fwd": (ctypes.c_int, [SHAPE_P, vp, vp, vp, vp, vp]),
     "nnue_ft_fwd_indexed": (ctypes.c_int, [ctypes.c_int] * 4 + [vp] * 6),
@@ -42,8 +42,8 @@ SIGNATURES = {
     "nnue_ce_fwd_bwd": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, vp, f32, vp, vp, vp, vp, vp, sz, vp]),
     "nnue_head_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 15 + [sz, vp]),
     "nnue_ft_bwd_dw": (ctypes.c_int, [SHAPE_P, vp, vp, vp, vp, vp, sz, vp]),
-    "nnue_ft_bwd_dval": (ctypes.c_int, [SHAPE_P, vp, vp, vp, vp, vp]),
-    "nnue_extract_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 8 + [sz, vp]),
+    "nnue_ft_bwd_dval": (ctypes.c_int, [SHAPE_P] + [vp] * 8 + [sz, vp]),
+    "nnue_extract_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 5 + [sz, vp]),
     "nnue_q_load": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(vp)]),
     "nnue_q_load_memory": (ctypes.c_int, [vp, sz, ctypes.POINTER(vp)]),
     "nnue_q_free": (None, [vp]),

@@ -72,6 +72,7 @@ size_t nnue_workspace_bytes(const nnue_shape *s) {
     size_t m = nnue::ws_head_bwd(*s);
     size_t v = nnue::ws_ft_bwd_dw(*s); if (v > m) m = v;
     v = nnue::ws_extract_bwd(*s); if (v > m) m = v;
+    v = nnue::ws_ft_bwd_dval(*s); if (v > m) m = v;
     v = nnue::ws_ce(s->B); if (v > m) m = v;
     return m + 256;
 }

@@ -10,7 +10,6 @@
 namespace nnue {
 
 constexpr int kExtThreads = 256;
-constexpr float kSteSharpness = 10.0f;  // nnue.py:41
 
 // conv weights are staged in shared memory padded to 28 floats per channel so that a channel's
 // 27 taps are read with 7 broadcast LDS.128
@@ -23,21 +22,29 @@ __device__ __forceinline__ void stage_conv_weights(float *sw, float *sthr, const
     for (int i = threadIdx.x; i < cn; i += blockDim.x) sthr[i] = thr[c0 + i];
 }
 
-// patch[ic*9 + kh*3 + kw] (PyTorch OIHW tap order), zero outside the image (padding = 1)
+// patch[ic*9 + kh*3 + kw] (PyTorch OIHW tap order), zero outside the image (padding = 1).
+// Row / column validity and the 9 in-plane offsets are computed once; the three input channels
+// reuse them (32-bit offsets: one image plane is < 2^31 elements).
 __device__ __forceinline__ void load_patch(float (&patch)[28], const float *img, int H, int W, int oy, int ox,
                                            int stride, bool valid) {
+    const int plane = H * W;
+    const int y0 = oy * stride - 1, x0 = ox * stride - 1;
+    bool rok[3], cok[3];
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-        const int iy = oy * stride + kh - 1;
+    for (int k = 0; k < 3; ++k) {
+        rok[k] = valid && (unsigned)(y0 + k) < (unsigned)H;
+        cok[k] = (unsigned)(x0 + k) < (unsigned)W;
+    }
+    const float *p0 = img + y0 * W + x0;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-            const int ix = ox * stride + kw - 1;
-            const bool in = valid && iy >= 0 && iy < H && ix >= 0 && ix < W;
+            const bool in = rok[kh] && cok[kw];
+            const float *p = p0 + kh * W + kw;
 #pragma unroll
-            for (int ic = 0; ic < 3; ++ic)
-                patch[ic * 9 + kh * 3 + kw] = in ? __ldg(img + ((size_t)ic * H + iy) * W + ix) : 0.0f;
+            for (int ic = 0; ic < 3; ++ic) patch[ic * 9 + kh * 3 + kw] = in ? __ldg(p + ic * plane) : 0.0f;
         }
-    }
     patch[27] = 0.0f;
 }
 
@@ -58,7 +65,8 @@ __device__ __forceinline__ float conv_tap_sum(const float (&patch)[28], const fl
 
 __global__ void __launch_bounds__(kExtThreads)
 extract_fwd_kernel(const nnue_shape s, const float *__restrict__ images, const float *__restrict__ conv_w,
-                   const float *__restrict__ thr, uint32_t *__restrict__ bits_s, float *__restrict__ conv_out) {
+                   const float *__restrict__ thr, uint32_t *__restrict__ bits_s, float *__restrict__ xpad,
+                   float *__restrict__ conv_out) {
     extern __shared__ __align__(16) float smem[];
     float *sw = smem;                 // [C][28]
     float *sthr = smem + s.C * 28;    // [C]
@@ -79,6 +87,7 @@ extract_fwd_kernel(const nnue_shape s, const float *__restrict__ images, const f
             const float x = conv_tap_sum(patch, sw + c * 28);
             const unsigned word = __ballot_sync(kFull, valid && x > sthr[c]);
             if (lane == 0) bits_s[(size_t)b * s.NW + c * s.CW + j] = word;
+            if (xpad) xpad[(size_t)b * s.PP + (size_t)(c * s.CW + j) * 32 + lane] = x;  // coalesced 128 B
             if (conv_out && valid) conv_out[((size_t)b * s.C + c) * cells + cell] = x;
         }
     }
@@ -148,90 +157,82 @@ __global__ void sparse_from_bits_kernel(const nnue_shape s, const uint32_t *__re
     }
 }
 
-// ---- backward ----------------------------------------------------------------------------
-// g_x = g_bin (straight-through), g_thr[c] = -sum g_bin * k * sig * (1 - sig), g_conv_w =
-// conv2d_weight(images, g_x).  g_bin is non-zero only at active positions, so both sums run over
-// set bits.  The pre-threshold activation is recomputed with the forward's exact tap order.
-// grid = (units share, channel chunk of kExbCCH); each thread keeps kExbCCH x 27 tap accumulators.
-__global__ void __launch_bounds__(kExbThreads)
-extract_bwd_kernel(const nnue_shape s, const float *__restrict__ images, const float *__restrict__ conv_w,
-                   const float *__restrict__ thr, const uint32_t *__restrict__ bits_s,
-                   const float *__restrict__ dval, float *__restrict__ partial) {
-    __shared__ __align__(16) float sw[kExbCCH * 28];
-    __shared__ float sthr[kExbCCH];
-    __shared__ float red[kExbThreads / 32][kExbCCH * 28];
-    const int c0 = blockIdx.y * kExbCCH;
-    const int cn = min(kExbCCH, s.C - c0);
-    stage_conv_weights(sw, sthr, conv_w, thr, c0, cn);
-    __syncthreads();
+// ---- backward: conv weight gradient --------------------------------------------------------
+// g_conv_w[c][t] = sum over (b, cell) of g_bin[b, c, cell] * patch[b, cell][t], g_bin = dval at active
+// positions and 0 elsewhere (the straight-through estimator passes g_bin to the conv unchanged; the
+// threshold gradient is produced by nnue_ft_bwd_dval).  A warp owns kExbCCH channels and keeps their
+// 27 tap accumulators in registers while it streams over cell words (one cell per lane, the lane's
+// 3x3x3 patch in registers); the `cpc` channel chunks of a CTA walk the SAME cell words side by side,
+// so the image is pulled from HBM once and the sibling warps hit L1.
+__global__ void __launch_bounds__(kExbThreads, 2)
+extract_bwd_kernel(const nnue_shape s, const float *__restrict__ images, const uint32_t *__restrict__ bits_s,
+                   const float *__restrict__ dval, float *__restrict__ partial, int cpc) {
+    __shared__ float red[kExbWarps][kExbCCH * 27];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int streams = kExbWarps / cpc;
+    const int chunk_local = warp % cpc, stream = warp / cpc;
+    const int cbase = blockIdx.y * cpc * kExbCCH;            // first channel of this CTA
+    const int c0 = cbase + chunk_local * kExbCCH;            // first channel of this warp
+    const int cn = max(0, min(kExbCCH, s.C - c0));
+    const int cta_cn = max(0, min(cpc * kExbCCH, s.C - cbase));
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int cells = s.Gh * s.Gw;
     float acc[kExbCCH][27];
-    float dth[kExbCCH];
 #pragma unroll
-    for (int cc = 0; cc < kExbCCH; ++cc) {
-        dth[cc] = 0.0f;
+    for (int cc = 0; cc < kExbCCH; ++cc)
 #pragma unroll
         for (int t = 0; t < 27; ++t) acc[cc][t] = 0.0f;
-    }
-    const long long units = 1LL * s.B * s.CW;
-    for (long long u = 1LL * blockIdx.x * wpb + warp; u < units; u += 1LL * gridDim.x * wpb) {
-        const int b = (int)(u / s.CW), j = (int)(u % s.CW);
-        unsigned words[kExbCCH];
-        unsigned any = 0;
+    const int units = s.B * s.CW;
+    if (cn > 0) {
+        for (int u = blockIdx.x * streams + stream; u < units; u += gridDim.x * streams) {
+            const int b = u / s.CW, j = u % s.CW;
+            unsigned words[kExbCCH];
+            unsigned any = 0;
 #pragma unroll
-        for (int cc = 0; cc < kExbCCH; ++cc) {
-            words[cc] = cc < cn ? __ldg(bits_s + (size_t)b * s.NW + (c0 + cc) * s.CW + j) : 0u;
-            any |= words[cc];
-        }
-        if (!any) continue;  // warp-uniform
-        const int cell = j * 32 + lane;
-        const bool valid = cell < cells;
-        const int oy = valid ? cell / s.Gw : 0, ox = valid ? cell % s.Gw : 0;
-        float patch[28];
-        load_patch(patch, images + (size_t)b * 3 * s.H * s.W, s.H, s.W, oy, ox, s.stride, valid);
+            for (int cc = 0; cc < kExbCCH; ++cc) {
+                words[cc] = cc < cn ? __ldg(bits_s + (size_t)b * s.NW + (c0 + cc) * s.CW + j) : 0u;
+                any |= words[cc];
+            }
+            if (!any) continue;  // warp-uniform
+            const int cell = j * 32 + lane;
+            const bool valid = cell < cells;
+            const int oy = valid ? cell / s.Gw : 0, ox = valid ? cell % s.Gw : 0;
+            float patch[28];
+            load_patch(patch, images + (size_t)b * 3 * s.H * s.W, s.H, s.W, oy, ox, s.stride, valid);
 #pragma unroll
-        for (int cc = 0; cc < kExbCCH; ++cc) {
-            if (!words[cc]) continue;  // warp-uniform
-            const bool on = (words[cc] >> lane) & 1u;
-            const float g = on ? __ldg(dval + (size_t)b * s.PP + ((size_t)(c0 + cc) * s.CW + j) * 32 + lane) : 0.0f;
-            const float x = conv_tap_sum(patch, sw + cc * 28);
-            const float sg = 1.0f / (1.0f + expf(-kSteSharpness * (x - sthr[cc])));
-            dth[cc] -= g * (kSteSharpness * sg * (1.0f - sg));
+            for (int cc = 0; cc < kExbCCH; ++cc) {
+                if (!words[cc]) continue;  // warp-uniform
+                const bool on = (words[cc] >> lane) & 1u;
+                const float g = on ? __ldg(dval + (size_t)b * s.PP + (size_t)((c0 + cc) * s.CW + j) * 32 + lane) : 0.0f;
 #pragma unroll
-            for (int t = 0; t < 27; ++t) acc[cc][t] = fmaf(g, patch[t], acc[cc][t]);
+                for (int t = 0; t < 27; ++t) acc[cc][t] = fmaf(g, patch[t], acc[cc][t]);
+            }
         }
     }
-    // block reduction: warp shuffle, then across warps through shared memory (fixed order)
+    // block reduction: warp shuffle, then across the streams of each chunk through shared memory (fixed order)
 #pragma unroll
-    for (int cc = 0; cc < kExbCCH; ++cc) {
+    for (int cc = 0; cc < kExbCCH; ++cc)
 #pragma unroll
         for (int t = 0; t < 27; ++t) {
             const float v = warp_sum(acc[cc][t]);
-            if (lane == 0) red[warp][cc * 28 + t] = v;
+            if (lane == 0) red[warp][cc * 27 + t] = v;
         }
-        const float v = warp_sum(dth[cc]);
-        if (lane == 0) red[warp][cc * 28 + 27] = v;
-    }
     __syncthreads();
-    for (int i = threadIdx.x; i < cn * 28; i += blockDim.x) {
+    for (int i = threadIdx.x; i < cta_cn * 27; i += blockDim.x) {
+        const int cl = i / (kExbCCH * 27), jj = i % (kExbCCH * 27);
         float v = 0.0f;
-        for (int w = 0; w < wpb; ++w) v += red[w][i];
-        partial[((size_t)blockIdx.x * s.C + c0) * 28 + i] = v;
+        for (int st = 0; st < streams; ++st) v += red[st * cpc + cl][jj];
+        partial[((size_t)blockIdx.x * s.C + cbase) * 27 + i] = v;
     }
 }
 
-// out: g_conv_w[c*27 + t], g_thr[c]; partial [nblk][C][28] summed in block order
-__global__ void extract_bwd_finish_kernel(int C, int nblk, const float *__restrict__ partial,
-                                          float *__restrict__ g_conv_w, float *__restrict__ g_thr) {
+// out[i] = sum over blocks (in block order) of partial[blk][i]
+__global__ void fold_rows_kernel(int n, int nblk, const float *__restrict__ partial, float *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C * 28) return;
+    if (i >= n) return;
     float v = 0.0f;
-    for (int k = 0; k < nblk; ++k) v += partial[(size_t)k * C * 28 + i];
-    const int c = i / 28, t = i % 28;
-    if (t < 27) g_conv_w[c * 27 + t] = v;
-    else g_thr[c] = v;
+    for (int k = 0; k < nblk; ++k) v += partial[(size_t)k * n + i];
+    out[i] = v;
 }
 
 }  // namespace nnue
@@ -241,7 +242,8 @@ using namespace nnue;
 extern "C" {
 
 int nnue_extract_fwd(const nnue_shape *s, const float *images_d, const float *conv_w_d, const float *thr_d,
-                     uint32_t *bits_s_d, uint32_t *bits_t_d, float *conv_out_d, int32_t *nnz_d, void *stream) {
+                     uint32_t *bits_s_d, uint32_t *bits_t_d, float *xpad_d, float *conv_out_d, int32_t *nnz_d,
+                     void *stream) {
     if (!s || !images_d || !conv_w_d || !thr_d || !bits_s_d) return NNUE_ERR_INVALID_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t smem = (size_t)s->C * 29 * sizeof(float);
@@ -251,7 +253,8 @@ int nnue_extract_fwd(const nnue_shape *s, const float *images_d, const float *co
     long long grid = (units + wpb - 1) / wpb;
     const long long cap = 32LL * kNumSMs;
     if (grid > cap) grid = cap;
-    extract_fwd_kernel<<<(int)grid, kExtThreads, smem, st>>>(*s, images_d, conv_w_d, thr_d, bits_s_d, conv_out_d);
+    extract_fwd_kernel<<<(int)grid, kExtThreads, smem, st>>>(*s, images_d, conv_w_d, thr_d, bits_s_d, xpad_d,
+                                                            conv_out_d);
     NNUE_CHECK_LAUNCH("extract_fwd_kernel");
     if (bits_t_d) {
         dim3 g(ceil_div(s->NW, 32), ceil_div(s->BW, kTrGroups)), blk(32, 32);
@@ -274,20 +277,18 @@ int nnue_sparse_from_bits(const nnue_shape *s, const uint32_t *bits_s_d, int K, 
     return NNUE_OK;
 }
 
-int nnue_extract_bwd(const nnue_shape *s, const float *images_d, const float *conv_w_d, const float *thr_d,
-                     const uint32_t *bits_s_d, const float *dval_d, float *g_conv_w_d, float *g_thr_d,
-                     void *workspace_d, size_t workspace_bytes, void *stream) {
-    if (!s || !images_d || !conv_w_d || !thr_d || !bits_s_d || !dval_d || !g_conv_w_d || !g_thr_d || !workspace_d)
-        return NNUE_ERR_INVALID_ARG;
+int nnue_extract_bwd(const nnue_shape *s, const float *images_d, const uint32_t *bits_s_d, const float *dval_d,
+                     float *g_conv_w_d, void *workspace_d, size_t workspace_bytes, void *stream) {
+    if (!s || !images_d || !bits_s_d || !dval_d || !g_conv_w_d || !workspace_d) return NNUE_ERR_INVALID_ARG;
     if (workspace_bytes < ws_extract_bwd(*s)) return NNUE_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float *partial = static_cast<float *>(workspace_d);
     const int gx = exb_grid_x(*s);
-    dim3 grid(gx, ceil_div(s->C, kExbCCH));
-    extract_bwd_kernel<<<grid, kExbThreads, 0, st>>>(*s, images_d, conv_w_d, thr_d, bits_s_d, dval_d, partial);
+    dim3 grid(gx, exb_grid_y(s->C));
+    extract_bwd_kernel<<<grid, kExbThreads, 0, st>>>(*s, images_d, bits_s_d, dval_d, partial, exb_cpc(s->C));
     NNUE_CHECK_LAUNCH("extract_bwd_kernel");
-    extract_bwd_finish_kernel<<<ceil_div(s->C * 28, 128), 128, 0, st>>>(s->C, gx, partial, g_conv_w_d, g_thr_d);
-    NNUE_CHECK_LAUNCH("extract_bwd_finish_kernel");
+    fold_rows_kernel<<<ceil_div(s->C * 27, 128), 128, 0, st>>>(s->C * 27, gx, partial, g_conv_w_d);
+    NNUE_CHECK_LAUNCH("fold_rows_kernel");
     return NNUE_OK;
 }
 

@@ -4,25 +4,89 @@
 // Column geometry (plan.cuh ColPlan): a table row is read as float4s by LPR lanes (one
 // coalesced 16*LPR-byte segment); with LPR < 32 a warp splits into NG = 32/LPR lane groups that
 // take different active features and are combined with __shfl_xor at the end.
+//
+// Active features are walked straight off the bitmask words (BitWalk): no index lists are
+// materialised.  When the table fits one CTA's shared memory it is staged there once per
+// persistent CTA with bulk TMA copies (cp.async.bulk -> UBLKCP) and rows are read with LDS.128.
 #include "common.cuh"
 #include "plan.cuh"
 
 namespace nnue {
 
 constexpr int kFtThreads = 256;
+constexpr int kFtStagedThreads = 1024;  // one persistent CTA per SM owns the shared-memory table
+constexpr int kDvalStagedThreads = 512;  // the value-gradient kernel keeps 4 dots in flight: 16 warps x 128 registers
 
-// The set bit of rank g (0-based) among the NG lowest set bits of `word`, or -1 when the word
-// has fewer; the NG lowest set bits are then stripped.  __ffs(0) == 0 gives the -1 for free.
+// Splits the set bits of a warp-uniform 32-bit word over NG lane groups without any cross-lane
+// traffic.  The word is cut into NS = max(1, NG/2) segments; inside a segment the "up" group takes
+// the bits from the low end and its partner from the high end until they meet, so the two always
+// share the work evenly.  Bits are taken most-significant-first with one FLO (the up group walks the
+// bit-reversed segment): 4 integer instructions per bit.
 template <int NG>
-__device__ __forceinline__ int take_bit(unsigned &word, int g) {
-    int k = -1;
-#pragma unroll
-    for (int t = 0; t < NG; ++t) {
-        const int kt = __ffs(word) - 1;
-        if (t == g) k = kt;
-        word &= word - 1;
+struct BitWalk {
+    static constexpr int NS = NG >= 2 ? NG / 2 : 1;
+    static constexpr int SW = 32 / NS;
+    int seg_shift, flip;
+    bool up;
+    __device__ __forceinline__ explicit BitWalk(int g) {
+        seg_shift = NG >= 2 ? (g >> 1) * SW : 0;
+        up = NG == 1 || !(g & 1);
+        flip = up ? 0 : 31;
     }
-    return k;
+    // my group's view of the word: top-aligned for the up walker, bottom-aligned for the down walker
+    __device__ __forceinline__ unsigned view(unsigned word) const {
+        const unsigned sub = NS == 1 ? word : (word >> seg_shift) & ((1u << (SW & 31)) - 1u);
+        return up ? __brev(sub) : sub;
+    }
+    // pop the next bit of a view; returns its position in the original word
+    __device__ __forceinline__ int take(unsigned &x) const {
+        const int c = __clz(x);
+        x &= ~(0x80000000u >> c);
+        return (c ^ flip) + seg_shift;
+    }
+    // bits of `word` this group takes, and (warp-uniform) the most any group takes
+    __device__ __forceinline__ int mine(unsigned word) const {
+        const unsigned sub = NS == 1 ? word : (word >> seg_shift) & ((1u << (SW & 31)) - 1u);
+        const int c = __popc(sub);
+        return NG == 1 ? c : (up ? (c + 1) >> 1 : c >> 1);
+    }
+    static __device__ __forceinline__ int trips(unsigned word) {
+        int t = 0;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const unsigned seg = NS == 1 ? word : (word >> (s * SW)) & ((1u << (SW & 31)) - 1u);
+            const int c = __popc(seg);
+            t = max(t, NG >= 2 ? (c + 1) >> 1 : c);
+        }
+        return t;
+    }
+};
+
+// Calls f(k, slot) for every bit k of the warp-uniform `word` that belongs to this lane's group; slot
+// alternates 0/1 so callers can keep two independent accumulators.  For NG <= 2 (L1 >= 64) all
+// iterations but at most one are executed by the whole warp with no validity test.
+template <int NG, typename F>
+__device__ __forceinline__ void for_my_bits(unsigned word, const BitWalk<NG> &walk, F &&f) {
+    unsigned x = walk.view(word);
+    if (NG <= 2) {
+        const int c = __popc(word);
+        const int full = NG == 2 ? c >> 1 : c;  // bits every group takes
+        int i = 0;
+        for (; i + 1 < full; i += 2) {
+            const int k0 = walk.take(x), k1 = walk.take(x);
+            f(k0, 0);
+            f(k1, 1);
+        }
+        if (i < full) f(walk.take(x), 0);
+        if (NG == 2 && (c & 1) && walk.up) f(walk.take(x), 1);  // odd count: the up group takes the middle bit
+    } else {
+        const int n = walk.mine(word), trips = BitWalk<NG>::trips(word);
+        for (int i = 0; i < trips; i += 2) {
+            const int k0 = walk.take(x), k1 = walk.take(x);
+            if (i < n) f(k0, 0);
+            if (i + 1 < n) f(k1, 1);
+        }
+    }
 }
 
 // Sum a float4 across the NG lane groups of a warp (lanes l, l+LPR, l+2*LPR, ...).
@@ -38,60 +102,85 @@ __device__ __forceinline__ float4 group_sum(float4 v) {
     return v;
 }
 
+// Keeps a value in a register: stops the compiler from re-deriving shared-window addresses (S2UR +
+// ULEA) inside the hot loops.
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
+    asm volatile("mov.u32 %0, %0;" : "+r"(v));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+
+// Row source: the global table (read-only path) or its shared-memory copy.
+template <bool STAGED>
+struct RowSrc {
+    const float *g;   // global: table + column offset
+    uint32_t s;       // shared: byte address of table + column offset
+    int row_elems;    // L1
+    __device__ __forceinline__ float4 load(int row) const {
+        if (STAGED) return lds_f4(s + (uint32_t)(row * row_elems) * 4u);
+        return __ldg(reinterpret_cast<const float4 *>(g + (size_t)row * row_elems));
+    }
+};
+
+// CHW position of bit 0 of bitmask word `widx` (word c*CW + j covers cells 32j..32j+31 of channel c)
+__device__ __forceinline__ int word_base(const nnue_shape &s, int widx, int cells) {
+    return (widx / s.CW) * cells + (widx % s.CW) * 32;
+}
+
 // ---- forward on the bitmask ----------------------------------------------------------------
-// unit = (sample, column chunk); one warp per unit.  STAGED: the whole table sits in shared
-// memory, brought in by bulk TMA copies once per (persistent) CTA.
+// unit = (sample, column chunk); one warp per unit.
 template <int LPR, bool STAGED>
-__global__ void __launch_bounds__(kFtThreads)
+__global__ void __launch_bounds__(STAGED ? kFtStagedThreads : kFtThreads)
 ft_fwd_bits_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const float *__restrict__ w,
                    const float *__restrict__ bias, float *__restrict__ out, int nchunks) {
     constexpr int NG = 32 / LPR;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const float *table = w;
     if (STAGED) {
         uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-        float *stab = reinterpret_cast<float *>(smem_raw + 128);
         if (threadIdx.x == 0) {
             mbar_init(bar, 1);
             mbar_fence_init();
         }
         __syncthreads();
-        tma_stage(stab, w, (uint32_t)((size_t)s.F * s.L1 * sizeof(float)), bar, 0);
-        table = stab;
+        tma_stage(smem_raw + 128, w, (uint32_t)((size_t)s.F * s.L1 * sizeof(float)), bar, 0);
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int g = lane / LPR, li = lane % LPR;
     const int cells = s.Gh * s.Gw;
-    const long long units = 1LL * s.B * nchunks;
-    for (long long u = 1LL * blockIdx.x * wpb + warp; u < units; u += 1LL * gridDim.x * wpb) {
-        const int b = (int)(u / nchunks), ch = (int)(u % nchunks);
+    const int last_row = s.F - 1;
+    BitWalk<NG> walk(g);
+    const uint32_t tab = pin_u32(smem_u32(smem_raw + 128));
+    const int units = s.B * nchunks;
+    for (int u = blockIdx.x * wpb + warp; u < units; u += gridDim.x * wpb) {
+        const int b = nchunks == 1 ? u : u / nchunks, ch = nchunks == 1 ? 0 : u % nchunks;
         const int col = ch * (4 * LPR) + li * 4;
-        const float *tcol = table + col;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        RowSrc<STAGED> src{w + col, tab + (uint32_t)col * 4u, s.L1};
+        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
         for (int w0 = 0; w0 < s.NW; w0 += 32) {
-            const unsigned mine = (w0 + lane < s.NW) ? __ldg(bits_s + (size_t)b * s.NW + w0 + lane) : 0u;
+            const bool have = w0 + lane < s.NW;
+            const unsigned mine = have ? __ldg(bits_s + (size_t)b * s.NW + w0 + lane) : 0u;
+            const int mybase = have ? word_base(s, w0 + lane, cells) : 0;
             unsigned nonzero = __ballot_sync(kFull, mine != 0u);
             while (nonzero) {
                 const int jw = __ffs(nonzero) - 1;
                 nonzero &= nonzero - 1;
-                unsigned word = __shfl_sync(kFull, mine, jw);
-                const int widx = w0 + jw;
-                const int base = (widx / s.CW) * cells + (widx % s.CW) * 32;
-                while (word) {
-                    const int k = take_bit<NG>(word, g);
-                    if (k >= 0) {
-                        const int row = min(base + k, s.F - 1);  // clamp of nnue.py:701
-                        const float4 v = STAGED ? *reinterpret_cast<const float4 *>(tcol + (size_t)row * s.L1)
-                                                : __ldg(reinterpret_cast<const float4 *>(tcol + (size_t)row * s.L1));
-                        acc = f4_add(acc, v);
-                    }
-                }
+                const unsigned word = __shfl_sync(kFull, mine, jw);
+                const int base = __shfl_sync(kFull, mybase, jw);
+                for_my_bits<NG>(word, walk, [&](int k, int slot) {
+                    const float4 v = src.load(min(base + k, last_row));  // clamp of nnue.py:701
+                    if (slot) acc1 = f4_add(acc1, v);
+                    else acc0 = f4_add(acc0, v);
+                });
             }
         }
-        acc = group_sum<LPR>(acc);
+        acc0 = group_sum<LPR>(f4_add(acc0, acc1));
         if (g == 0) {
             const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + col));
-            *reinterpret_cast<float4 *>(out + (size_t)b * s.L1 + col) = f4_add(bv, acc);
+            *reinterpret_cast<float4 *>(out + (size_t)b * s.L1 + col) = f4_add(bv, acc0);
         }
     }
 }
@@ -109,7 +198,7 @@ ft_fwd_bits_generic_kernel(const nnue_shape s, const uint32_t *__restrict__ bits
         float acc = 0.0f;
         for (int widx = 0; widx < s.NW; ++widx) {
             unsigned word = __ldg(bits_s + (size_t)b * s.NW + widx);
-            const int base = (widx / s.CW) * cells + (widx % s.CW) * 32;
+            const int base = word_base(s, widx, cells);
             while (word) {
                 const int k = __ffs(word) - 1;
                 word &= word - 1;
@@ -224,7 +313,7 @@ __global__ void fold_partials_kernel(int n, int nparts, const float *__restrict_
 // and adds the staged rows into register accumulators.  Output: partial[group][p][L1] (or g_w
 // directly when there is a single group and no clamp aliasing).
 template <int LPR>
-__global__ void __launch_bounds__(kDwWarps * 32)
+__global__ void __launch_bounds__(kDwWarps * 32, 2)
 ft_bwd_dw_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_t, const float *__restrict__ g_ft,
                  float *__restrict__ dst, int TS, int tpg, int ntiles, int direct) {
     constexpr int NG = 32 / LPR;
@@ -237,7 +326,7 @@ ft_bwd_dw_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_t, const 
     const int ch = blockIdx.y, group = blockIdx.z;
     const int col0 = ch * CC;
     const int cells = s.Gh * s.Gw;
-    const int wpt = TS / 32;  // bitmask words per tile
+    const int wpt = TS / 32;  // bitmask words per tile (<= 8)
 
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -249,6 +338,8 @@ ft_bwd_dw_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_t, const 
 #pragma unroll
     for (int q = 0; q < kDwPPW; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int pp0 = blockIdx.x * kDwPPC + warp * kDwPPW;
+    BitWalk<NG> walk(g);
+    const uint32_t tcol = pin_u32(smem_u32(tile) + (uint32_t)li * 16u);
 
     uint32_t parity = 0;
     const int t_begin = group * tpg, t_end = min(ntiles, t_begin + tpg);
@@ -270,25 +361,32 @@ ft_bwd_dw_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_t, const 
                     tma_bulk_g2s(tile + (size_t)r * CC, g_ft + (size_t)(b0 + r) * s.L1 + col0, CC * 4, bar);
             }
         }
-        mbar_wait(bar, parity);
-        parity ^= 1;
-        const float *tcol = tile + li * 4;
+        // fetch this tile's bitmask words for my positions while the copy is in flight
+        const int nw = min(wpt, s.BW - t * wpt);
+        unsigned mine[kDwPPW];
 #pragma unroll
         for (int q = 0; q < kDwPPW; ++q) {
             const int pp = pp0 + q;
-            if (pp >= s.PP || (pp & 31) + ((pp >> 5) % s.CW) * 32 >= cells) continue;  // warp-uniform
-            const uint32_t *wrow = bits_t + (size_t)pp * s.BW + (size_t)t * wpt;
-            const int nw = min(wpt, s.BW - t * wpt);
-            const unsigned mine = lane < nw ? __ldg(wrow + lane) : 0u;  // wpt <= 8 words
-            unsigned nonzero = __ballot_sync(kFull, mine != 0u);
+            const bool live = pp < s.PP && (pp & 31) + ((pp >> 5) % s.CW) * 32 < cells && lane < nw;
+            mine[q] = live ? __ldg(bits_t + (size_t)pp * s.BW + (size_t)t * wpt + lane) : 0u;
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1;
+#pragma unroll
+        for (int q = 0; q < kDwPPW; ++q) {
+            unsigned nonzero = __ballot_sync(kFull, mine[q] != 0u);
             while (nonzero) {
                 const int jw = __ffs(nonzero) - 1;
                 nonzero &= nonzero - 1;
-                unsigned word = __shfl_sync(kFull, mine, jw);
-                while (word) {
-                    const int k = take_bit<NG>(word, g);
-                    if (k >= 0) acc[q] = f4_add(acc[q], *reinterpret_cast<const float4 *>(tcol + (size_t)(jw * 32 + k) * CC));
-                }
+                const unsigned word = __shfl_sync(kFull, mine[q], jw);
+                const uint32_t wbase = tcol + (uint32_t)(jw * 32) * (CC * 4);
+                float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                for_my_bits<NG>(word, walk, [&](int k, int slot) {
+                    const float4 v = lds_f4(wbase + (uint32_t)k * (CC * 4));
+                    if (slot) a1 = f4_add(a1, v);
+                    else acc[q] = f4_add(acc[q], v);
+                });
+                acc[q] = f4_add(acc[q], a1);
             }
         }
         __syncthreads();  // everyone done with the tile before the next bulk copy overwrites it
@@ -308,19 +406,41 @@ ft_bwd_dw_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_t, const 
     }
 }
 
-// g_w[r] = sum over groups and over positions p with min(p, F-1) == r of partial[group][p]
+// Fold stage 1: every position p sums its partials over the tile groups.  Positions below F-1 are
+// table rows and go straight to g_w; positions >= F-1 all alias onto the last row (the clamp of
+// nnue.py:701) and are parked in `alias` [P-(F-1)][L1] for stage 2; rows in [P, F-1) get zeros.
 __global__ void ft_bwd_dw_fold_kernel(const nnue_shape s, int ngroups, const float *__restrict__ partial,
-                                      float *__restrict__ g_w) {
+                                      float *__restrict__ g_w, float *__restrict__ alias) {
     const int v4 = s.L1 / 4;
+    const int nrows = max(s.P, s.F - 1);
     const long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 1LL * s.F * v4) return;
-    const int r = (int)(i / v4), c4 = (int)(i % v4);
+    if (i >= 1LL * nrows * v4) return;
+    const int p = (int)(i / v4), c4 = (int)(i % v4);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int p_begin = r, p_end = (r == s.F - 1) ? s.P : min(r + 1, s.P);
-    for (int p = p_begin; p < p_end; ++p)
+    if (p < s.P)
         for (int gI = 0; gI < ngroups; ++gI)
             acc = f4_add(acc, __ldg(reinterpret_cast<const float4 *>(partial + ((size_t)gI * s.P + p) * s.L1) + c4));
-    reinterpret_cast<float4 *>(g_w + (size_t)r * s.L1)[c4] = acc;
+    if (p < s.F - 1) reinterpret_cast<float4 *>(g_w + (size_t)p * s.L1)[c4] = acc;
+    else reinterpret_cast<float4 *>(alias + (size_t)(p - (s.F - 1)) * s.L1)[c4] = acc;
+}
+// Fold stage 2: g_w[F-1] = sum of the parked rows, 8 slices per column combined in a fixed order.
+__global__ void __launch_bounds__(256)
+ft_bwd_dw_fold_last_kernel(const nnue_shape s, const float *__restrict__ alias, float *__restrict__ g_w) {
+    __shared__ float4 red[256];
+    const int v4 = s.L1 / 4;
+    const int nalias = max(0, s.P - (s.F - 1));
+    const int col = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int c4 = blockIdx.x * 32 + col;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < v4)
+        for (int i = sl; i < nalias; i += 8)
+            acc = f4_add(acc, __ldg(reinterpret_cast<const float4 *>(alias + (size_t)i * s.L1) + c4));
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (sl == 0 && c4 < v4) {
+        for (int k = 1; k < 8; ++k) acc = f4_add(acc, red[k * 32 + col]);
+        reinterpret_cast<float4 *>(g_w + (size_t)(s.F - 1) * s.L1)[c4] = acc;
+    }
 }
 
 // any L1: one warp per table row, walks every position that maps to the row and every sample bit
@@ -351,75 +471,168 @@ ft_bwd_dw_generic_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_t
     }
 }
 
-// ---- value gradient at active positions --------------------------------------------------------
-// one warp per sample; each lane group takes an active position and all its lanes share the dot.
-template <int LPR>
-__global__ void __launch_bounds__(kFtThreads)
+// ---- value gradient at active positions (+ threshold gradient) ---------------------------------
+// dval[b, p] = <W[min(p, F-1)], g_ft[b]>.  One warp per sample; each lane group takes an active
+// position and its LPR lanes share the dot.  Four positions per group are in flight at once and
+// their partial dots are combined with a transposed shuffle reduction (5 shuffles for 4 dots
+// instead of 4 x log2(LPR)); the lanes holding a finished dot store it.
+// The same lanes fold in the straight-through threshold gradient (nnue.py:36-52):
+//   g_thr[c] = -sum over active (b, p in channel c) of dval * k * sig * (1 - sig),  sig = sigmoid(k (x - thr[c]))
+// with x the stored pre-threshold activation; per-CTA partials go to thr_partial[blockIdx.x][C].
+constexpr float kSteSharpnessFt = 10.0f;  // nnue.py:41
+
+template <int LPR, bool STAGED>
+__global__ void __launch_bounds__(STAGED ? kDvalStagedThreads : kFtThreads, 1)
 ft_bwd_dval_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const float *__restrict__ w,
-                   const float *__restrict__ g_ft, float *__restrict__ dval, int nchunks) {
+                   const float *__restrict__ g_ft, const float *__restrict__ xpad, const float *__restrict__ thr,
+                   float *__restrict__ dval, float *__restrict__ thr_partial, int nchunks) {
     constexpr int NG = 32 / LPR;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // layout: [0,128) mbarrier | per-warp threshold-gradient sums [wpb][C] | table (STAGED only)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float *sdth = reinterpret_cast<float *>(smem_raw + 128);
+    const uint32_t tab_off = 128 + (uint32_t)align_up((size_t)wpb * s.C * 4, 128);
+    for (int i = threadIdx.x; i < wpb * s.C; i += blockDim.x) sdth[i] = 0.0f;
+    if (STAGED) {
+        uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        tma_stage(smem_raw + tab_off, w, (uint32_t)((size_t)s.F * s.L1 * sizeof(float)), bar, 0);
+    } else {
+        __syncthreads();
+    }
     const int g = lane / LPR, li = lane % LPR;
     const int cells = s.Gh * s.Gw;
+    const int last_row = s.F - 1;
+    const bool hi = (li & (LPR / 2)) != 0, hi2 = (li & (LPR / 4)) != 0;
+    const int my_slot = (hi ? 2 : 0) + (hi2 ? 1 : 0);  // which of the 4 in-flight dots this lane finishes
+    const bool storer = (li & (LPR / 4 - 1)) == 0;
+    BitWalk<NG> walk(g);
+    RowSrc<STAGED> src{w + li * 4, pin_u32(smem_u32(smem_raw + tab_off) + (uint32_t)li * 16u), s.L1};
+    float dth = 0.0f;   // this lane's share of g_thr[cur_c]
+    int cur_c = 0;
+    float *my_sdth = sdth + warp * s.C;
     for (int b = blockIdx.x * wpb + warp; b < s.B; b += gridDim.x * wpb) {
         const float *grow = g_ft + (size_t)b * s.L1 + li * 4;
-        float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (nchunks == 1) g0 = __ldg(reinterpret_cast<const float4 *>(grow));
+        const float4 g0 = nchunks == 1 ? __ldg(reinterpret_cast<const float4 *>(grow)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float *drow = dval + (size_t)b * s.PP;
+        const float *xrow = xpad + (size_t)b * s.PP;
         for (int w0 = 0; w0 < s.NW; w0 += 32) {
-            const unsigned mine = (w0 + lane < s.NW) ? __ldg(bits_s + (size_t)b * s.NW + w0 + lane) : 0u;
+            const bool have = w0 + lane < s.NW;
+            const unsigned mine = have ? __ldg(bits_s + (size_t)b * s.NW + w0 + lane) : 0u;
+            const int myc = have ? (w0 + lane) / s.CW : 0;
             unsigned nonzero = __ballot_sync(kFull, mine != 0u);
             while (nonzero) {
                 const int jw = __ffs(nonzero) - 1;
                 nonzero &= nonzero - 1;
-                unsigned word = __shfl_sync(kFull, mine, jw);
+                const unsigned word = __shfl_sync(kFull, mine, jw);
+                const int c = __shfl_sync(kFull, myc, jw);
                 const int widx = w0 + jw;
-                const int base = (widx / s.CW) * cells + (widx % s.CW) * 32;
-                while (word) {  // warp-uniform trip count
-                    const int k = take_bit<NG>(word, g);
-                    float d = 0.0f;
-                    if (k >= 0) {
-                        const int row = min(base + k, s.F - 1);
-                        const float *wrow = w + (size_t)row * s.L1 + li * 4;
-                        if (nchunks == 1) {
-                            const float4 v = __ldg(reinterpret_cast<const float4 *>(wrow));
-                            d = fmaf(v.x, g0.x, fmaf(v.y, g0.y, fmaf(v.z, g0.z, v.w * g0.w)));
-                        } else {
-                            for (int ch = 0; ch < nchunks; ++ch) {
-                                const float4 v = __ldg(reinterpret_cast<const float4 *>(wrow + ch * 128));
-                                const float4 gv = __ldg(reinterpret_cast<const float4 *>(grow + ch * 128));
-                                d = fmaf(v.x, gv.x, fmaf(v.y, gv.y, fmaf(v.z, gv.z, fmaf(v.w, gv.w, d))));
+                const int base = c * cells + (widx - c * s.CW) * 32;
+                if (c != cur_c) {  // warp-uniform: close the running channel sum
+                    const float v = warp_sum(dth);
+                    if (lane == 0) my_sdth[cur_c] += v;
+                    dth = 0.0f;
+                    cur_c = c;
+                }
+                const float thr_c = __ldg(thr + c);
+                unsigned x = walk.view(word);
+                const int n = walk.mine(word), trips = BitWalk<NG>::trips(word);
+                for (int i = 0; i < trips; i += 4) {
+                    int k[4];
+                    float d[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        k[u] = walk.take(x);
+                        d[u] = 0.0f;
+                        if (i + u < n) {
+                            const int row = min(base + k[u], last_row);
+                            if (nchunks == 1) {
+                                const float4 v = src.load(row);
+                                d[u] = fmaf(v.x, g0.x, fmaf(v.y, g0.y, fmaf(v.z, g0.z, v.w * g0.w)));
+                            } else {
+                                const float *wrow = w + (size_t)row * s.L1 + li * 4;
+                                for (int ch = 0; ch < nchunks; ++ch) {
+                                    const float4 v = __ldg(reinterpret_cast<const float4 *>(wrow + ch * 128));
+                                    const float4 gv = __ldg(reinterpret_cast<const float4 *>(grow + ch * 128));
+                                    d[u] = fmaf(v.x, gv.x, fmaf(v.y, gv.y, fmaf(v.z, gv.z, fmaf(v.w, gv.w, d[u]))));
+                                }
                             }
                         }
                     }
+                    // transposed reduction: 4 dots x LPR lanes -> each lane ends with one full dot
+                    float k0 = hi ? d[2] : d[0], k1 = hi ? d[3] : d[1];
+                    k0 += __shfl_xor_sync(kFull, hi ? d[0] : d[2], LPR / 2);
+                    k1 += __shfl_xor_sync(kFull, hi ? d[1] : d[3], LPR / 2);
+                    float r = hi2 ? k1 : k0;
+                    r += __shfl_xor_sync(kFull, hi2 ? k0 : k1, LPR / 4);
 #pragma unroll
-                    for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(kFull, d, o);
-                    if (k >= 0 && li == 0) dval[(size_t)b * s.PP + (size_t)widx * 32 + k] = d;
+                    for (int o = LPR / 8; o > 0; o >>= 1) r += __shfl_xor_sync(kFull, r, o);
+                    const int kk = my_slot == 0 ? k[0] : my_slot == 1 ? k[1] : my_slot == 2 ? k[2] : k[3];
+                    if (storer && i + my_slot < n) {
+                        const int pp = widx * 32 + kk;
+                        drow[pp] = r;
+                        const float z = kSteSharpnessFt * (__ldg(xrow + pp) - thr_c);
+                        const float sg = __fdividef(1.0f, 1.0f + __expf(-z));
+                        dth = fmaf(-r, kSteSharpnessFt * sg * (1.0f - sg), dth);
+                    }
                 }
             }
         }
     }
+    {
+        const float v = warp_sum(dth);
+        if (lane == 0) my_sdth[cur_c] += v;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < s.C; c += blockDim.x) {
+        float v = 0.0f;
+        for (int wv = 0; wv < wpb; ++wv) v += sdth[wv * s.C + c];
+        thr_partial[(size_t)blockIdx.x * s.C + c] = v;
+    }
 }
 
+// any L1: one warp per sample and one dot at a time; same outputs as the vector kernel
 __global__ void __launch_bounds__(kFtThreads)
 ft_bwd_dval_generic_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const float *__restrict__ w,
-                           const float *__restrict__ g_ft, float *__restrict__ dval) {
-    const int lane = threadIdx.x & 31;
-    const int b = (int)((1LL * blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (b >= s.B) return;
+                           const float *__restrict__ g_ft, const float *__restrict__ xpad,
+                           const float *__restrict__ thr, float *__restrict__ dval, float *__restrict__ thr_partial) {
+    extern __shared__ float sdth_gen[];  // [wpb][C]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < wpb * s.C; i += blockDim.x) sdth_gen[i] = 0.0f;
+    __syncthreads();
     const int cells = s.Gh * s.Gw;
-    for (int widx = 0; widx < s.NW; ++widx) {
-        unsigned word = __ldg(bits_s + (size_t)b * s.NW + widx);
-        const int base = (widx / s.CW) * cells + (widx % s.CW) * 32;
-        while (word) {
-            const int k = __ffs(word) - 1;
-            word &= word - 1;
-            const int row = min(base + k, s.F - 1);
-            float d = 0.0f;
-            for (int col = lane; col < s.L1; col += 32)
-                d = fmaf(__ldg(w + (size_t)row * s.L1 + col), __ldg(g_ft + (size_t)b * s.L1 + col), d);
-            d = warp_sum(d);
-            if (lane == 0) dval[(size_t)b * s.PP + (size_t)widx * 32 + k] = d;
+    for (int b = blockIdx.x * wpb + warp; b < s.B; b += gridDim.x * wpb) {
+        for (int widx = 0; widx < s.NW; ++widx) {
+            unsigned word = __ldg(bits_s + (size_t)b * s.NW + widx);
+            const int c = widx / s.CW;
+            const int base = word_base(s, widx, cells);
+            while (word) {
+                const int k = __ffs(word) - 1;
+                word &= word - 1;
+                const int row = min(base + k, s.F - 1);
+                float d = 0.0f;
+                for (int col = lane; col < s.L1; col += 32)
+                    d = fmaf(__ldg(w + (size_t)row * s.L1 + col), __ldg(g_ft + (size_t)b * s.L1 + col), d);
+                d = warp_sum(d);
+                if (lane == 0) {
+                    const size_t o = (size_t)b * s.PP + (size_t)widx * 32 + k;
+                    dval[o] = d;
+                    const float z = kSteSharpnessFt * (__ldg(xpad + o) - __ldg(thr + c));
+                    const float sg = __fdividef(1.0f, 1.0f + __expf(-z));
+                    sdth_gen[warp * s.C + c] = fmaf(-d, kSteSharpnessFt * sg * (1.0f - sg), sdth_gen[warp * s.C + c]);
+                }
+            }
         }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < s.C; c += blockDim.x) {
+        float v = 0.0f;
+        for (int wv = 0; wv < wpb; ++wv) v += sdth_gen[wv * s.C + c];
+        thr_partial[(size_t)blockIdx.x * s.C + c] = v;
     }
 }
 
@@ -434,23 +647,26 @@ static int max_dyn_smem() {
     return v;
 }
 
+// Stage the table when it fits one CTA's shared memory and there is enough work to amortise it.
+static bool use_staging(const nnue_shape &s, int nchunks, long long units) {
+    const size_t table_bytes = (size_t)s.F * s.L1 * 4;
+    const int mode = get_option(kOptFtFwdStaging);  // 0 never, 1 auto, 2 whenever it fits
+    const bool fits = nchunks == 1 && table_bytes + 128 <= (size_t)max_dyn_smem() && table_bytes % 16 == 0 &&
+                      table_bytes < (1u << 20);
+    return fits && (mode == 2 || (mode == 1 && units >= 8LL * kNumSMs));
+}
+
 template <int LPR>
 static int launch_ft_fwd(const nnue_shape &s, const uint32_t *bits, const float *w, const float *b, float *out,
                          int nchunks, cudaStream_t st) {
-    const size_t table_bytes = (size_t)s.F * s.L1 * 4;
-    const size_t staged_smem = table_bytes + 128;
-    const int wpb = kFtThreads / 32;
+    const size_t staged_smem = (size_t)s.F * s.L1 * 4 + 128;
     const long long units = 1LL * s.B * nchunks;
-    // stage the table when it fits one CTA's shared memory and there is enough work to amortise it
-    const int mode = get_option(kOptFtFwdStaging);  // 0 never, 1 auto, 2 whenever it fits
-    const bool fits = nchunks == 1 && staged_smem <= (size_t)max_dyn_smem() && table_bytes % 16 == 0 &&
-                      table_bytes < (1u << 20);
-    const bool staged = fits && (mode == 2 || (mode == 1 && units >= 8LL * kNumSMs));
-    if (staged) {
+    if (use_staging(s, nchunks, units)) {
         auto k = ft_fwd_bits_kernel<LPR, true>;
         NNUE_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem));
-        k<<<kNumSMs, kFtThreads, staged_smem, st>>>(s, bits, w, b, out, nchunks);
+        k<<<kNumSMs, kFtStagedThreads, staged_smem, st>>>(s, bits, w, b, out, nchunks);
     } else {
+        const int wpb = kFtThreads / 32;
         long long grid = (units + wpb - 1) / wpb;
         if (grid > 64LL * kNumSMs) grid = 64LL * kNumSMs;
         ft_fwd_bits_kernel<LPR, false><<<(int)grid, kFtThreads, 0, st>>>(s, bits, w, b, out, nchunks);
@@ -472,11 +688,18 @@ static int launch_ft_bwd_dw(const nnue_shape &s, const DwPlan &d, const uint32_t
 
 template <int LPR>
 static int launch_ft_bwd_dval(const nnue_shape &s, const uint32_t *bits, const float *w, const float *g_ft,
-                              float *dval, int nchunks, cudaStream_t st) {
-    const int wpb = kFtThreads / 32;
-    long long grid = (s.B + wpb - 1) / wpb;
-    if (grid > 64LL * kNumSMs) grid = 64LL * kNumSMs;
-    ft_bwd_dval_kernel<LPR><<<(int)grid, kFtThreads, 0, st>>>(s, bits, w, g_ft, dval, nchunks);
+                              const float *xpad, const float *thr, float *dval, float *thr_partial, int grid,
+                              bool staged, int nchunks, cudaStream_t st) {
+    if (staged) {
+        const size_t smem = 128 + align_up((size_t)(kDvalStagedThreads / 32) * s.C * 4, 128) + (size_t)s.F * s.L1 * 4;
+        auto k = ft_bwd_dval_kernel<LPR, true>;
+        NNUE_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kDvalStagedThreads, smem, st>>>(s, bits, w, g_ft, xpad, thr, dval, thr_partial, nchunks);
+    } else {
+        const size_t smem = 128 + align_up((size_t)(kFtThreads / 32) * s.C * 4, 128);
+        ft_bwd_dval_kernel<LPR, false><<<grid, kFtThreads, smem, st>>>(s, bits, w, g_ft, xpad, thr, dval, thr_partial,
+                                                                       nchunks);
+    }
     NNUE_CHECK_LAUNCH("ft_bwd_dval_kernel");
     return NNUE_OK;
 }
@@ -570,27 +793,50 @@ int nnue_ft_bwd_dw(const nnue_shape *s, const uint32_t *bits_t_d, const float *g
     NNUE_DISPATCH_LPR(d.col.LPR, rc = launch_ft_bwd_dw<LPR>(*s, d, bits_t_d, g_ft_d, dst, st));
     if (rc != NNUE_OK) return rc;
     if (!d.direct) {
-        const long long n = 1LL * s->F * (s->L1 / 4);
-        ft_bwd_dw_fold_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(*s, d.ngroups, partial, g_w_d);
-        NNUE_CHECK_LAUNCH("ft_bwd_dw_fold_kernel");
+        float *alias = partial + (size_t)d.ngroups * s->P * s->L1;
+        const long long n = 1LL * (s->P > s->F - 1 ? s->P : s->F - 1) * (s->L1 / 4);
+        if (n > 0) {
+            ft_bwd_dw_fold_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(*s, d.ngroups, partial, g_w_d, alias);
+            NNUE_CHECK_LAUNCH("ft_bwd_dw_fold_kernel");
+        }
+        ft_bwd_dw_fold_last_kernel<<<ceil_div(s->L1 / 4, 32), 256, 0, st>>>(*s, alias, g_w_d);
+        NNUE_CHECK_LAUNCH("ft_bwd_dw_fold_last_kernel");
     }
     return NNUE_OK;
 }
 
 int nnue_ft_bwd_dval(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w_d, const float *g_ft_d,
-                     float *dval_d, void *stream) {
-    if (!s || !bits_s_d || !ft_w_d || !g_ft_d || !dval_d) return NNUE_ERR_INVALID_ARG;
+                     const float *xpad_d, const float *thr_d, float *dval_d, float *g_thr_d, void *workspace_d,
+                     size_t workspace_bytes, void *stream) {
+    if (!s || !bits_s_d || !ft_w_d || !g_ft_d || !xpad_d || !thr_d || !dval_d || !g_thr_d || !workspace_d)
+        return NNUE_ERR_INVALID_ARG;
+    if (workspace_bytes < ws_ft_bwd_dval(*s)) return NNUE_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float *thr_partial = static_cast<float *>(workspace_d);
     const ColPlan cp = col_plan(s->L1);
+    const int grid = dval_grid(*s);
     if (!cp.LPR) {
-        ft_bwd_dval_generic_kernel<<<ceil_div(s->B, kFtThreads / 32), kFtThreads, 0, st>>>(*s, bits_s_d, ft_w_d, g_ft_d,
-                                                                                          dval_d);
+        ft_bwd_dval_generic_kernel<<<grid, kFtThreads, (size_t)(kFtThreads / 32) * s->C * 4, st>>>(
+            *s, bits_s_d, ft_w_d, g_ft_d, xpad_d, thr_d, dval_d, thr_partial);
         NNUE_CHECK_LAUNCH("ft_bwd_dval_generic_kernel");
-        return NNUE_OK;
+    } else {
+        const size_t staged_smem =
+            128 + align_up((size_t)(kDvalStagedThreads / 32) * s->C * 4, 128) + (size_t)s->F * s->L1 * 4;
+        const bool staged = use_staging(*s, cp.nchunks, s->B) && staged_smem <= (size_t)max_dyn_smem();
+        int rc = NNUE_OK;
+        NNUE_DISPATCH_LPR(cp.LPR, rc = launch_ft_bwd_dval<LPR>(*s, bits_s_d, ft_w_d, g_ft_d, xpad_d, thr_d, dval_d,
+                                                              thr_partial, staged ? kNumSMs : grid, staged,
+                                                              cp.nchunks, st));
+        if (rc != NNUE_OK) return rc;
+        if (staged) {  // the staged kernel always runs kNumSMs CTAs
+            fold_partials_kernel<<<ceil_div(s->C, 128), 128, 0, st>>>(s->C, kNumSMs, thr_partial, g_thr_d);
+            NNUE_CHECK_LAUNCH("fold_partials_kernel");
+            return NNUE_OK;
+        }
     }
-    int rc = NNUE_OK;
-    NNUE_DISPATCH_LPR(cp.LPR, rc = launch_ft_bwd_dval<LPR>(*s, bits_s_d, ft_w_d, g_ft_d, dval_d, cp.nchunks, st));
-    return rc;
+    fold_partials_kernel<<<ceil_div(s->C, 128), 128, 0, st>>>(s->C, grid, thr_partial, g_thr_d);
+    NNUE_CHECK_LAUNCH("fold_partials_kernel");
+    return NNUE_OK;
 }
 
 }  // extern "C"

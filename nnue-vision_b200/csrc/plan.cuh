@@ -49,13 +49,13 @@ inline DwPlan plan_ft_bwd_dw(const nnue_shape &s) {
     const int CC = d.col.LPR ? d.col.CC : 0;
     if (!CC) return d;
     int TS = 256;
-    while (TS > 32 && (size_t)TS * CC * 4 > 64 * 1024) TS >>= 1;
+    while (TS > 32 && (size_t)TS * CC * 4 > 32 * 1024) TS >>= 1;
     while (TS > 32 && TS / 2 >= s.B) TS >>= 1;
     d.TS = TS;
     d.ntiles = ceil_div(s.B, TS);
     d.pchunks = ceil_div(s.PP, kDwPPC);
     const long long ctas_per_group = 1LL * d.pchunks * d.col.nchunks;
-    int want_groups = (int)((2LL * kNumSMs + ctas_per_group - 1) / ctas_per_group);
+    int want_groups = (int)((4LL * kNumSMs + ctas_per_group - 1) / ctas_per_group);
     if (want_groups < 1) want_groups = 1;
     // partial buffers cost ngroups * P * L1 floats: cap them at 64 MiB
     const long long per_group = 1LL * s.P * s.L1 * 4;
@@ -73,18 +73,38 @@ constexpr int kColsumRows = 256;  // rows per column-sum partial
 inline size_t ws_ft_bwd_dw(const nnue_shape &s) {
     const DwPlan d = plan_ft_bwd_dw(s);
     size_t bytes = align_up((size_t)ceil_div(s.B, kColsumRows) * s.L1 * 4, 256);
-    if (d.col.LPR && !d.direct) bytes += (size_t)d.ngroups * s.P * s.L1 * 4;
+    if (d.col.LPR && !d.direct)  // per-group partials + the rows parked for the aliased last row
+        bytes += ((size_t)d.ngroups * s.P + (size_t)(s.P > s.F - 1 ? s.P - (s.F - 1) : 0)) * s.L1 * 4;
     return bytes;
 }
 
+// ---- FT value gradient: per-CTA threshold-gradient partials [grid][C] ----------------------
+inline int dval_grid(const nnue_shape &s) {
+    long long grid = (s.B + 7) / 8;  // 8 warps (samples) per CTA
+    if (grid > 64LL * kNumSMs) grid = 64LL * kNumSMs;
+    if (grid < kNumSMs) grid = kNumSMs;  // the staged variant always runs kNumSMs CTAs
+    return (int)grid;
+}
+inline size_t ws_ft_bwd_dval(const nnue_shape &s) { return (size_t)dval_grid(s) * s.C * 4; }
+
 // ---- extraction backward -----------------------------------------------------------------
-constexpr int kExbCCH = 4;      // channels per CTA (register accumulators: 4 x 27 + 4)
+constexpr int kExbCCH = 2;      // channels per warp (register accumulators: 2 x 27 + 2)
 constexpr int kExbThreads = 256;
+constexpr int kExbWarps = kExbThreads / 32;
+// channel chunks handled side by side by the warps of one CTA (they share the image reads through L1)
+inline int exb_cpc(int C) {
+    const int nchunks = ceil_div(C, kExbCCH);
+    int cpc = 1;
+    while (cpc * 2 <= nchunks && cpc * 2 <= kExbWarps) cpc *= 2;
+    return cpc;
+}
+inline int exb_grid_y(int C) { return ceil_div(ceil_div(C, kExbCCH), exb_cpc(C)); }
 inline int exb_grid_x(const nnue_shape &s) {
     const long long units = 1LL * s.B * s.CW;
-    const int cchunks = ceil_div(s.C, kExbCCH);
-    long long gx = (4LL * kNumSMs + cchunks - 1) / cchunks;
-    const long long max_gx = (units + (kExbThreads / 32) - 1) / (kExbThreads / 32);
+    const int streams = kExbWarps / exb_cpc(s.C);
+    const int gy = exb_grid_y(s.C);
+    long long gx = (8LL * kNumSMs + gy - 1) / gy;
+    const long long max_gx = (units + streams - 1) / streams;
     if (gx > max_gx) gx = max_gx;
     return gx < 1 ? 1 : (int)gx;
 }

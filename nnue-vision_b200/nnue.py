@@ -164,7 +164,7 @@ class SimpleClassifier(nn.Module):
 
 class _Saved:
     """Forward products the backward needs (kept on the autograd ctx)."""
-    __slots__ = ("shape", "images", "bits_s", "bits_t", "ft_out", "act1", "act2", "params")
+    __slots__ = ("shape", "images", "bits_s", "bits_t", "xpad", "ft_out", "act1", "act2", "params")
 
 
 def _mark(marks, name):
@@ -183,8 +183,10 @@ def _run_forward(shape, images, params, need_backward, marks=None):
     sp = ctypes.byref(shape)
     bits_s = _empty((shape.B, shape.NW), torch.int32, images)
     bits_t = _empty((shape.PP, shape.BW), torch.int32, images) if need_backward else None
+    xpad = _empty((shape.B, shape.PP), torch.float32, images) if need_backward else None
     _mark(marks, "start")
-    check(L.nnue_extract_fwd(sp, dptr(images), dptr(conv_w), dptr(thr), dptr(bits_s), dptr(bits_t), None, None, st))
+    check(L.nnue_extract_fwd(sp, dptr(images), dptr(conv_w), dptr(thr), dptr(bits_s), dptr(bits_t), dptr(xpad), None,
+                             None, st))
     _mark(marks, "extract_fwd")
     ft_out = _empty((shape.B, shape.L1), torch.float32, images)
     check(L.nnue_ft_fwd(sp, dptr(bits_s), dptr(ft_w), dptr(ft_b), dptr(ft_out), st))
@@ -195,10 +197,10 @@ def _run_forward(shape, images, params, need_backward, marks=None):
     check(L.nnue_head_fwd(sp, dptr(ft_out), dptr(w1), dptr(b1), dptr(w2), dptr(b2), dptr(w3), dptr(b3), dptr(act1),
                           dptr(act2), dptr(logits), st))
     _mark(marks, "head_fwd")
-    return logits, bits_s, bits_t, ft_out, act1, act2
+    return logits, bits_s, bits_t, xpad, ft_out, act1, act2
 
 
-def _run_backward(shape, images, params, bits_s, bits_t, ft_out, act1, act2, g_logits, grads=None, marks=None):
+def _run_backward(shape, images, params, bits_s, bits_t, xpad, ft_out, act1, act2, g_logits, grads=None, marks=None):
     """All parameter gradients from g_logits.  `grads` (optional) are preallocated output tensors in
     parameter order (thr, conv_w, ft_w, ft_b, w1, b1, w2, b2, w3, b3) -- e.g. views of a flat
     data-parallel gradient buffer -- otherwise fresh tensors are returned."""
@@ -219,10 +221,10 @@ def _run_backward(shape, images, params, bits_s, bits_t, ft_out, act1, act2, g_l
     check(L.nnue_ft_bwd_dw(sp, dptr(bits_t), dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(ws), ws_bytes, st))
     _mark(marks, "ft_bwd_dw")
     dval = _empty((shape.B, shape.PP), torch.float32, images)
-    check(L.nnue_ft_bwd_dval(sp, dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(dval), st))
+    check(L.nnue_ft_bwd_dval(sp, dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(xpad), dptr(thr), dptr(dval), dptr(g_thr),
+                             dptr(ws), ws_bytes, st))
     _mark(marks, "ft_bwd_dval")
-    check(L.nnue_extract_bwd(sp, dptr(images), dptr(conv_w), dptr(thr), dptr(bits_s), dptr(dval), dptr(g_conv_w),
-                             dptr(g_thr), dptr(ws), ws_bytes, st))
+    check(L.nnue_extract_bwd(sp, dptr(images), dptr(bits_s), dptr(dval), dptr(g_conv_w), dptr(ws), ws_bytes, st))
     _mark(marks, "extract_bwd")
     return grads
 
@@ -236,10 +238,10 @@ class _NNUEForward(torch.autograd.Function):
         B, _, H, W = images.shape
         shape = _lib.make_shape(B, H, W, C, G, ft_w.shape[1], w1.shape[0], w2.shape[0], w3.shape[0], stride)
         need_bwd = any(ctx.needs_input_grad[4:])
-        logits, bits_s, bits_t, ft_out, act1, act2 = _run_forward(shape, images, params, need_bwd)
+        logits, bits_s, bits_t, xpad, ft_out, act1, act2 = _run_forward(shape, images, params, need_bwd)
         if need_bwd:
             sv = _Saved()
-            sv.shape, sv.images, sv.bits_s, sv.bits_t = shape, images, bits_s, bits_t
+            sv.shape, sv.images, sv.bits_s, sv.bits_t, sv.xpad = shape, images, bits_s, bits_t, xpad
             sv.ft_out, sv.act1, sv.act2, sv.params = ft_out, act1, act2, params
             ctx.sv = sv
         return logits
@@ -247,7 +249,7 @@ class _NNUEForward(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_logits):
         sv = ctx.sv
-        g = _run_backward(sv.shape, sv.images, sv.params, sv.bits_s, sv.bits_t, sv.ft_out, sv.act1, sv.act2,
+        g = _run_backward(sv.shape, sv.images, sv.params, sv.bits_s, sv.bits_t, sv.xpad, sv.ft_out, sv.act1, sv.act2,
                           g_logits.contiguous().float())
         return (None, None, None, None) + tuple(g)
 
@@ -261,14 +263,14 @@ class _NNUELoss(torch.autograd.Function):
         B, _, H, W = images.shape
         shape = _lib.make_shape(B, H, W, C, G, ft_w.shape[1], w1.shape[0], w2.shape[0], w3.shape[0], stride)
         need_bwd = any(ctx.needs_input_grad[6:])
-        logits, bits_s, bits_t, ft_out, act1, act2 = _run_forward(shape, images, params, need_bwd)
+        logits, bits_s, bits_t, xpad, ft_out, act1, act2 = _run_forward(shape, images, params, need_bwd)
         loss = _empty((1,), torch.float32, images)
         per = _empty((B,), torch.float32, images)
         check(_lib.lib().nnue_ce_fwd_bwd(B, shape.NC, dptr(logits), dptr(labels), inv_count, None, dptr(loss),
                                          dptr(per), None, None, 0, stream_ptr()))
         if need_bwd:
             sv = _Saved()
-            sv.shape, sv.images, sv.bits_s, sv.bits_t = shape, images, bits_s, bits_t
+            sv.shape, sv.images, sv.bits_s, sv.bits_t, sv.xpad = shape, images, bits_s, bits_t, xpad
             sv.ft_out, sv.act1, sv.act2, sv.params = ft_out, act1, act2, params
             ctx.sv, ctx.logits, ctx.labels, ctx.inv_count = sv, logits, labels, inv_count
         return loss.reshape(())
@@ -280,7 +282,8 @@ class _NNUELoss(torch.autograd.Function):
         g_scale = g_loss.detach().reshape(1).float().contiguous()
         check(_lib.lib().nnue_ce_fwd_bwd(sv.shape.B, sv.shape.NC, dptr(ctx.logits), dptr(ctx.labels), ctx.inv_count,
                                          dptr(g_scale), None, None, dptr(g_logits), None, 0, stream_ptr()))
-        g = _run_backward(sv.shape, sv.images, sv.params, sv.bits_s, sv.bits_t, sv.ft_out, sv.act1, sv.act2, g_logits)
+        g = _run_backward(sv.shape, sv.images, sv.params, sv.bits_s, sv.bits_t, sv.xpad, sv.ft_out, sv.act1, sv.act2,
+                          g_logits)
         return (None,) * 6 + tuple(g)
 
 
@@ -379,7 +382,7 @@ class NNUE(nn.Module):
         bits = _empty((B, shape.NW), torch.int32, images)
         check(_lib.lib().nnue_extract_fwd(ctypes.byref(shape), dptr(images), dptr(self.conv.weight.detach().contiguous()),
                                           dptr(self.visual_threshold.detach().contiguous()), dptr(bits), None, None,
-                                          None, stream_ptr()))
+                                          None, None, stream_ptr()))
         return shape, bits
 
     def _to_sparse_features(self, binary_features: torch.Tensor):

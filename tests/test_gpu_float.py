@@ -114,13 +114,18 @@ def test_full_step_against_oracle(name):
     bits_t = torch.empty((shape.PP, shape.BW), dtype=torch.int32, device="cuda")
     conv_out = torch.empty((B, shape.C, shape.Gh, shape.Gw), dtype=torch.float32, device="cuda")
     nnz = torch.empty((B,), dtype=torch.int32, device="cuda")
+    xpad = torch.full((B, shape.PP), float("nan"), dtype=torch.float32, device="cuda")
     lib.check(lib.lib().nnue_extract_fwd(
         ctypes.byref(shape), lib.dptr(images), lib.dptr(model.conv.weight.detach().contiguous()),
         lib.dptr(model.visual_threshold.detach().contiguous()), lib.dptr(bits_s), lib.dptr(bits_t),
-        lib.dptr(conv_out), lib.dptr(nnz), lib.stream_ptr()))
+        lib.dptr(xpad), lib.dptr(conv_out), lib.dptr(nnz), lib.stream_ptr()))
     torch.cuda.synchronize()
     assert tuple(conv_out.shape) == tuple(ref["conv_out"].shape)
     assert_close(conv_out, ref["conv_out"], "conv_out")
+    # the padded-layout copy kept for the threshold gradient holds the same activations
+    cells = shape.Gh * shape.Gw
+    xp = xpad.view(B, shape.C, shape.CW * 32)[:, :, :cells].reshape(B, shape.C, shape.Gh, shape.Gw)
+    assert torch.equal(xp, conv_out)
     got_bits = unpack_bits(shape, bits_s)
     ref_bits = ref["bits"].reshape(B, shape.C, -1).numpy()
     amb = ambiguous_samples(ref["conv_out"].numpy(), model.visual_threshold.detach().cpu().numpy())
