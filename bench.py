@@ -374,9 +374,9 @@ def run_b200(args):
     algo = {  # algorithmic bytes per launch, SURVEY.md section 8(d)
         "ft_fwd": nnz_total * L1 * 4 + B * L1 * 4 + nnz_total * 4,
         "ft_bwd_dw": nnz_total * L1 * 4 + F * L1 * 4,
-        "ft_bwd_dval": nnz_total * L1 * 4 + B * L1 * 4 + nnz_total * 4,
-        "extract_fwd": img_bytes + B * shape.NW * 4 + shape.PP * shape.BW * 4,
-        "extract_bwd": img_bytes + nnz_total * 4 + B * shape.NW * 4,
+        # value gradient (W row reads per active position + g_ft) fused with the conv gradient (image + bitmask)
+        "input_bwd": nnz_total * L1 * 4 + B * L1 * 4 + img_bytes + B * shape.NW * 4,
+        "extract_fwd": img_bytes + B * shape.NW * 4,
     }
     peak, peak_src = peaks()
     roofs = {}

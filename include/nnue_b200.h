@@ -71,6 +71,10 @@ unsigned long long nnue_launch_count(int reset);
  * Tuning knobs (process-wide; defaults work).  Keys:
  *   "ft_fwd_staging"  0 = gather table rows from global/L2, 1 = auto (default), 2 = stage the
  *                     whole table in shared memory with bulk TMA copies whenever it fits.
+ *   "ft_bwd_dw_owner" 1 (default) = row-owner weight gradient where the shape allows, 0 = always
+ *                     the transposed-bitmask segment reduction.
+ *   "input_bwd_fused" 1 (default) = fused input-gradient kernel where the shape allows, 0 = always
+ *                     the value-gradient + conv-gradient kernel pair.
  */
 int nnue_set_option(const char *key, int value);
 
@@ -175,14 +179,19 @@ int nnue_head_bwd(const nnue_shape *s, const float *g_logits_d, const float *ft_
                   size_t workspace_bytes, void *stream);
 
 /*
- * Feature-transformer weight/bias gradient on the transposed bitmask: a segment
- * reduction over (feature, sample) pairs already sorted by feature (the bit-matrix
- * transpose is the sort), no atomics, deterministic.  Rows p >= F fold onto row F-1.
+ * Feature-transformer weight/bias gradient: a segment reduction over (feature, sample)
+ * pairs sorted by feature, no atomics, deterministic.  Rows p >= F fold onto row F-1.
  * Replaces the B IndexBackward / index_put nodes autograd builds for nnue.py:702-708.
- *   bits_t_d [PP][BW]; g_ft_d [B,L1]; g_w_d [F,L1] fully written; g_b_d [L1]
+ * Two forms, chosen by shape (nnue_wants_transposed_bits tells which):
+ *   - row-owner (L1 <= 64): a lane owns one table row's gradient in registers and walks the
+ *     samples in order off bits_s; bits_t_d may be NULL;
+ *   - transposed bitmask (any other L1): the bit-matrix transpose is the sort; needs bits_t_d.
+ *   bits_s_d [B][NW]; bits_t_d [PP][BW]; g_ft_d [B,L1]; g_w_d [F,L1] fully written; g_b_d [L1]
  */
-int nnue_ft_bwd_dw(const nnue_shape *s, const uint32_t *bits_t_d, const float *g_ft_d, float *g_w_d,
-                   float *g_b_d, void *workspace_d, size_t workspace_bytes, void *stream);
+int nnue_wants_transposed_bits(const nnue_shape *s);
+int nnue_ft_bwd_dw(const nnue_shape *s, const uint32_t *bits_s_d, const uint32_t *bits_t_d,
+                   const float *g_ft_d, float *g_w_d, float *g_b_d, void *workspace_d,
+                   size_t workspace_bytes, void *stream);
 
 /*
  * Gradient w.r.t. the feature values at ACTIVE positions: dval[b,p] = <W[min(p,F-1)], g_ft[b]>
@@ -204,6 +213,20 @@ int nnue_ft_bwd_dval(const nnue_shape *s, const uint32_t *bits_s_d, const float 
 int nnue_extract_bwd(const nnue_shape *s, const float *images_d, const uint32_t *bits_s_d,
                      const float *dval_d, float *g_conv_w_d, void *workspace_d,
                      size_t workspace_bytes, void *stream);
+
+/*
+ * Everything upstream of the feature transformer's input in one call: the value gradient at
+ * active positions, the straight-through threshold gradient and the conv weight gradient
+ * (= nnue_ft_bwd_dval + nnue_extract_bwd, nnue.py:28-52, 602-603, 640, 705).  For CIFAR-sized
+ * images and L1 <= 64 this is ONE fused kernel that recomputes the conv from TMA-staged image
+ * tiles and never materialises dval or the pre-threshold activations; other shapes run the
+ * two-kernel path on scratch carved from the workspace.
+ *   g_conv_w_d [C,3,3,3]; g_thr_d [C]
+ */
+int nnue_input_bwd(const nnue_shape *s, const float *images_d, const uint32_t *bits_s_d,
+                   const float *ft_w_d, const float *g_ft_d, const float *conv_w_d, const float *thr_d,
+                   float *g_conv_w_d, float *g_thr_d, void *workspace_d, size_t workspace_bytes,
+                   void *stream);
 
 /* ------------------------------------------------------------------------- *
  *  Quantized integer inference path (bit-exact vs serialize.py + engine)     *

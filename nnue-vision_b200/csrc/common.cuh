@@ -40,7 +40,7 @@ void note_launch();
     } while (0)
 
 // Tuning knobs settable through nnue_set_option (api.cu); every value has a working default.
-enum Option { kOptFtFwdStaging = 0, kNumOptions };
+enum Option { kOptFtFwdStaging = 0, kOptDwOwner, kOptInputFused, kNumOptions };
 int get_option(int which);
 
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -76,6 +76,9 @@ __device__ __forceinline__ void mbar_fence_init() {
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(

@@ -86,7 +86,7 @@ extract_fwd_kernel(const nnue_shape s, const float *__restrict__ images, const f
         for (int c = 0; c < s.C; ++c) {
             const float x = conv_tap_sum(patch, sw + c * 28);
             const unsigned word = __ballot_sync(kFull, valid && x > sthr[c]);
-            if (lane == 0) bits_s[(size_t)b * s.NW + c * s.CW + j] = word;
+            if (bits_s && lane == 0) bits_s[(size_t)b * s.NW + c * s.CW + j] = word;
             if (xpad) xpad[(size_t)b * s.PP + (size_t)(c * s.CW + j) * 32 + lane] = x;  // coalesced 128 B
             if (conv_out && valid) conv_out[((size_t)b * s.C + c) * cells + cell] = x;
         }
@@ -235,6 +235,25 @@ __global__ void fold_rows_kernel(int n, int nblk, const float *__restrict__ part
     out[i] = v;
 }
 
+static int launch_extract_fwd(const nnue_shape &s, const float *images, const float *conv_w, const float *thr,
+                              uint32_t *bits_s, float *xpad, float *conv_out, cudaStream_t st) {
+    const size_t smem = (size_t)s.C * 29 * sizeof(float);
+    if (smem > 48 * 1024) return NNUE_ERR_UNSUPPORTED;  // C <= 423 channels
+    const long long units = 1LL * s.B * s.CW;
+    const int wpb = kExtThreads / 32;
+    long long grid = (units + wpb - 1) / wpb;
+    const long long cap = 32LL * kNumSMs;
+    if (grid > cap) grid = cap;
+    extract_fwd_kernel<<<(int)grid, kExtThreads, smem, st>>>(s, images, conv_w, thr, bits_s, xpad, conv_out);
+    NNUE_CHECK_LAUNCH("extract_fwd_kernel");
+    return NNUE_OK;
+}
+
+int extract_xpad(const nnue_shape &s, const float *images, const float *conv_w, const float *thr, float *xpad,
+                 cudaStream_t st) {
+    return launch_extract_fwd(s, images, conv_w, thr, nullptr, xpad, nullptr, st);
+}
+
 }  // namespace nnue
 
 using namespace nnue;
@@ -246,16 +265,8 @@ int nnue_extract_fwd(const nnue_shape *s, const float *images_d, const float *co
                      void *stream) {
     if (!s || !images_d || !conv_w_d || !thr_d || !bits_s_d) return NNUE_ERR_INVALID_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t smem = (size_t)s->C * 29 * sizeof(float);
-    if (smem > 48 * 1024) return NNUE_ERR_UNSUPPORTED;  // C <= 423 channels
-    const long long units = 1LL * s->B * s->CW;
-    const int wpb = kExtThreads / 32;
-    long long grid = (units + wpb - 1) / wpb;
-    const long long cap = 32LL * kNumSMs;
-    if (grid > cap) grid = cap;
-    extract_fwd_kernel<<<(int)grid, kExtThreads, smem, st>>>(*s, images_d, conv_w_d, thr_d, bits_s_d, xpad_d,
-                                                            conv_out_d);
-    NNUE_CHECK_LAUNCH("extract_fwd_kernel");
+    const int rc = launch_extract_fwd(*s, images_d, conv_w_d, thr_d, bits_s_d, xpad_d, conv_out_d, st);
+    if (rc != NNUE_OK) return rc;
     if (bits_t_d) {
         dim3 g(ceil_div(s->NW, 32), ceil_div(s->BW, kTrGroups)), blk(32, 32);
         bits_transpose_kernel<<<g, blk, 0, st>>>(*s, bits_s_d, bits_t_d);

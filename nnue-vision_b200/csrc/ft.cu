@@ -406,6 +406,113 @@ ft_bwd_dw_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_t, const 
     }
 }
 
+// ---- weight gradient, row-owner form -----------------------------------------------------------
+// For tables small enough that one lane can keep a whole row's gradient in registers (L1 <= 64):
+// a warp owns one bitmask word (32 positions, one per lane) for the whole kernel and walks its
+// sample stream in order; every sample contributes g_ft[b] (broadcast LDS.128 from a TMA-staged
+// tile) to the lanes whose bit is set.  The per-position sample list is consumed in sorted order,
+// nothing is atomic, and the result is written as partial[stream][p][L1] for the same fold kernels
+// as the transposed-bitmask path.  One extra warp sums the staged g_ft tile into the bias gradient.
+template <int L1>
+__global__ void __launch_bounds__((kOwnWarps + 2) * 32, 1)
+ft_bwd_dw_owner_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const float *__restrict__ g_ft,
+                       float *__restrict__ partial, float *__restrict__ bias_partial, const OwnPlan pl) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *empty = full + kOwnStages;
+    float *stages = reinterpret_cast<float *>(smem_raw + 128);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int role = blockIdx.x % pl.NH, q = blockIdx.x / pl.NH;
+    const bool do_bias = role == 0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kOwnStages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], kOwnWarps + (do_bias ? 1 : 0));
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kOwnWarps) {  // ---- producer: one g_ft tile + one bitmask tile per stage ----
+        if (lane == 0) {
+            int i = 0;
+            for (int t = q; t < pl.ntiles; t += pl.nq, ++i) {
+                const int st = i % kOwnStages;
+                if (i >= kOwnStages) mbar_wait(&empty[st], ((i / kOwnStages) - 1) & 1);
+                const int b0 = t * kOwnTS, rows = min(kOwnTS, s.B - b0);
+                float *stg = stages + (size_t)st * pl.stage_floats;
+                mbar_arrive_expect_tx(&full[st], (uint32_t)rows * (L1 + s.NW) * 4u);
+                tma_bulk_g2s(stg, g_ft + (size_t)b0 * L1, (uint32_t)rows * L1 * 4u, &full[st]);
+                tma_bulk_g2s(stg + kOwnTS * L1, bits_s + (size_t)b0 * s.NW, (uint32_t)rows * s.NW * 4u, &full[st]);
+            }
+        }
+        return;
+    }
+    if (warp == kOwnWarps + 1) {  // ---- bias gradient: column sums of the staged g_ft tiles ----
+        if (!do_bias) return;
+        float accb[L1 / 32];
+#pragma unroll
+        for (int k = 0; k < L1 / 32; ++k) accb[k] = 0.0f;
+        int i = 0;
+        for (int t = q; t < pl.ntiles; t += pl.nq, ++i) {
+            const int st = i % kOwnStages;
+            mbar_wait(&full[st], (i / kOwnStages) & 1);
+            const float *sg = stages + (size_t)st * pl.stage_floats;
+            const int rows = min(kOwnTS, s.B - t * kOwnTS);
+            for (int r = 0; r < rows; ++r)
+#pragma unroll
+                for (int k = 0; k < L1 / 32; ++k) accb[k] += sg[r * L1 + k * 32 + lane];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+#pragma unroll
+        for (int k = 0; k < L1 / 32; ++k) bias_partial[(size_t)q * L1 + k * 32 + lane] = accb[k];
+        return;
+    }
+    // ---- row owners ----
+    const int cells = s.Gh * s.Gw;
+    const int widx = role * kOwnWarps + warp;
+    const bool active = widx < s.NW;
+    const int c = active ? widx / s.CW : 0, j = active ? widx % s.CW : 0;
+    const int cell = j * 32 + lane;
+    float acc[L1];
+#pragma unroll
+    for (int k = 0; k < L1; ++k) acc[k] = 0.0f;
+    int i = 0;
+    for (int t = q; t < pl.ntiles; t += pl.nq, ++i) {
+        const int st = i % kOwnStages;
+        mbar_wait(&full[st], (i / kOwnStages) & 1);
+        if (active) {
+            const float *stg = stages + (size_t)st * pl.stage_floats;
+            const float4 *sg = reinterpret_cast<const float4 *>(stg);
+            const uint32_t *sb = reinterpret_cast<const uint32_t *>(stg + kOwnTS * L1) + widx;
+            const int rows = min(kOwnTS, s.B - t * kOwnTS);
+#pragma unroll 2
+            for (int r = 0; r < rows; ++r) {
+                const unsigned word = sb[r * s.NW];
+                if (!word) continue;  // warp-uniform
+                const float on = ((word >> lane) & 1u) ? 1.0f : 0.0f;
+#pragma unroll
+                for (int v = 0; v < L1 / 4; ++v) {
+                    const float4 g = sg[r * (L1 / 4) + v];
+                    acc[4 * v + 0] = fmaf(on, g.x, acc[4 * v + 0]);
+                    acc[4 * v + 1] = fmaf(on, g.y, acc[4 * v + 1]);
+                    acc[4 * v + 2] = fmaf(on, g.z, acc[4 * v + 2]);
+                    acc[4 * v + 3] = fmaf(on, g.w, acc[4 * v + 3]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+    }
+    if (active && cell < cells) {
+        const int p = c * cells + cell;
+        float4 *o = reinterpret_cast<float4 *>(partial + ((size_t)q * s.P + p) * L1);
+#pragma unroll
+        for (int v = 0; v < L1 / 4; ++v) o[v] = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+    }
+}
+
 // Fold stage 1: every position p sums its partials over the tile groups.  Positions below F-1 are
 // table rows and go straight to g_w; positions >= F-1 all alias onto the last row (the clamp of
 // nnue.py:701) and are parked in `alias` [P-(F-1)][L1] for stage 2; rows in [P, F-1) get zeros.
@@ -765,11 +872,40 @@ int nnue_ft_bwd_indexed(int B, int K, int F, int L1, const int64_t *idx_d, const
     return NNUE_OK;
 }
 
-int nnue_ft_bwd_dw(const nnue_shape *s, const uint32_t *bits_t_d, const float *g_ft_d, float *g_w_d, float *g_b_d,
-                   void *workspace_d, size_t workspace_bytes, void *stream) {
-    if (!s || !bits_t_d || !g_ft_d || !g_w_d || !g_b_d || !workspace_d) return NNUE_ERR_INVALID_ARG;
+int nnue_wants_transposed_bits(const nnue_shape *s) { return s && plan_ft_bwd_dw_owner(*s).ok ? 0 : 1; }
+
+int nnue_ft_bwd_dw(const nnue_shape *s, const uint32_t *bits_s_d, const uint32_t *bits_t_d, const float *g_ft_d,
+                   float *g_w_d, float *g_b_d, void *workspace_d, size_t workspace_bytes, void *stream) {
+    if (!s || !g_ft_d || !g_w_d || !g_b_d || !workspace_d) return NNUE_ERR_INVALID_ARG;
     if (workspace_bytes < ws_ft_bwd_dw(*s)) return NNUE_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const OwnPlan own = plan_ft_bwd_dw_owner(*s);
+    if (own.ok) {
+        if (!bits_s_d) return NNUE_ERR_INVALID_ARG;
+        float *bias_partial = static_cast<float *>(workspace_d);
+        float *partial = reinterpret_cast<float *>(static_cast<char *>(workspace_d) +
+                                                   align_up((size_t)own.nq * s->L1 * 4, 256));
+        float *alias = partial + (size_t)own.nq * s->P * s->L1;
+        if (s->L1 == 64) {
+            auto k = ft_bwd_dw_owner_kernel<64>;
+            NNUE_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)own.smem));
+            k<<<own.grid, (kOwnWarps + 2) * 32, own.smem, st>>>(*s, bits_s_d, g_ft_d, partial, bias_partial, own);
+        } else {
+            auto k = ft_bwd_dw_owner_kernel<32>;
+            NNUE_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)own.smem));
+            k<<<own.grid, (kOwnWarps + 2) * 32, own.smem, st>>>(*s, bits_s_d, g_ft_d, partial, bias_partial, own);
+        }
+        NNUE_CHECK_LAUNCH("ft_bwd_dw_owner_kernel");
+        fold_partials_kernel<<<ceil_div(s->L1, 128), 128, 0, st>>>(s->L1, own.nq, bias_partial, g_b_d);
+        NNUE_CHECK_LAUNCH("fold_partials_kernel");
+        const long long n = 1LL * (s->P > s->F - 1 ? s->P : s->F - 1) * (s->L1 / 4);
+        ft_bwd_dw_fold_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(*s, own.nq, partial, g_w_d, alias);
+        NNUE_CHECK_LAUNCH("ft_bwd_dw_fold_kernel");
+        ft_bwd_dw_fold_last_kernel<<<ceil_div(s->L1 / 4, 32), 256, 0, st>>>(*s, alias, g_w_d);
+        NNUE_CHECK_LAUNCH("ft_bwd_dw_fold_last_kernel");
+        return NNUE_OK;
+    }
+    if (!bits_t_d) return NNUE_ERR_INVALID_ARG;
     // bias gradient = column sums of g_ft
     float *cs_partial = static_cast<float *>(workspace_d);
     const int nrow_chunks = ceil_div(s->B, kColsumRows);

@@ -69,8 +69,42 @@ inline DwPlan plan_ft_bwd_dw(const nnue_shape &s) {
     d.smem = (size_t)TS * CC * 4 + 64;
     return d;
 }
+// ---- FT weight gradient, row-owner form (small tables: a lane keeps its row's gradient in registers) ----
+constexpr int kOwnWarps = 16;   // consumer warps per CTA (+ 1 producer warp + 1 bias warp)
+constexpr int kOwnTS = 32;      // samples per staged tile
+constexpr int kOwnStages = 4;
+struct OwnPlan {
+    bool ok;
+    int NH;            // CTAs ("roles") needed to cover the NW bitmask words
+    int nq;            // sample streams; grid = nq * NH
+    int grid, ntiles;
+    int stage_floats;  // g_ft tile [TS][L1] + bitmask tile [TS][NW]
+    size_t smem;
+};
+inline OwnPlan plan_ft_bwd_dw_owner(const nnue_shape &s) {
+    OwnPlan o{};
+    if (!get_option(kOptDwOwner) || !(s.L1 == 64 || s.L1 == 32) || s.NW % 4) return o;
+    o.NH = ceil_div(s.NW, kOwnWarps);
+    if (o.NH > kNumSMs) return o;
+    o.ntiles = ceil_div(s.B, kOwnTS);
+    o.nq = kNumSMs / o.NH;
+    if (o.nq > o.ntiles) o.nq = o.ntiles;
+    if (o.nq < 1) o.nq = 1;
+    if ((size_t)o.nq * s.P * s.L1 * 4 > ((size_t)256 << 20)) return o;  // partial buffers capped at 256 MiB
+    o.grid = o.nq * o.NH;
+    o.stage_floats = kOwnTS * (s.L1 + s.NW);
+    o.smem = 128 + (size_t)kOwnStages * o.stage_floats * 4;
+    if (o.smem > 200 * 1024) return o;
+    o.ok = true;
+    return o;
+}
+
 constexpr int kColsumRows = 256;  // rows per column-sum partial
 inline size_t ws_ft_bwd_dw(const nnue_shape &s) {
+    const size_t alias_rows = (size_t)(s.P > s.F - 1 ? s.P - (s.F - 1) : 0);
+    const OwnPlan o = plan_ft_bwd_dw_owner(s);
+    if (o.ok)  // bias partials [nq][L1] | row partials [nq][P][L1] | rows parked for the aliased last row
+        return align_up((size_t)o.nq * s.L1 * 4, 256) + ((size_t)o.nq * s.P + alias_rows) * s.L1 * 4;
     const DwPlan d = plan_ft_bwd_dw(s);
     size_t bytes = align_up((size_t)ceil_div(s.B, kColsumRows) * s.L1 * 4, 256);
     if (d.col.LPR && !d.direct)  // per-group partials + the rows parked for the aliased last row
@@ -110,6 +144,41 @@ inline int exb_grid_x(const nnue_shape &s) {
 }
 inline size_t ws_extract_bwd(const nnue_shape &s) { return (size_t)exb_grid_x(s) * s.C * 28 * 4; }
 
+// ---- fused input gradient (value gradient + threshold gradient + conv weight gradient) ------
+constexpr int kInWarps = 8;      // warps per CTA (lane 0 of warp 0 doubles as the TMA producer)
+constexpr int kInCH = 2;         // channels of one cell word owned by a warp
+constexpr int kInMaxStages = 8;
+constexpr int kInLag = 2;        // the producer refills a stage this many samples after its release
+constexpr size_t kMaxSmemOptin = 227 * 1024;  // sm_100: opt-in dynamic shared memory per CTA
+struct InPlan {
+    bool fused;
+    int NH, nq, grid, ST;
+    int stage_floats;  // 3 x (H*W + 4 pad) image planes | g_ft row [L1] | bitmask row [NW], padded to 128 B
+    int stage_off;     // byte offset of stage 0 in dynamic shared memory
+    size_t smem;
+};
+inline InPlan plan_input_bwd(const nnue_shape &s) {
+    InPlan p{};
+    const long long HW = 1LL * s.H * s.W;
+    if (!get_option(kOptInputFused) || !(s.L1 == 64 || s.L1 == 32) || HW % 4 || s.NW % 4 || HW > 16384) return p;
+    const int units = ceil_div(s.C, kInCH) * s.CW;
+    p.NH = ceil_div(units, kInWarps);
+    if (p.NH > 8) return p;
+    p.stage_floats = (int)align_up((size_t)(3 * (HW + 4) + s.L1 + s.NW), 32);
+    p.stage_off = (int)align_up(128 + ((size_t)s.C * 28 + align_up((size_t)s.C, 4) + kInWarps * kInCH * 28) * 4, 128);
+    const size_t room = kMaxSmemOptin - (size_t)p.stage_off;
+    int ST = (int)(room / ((size_t)p.stage_floats * 4));
+    if (ST > 6) ST = 6;
+    if (ST < 2) return p;
+    p.ST = ST;
+    p.nq = kNumSMs / p.NH;
+    if (p.nq > s.B) p.nq = s.B;
+    p.grid = p.nq * p.NH;
+    p.smem = (size_t)p.stage_off + (size_t)ST * p.stage_floats * 4;
+    p.fused = true;
+    return p;
+}
+
 // ---- head (dense layers) -----------------------------------------------------------------
 constexpr int kGemmBK = 16;
 inline int gemm_splits(int M, int N, int K, int BM, int BN) {
@@ -129,6 +198,15 @@ inline size_t ws_head_bwd(const nnue_shape &s) {
     bytes += align_up(B * s.L3 * 4, 256) + align_up(B * s.L2 * 4, 256) + align_up(B * s.L1 * 4, 256);
     return bytes;
 }
+inline size_t ws_input_bwd(const nnue_shape &s) {
+    const InPlan p = plan_input_bwd(s);
+    if (p.fused) return (size_t)p.grid * s.C * 28 * 4;
+    const size_t a = ws_ft_bwd_dval(s), b = ws_extract_bwd(s);
+    return 2 * align_up((size_t)s.B * s.PP * 4, 256) + (a > b ? a : b);
+}
+// pre-threshold conv activations in padded-position layout (extract.cu); used by the general input-gradient path
+int extract_xpad(const nnue_shape &s, const float *images, const float *conv_w, const float *thr, float *xpad,
+                 cudaStream_t st);
 inline size_t ws_ce(int B) { return align_up((size_t)B * 4, 256); }
 
 }  // namespace nnue

@@ -182,8 +182,9 @@ def _run_forward(shape, images, params, need_backward, marks=None):
     thr, conv_w, ft_w, ft_b, w1, b1, w2, b2, w3, b3 = params
     sp = ctypes.byref(shape)
     bits_s = _empty((shape.B, shape.NW), torch.int32, images)
-    bits_t = _empty((shape.PP, shape.BW), torch.int32, images) if need_backward else None
-    xpad = _empty((shape.B, shape.PP), torch.float32, images) if need_backward else None
+    want_t = need_backward and L.nnue_wants_transposed_bits(sp)
+    bits_t = _empty((shape.PP, shape.BW), torch.int32, images) if want_t else None
+    xpad = None  # the backward recomputes the conv activations instead of storing them
     _mark(marks, "start")
     check(L.nnue_extract_fwd(sp, dptr(images), dptr(conv_w), dptr(thr), dptr(bits_s), dptr(bits_t), dptr(xpad), None,
                              None, st))
@@ -218,14 +219,12 @@ def _run_backward(shape, images, params, bits_s, bits_t, xpad, ft_out, act1, act
                           dptr(g_w1), dptr(g_b1), dptr(g_w2), dptr(g_b2), dptr(g_w3), dptr(g_b3), dptr(g_ft),
                           dptr(ws), ws_bytes, st))
     _mark(marks, "head_bwd")
-    check(L.nnue_ft_bwd_dw(sp, dptr(bits_t), dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(ws), ws_bytes, st))
+    check(L.nnue_ft_bwd_dw(sp, dptr(bits_s), dptr(bits_t), dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(ws), ws_bytes,
+                           st))
     _mark(marks, "ft_bwd_dw")
-    dval = _empty((shape.B, shape.PP), torch.float32, images)
-    check(L.nnue_ft_bwd_dval(sp, dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(xpad), dptr(thr), dptr(dval), dptr(g_thr),
-                             dptr(ws), ws_bytes, st))
-    _mark(marks, "ft_bwd_dval")
-    check(L.nnue_extract_bwd(sp, dptr(images), dptr(bits_s), dptr(dval), dptr(g_conv_w), dptr(ws), ws_bytes, st))
-    _mark(marks, "extract_bwd")
+    check(L.nnue_input_bwd(sp, dptr(images), dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(conv_w), dptr(thr),
+                           dptr(g_conv_w), dptr(g_thr), dptr(ws), ws_bytes, st))
+    _mark(marks, "input_bwd")
     return grads
 
 

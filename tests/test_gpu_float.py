@@ -194,6 +194,33 @@ def test_ft_forward_staging_modes_agree(mode):
     assert_close(out[torch.as_tensor(~amb).cuda()], ref["ft_out"][torch.as_tensor(~amb)], "ft_out")
 
 
+@pytest.mark.parametrize("options", [dict(ft_bwd_dw_owner=0), dict(input_bwd_fused=0),
+                                     dict(ft_bwd_dw_owner=0, input_bwd_fused=0)], ids=str)
+@pytest.mark.parametrize("name", ["D", "T", "big_into_small"])
+def test_backward_kernel_variants_agree(name, options):
+    """The general kernels (transposed-bitmask segment reduction; value-gradient + conv-gradient pair)
+    stay correct on the shapes where the row-owner / fused kernels normally run."""
+    lib = _lib()
+    cfg, model, images, labels = _make(name)
+    ref = oracle_step(model, images, labels, dtype=torch.float64)
+    amb = ambiguous_samples(ref["conv_out"].numpy(), model.visual_threshold.detach().cpu().numpy())
+    if amb.any():
+        keep = torch.as_tensor(~amb).cuda()
+        images, labels = images[keep].contiguous(), labels[keep].contiguous()
+        ref = oracle_step(model, images, labels, dtype=torch.float64)
+    for k, v in options.items():
+        lib.set_option(k, v)
+    try:
+        model.zero_grad()
+        model.loss(images, labels).backward()
+        torch.cuda.synchronize()
+    finally:
+        for k in options:
+            lib.set_option(k, 1)
+    for k, g in ref["grads"].items():
+        assert_close(dict(model.named_parameters())[k].grad, g, "grad " + k)
+
+
 def test_feature_transformer_indexed_interface():
     """model.input(idx, val) with repeated / unsorted / out-of-range / -1 indices and float values
     (tests/test_model.py:1026-1064 use this sub-interface), forward and all three gradients."""
