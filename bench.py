@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-int", action="store_true", help="skip the integer-inference side measurement")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="library tuning knob (nnue_set_option), e.g. --opt input_bwd_variant=1")
     return ap.parse_args()
 
 
@@ -298,6 +300,9 @@ def run_b200(args):
     if args.batch:
         w["batch"] = args.batch
     B = w["batch"]
+    for kv in args.opt:
+        key, val = kv.split("=")
+        _lib.set_option(key, int(val))
     model = build_model(w, device)
     dp = train.DataParallelStep(model)
     if world > 1:  # identical replicas

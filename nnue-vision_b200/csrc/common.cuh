@@ -40,7 +40,7 @@ void note_launch();
     } while (0)
 
 // Tuning knobs settable through nnue_set_option (api.cu); every value has a working default.
-enum Option { kOptFtFwdStaging = 0, kOptDwOwner, kOptInputFused, kNumOptions };
+enum Option { kOptFtFwdStaging = 0, kOptDwOwner, kOptInputFused, kOptInputVariant, kNumOptions };
 int get_option(int which);
 
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -55,6 +55,19 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
     return v;
+}
+
+// 32x32 bit-matrix transpose across a warp: lane i passes row i, lane i returns column i
+// (bit r of the result = bit i of lane r's input).  Five butterfly stages of one shuffle each.
+__device__ __forceinline__ unsigned warp_bit_transpose(unsigned x, int lane) {
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) {
+        const unsigned m = sft == 16 ? 0xFFFF0000u : sft == 8 ? 0xFF00FF00u : sft == 4 ? 0xF0F0F0F0u
+                         : sft == 2 ? 0xCCCCCCCCu : 0xAAAAAAAAu;
+        const unsigned o = __shfl_xor_sync(kFull, x, sft);
+        x = (lane & sft) ? ((x & m) | ((o >> sft) & ~m)) : ((x & ~m) | ((o << sft) & m));
+    }
+    return x;
 }
 
 __device__ __forceinline__ float4 f4_add(float4 a, const float4 b) {

@@ -406,69 +406,89 @@ ft_bwd_dw_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_t, const 
     }
 }
 
-// ---- weight gradient, row-owner form -----------------------------------------------------------
-// For tables small enough that one lane can keep a whole row's gradient in registers (L1 <= 64):
-// a warp owns one bitmask word (32 positions, one per lane) for the whole kernel and walks its
-// sample stream in order; every sample contributes g_ft[b] (broadcast LDS.128 from a TMA-staged
-// tile) to the lanes whose bit is set.  The per-position sample list is consumed in sorted order,
-// nothing is atomic, and the result is written as partial[stream][p][L1] for the same fold kernels
-// as the transposed-bitmask path.  One extra warp sums the staged g_ft tile into the bias gradient.
+// ---- dense, register-stationary backward kernels (small tables) ----------------------------------
+// With ~43 % of the positions active an index-driven walk spends more
+// instructions on bit scanning and cross-lane reductions than a masked dense pass over every
+// (sample, position) pair costs, as long as the per-position operand never leaves the register
+// file.  Both kernels below give a warp one bitmask word (32 positions, one per lane) for the
+// whole kernel and stream the g_ft rows of its sample tiles through shared memory (one bulk TMA
+// copy per 32-sample tile, full/empty mbarrier ring, producer = lane 0 of warp 0); a g_ft row is
+// read as broadcast LDS.128.  The 32 bitmask words of a tile are loaded one per lane and
+// transposed in-register (warp_bit_transpose), so a lane tests "is my position active in sample
+// r" with a shift, and the inner loops are branch-free.
+
+// Stage ring shared by the two kernels: tile i of this CTA's stream is tile q + i * nq.
+struct TileRing {
+    uint64_t *full, *empty;
+    float *stages;
+    int stage_floats, nq, q, n_mine;
+    int p_st; uint32_t p_ph;  // producer cursor: stage of tile i + ahead, parity of the release it waits for
+    int st; uint32_t ph;      // consumer cursor
+};
+constexpr int kTileAhead = kTileStages - 1;  // tiles in flight
 template <int L1>
-__global__ void __launch_bounds__((kOwnWarps + 2) * 32, 1)
-ft_bwd_dw_owner_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const float *__restrict__ g_ft,
-                       float *__restrict__ partial, float *__restrict__ bias_partial, const OwnPlan pl) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
-    uint64_t *empty = full + kOwnStages;
-    float *stages = reinterpret_cast<float *>(smem_raw + 128);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int role = blockIdx.x % pl.NH, q = blockIdx.x / pl.NH;
-    const bool do_bias = role == 0;
+__device__ __forceinline__ void ring_produce(const TileRing &rg, const nnue_shape &s, const float *g_ft, int ii, int st,
+                                             uint32_t ph) {
+    if (ii >= kTileStages) mbar_wait(&rg.empty[st], ph);
+    const int b0 = (rg.q + ii * rg.nq) * kTileTS, rows = min(kTileTS, s.B - b0);
+    mbar_arrive_expect_tx(&rg.full[st], (uint32_t)rows * L1 * 4u);
+    tma_bulk_g2s(rg.stages + (size_t)st * rg.stage_floats, g_ft + (size_t)b0 * L1, (uint32_t)rows * L1 * 4u,
+                 &rg.full[st]);
+}
+template <int L1>
+__device__ __forceinline__ TileRing ring_init(unsigned char *smem_raw, const nnue_shape &s, const float *g_ft, int ntiles,
+                                              int nq, int q, int consumers) {
+    TileRing rg;
+    rg.full = reinterpret_cast<uint64_t *>(smem_raw);
+    rg.empty = rg.full + kTileStages;
+    rg.stages = reinterpret_cast<float *>(smem_raw + 128);
+    rg.stage_floats = kTileTS * L1;
+    rg.nq = nq; rg.q = q;
+    rg.n_mine = ntiles > q ? (ntiles - q + nq - 1) / nq : 0;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kOwnStages; ++i) {
-            mbar_init(&full[i], 1);
-            mbar_init(&empty[i], kOwnWarps + (do_bias ? 1 : 0));
+        for (int i = 0; i < kTileStages; ++i) {
+            mbar_init(&rg.full[i], 1);
+            mbar_init(&rg.empty[i], consumers);
         }
         mbar_fence_init();
     }
     __syncthreads();
+    if (threadIdx.x == 0)
+        for (int ii = 0; ii < kTileAhead && ii < rg.n_mine; ++ii) ring_produce<L1>(rg, s, g_ft, ii, ii, 0);
+    // tile kTileAhead goes to stage kTileAhead (first use, no wait); the first real wait is on parity 0
+    rg.p_st = kTileAhead % kTileStages; rg.p_ph = 1u;
+    rg.st = 0; rg.ph = 0;
+    return rg;
+}
+// top of consumer iteration i: the producer lane refills the ring, then everyone waits for tile i
+template <int L1>
+__device__ __forceinline__ void ring_acquire(TileRing &rg, const nnue_shape &s, const float *g_ft, int i) {
+    const int ii = i + kTileAhead;
+    if (threadIdx.x == 0 && ii < rg.n_mine) ring_produce<L1>(rg, s, g_ft, ii, rg.p_st, rg.p_ph);
+    if (++rg.p_st == kTileStages) { rg.p_st = 0; rg.p_ph ^= 1u; }
+    __syncwarp();
+    mbar_wait(&rg.full[rg.st], rg.ph);
+}
+__device__ __forceinline__ void ring_release(TileRing &rg, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&rg.empty[rg.st]);
+    if (++rg.st == kTileStages) { rg.st = 0; rg.ph ^= 1u; }
+}
 
-    if (warp == kOwnWarps) {  // ---- producer: one g_ft tile + one bitmask tile per stage ----
-        if (lane == 0) {
-            int i = 0;
-            for (int t = q; t < pl.ntiles; t += pl.nq, ++i) {
-                const int st = i % kOwnStages;
-                if (i >= kOwnStages) mbar_wait(&empty[st], ((i / kOwnStages) - 1) & 1);
-                const int b0 = t * kOwnTS, rows = min(kOwnTS, s.B - b0);
-                float *stg = stages + (size_t)st * pl.stage_floats;
-                mbar_arrive_expect_tx(&full[st], (uint32_t)rows * (L1 + s.NW) * 4u);
-                tma_bulk_g2s(stg, g_ft + (size_t)b0 * L1, (uint32_t)rows * L1 * 4u, &full[st]);
-                tma_bulk_g2s(stg + kOwnTS * L1, bits_s + (size_t)b0 * s.NW, (uint32_t)rows * s.NW * 4u, &full[st]);
-            }
-        }
-        return;
-    }
-    if (warp == kOwnWarps + 1) {  // ---- bias gradient: column sums of the staged g_ft tiles ----
-        if (!do_bias) return;
-        float accb[L1 / 32];
-#pragma unroll
-        for (int k = 0; k < L1 / 32; ++k) accb[k] = 0.0f;
-        int i = 0;
-        for (int t = q; t < pl.ntiles; t += pl.nq, ++i) {
-            const int st = i % kOwnStages;
-            mbar_wait(&full[st], (i / kOwnStages) & 1);
-            const float *sg = stages + (size_t)st * pl.stage_floats;
-            const int rows = min(kOwnTS, s.B - t * kOwnTS);
-            for (int r = 0; r < rows; ++r)
-#pragma unroll
-                for (int k = 0; k < L1 / 32; ++k) accb[k] += sg[r * L1 + k * 32 + lane];
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[st]);
-        }
-#pragma unroll
-        for (int k = 0; k < L1 / 32; ++k) bias_partial[(size_t)q * L1 + k * 32 + lane] = accb[k];
-        return;
-    }
+// Weight gradient, row-owner form: a lane keeps its table row's gradient (L1 floats) in registers and
+// adds g_ft[b] for every sample whose bit is set, walking the samples in order -- the per-position
+// sample list is consumed sorted, nothing is atomic.  Output partial[stream][p][L1] for the fold
+// kernels below.  The warps of role 0 also sum one float4 column slice of the staged tiles each: the
+// bias gradient (column sums of g_ft).
+template <int L1>
+__global__ void __launch_bounds__(kOwnWarps * 32, 1)
+ft_bwd_dw_owner_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const float *__restrict__ g_ft,
+                       float *__restrict__ partial, float *__restrict__ bias_partial, const OwnPlan pl) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int role = blockIdx.x % pl.NH, q = blockIdx.x / pl.NH;
+    TileRing rg = ring_init<L1>(smem_raw, s, g_ft, pl.ntiles, pl.nq, q, kOwnWarps);
+
     // ---- row owners ----
     const int cells = s.Gh * s.Gw;
     const int widx = role * kOwnWarps + warp;
@@ -478,20 +498,25 @@ ft_bwd_dw_owner_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, 
     float acc[L1];
 #pragma unroll
     for (int k = 0; k < L1; ++k) acc[k] = 0.0f;
-    int i = 0;
-    for (int t = q; t < pl.ntiles; t += pl.nq, ++i) {
-        const int st = i % kOwnStages;
-        mbar_wait(&full[st], (i / kOwnStages) & 1);
+    const bool do_bias = role == 0 && warp < L1 / 4;  // role 0 always has at least L1/4 <= kOwnWarps warps
+    float4 accb = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto tile_word = [&](int i) -> unsigned {  // this lane's row of tile i: sample b0 + lane
+        const int b = (q + i * pl.nq) * kTileTS + lane;
+        return (active && i < rg.n_mine && b < s.B) ? __ldg(bits_s + (size_t)b * s.NW + widx) : 0u;
+    };
+    unsigned next_word = tile_word(0);
+    for (int i = 0; i < rg.n_mine; ++i) {
+        const unsigned mybits = warp_bit_transpose(next_word, lane);  // bit r: my position is active in sample b0 + r
+        ring_acquire<L1>(rg, s, g_ft, i);
+        next_word = tile_word(i + 1);
+        const float4 *sg = reinterpret_cast<const float4 *>(rg.stages + (size_t)rg.st * rg.stage_floats);
+        const int rows = min(kTileTS, s.B - (q + i * pl.nq) * kTileTS);
+        if (do_bias)
+            for (int r = 0; r < rows; ++r) accb = f4_add(accb, sg[r * (L1 / 4) + warp]);
         if (active) {
-            const float *stg = stages + (size_t)st * pl.stage_floats;
-            const float4 *sg = reinterpret_cast<const float4 *>(stg);
-            const uint32_t *sb = reinterpret_cast<const uint32_t *>(stg + kOwnTS * L1) + widx;
-            const int rows = min(kOwnTS, s.B - t * kOwnTS);
-#pragma unroll 2
+#pragma unroll 1
             for (int r = 0; r < rows; ++r) {
-                const unsigned word = sb[r * s.NW];
-                if (!word) continue;  // warp-uniform
-                const float on = ((word >> lane) & 1u) ? 1.0f : 0.0f;
+                const float on = (float)((mybits >> r) & 1u);
 #pragma unroll
                 for (int v = 0; v < L1 / 4; ++v) {
                     const float4 g = sg[r * (L1 / 4) + v];
@@ -502,14 +527,95 @@ ft_bwd_dw_owner_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, 
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
+        ring_release(rg, lane);
     }
+    if (do_bias && lane == 0) reinterpret_cast<float4 *>(bias_partial + (size_t)q * L1)[warp] = accb;
     if (active && cell < cells) {
         const int p = c * cells + cell;
         float4 *o = reinterpret_cast<float4 *>(partial + ((size_t)q * s.P + p) * L1);
 #pragma unroll
         for (int v = 0; v < L1 / 4; ++v) o[v] = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+    }
+}
+
+// Value gradient, dense form: a warp keeps the table rows of kDvCH channels of one cell word in
+// registers and computes dval[b, p] = <W[min(p, F-1)], g_ft[b]> for every sample of its stream,
+// masked by the bit (inactive positions get 0): dval [B][PP], one coalesced 128-byte store per
+// (sample, word).  Feeds conv_bwd_kernel (input_bwd.cu), which needs no bitmask any more.
+template <int L1>
+__global__ void __launch_bounds__(kDvWarps * 32, 1)
+ft_bwd_dval_dense_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const float *__restrict__ ft_w,
+                         const float *__restrict__ g_ft, float *__restrict__ dval, const DvPlan pl) {
+    constexpr int CH = kDvCH;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int role = blockIdx.x % pl.NH, q = blockIdx.x / pl.NH;
+    TileRing rg = ring_init<L1>(smem_raw, s, g_ft, pl.ntiles, pl.nq, q, kDvWarps);
+
+    const int cells = s.Gh * s.Gw;
+    const int CP = ceil_div(s.C, CH);
+    const int unit = role * kDvWarps + warp;  // (channel group, cell word)
+    const bool active = unit < CP * s.CW;
+    const int cg = active ? unit / s.CW : 0, j = active ? unit % s.CW : 0;
+    const int cell = j * 32 + lane;
+    float wr[CH][L1];
+    bool chan_ok[CH];
+    int widx[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        const int c = cg * CH + k;
+        chan_ok[k] = active && c < s.C;
+        widx[k] = chan_ok[k] ? c * s.CW + j : 0;
+        const int row = min(c * cells + cell, s.F - 1);  // clamp of nnue.py:701
+        const bool ok = chan_ok[k] && cell < cells;
+#pragma unroll
+        for (int v = 0; v < L1 / 4; ++v) {
+            const float4 t = ok ? __ldg(reinterpret_cast<const float4 *>(ft_w + (size_t)row * L1) + v)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            wr[k][4 * v + 0] = t.x; wr[k][4 * v + 1] = t.y; wr[k][4 * v + 2] = t.z; wr[k][4 * v + 3] = t.w;
+        }
+    }
+    auto tile_word = [&](int i, int k) -> unsigned {
+        const int b = (q + i * pl.nq) * kTileTS + lane;
+        return (chan_ok[k] && i < rg.n_mine && b < s.B) ? __ldg(bits_s + (size_t)b * s.NW + widx[k]) : 0u;
+    };
+    unsigned next_word[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) next_word[k] = tile_word(0, k);
+    for (int i = 0; i < rg.n_mine; ++i) {
+        unsigned mybits[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) mybits[k] = warp_bit_transpose(next_word[k], lane);
+        ring_acquire<L1>(rg, s, g_ft, i);
+#pragma unroll
+        for (int k = 0; k < CH; ++k) next_word[k] = tile_word(i + 1, k);
+        if (active) {
+            const float4 *sg = reinterpret_cast<const float4 *>(rg.stages + (size_t)rg.st * rg.stage_floats);
+            const int b0 = (q + i * pl.nq) * kTileTS, rows = min(kTileTS, s.B - b0);
+#pragma unroll 2
+            for (int r = 0; r < rows; ++r) {
+                float d[CH][4];
+#pragma unroll
+                for (int k = 0; k < CH; ++k) d[k][0] = d[k][1] = d[k][2] = d[k][3] = 0.0f;
+#pragma unroll
+                for (int v = 0; v < L1 / 4; ++v) {
+                    const float4 g = sg[r * (L1 / 4) + v];
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) {
+                        d[k][0] = fmaf(wr[k][4 * v + 0], g.x, d[k][0]);
+                        d[k][1] = fmaf(wr[k][4 * v + 1], g.y, d[k][1]);
+                        d[k][2] = fmaf(wr[k][4 * v + 2], g.z, d[k][2]);
+                        d[k][3] = fmaf(wr[k][4 * v + 3], g.w, d[k][3]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    const float v = ((mybits[k] >> r) & 1u) ? (d[k][0] + d[k][1]) + (d[k][2] + d[k][3]) : 0.0f;
+                    if (chan_ok[k]) dval[(size_t)(b0 + r) * s.PP + (size_t)widx[k] * 32 + lane] = v;
+                }
+            }
+        }
+        ring_release(rg, lane);
     }
 }
 
@@ -811,6 +917,17 @@ static int launch_ft_bwd_dval(const nnue_shape &s, const uint32_t *bits, const f
     return NNUE_OK;
 }
 
+int launch_ft_bwd_dval_dense(const nnue_shape &s, const uint32_t *bits_s, const float *ft_w, const float *g_ft,
+                             float *dval, cudaStream_t st) {
+    const DvPlan pl = plan_ft_bwd_dval_dense(s);
+    if (!pl.ok) return NNUE_ERR_UNSUPPORTED;
+    auto k = s.L1 == 64 ? ft_bwd_dval_dense_kernel<64> : ft_bwd_dval_dense_kernel<32>;
+    NNUE_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    k<<<pl.grid, kDvWarps * 32, pl.smem, st>>>(s, bits_s, ft_w, g_ft, dval, pl);
+    NNUE_CHECK_LAUNCH("ft_bwd_dval_dense_kernel");
+    return NNUE_OK;
+}
+
 }  // namespace nnue
 
 using namespace nnue;
@@ -889,11 +1006,11 @@ int nnue_ft_bwd_dw(const nnue_shape *s, const uint32_t *bits_s_d, const uint32_t
         if (s->L1 == 64) {
             auto k = ft_bwd_dw_owner_kernel<64>;
             NNUE_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)own.smem));
-            k<<<own.grid, (kOwnWarps + 2) * 32, own.smem, st>>>(*s, bits_s_d, g_ft_d, partial, bias_partial, own);
+            k<<<own.grid, kOwnWarps * 32, own.smem, st>>>(*s, bits_s_d, g_ft_d, partial, bias_partial, own);
         } else {
             auto k = ft_bwd_dw_owner_kernel<32>;
             NNUE_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)own.smem));
-            k<<<own.grid, (kOwnWarps + 2) * 32, own.smem, st>>>(*s, bits_s_d, g_ft_d, partial, bias_partial, own);
+            k<<<own.grid, kOwnWarps * 32, own.smem, st>>>(*s, bits_s_d, g_ft_d, partial, bias_partial, own);
         }
         NNUE_CHECK_LAUNCH("ft_bwd_dw_owner_kernel");
         fold_partials_kernel<<<ceil_div(s->L1, 128), 128, 0, st>>>(s->L1, own.nq, bias_partial, g_b_d);

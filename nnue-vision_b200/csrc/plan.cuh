@@ -69,35 +69,56 @@ inline DwPlan plan_ft_bwd_dw(const nnue_shape &s) {
     d.smem = (size_t)TS * CC * 4 + 64;
     return d;
 }
-// ---- FT weight gradient, row-owner form (small tables: a lane keeps its row's gradient in registers) ----
-constexpr int kOwnWarps = 16;   // consumer warps per CTA (+ 1 producer warp + 1 bias warp)
-constexpr int kOwnTS = 32;      // samples per staged tile
-constexpr int kOwnStages = 4;
+// ---- dense register-stationary backward kernels (small tables), see ft.cu ------------------------
+constexpr int kTileTS = 32;      // samples per staged g_ft tile (= one transposed bitmask word)
+constexpr int kTileStages = 4;
+constexpr int kOwnWarps = 16;    // row-owner warps per CTA
 struct OwnPlan {
     bool ok;
     int NH;            // CTAs ("roles") needed to cover the NW bitmask words
     int nq;            // sample streams; grid = nq * NH
     int grid, ntiles;
-    int stage_floats;  // g_ft tile [TS][L1] + bitmask tile [TS][NW]
     size_t smem;
 };
+inline bool dense_shape_ok(const nnue_shape &s) { return s.L1 == 64 || s.L1 == 32; }
 inline OwnPlan plan_ft_bwd_dw_owner(const nnue_shape &s) {
     OwnPlan o{};
-    if (!get_option(kOptDwOwner) || !(s.L1 == 64 || s.L1 == 32) || s.NW % 4) return o;
+    if (!get_option(kOptDwOwner) || !dense_shape_ok(s)) return o;
     o.NH = ceil_div(s.NW, kOwnWarps);
     if (o.NH > kNumSMs) return o;
-    o.ntiles = ceil_div(s.B, kOwnTS);
+    o.ntiles = ceil_div(s.B, kTileTS);
     o.nq = kNumSMs / o.NH;
     if (o.nq > o.ntiles) o.nq = o.ntiles;
     if (o.nq < 1) o.nq = 1;
     if ((size_t)o.nq * s.P * s.L1 * 4 > ((size_t)256 << 20)) return o;  // partial buffers capped at 256 MiB
     o.grid = o.nq * o.NH;
-    o.stage_floats = kOwnTS * (s.L1 + s.NW);
-    o.smem = 128 + (size_t)kOwnStages * o.stage_floats * 4;
-    if (o.smem > 200 * 1024) return o;
+    o.smem = 128 + (size_t)kTileStages * kTileTS * s.L1 * 4;
     o.ok = true;
     return o;
 }
+constexpr int kDvWarps = 8;      // 8 warps x up to 255 registers: kDvCH table rows of L1 floats per lane
+constexpr int kDvCH = 2;
+struct DvPlan {
+    bool ok;
+    int NH, nq, grid, ntiles;
+    size_t smem;
+};
+inline DvPlan plan_ft_bwd_dval_dense(const nnue_shape &s) {
+    DvPlan d{};
+    if (!dense_shape_ok(s)) return d;
+    d.NH = ceil_div(ceil_div(s.C, kDvCH) * s.CW, kDvWarps);
+    if (d.NH > kNumSMs) return d;
+    d.ntiles = ceil_div(s.B, kTileTS);
+    d.nq = kNumSMs / d.NH;
+    if (d.nq > d.ntiles) d.nq = d.ntiles;
+    if (d.nq < 1) d.nq = 1;
+    d.grid = d.nq * d.NH;
+    d.smem = 128 + (size_t)kTileStages * kTileTS * s.L1 * 4;
+    d.ok = true;
+    return d;
+}
+int launch_ft_bwd_dval_dense(const nnue_shape &s, const uint32_t *bits_s, const float *ft_w, const float *g_ft,
+                             float *dval, cudaStream_t st);
 
 constexpr int kColsumRows = 256;  // rows per column-sum partial
 inline size_t ws_ft_bwd_dw(const nnue_shape &s) {
@@ -144,28 +165,30 @@ inline int exb_grid_x(const nnue_shape &s) {
 }
 inline size_t ws_extract_bwd(const nnue_shape &s) { return (size_t)exb_grid_x(s) * s.C * 28 * 4; }
 
-// ---- fused input gradient (value gradient + threshold gradient + conv weight gradient) ------
-constexpr int kInWarps = 8;      // warps per CTA (lane 0 of warp 0 doubles as the TMA producer)
-constexpr int kInCH = 2;         // channels of one cell word owned by a warp
+// ---- input gradient: dense value gradient (ft.cu) + conv gradient from TMA-staged images (input_bwd.cu) ----
+// conv-gradient variant 0: 16 warps x 2 channels of a cell word per warp; 1: 8 warps x 4 channels
 constexpr int kInMaxStages = 8;
 constexpr int kInLag = 2;        // the producer refills a stage this many samples after its release
 constexpr size_t kMaxSmemOptin = 227 * 1024;  // sm_100: opt-in dynamic shared memory per CTA
 struct InPlan {
     bool fused;
+    int CH, WARPS;     // channels of one cell word owned by a warp; warps per CTA (lane 0 of warp 0 is the TMA producer)
     int NH, nq, grid, ST;
-    int stage_floats;  // 3 x (H*W + 4 pad) image planes | g_ft row [L1] | bitmask row [NW], padded to 128 B
+    int stage_floats;  // 3 x (H*W + 4 pad) image planes | dval row [PP], padded to 128 B
     int stage_off;     // byte offset of stage 0 in dynamic shared memory
     size_t smem;
 };
 inline InPlan plan_input_bwd(const nnue_shape &s) {
     InPlan p{};
     const long long HW = 1LL * s.H * s.W;
-    if (!get_option(kOptInputFused) || !(s.L1 == 64 || s.L1 == 32) || HW % 4 || s.NW % 4 || HW > 16384) return p;
-    const int units = ceil_div(s.C, kInCH) * s.CW;
-    p.NH = ceil_div(units, kInWarps);
+    if (!get_option(kOptInputFused) || !dense_shape_ok(s) || HW % 4 || HW > 16384) return p;
+    p.CH = get_option(kOptInputVariant) == 1 ? 4 : 2;
+    p.WARPS = 32 / p.CH;
+    const int units = ceil_div(s.C, p.CH) * s.CW;
+    p.NH = ceil_div(units, p.WARPS);
     if (p.NH > 8) return p;
-    p.stage_floats = (int)align_up((size_t)(3 * (HW + 4) + s.L1 + s.NW), 32);
-    p.stage_off = (int)align_up(128 + ((size_t)s.C * 28 + align_up((size_t)s.C, 4) + kInWarps * kInCH * 28) * 4, 128);
+    p.stage_floats = (int)align_up((size_t)(3 * (HW + 4) + s.PP), 32);
+    p.stage_off = (int)align_up(128 + ((size_t)s.C * 28 + align_up((size_t)s.C, 4) + 32 * 28) * 4, 128);
     const size_t room = kMaxSmemOptin - (size_t)p.stage_off;
     int ST = (int)(room / ((size_t)p.stage_floats * 4));
     if (ST > 6) ST = 6;
@@ -200,7 +223,7 @@ inline size_t ws_head_bwd(const nnue_shape &s) {
 }
 inline size_t ws_input_bwd(const nnue_shape &s) {
     const InPlan p = plan_input_bwd(s);
-    if (p.fused) return (size_t)p.grid * s.C * 28 * 4;
+    if (p.fused) return align_up((size_t)s.B * s.PP * 4, 256) + (size_t)p.grid * s.C * 28 * 4;
     const size_t a = ws_ft_bwd_dval(s), b = ws_extract_bwd(s);
     return 2 * align_up((size_t)s.B * s.PP * 4, 256) + (a > b ? a : b);
 }
