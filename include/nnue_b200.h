@@ -73,8 +73,10 @@ unsigned long long nnue_launch_count(int reset);
  *                     whole table in shared memory with bulk TMA copies whenever it fits.
  *   "ft_bwd_dw_owner" 1 (default) = row-owner weight gradient where the shape allows, 0 = always
  *                     the transposed-bitmask segment reduction.
- *   "input_bwd_fused" 1 (default) = fused input-gradient kernel where the shape allows, 0 = always
- *                     the value-gradient + conv-gradient kernel pair.
+ *   "input_bwd_fused" 1 (default) = dense value-gradient + conv-gradient kernels where the shape
+ *                     allows, 0 = always the index-driven kernel pair.
+ *   "input_bwd_variant" conv-gradient kernel: 0 = 16 warps x 2 channels, 1 (default) = 8 warps x 4.
+ *   "head_fused"      1 (default) = one-kernel head training step for small stacks, 0 = layer kernels.
  */
 int nnue_set_option(const char *key, int value);
 
@@ -177,6 +179,19 @@ int nnue_head_bwd(const nnue_shape *s, const float *g_logits_d, const float *ft_
                   const float *w3_d, float *g_w1_d, float *g_b1_d, float *g_w2_d, float *g_b2_d,
                   float *g_w3_d, float *g_b3_d, float *g_ft_d, void *workspace_d,
                   size_t workspace_bytes, void *stream);
+
+/*
+ * The training step of the head in one call: nnue_head_fwd + nnue_ce_fwd_bwd + nnue_head_bwd
+ * (nnue.py:660-669, 713-738; train.py:250-254) with every activation kept on chip.  Small stacks
+ * (L1 <= 64, L2 <= 32, L3 <= 8, NC <= 16) run ONE kernel, a sample per thread; larger ones run
+ * the layer kernels on scratch carved from the workspace.
+ *   loss_d [1] = sum_b CE_b * inv_count; g_ft_d [B,L1]; g_w*, g_b* as nnue_head_bwd
+ */
+int nnue_head_train(const nnue_shape *s, const float *ft_out_d, const int64_t *labels_d, float inv_count,
+                    const float *w1_d, const float *b1_d, const float *w2_d, const float *b2_d,
+                    const float *w3_d, const float *b3_d, float *loss_d, float *g_ft_d, float *g_w1_d,
+                    float *g_b1_d, float *g_w2_d, float *g_b2_d, float *g_w3_d, float *g_b3_d,
+                    void *workspace_d, size_t workspace_bytes, void *stream);
 
 /*
  * Feature-transformer weight/bias gradient: a segment reduction over (feature, sample)

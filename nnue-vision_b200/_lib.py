@@ -41,6 +41,7 @@ SIGNATURES = {
     "nnue_head_fwd": (ctypes.c_int, [SHAPE_P] + [vp] * 11),
     "nnue_ce_fwd_bwd": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, vp, f32, vp, vp, vp, vp, vp, sz, vp]),
     "nnue_head_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 15 + [sz, vp]),
+    "nnue_head_train": (ctypes.c_int, [SHAPE_P, vp, vp, f32] + [vp] * 14 + [vp, sz, vp]),
     "nnue_wants_transposed_bits": (ctypes.c_int, [SHAPE_P]),
     "nnue_ft_bwd_dw": (ctypes.c_int, [SHAPE_P, vp, vp, vp, vp, vp, vp, sz, vp]),
     "nnue_input_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 9 + [sz, vp]),

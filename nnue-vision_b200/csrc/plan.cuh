@@ -230,6 +230,22 @@ inline size_t ws_input_bwd(const nnue_shape &s) {
 // pre-threshold conv activations in padded-position layout (extract.cu); used by the general input-gradient path
 int extract_xpad(const nnue_shape &s, const float *images, const float *conv_w, const float *thr, float *xpad,
                  cudaStream_t st);
+// ---- fused head training step (head_fused.cu): small stacks only ---------------------------------
+constexpr int kHeadTile = 128;       // samples (= threads) per CTA tile
+constexpr int kHeadPartial = 2492;   // floats per per-CTA gradient block (HeadLayout<64,32,8,16>::pTotal)
+inline bool head_train_fused_ok(const nnue_shape &s) {
+    return get_option(kOptHeadFused) && s.L1 % 2 == 0 && s.L1 <= 64 && s.L2 <= 32 && s.L3 <= 8 && s.NC <= 16;
+}
+inline int head_train_grid(const nnue_shape &s) {
+    const int ntiles = ceil_div(s.B, kHeadTile);
+    return ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs;
+}
+inline size_t ws_head_train(const nnue_shape &s) {
+    if (head_train_fused_ok(s)) return (size_t)head_train_grid(s) * kHeadPartial * 4;
+    const size_t B = s.B;
+    return align_up(B * s.L2 * 4, 256) + align_up(B * s.L3 * 4, 256) + 2 * align_up(B * s.NC * 4, 256) +
+           align_up(B * 4, 256) + ws_head_bwd(s);
+}
 inline size_t ws_ce(int B) { return align_up((size_t)B * 4, 256); }
 
 }  // namespace nnue

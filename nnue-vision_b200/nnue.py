@@ -253,37 +253,70 @@ class _NNUEForward(torch.autograd.Function):
         return (None, None, None, None) + tuple(g)
 
 
+def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_out=None, marks=None):
+    """One whole training step of the hot path -- forward, mean cross-entropy, every parameter gradient --
+    in seven launches: extract, feature transformer, fused head step (forward + loss + backward), the two
+    feature-transformer gradients, conv / threshold gradients.  `grads` / `loss_out` may be preallocated
+    (views of a flat data-parallel buffer).  Returns (loss [1], grads in parameter order)."""
+    L = _lib.lib()
+    st = stream_ptr()
+    thr, conv_w, ft_w, ft_b, w1, b1, w2, b2, w3, b3 = params
+    sp = ctypes.byref(shape)
+    if grads is None:
+        grads = tuple(torch.empty_like(p) for p in params)
+    if loss_out is None:
+        loss_out = _empty((1,), torch.float32, images)
+    g_thr, g_conv_w, g_ft_w, g_ft_b, g_w1, g_b1, g_w2, g_b2, g_w3, g_b3 = grads
+    bits_s = _empty((shape.B, shape.NW), torch.int32, images)
+    bits_t = _empty((shape.PP, shape.BW), torch.int32, images) if L.nnue_wants_transposed_bits(sp) else None
+    _mark(marks, "start")
+    check(L.nnue_extract_fwd(sp, dptr(images), dptr(conv_w), dptr(thr), dptr(bits_s), dptr(bits_t), None, None, None,
+                             st))
+    _mark(marks, "extract_fwd")
+    ft_out = _empty((shape.B, shape.L1), torch.float32, images)
+    check(L.nnue_ft_fwd(sp, dptr(bits_s), dptr(ft_w), dptr(ft_b), dptr(ft_out), st))
+    _mark(marks, "ft_fwd")
+    ws_bytes = _lib.workspace_bytes(shape)
+    ws = _empty((ws_bytes,), torch.uint8, images)
+    g_ft = _empty((shape.B, shape.L1), torch.float32, images)
+    check(L.nnue_head_train(sp, dptr(ft_out), dptr(labels), inv_count, dptr(w1), dptr(b1), dptr(w2), dptr(b2),
+                            dptr(w3), dptr(b3), dptr(loss_out), dptr(g_ft), dptr(g_w1), dptr(g_b1), dptr(g_w2),
+                            dptr(g_b2), dptr(g_w3), dptr(g_b3), dptr(ws), ws_bytes, st))
+    _mark(marks, "head_train")
+    check(L.nnue_ft_bwd_dw(sp, dptr(bits_s), dptr(bits_t), dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(ws), ws_bytes,
+                           st))
+    _mark(marks, "ft_bwd_dw")
+    check(L.nnue_input_bwd(sp, dptr(images), dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(conv_w), dptr(thr),
+                           dptr(g_conv_w), dptr(g_thr), dptr(ws), ws_bytes, st))
+    _mark(marks, "input_bwd")
+    return loss_out, grads
+
+
 class _NNUELoss(torch.autograd.Function):
-    """images, labels -> mean cross-entropy (train.py:250-254) with the CE fused in."""
+    """images, labels -> mean cross-entropy (train.py:250-254).  The loss is a scalar, so every parameter
+    gradient is linear in the upstream gradient: when gradients are wanted the whole step (forward, loss,
+    backward) runs inside `forward` through the fused kernels, and `backward` only scales the stored
+    gradients by the incoming scalar."""
 
     @staticmethod
     def forward(ctx, images, labels, stride, C, G, inv_count, thr, conv_w, ft_w, ft_b, w1, b1, w2, b2, w3, b3):
         params = tuple(p.detach().contiguous() for p in (thr, conv_w, ft_w, ft_b, w1, b1, w2, b2, w3, b3))
         B, _, H, W = images.shape
         shape = _lib.make_shape(B, H, W, C, G, ft_w.shape[1], w1.shape[0], w2.shape[0], w3.shape[0], stride)
-        need_bwd = any(ctx.needs_input_grad[6:])
-        logits, bits_s, bits_t, xpad, ft_out, act1, act2 = _run_forward(shape, images, params, need_bwd)
+        if any(ctx.needs_input_grad[6:]):
+            loss, ctx.grads = _run_train_step(shape, images, labels, params, inv_count)
+            return loss.reshape(())
+        logits = _run_forward(shape, images, params, False)[0]
         loss = _empty((1,), torch.float32, images)
         per = _empty((B,), torch.float32, images)
         check(_lib.lib().nnue_ce_fwd_bwd(B, shape.NC, dptr(logits), dptr(labels), inv_count, None, dptr(loss),
                                          dptr(per), None, None, 0, stream_ptr()))
-        if need_bwd:
-            sv = _Saved()
-            sv.shape, sv.images, sv.bits_s, sv.bits_t, sv.xpad = shape, images, bits_s, bits_t, xpad
-            sv.ft_out, sv.act1, sv.act2, sv.params = ft_out, act1, act2, params
-            ctx.sv, ctx.logits, ctx.labels, ctx.inv_count = sv, logits, labels, inv_count
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, g_loss):
-        sv = ctx.sv
-        g_logits = torch.empty_like(ctx.logits)
-        g_scale = g_loss.detach().reshape(1).float().contiguous()
-        check(_lib.lib().nnue_ce_fwd_bwd(sv.shape.B, sv.shape.NC, dptr(ctx.logits), dptr(ctx.labels), ctx.inv_count,
-                                         dptr(g_scale), None, None, dptr(g_logits), None, 0, stream_ptr()))
-        g = _run_backward(sv.shape, sv.images, sv.params, sv.bits_s, sv.bits_t, sv.xpad, sv.ft_out, sv.act1, sv.act2,
-                          g_logits)
-        return (None,) * 6 + tuple(g)
+        g = g_loss.detach().float()
+        return (None,) * 6 + tuple(gr * g for gr in ctx.grads)
 
 
 class NNUE(nn.Module):

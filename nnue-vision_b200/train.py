@@ -64,22 +64,10 @@ def _cuda_local_step(model):
         params = tuple(p.detach().contiguous() for p in model._hot_params())
         shape = _lib.make_shape(B, H, W, fs.num_features_per_square, fs.grid_size, model.l1_size, model.l2_size,
                                 model.l3_size, model.num_classes, model.conv.stride[0])
-        logits, bits_s, bits_t, xpad, ft_out, act1, act2 = _nnue._run_forward(shape, images, params, True, marks)
-        g_logits = torch.empty_like(logits)
-        _lib.check(_lib.lib().nnue_ce_fwd_bwd(B, shape.NC, _lib.dptr(logits), _lib.dptr(labels), inv_count, None,
-                                              _lib.dptr(buf.loss), None, _lib.dptr(g_logits),
-                                              _lib.dptr(run.ws(B, images)), B * 4 + 256, _lib.stream_ptr()))
-        _nnue._mark(marks, "ce")
-        _nnue._run_backward(shape, images, params, bits_s, bits_t, xpad, ft_out, act1, act2, g_logits, grads=buf.views,
-                            marks=marks)
+        # gradients land directly in the flat buffer's views, the loss in its trailing slot
+        _nnue._run_train_step(shape, images, labels, params, inv_count, grads=buf.views, loss_out=buf.loss,
+                              marks=marks)
 
-    def ws(B, like):
-        if run._ws is None or run._ws.numel() < B * 4 + 256 or run._ws.device != like.device:
-            run._ws = torch.empty(B * 4 + 256, dtype=torch.uint8, device=like.device)
-        return run._ws
-
-    run._ws = None
-    run.ws = ws
     return run
 
 

@@ -194,8 +194,9 @@ def test_ft_forward_staging_modes_agree(mode):
     assert_close(out[torch.as_tensor(~amb).cuda()], ref["ft_out"][torch.as_tensor(~amb)], "ft_out")
 
 
-@pytest.mark.parametrize("options", [dict(ft_bwd_dw_owner=0), dict(input_bwd_fused=0),
-                                     dict(ft_bwd_dw_owner=0, input_bwd_fused=0)], ids=str)
+@pytest.mark.parametrize("options", [dict(ft_bwd_dw_owner=0), dict(input_bwd_fused=0), dict(input_bwd_variant=0),
+                                     dict(head_fused=0), dict(ft_bwd_dw_owner=0, input_bwd_fused=0, head_fused=0)],
+                         ids=str)
 @pytest.mark.parametrize("name", ["D", "T", "big_into_small"])
 def test_backward_kernel_variants_agree(name, options):
     """The general kernels (transposed-bitmask segment reduction; value-gradient + conv-gradient pair)
@@ -212,11 +213,13 @@ def test_backward_kernel_variants_agree(name, options):
         lib.set_option(k, v)
     try:
         model.zero_grad()
-        model.loss(images, labels).backward()
+        loss = model.loss(images, labels)
+        loss.backward()
         torch.cuda.synchronize()
     finally:
         for k in options:
             lib.set_option(k, 1)
+    assert_close(loss, ref["loss"], "loss")
     for k, g in ref["grads"].items():
         assert_close(dict(model.named_parameters())[k].grad, g, "grad " + k)
 
