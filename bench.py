@@ -379,7 +379,12 @@ def run_b200(args):
     algo = {  # algorithmic bytes per launch, SURVEY.md section 8(d)
         "ft_fwd": nnz_total * L1 * 4 + B * L1 * 4 + nnz_total * 4,
         "ft_bwd_dw": nnz_total * L1 * 4 + F * L1 * 4,
-        # value gradient (W row reads per active position + g_ft) fused with the conv gradient (image + bitmask)
+        # both FT gradients in one kernel: g_ft rows per active position for dW + table rows for dval + outputs
+        "ft_bwd": 2 * nnz_total * L1 * 4 + F * L1 * 4 + B * L1 * 4 + B * shape.PP * 4,
+        # value gradient: W row reads per active position + g_ft read + g_bin write
+        "ft_bwd_gbin": nnz_total * L1 * 4 + B * L1 * 4 + B * shape.PP * 4,
+        # conv / threshold gradient: image read + g_bin read
+        "conv_bwd": img_bytes + B * shape.PP * 4,
         "input_bwd": nnz_total * L1 * 4 + B * L1 * 4 + img_bytes + B * shape.NW * 4,
         "extract_fwd": img_bytes + B * shape.NW * 4,
     }

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NNUE_B200_ABI_VERSION 1
+#define NNUE_B200_ABI_VERSION 2
 
 enum {
     NNUE_OK = 0,
@@ -76,6 +76,9 @@ unsigned long long nnue_launch_count(int reset);
  *   "input_bwd_fused" 1 (default) = dense value-gradient + conv-gradient kernels where the shape
  *                     allows, 0 = always the index-driven kernel pair.
  *   "input_bwd_variant" conv-gradient kernel: 0 = 16 warps x 2 channels, 1 (default) = 8 warps x 4.
+ *   "ft_mma"          1 (default) = tensor-core (bf16-split, fp32-exact products) feature-transformer
+ *                     contractions for small tables, 0 = CUDA-core kernels only.
+ *   "ft_bwd_both"     1 (default) = one kernel for both feature-transformer gradients (small tables).
  *   "head_fused"      1 (default) = one-kernel head training step for small stacks, 0 = layer kernels.
  */
 int nnue_set_option(const char *key, int value);
@@ -120,9 +123,14 @@ int nnue_sparse_from_bits(const nnue_shape *s, const uint32_t *bits_s_d, int K, 
  * out[b] = bias + sum over active p of W[min(p, F-1)].  Replaces
  * FeatureTransformer.forward as called from NNUE.forward (nnue.py:653, 686-710).
  *   ft_w_d [F,L1] f32; ft_b_d [L1] f32; ft_out_d [B,L1] f32
+ * Two forms: the row gather (table staged in shared memory by bulk TMA, rows read as LDS.128,
+ * lane groups combined with warp shuffles) and, for small tables when a workspace is passed, a
+ * tensor-core contraction bits x (W split into three exact bf16 terms) with fp32 accumulation.
+ * workspace_d may be NULL (gather only).
  */
 int nnue_ft_fwd(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w_d,
-                const float *ft_b_d, float *ft_out_d, void *stream);
+                const float *ft_b_d, float *ft_out_d, void *workspace_d, size_t workspace_bytes,
+                void *stream);
 
 /*
  * General FeatureTransformer.forward(feature_indices, feature_values) (nnue.py:686-710) for
@@ -204,6 +212,15 @@ int nnue_head_train(const nnue_shape *s, const float *ft_out_d, const int64_t *l
  *   bits_s_d [B][NW]; bits_t_d [PP][BW]; g_ft_d [B,L1]; g_w_d [F,L1] fully written; g_b_d [L1]
  */
 int nnue_wants_transposed_bits(const nnue_shape *s);
+/*
+ * Both feature-transformer gradients in one pass over g_ft (small tables; returns
+ * NNUE_ERR_UNSUPPORTED otherwise -- ask nnue_ft_bwd_is_fused first): g_w / g_b as nnue_ft_bwd_dw,
+ * gbin_d [B][PP] as nnue_ft_bwd_gbin.  A lane keeps its table row and that row's gradient in registers.
+ */
+int nnue_ft_bwd_is_fused(const nnue_shape *s);
+int nnue_ft_bwd(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w_d, const float *g_ft_d,
+                float *g_w_d, float *g_b_d, float *gbin_d, void *workspace_d, size_t workspace_bytes,
+                void *stream);
 int nnue_ft_bwd_dw(const nnue_shape *s, const uint32_t *bits_s_d, const uint32_t *bits_t_d,
                    const float *g_ft_d, float *g_w_d, float *g_b_d, void *workspace_d,
                    size_t workspace_bytes, void *stream);
@@ -238,6 +255,14 @@ int nnue_extract_bwd(const nnue_shape *s, const float *images_d, const uint32_t 
  * two-kernel path on scratch carved from the workspace.
  *   g_conv_w_d [C,3,3,3]; g_thr_d [C]
  */
+int nnue_input_bwd_is_dense(const nnue_shape *s);  /* 1 when the two dense kernels below serve this shape */
+/* dense half 1: g_bin[b,p] = bit(b,p) ? <W[min(p,F-1)], g_ft[b]> : 0, gbin_d [B][PP] f32 */
+int nnue_ft_bwd_gbin(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w_d,
+                     const float *g_ft_d, float *gbin_d, void *stream);
+/* dense half 2: g_conv_w = conv2d_weight(images, g_bin); g_thr from the recomputed activations */
+int nnue_conv_bwd(const nnue_shape *s, const float *images_d, const float *gbin_d, const float *conv_w_d,
+                  const float *thr_d, float *g_conv_w_d, float *g_thr_d, void *workspace_d,
+                  size_t workspace_bytes, void *stream);
 int nnue_input_bwd(const nnue_shape *s, const float *images_d, const uint32_t *bits_s_d,
                    const float *ft_w_d, const float *g_ft_d, const float *conv_w_d, const float *thr_d,
                    float *g_conv_w_d, float *g_thr_d, void *workspace_d, size_t workspace_bytes,

@@ -35,15 +35,20 @@ SIGNATURES = {
     "nnue_workspace_bytes": (sz, [SHAPE_P]),
     "nnue_extract_fwd": (ctypes.c_int, [SHAPE_P] + [vp] * 9),
     "nnue_sparse_from_bits": (ctypes.c_int, [SHAPE_P, vp, ctypes.c_int, vp, vp, vp]),
-    "nnue_ft_fwd": (ctypes.c_int, [SHAPE_P, vp, vp, vp, vp, vp]),
+    "nnue_ft_fwd": (ctypes.c_int, [SHAPE_P, vp, vp, vp, vp, vp, sz, vp]),
     "nnue_ft_fwd_indexed": (ctypes.c_int, [ctypes.c_int] * 4 + [vp] * 6),
     "nnue_ft_bwd_indexed": (ctypes.c_int, [ctypes.c_int] * 4 + [vp, vp, vp, ctypes.c_int] + [vp] * 7),
     "nnue_head_fwd": (ctypes.c_int, [SHAPE_P] + [vp] * 11),
     "nnue_ce_fwd_bwd": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, vp, f32, vp, vp, vp, vp, vp, sz, vp]),
     "nnue_head_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 15 + [sz, vp]),
     "nnue_head_train": (ctypes.c_int, [SHAPE_P, vp, vp, f32] + [vp] * 14 + [vp, sz, vp]),
+    "nnue_ft_bwd_is_fused": (ctypes.c_int, [SHAPE_P]),
+    "nnue_ft_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 7 + [sz, vp]),
     "nnue_wants_transposed_bits": (ctypes.c_int, [SHAPE_P]),
     "nnue_ft_bwd_dw": (ctypes.c_int, [SHAPE_P, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "nnue_input_bwd_is_dense": (ctypes.c_int, [SHAPE_P]),
+    "nnue_ft_bwd_gbin": (ctypes.c_int, [SHAPE_P, vp, vp, vp, vp, vp]),
+    "nnue_conv_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 7 + [sz, vp]),
     "nnue_input_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 9 + [sz, vp]),
     "nnue_ft_bwd_dval": (ctypes.c_int, [SHAPE_P] + [vp] * 8 + [sz, vp]),
     "nnue_extract_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 5 + [sz, vp]),
@@ -76,7 +81,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError here = header/library mismatch
             fn.restype = res
             fn.argtypes = args
-        if handle.nnue_b200_abi_version() != 1:
+        if handle.nnue_b200_abi_version() != 2:
             raise NnueError("libnnue_b200.so ABI version mismatch; rebuild it")
         _lib = handle
     return _lib

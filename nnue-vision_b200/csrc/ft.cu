@@ -619,6 +619,135 @@ ft_bwd_dval_dense_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s
     }
 }
 
+// Both feature-transformer gradients in one pass over g_ft (the training path for small tables): a
+// lane keeps its table row AND that row's gradient in registers (2 x L1 floats), so every broadcast
+// g_ft float4 feeds eight FMAs -- four for the value gradient <W[row], g_ft[b]>, four for the
+// row-owner accumulation -- and shared-memory bandwidth stops being the limit.  Outputs: g_bin
+// [B][PP] (masked value gradient), partial[stream][p][L1] and the bias-gradient partials.
+template <int L1>
+__global__ void __launch_bounds__(kFbWarps * 32, 1)
+ft_bwd_both_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const float *__restrict__ ft_w,
+                   const float *__restrict__ g_ft, float *__restrict__ gbin, float *__restrict__ partial,
+                   float *__restrict__ bias_partial, const FbPlan pl) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int role = blockIdx.x % pl.NH, q = blockIdx.x / pl.NH;
+    TileRing rg = ring_init<L1>(smem_raw, s, g_ft, pl.ntiles, pl.nq, q, kFbWarps);
+
+    const int cells = s.Gh * s.Gw;
+    const int widx = role * kFbWarps + warp;
+    const bool active = widx < s.NW;
+    const int c = active ? widx / s.CW : 0, j = active ? widx % s.CW : 0;
+    const int cell = j * 32 + lane;
+    const bool valid = active && cell < cells;
+    const int p = c * cells + cell;
+    float wr[L1], acc[L1];
+    {
+        const int row = min(p, s.F - 1);  // clamp of nnue.py:701
+#pragma unroll
+        for (int v = 0; v < L1 / 4; ++v) {
+            const float4 t = valid ? __ldg(reinterpret_cast<const float4 *>(ft_w + (size_t)row * L1) + v)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            wr[4 * v + 0] = t.x; wr[4 * v + 1] = t.y; wr[4 * v + 2] = t.z; wr[4 * v + 3] = t.w;
+            acc[4 * v + 0] = acc[4 * v + 1] = acc[4 * v + 2] = acc[4 * v + 3] = 0.0f;
+        }
+    }
+    // bias gradient: the warps of role 0 each sum kFbBiasSlices float4 column slices of the staged tiles
+    constexpr int kSlices = (L1 / 4 + kFbWarps - 1) / kFbWarps;
+    float4 accb[kSlices];
+#pragma unroll
+    for (int k = 0; k < kSlices; ++k) accb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool do_bias = role == 0;
+
+    auto tile_word = [&](int i) -> unsigned {
+        const int b = (q + i * pl.nq) * kTileTS + lane;
+        return (active && i < rg.n_mine && b < s.B) ? __ldg(bits_s + (size_t)b * s.NW + widx) : 0u;
+    };
+    unsigned next_word = tile_word(0);
+    for (int i = 0; i < rg.n_mine; ++i) {
+        const unsigned mybits = warp_bit_transpose(next_word, lane);
+        ring_acquire<L1>(rg, s, g_ft, i);
+        next_word = tile_word(i + 1);
+        const float4 *sg = reinterpret_cast<const float4 *>(rg.stages + (size_t)rg.st * rg.stage_floats);
+        const int b0 = (q + i * pl.nq) * kTileTS, rows = min(kTileTS, s.B - b0);
+        if (do_bias)
+            for (int r = 0; r < rows; ++r)
+#pragma unroll
+                for (int k = 0; k < kSlices; ++k)
+                    if (warp + k * kFbWarps < L1 / 4) accb[k] = f4_add(accb[k], sg[r * (L1 / 4) + warp + k * kFbWarps]);
+        if (active) {
+            float *grow = gbin + (size_t)b0 * s.PP + (size_t)widx * 32 + lane;
+            // Four samples per pass.  The FP32 pipe issues one FFMA per cycle only when at most one new
+            // register per bank is read, so the loops are ordered for the operand-reuse cache: a table-row
+            // element (wr) is reused by the four samples' dots, a sample's 0/1 flag (on) by four columns.
+            int r = 0;
+#pragma unroll 1
+            for (; r + 4 <= rows; r += 4) {
+                const unsigned m4 = mybits >> r;
+                const float on0 = (float)(m4 & 1u), on1 = (float)((m4 >> 1) & 1u), on2 = (float)((m4 >> 2) & 1u),
+                            on3 = (float)((m4 >> 3) & 1u);
+                float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+                const float4 *s0 = sg + r * (L1 / 4);
+#pragma unroll
+                for (int v = 0; v < L1 / 4; ++v) {
+                    const float4 g0 = s0[v], g1 = s0[L1 / 4 + v], g2 = s0[2 * (L1 / 4) + v], g3 = s0[3 * (L1 / 4) + v];
+                    d0 = fmaf(wr[4 * v + 0], g0.x, d0); d1 = fmaf(wr[4 * v + 0], g1.x, d1);
+                    d2 = fmaf(wr[4 * v + 0], g2.x, d2); d3 = fmaf(wr[4 * v + 0], g3.x, d3);
+                    d0 = fmaf(wr[4 * v + 1], g0.y, d0); d1 = fmaf(wr[4 * v + 1], g1.y, d1);
+                    d2 = fmaf(wr[4 * v + 1], g2.y, d2); d3 = fmaf(wr[4 * v + 1], g3.y, d3);
+                    d0 = fmaf(wr[4 * v + 2], g0.z, d0); d1 = fmaf(wr[4 * v + 2], g1.z, d1);
+                    d2 = fmaf(wr[4 * v + 2], g2.z, d2); d3 = fmaf(wr[4 * v + 2], g3.z, d3);
+                    d0 = fmaf(wr[4 * v + 3], g0.w, d0); d1 = fmaf(wr[4 * v + 3], g1.w, d1);
+                    d2 = fmaf(wr[4 * v + 3], g2.w, d2); d3 = fmaf(wr[4 * v + 3], g3.w, d3);
+                    acc[4 * v + 0] = fmaf(on0, g0.x, acc[4 * v + 0]); acc[4 * v + 1] = fmaf(on0, g0.y, acc[4 * v + 1]);
+                    acc[4 * v + 2] = fmaf(on0, g0.z, acc[4 * v + 2]); acc[4 * v + 3] = fmaf(on0, g0.w, acc[4 * v + 3]);
+                    acc[4 * v + 0] = fmaf(on1, g1.x, acc[4 * v + 0]); acc[4 * v + 1] = fmaf(on1, g1.y, acc[4 * v + 1]);
+                    acc[4 * v + 2] = fmaf(on1, g1.z, acc[4 * v + 2]); acc[4 * v + 3] = fmaf(on1, g1.w, acc[4 * v + 3]);
+                    acc[4 * v + 0] = fmaf(on2, g2.x, acc[4 * v + 0]); acc[4 * v + 1] = fmaf(on2, g2.y, acc[4 * v + 1]);
+                    acc[4 * v + 2] = fmaf(on2, g2.z, acc[4 * v + 2]); acc[4 * v + 3] = fmaf(on2, g2.w, acc[4 * v + 3]);
+                    acc[4 * v + 0] = fmaf(on3, g3.x, acc[4 * v + 0]); acc[4 * v + 1] = fmaf(on3, g3.y, acc[4 * v + 1]);
+                    acc[4 * v + 2] = fmaf(on3, g3.z, acc[4 * v + 2]); acc[4 * v + 3] = fmaf(on3, g3.w, acc[4 * v + 3]);
+                }
+                float *gr = grow + (size_t)r * s.PP;
+                gr[0] = d0 * on0;
+                gr[(size_t)s.PP] = d1 * on1;
+                gr[2 * (size_t)s.PP] = d2 * on2;
+                gr[3 * (size_t)s.PP] = d3 * on3;
+            }
+#pragma unroll 1
+            for (; r < rows; ++r) {  // tail of the batch's last tile
+                const bool bit = (mybits >> r) & 1u;
+                const float on = bit ? 1.0f : 0.0f;
+                float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+#pragma unroll
+                for (int v = 0; v < L1 / 4; ++v) {
+                    const float4 g = sg[r * (L1 / 4) + v];
+                    d0 = fmaf(wr[4 * v + 0], g.x, d0);
+                    d1 = fmaf(wr[4 * v + 1], g.y, d1);
+                    d2 = fmaf(wr[4 * v + 2], g.z, d2);
+                    d3 = fmaf(wr[4 * v + 3], g.w, d3);
+                    acc[4 * v + 0] = fmaf(on, g.x, acc[4 * v + 0]);
+                    acc[4 * v + 1] = fmaf(on, g.y, acc[4 * v + 1]);
+                    acc[4 * v + 2] = fmaf(on, g.z, acc[4 * v + 2]);
+                    acc[4 * v + 3] = fmaf(on, g.w, acc[4 * v + 3]);
+                }
+                grow[(size_t)r * s.PP] = bit ? (d0 + d1) + (d2 + d3) : 0.0f;
+            }
+        }
+        ring_release(rg, lane);
+    }
+    if (do_bias && lane == 0)
+#pragma unroll
+        for (int k = 0; k < kSlices; ++k)
+            if (warp + k * kFbWarps < L1 / 4)
+                reinterpret_cast<float4 *>(bias_partial + (size_t)q * L1)[warp + k * kFbWarps] = accb[k];
+    if (valid) {
+        float4 *o = reinterpret_cast<float4 *>(partial + ((size_t)q * s.P + p) * L1);
+#pragma unroll
+        for (int v = 0; v < L1 / 4; ++v) o[v] = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+    }
+}
+
 // Fold stage 1: every position p sums its partials over the tile groups.  Positions below F-1 are
 // table rows and go straight to g_w; positions >= F-1 all alias onto the last row (the clamp of
 // nnue.py:701) and are parked in `alias` [P-(F-1)][L1] for stage 2; rows in [P, F-1) get zeros.
@@ -943,9 +1072,12 @@ using namespace nnue;
 extern "C" {
 
 int nnue_ft_fwd(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w_d, const float *ft_b_d,
-                float *ft_out_d, void *stream) {
+                float *ft_out_d, void *workspace_d, size_t workspace_bytes, void *stream) {
     if (!s || !bits_s_d || !ft_w_d || !ft_b_d || !ft_out_d) return NNUE_ERR_INVALID_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // small tables with scratch available: tensor-core contraction (ft_mma.cu); otherwise the row gather
+    if (plan_ft_mma(*s).ok && workspace_d && workspace_bytes >= ws_ft_fwd(*s))
+        return launch_ft_fwd_mma(*s, bits_s_d, ft_w_d, ft_b_d, ft_out_d, workspace_d, st);
     const ColPlan cp = col_plan(s->L1);
     if (!cp.LPR) {
         ft_fwd_bits_generic_kernel<<<ceil_div(s->B, kFtThreads / 32), kFtThreads, 0, st>>>(*s, bits_s_d, ft_w_d, ft_b_d,
@@ -986,6 +1118,56 @@ int nnue_ft_bwd_indexed(int B, int K, int F, int L1, const int64_t *idx_d, const
                                                                             g_val_d);
         NNUE_CHECK_LAUNCH("ft_bwd_indexed_dval_kernel");
     }
+    return NNUE_OK;
+}
+
+int nnue_ft_bwd_is_fused(const nnue_shape *s) {
+    return s && (plan_ft_mma(*s).ok || plan_ft_bwd_both(*s).ok) && plan_input_bwd(*s).fused ? 1 : 0;
+}
+
+int nnue_ft_bwd(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w_d, const float *g_ft_d, float *g_w_d,
+                float *g_b_d, float *gbin_d, void *workspace_d, size_t workspace_bytes, void *stream) {
+    if (!s || !bits_s_d || !ft_w_d || !g_ft_d || !g_w_d || !g_b_d || !gbin_d || !workspace_d) return NNUE_ERR_INVALID_ARG;
+    if (plan_ft_mma(*s).ok) {  // tensor-core path
+        if (workspace_bytes < ws_ft_bwd_mma(*s)) return NNUE_ERR_WORKSPACE;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const MmaPlan mp = plan_ft_mma(*s);
+        char *ws = static_cast<char *>(workspace_d);
+        uint4 *wfrag = reinterpret_cast<uint4 *>(ws); ws += align_up(mma_wfrag_bytes(*s), 256);
+        uint4 *gfrag = reinterpret_cast<uint4 *>(ws); ws += align_up(mma_gfrag_bytes(*s), 256);
+        float *bias_partial = reinterpret_cast<float *>(ws); ws += align_up((size_t)mp.n_chunks * s->L1 * 4, 256);
+        float *partial = reinterpret_cast<float *>(ws);
+        float *alias = partial + (size_t)mp.n_chunks * s->P * s->L1;
+        int n_chunks = 0;
+        int rc = launch_ft_bwd_dw_mma(*s, bits_s_d, g_ft_d, gfrag, partial, bias_partial, &n_chunks, st);
+        if (rc != NNUE_OK) return rc;
+        fold_partials_kernel<<<ceil_div(s->L1, 128), 128, 0, st>>>(s->L1, n_chunks, bias_partial, g_b_d);
+        NNUE_CHECK_LAUNCH("fold_partials_kernel");
+        const long long n = 1LL * (s->P > s->F - 1 ? s->P : s->F - 1) * (s->L1 / 4);
+        ft_bwd_dw_fold_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(*s, n_chunks, partial, g_w_d, alias);
+        NNUE_CHECK_LAUNCH("ft_bwd_dw_fold_kernel");
+        ft_bwd_dw_fold_last_kernel<<<ceil_div(s->L1 / 4, 32), 256, 0, st>>>(*s, alias, g_w_d);
+        NNUE_CHECK_LAUNCH("ft_bwd_dw_fold_last_kernel");
+        return launch_ft_bwd_gbin_mma(*s, bits_s_d, ft_w_d, g_ft_d, wfrag, gbin_d, st);
+    }
+    const FbPlan fb = plan_ft_bwd_both(*s);
+    if (!fb.ok) return NNUE_ERR_UNSUPPORTED;
+    if (workspace_bytes < ws_ft_bwd_both(*s)) return NNUE_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float *bias_partial = static_cast<float *>(workspace_d);
+    float *partial = reinterpret_cast<float *>(static_cast<char *>(workspace_d) + align_up((size_t)fb.nq * s->L1 * 4, 256));
+    float *alias = partial + (size_t)fb.nq * s->P * s->L1;
+    auto k = s->L1 == 64 ? ft_bwd_both_kernel<64> : ft_bwd_both_kernel<32>;
+    NNUE_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb.smem));
+    k<<<fb.grid, kFbWarps * 32, fb.smem, st>>>(*s, bits_s_d, ft_w_d, g_ft_d, gbin_d, partial, bias_partial, fb);
+    NNUE_CHECK_LAUNCH("ft_bwd_both_kernel");
+    fold_partials_kernel<<<ceil_div(s->L1, 128), 128, 0, st>>>(s->L1, fb.nq, bias_partial, g_b_d);
+    NNUE_CHECK_LAUNCH("fold_partials_kernel");
+    const long long n = 1LL * (s->P > s->F - 1 ? s->P : s->F - 1) * (s->L1 / 4);
+    ft_bwd_dw_fold_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(*s, fb.nq, partial, g_w_d, alias);
+    NNUE_CHECK_LAUNCH("ft_bwd_dw_fold_kernel");
+    ft_bwd_dw_fold_last_kernel<<<ceil_div(s->L1 / 4, 32), 256, 0, st>>>(*s, alias, g_w_d);
+    NNUE_CHECK_LAUNCH("ft_bwd_dw_fold_last_kernel");
     return NNUE_OK;
 }
 

@@ -209,6 +209,34 @@ using namespace nnue;
 
 extern "C" {
 
+int nnue_input_bwd_is_dense(const nnue_shape *s) { return s && plan_input_bwd(*s).fused ? 1 : 0; }
+
+int nnue_ft_bwd_gbin(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w_d, const float *g_ft_d,
+                     float *gbin_d, void *stream) {
+    if (!s || !bits_s_d || !ft_w_d || !g_ft_d || !gbin_d) return NNUE_ERR_INVALID_ARG;
+    if (!plan_input_bwd(*s).fused) return NNUE_ERR_UNSUPPORTED;
+    return launch_ft_bwd_dval_dense(*s, bits_s_d, ft_w_d, g_ft_d, gbin_d, static_cast<cudaStream_t>(stream));
+}
+
+int nnue_conv_bwd(const nnue_shape *s, const float *images_d, const float *gbin_d, const float *conv_w_d,
+                  const float *thr_d, float *g_conv_w_d, float *g_thr_d, void *workspace_d, size_t workspace_bytes,
+                  void *stream) {
+    if (!s || !images_d || !gbin_d || !conv_w_d || !thr_d || !g_conv_w_d || !g_thr_d || !workspace_d)
+        return NNUE_ERR_INVALID_ARG;
+    const InPlan pl = plan_input_bwd(*s);
+    if (!pl.fused) return NNUE_ERR_UNSUPPORTED;
+    if (workspace_bytes < (size_t)pl.grid * s->C * 28 * 4) return NNUE_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float *partial = static_cast<float *>(workspace_d);
+    int rc;
+    if (pl.CH == 2) rc = launch_conv_bwd<2, 16>(*s, pl, images_d, gbin_d, conv_w_d, thr_d, partial, st);
+    else rc = launch_conv_bwd<4, 8>(*s, pl, images_d, gbin_d, conv_w_d, thr_d, partial, st);
+    if (rc != NNUE_OK) return rc;
+    input_bwd_fold_kernel<<<ceil_div(s->C * 28, 128), 128, 0, st>>>(s->C, pl.grid, partial, g_conv_w_d, g_thr_d);
+    NNUE_CHECK_LAUNCH("input_bwd_fold_kernel");
+    return NNUE_OK;
+}
+
 int nnue_input_bwd(const nnue_shape *s, const float *images_d, const uint32_t *bits_s_d, const float *ft_w_d,
                    const float *g_ft_d, const float *conv_w_d, const float *thr_d, float *g_conv_w_d, float *g_thr_d,
                    void *workspace_d, size_t workspace_bytes, void *stream) {
@@ -221,16 +249,11 @@ int nnue_input_bwd(const nnue_shape *s, const float *images_d, const uint32_t *b
     const size_t plane = align_up((size_t)s->B * s->PP * 4, 256);
     const InPlan pl = plan_input_bwd(*s);
     if (pl.fused) {
-        float *dval = reinterpret_cast<float *>(ws);
-        float *partial = reinterpret_cast<float *>(ws + plane);
-        int rc = launch_ft_bwd_dval_dense(*s, bits_s_d, ft_w_d, g_ft_d, dval, st);
+        float *gbin = reinterpret_cast<float *>(ws);
+        const int rc = nnue_ft_bwd_gbin(s, bits_s_d, ft_w_d, g_ft_d, gbin, stream);
         if (rc != NNUE_OK) return rc;
-        if (pl.CH == 2) rc = launch_conv_bwd<2, 16>(*s, pl, images_d, dval, conv_w_d, thr_d, partial, st);
-        else rc = launch_conv_bwd<4, 8>(*s, pl, images_d, dval, conv_w_d, thr_d, partial, st);
-        if (rc != NNUE_OK) return rc;
-        input_bwd_fold_kernel<<<ceil_div(s->C * 28, 128), 128, 0, st>>>(s->C, pl.grid, partial, g_conv_w_d, g_thr_d);
-        NNUE_CHECK_LAUNCH("input_bwd_fold_kernel");
-        return NNUE_OK;
+        return nnue_conv_bwd(s, images_d, gbin, conv_w_d, thr_d, g_conv_w_d, g_thr_d, ws + plane,
+                             workspace_bytes - plane, stream);
     }
     // General shapes: recompute the pre-threshold activations into scratch, then the index-driven pair.
     float *xpad = reinterpret_cast<float *>(ws);

@@ -117,10 +117,38 @@ inline DvPlan plan_ft_bwd_dval_dense(const nnue_shape &s) {
     d.ok = true;
     return d;
 }
+constexpr int kFbWarps = 8;      // both gradients at once: table row + its gradient per lane (2 x L1 registers)
+struct FbPlan {
+    bool ok;
+    int NH, nq, grid, ntiles;
+    size_t smem;
+};
+inline FbPlan plan_ft_bwd_both(const nnue_shape &s) {
+    FbPlan f{};
+    if (!get_option(kOptFtBwdBoth) || !get_option(kOptDwOwner) || !get_option(kOptInputFused) || !dense_shape_ok(s))
+        return f;
+    f.NH = ceil_div(s.NW, kFbWarps);
+    if (f.NH > kNumSMs) return f;
+    f.ntiles = ceil_div(s.B, kTileTS);
+    f.nq = kNumSMs / f.NH;
+    if (f.nq > f.ntiles) f.nq = f.ntiles;
+    if (f.nq < 1) f.nq = 1;
+    if ((size_t)f.nq * s.P * s.L1 * 4 > ((size_t)256 << 20)) return f;
+    f.grid = f.nq * f.NH;
+    f.smem = 128 + (size_t)kTileStages * kTileTS * s.L1 * 4;
+    f.ok = true;
+    return f;
+}
 int launch_ft_bwd_dval_dense(const nnue_shape &s, const uint32_t *bits_s, const float *ft_w, const float *g_ft,
                              float *dval, cudaStream_t st);
 
 constexpr int kColsumRows = 256;  // rows per column-sum partial
+inline size_t ws_ft_bwd_both(const nnue_shape &s) {
+    const FbPlan f = plan_ft_bwd_both(s);
+    if (!f.ok) return 0;
+    const size_t alias_rows = (size_t)(s.P > s.F - 1 ? s.P - (s.F - 1) : 0);
+    return align_up((size_t)f.nq * s.L1 * 4, 256) + ((size_t)f.nq * s.P + alias_rows) * s.L1 * 4;
+}
 inline size_t ws_ft_bwd_dw(const nnue_shape &s) {
     const size_t alias_rows = (size_t)(s.P > s.F - 1 ? s.P - (s.F - 1) : 0);
     const OwnPlan o = plan_ft_bwd_dw_owner(s);
@@ -230,6 +258,43 @@ inline size_t ws_input_bwd(const nnue_shape &s) {
 // pre-threshold conv activations in padded-position layout (extract.cu); used by the general input-gradient path
 int extract_xpad(const nnue_shape &s, const float *images, const float *conv_w, const float *thr, float *xpad,
                  cudaStream_t st);
+// ---- feature-transformer contractions on the tensor cores (ft_mma.cu) ------------------------------
+constexpr int kMmaThreads = 128;
+struct MmaPlan {
+    bool ok;
+    int n_chunks, chunk_blocks;  // weight gradient: K-chunks of `chunk_blocks` 32-sample blocks
+};
+inline MmaPlan plan_ft_mma(const nnue_shape &s) {
+    MmaPlan m{};
+    if (!get_option(kOptFtMma) || !dense_shape_ok(s)) return m;
+    int want = ceil_div(12 * kNumSMs, s.NW);  // ~12 warps per SM in flight
+    if (want < 1) want = 1;
+    m.chunk_blocks = ceil_div(s.BW, want);
+    m.n_chunks = ceil_div(s.BW, m.chunk_blocks);
+    while ((size_t)m.n_chunks * s.P * s.L1 * 4 > ((size_t)256 << 20) && m.n_chunks > 1) {
+        m.chunk_blocks *= 2;
+        m.n_chunks = ceil_div(s.BW, m.chunk_blocks);
+    }
+    m.ok = true;
+    return m;
+}
+inline size_t mma_wfrag_bytes(const nnue_shape &s) { return (size_t)(s.PP / 16) * 3 * (s.L1 / 16) * 32 * 16; }
+inline size_t mma_gfrag_bytes(const nnue_shape &s) { return (size_t)(s.BW * 2) * 3 * (s.L1 / 16) * 32 * 16; }
+inline size_t ws_ft_fwd(const nnue_shape &s) { return plan_ft_mma(s).ok ? mma_wfrag_bytes(s) : 0; }
+inline size_t ws_ft_bwd_mma(const nnue_shape &s) {
+    const MmaPlan m = plan_ft_mma(s);
+    if (!m.ok) return 0;
+    const size_t alias_rows = (size_t)(s.P > s.F - 1 ? s.P - (s.F - 1) : 0);
+    return align_up(mma_wfrag_bytes(s), 256) + align_up(mma_gfrag_bytes(s), 256) +
+           align_up((size_t)m.n_chunks * s.L1 * 4, 256) + ((size_t)m.n_chunks * s.P + alias_rows) * s.L1 * 4;
+}
+int launch_ft_fwd_mma(const nnue_shape &s, const uint32_t *bits_s, const float *w, const float *bias, float *out,
+                      void *workspace, cudaStream_t st);
+int launch_ft_bwd_dw_mma(const nnue_shape &s, const uint32_t *bits_s, const float *g_ft, uint4 *gfrag, float *partial,
+                         float *bias_partial, int *n_chunks, cudaStream_t st);
+int launch_ft_bwd_gbin_mma(const nnue_shape &s, const uint32_t *bits_s, const float *w, const float *g_ft, uint4 *wfrag,
+                           float *gbin, cudaStream_t st);
+
 // ---- fused head training step (head_fused.cu): small stacks only ---------------------------------
 constexpr int kHeadTile = 128;       // samples (= threads) per CTA tile
 constexpr int kHeadPartial = 2492;   // floats per per-CTA gradient block (HeadLayout<64,32,8,16>::pTotal)

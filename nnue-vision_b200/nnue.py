@@ -190,7 +190,9 @@ def _run_forward(shape, images, params, need_backward, marks=None):
                              None, st))
     _mark(marks, "extract_fwd")
     ft_out = _empty((shape.B, shape.L1), torch.float32, images)
-    check(L.nnue_ft_fwd(sp, dptr(bits_s), dptr(ft_w), dptr(ft_b), dptr(ft_out), st))
+    ws_bytes = _lib.workspace_bytes(shape)
+    ws = _empty((ws_bytes,), torch.uint8, images)
+    check(L.nnue_ft_fwd(sp, dptr(bits_s), dptr(ft_w), dptr(ft_b), dptr(ft_out), dptr(ws), ws_bytes, st))
     _mark(marks, "ft_fwd")
     act1 = _empty((shape.B, shape.L2), torch.float32, images)
     act2 = _empty((shape.B, shape.L3), torch.float32, images)
@@ -274,21 +276,38 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
                              st))
     _mark(marks, "extract_fwd")
     ft_out = _empty((shape.B, shape.L1), torch.float32, images)
-    check(L.nnue_ft_fwd(sp, dptr(bits_s), dptr(ft_w), dptr(ft_b), dptr(ft_out), st))
-    _mark(marks, "ft_fwd")
     ws_bytes = _lib.workspace_bytes(shape)
     ws = _empty((ws_bytes,), torch.uint8, images)
+    check(L.nnue_ft_fwd(sp, dptr(bits_s), dptr(ft_w), dptr(ft_b), dptr(ft_out), dptr(ws), ws_bytes, st))
+    _mark(marks, "ft_fwd")
     g_ft = _empty((shape.B, shape.L1), torch.float32, images)
     check(L.nnue_head_train(sp, dptr(ft_out), dptr(labels), inv_count, dptr(w1), dptr(b1), dptr(w2), dptr(b2),
                             dptr(w3), dptr(b3), dptr(loss_out), dptr(g_ft), dptr(g_w1), dptr(g_b1), dptr(g_w2),
                             dptr(g_b2), dptr(g_w3), dptr(g_b3), dptr(ws), ws_bytes, st))
     _mark(marks, "head_train")
+    if L.nnue_ft_bwd_is_fused(sp):  # small tables: both feature-transformer gradients in one pass over g_ft
+        gbin = _empty((shape.B, shape.PP), torch.float32, images)
+        check(L.nnue_ft_bwd(sp, dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(gbin), dptr(ws),
+                            ws_bytes, st))
+        _mark(marks, "ft_bwd")
+        check(L.nnue_conv_bwd(sp, dptr(images), dptr(gbin), dptr(conv_w), dptr(thr), dptr(g_conv_w), dptr(g_thr),
+                              dptr(ws), ws_bytes, st))
+        _mark(marks, "conv_bwd")
+        return loss_out, grads
     check(L.nnue_ft_bwd_dw(sp, dptr(bits_s), dptr(bits_t), dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(ws), ws_bytes,
                            st))
     _mark(marks, "ft_bwd_dw")
-    check(L.nnue_input_bwd(sp, dptr(images), dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(conv_w), dptr(thr),
-                           dptr(g_conv_w), dptr(g_thr), dptr(ws), ws_bytes, st))
-    _mark(marks, "input_bwd")
+    if L.nnue_input_bwd_is_dense(sp):
+        gbin = _empty((shape.B, shape.PP), torch.float32, images)
+        check(L.nnue_ft_bwd_gbin(sp, dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(gbin), st))
+        _mark(marks, "ft_bwd_gbin")
+        check(L.nnue_conv_bwd(sp, dptr(images), dptr(gbin), dptr(conv_w), dptr(thr), dptr(g_conv_w), dptr(g_thr),
+                              dptr(ws), ws_bytes, st))
+        _mark(marks, "conv_bwd")
+    else:
+        check(L.nnue_input_bwd(sp, dptr(images), dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(conv_w), dptr(thr),
+                               dptr(g_conv_w), dptr(g_thr), dptr(ws), ws_bytes, st))
+        _mark(marks, "input_bwd")
     return loss_out, grads
 
 

@@ -185,7 +185,7 @@ def test_ft_forward_staging_modes_agree(mode):
     try:
         lib.check(lib.lib().nnue_ft_fwd(ctypes.byref(shape), lib.dptr(bits),
                                         lib.dptr(model.input.weight.detach().contiguous()),
-                                        lib.dptr(model.input.bias.detach().contiguous()), lib.dptr(out),
+                                        lib.dptr(model.input.bias.detach().contiguous()), lib.dptr(out), None, 0,
                                         lib.stream_ptr()))
         torch.cuda.synchronize()
     finally:
@@ -194,8 +194,8 @@ def test_ft_forward_staging_modes_agree(mode):
     assert_close(out[torch.as_tensor(~amb).cuda()], ref["ft_out"][torch.as_tensor(~amb)], "ft_out")
 
 
-@pytest.mark.parametrize("options", [dict(ft_bwd_dw_owner=0), dict(input_bwd_fused=0), dict(input_bwd_variant=0),
-                                     dict(head_fused=0), dict(ft_bwd_dw_owner=0, input_bwd_fused=0, head_fused=0)],
+@pytest.mark.parametrize("options", [dict(ft_mma=0), dict(ft_mma=0, ft_bwd_both=0), dict(ft_mma=0, ft_bwd_dw_owner=0), dict(ft_mma=0, input_bwd_fused=0), dict(input_bwd_variant=0),
+                                     dict(head_fused=0), dict(ft_mma=0, ft_bwd_dw_owner=0, input_bwd_fused=0, head_fused=0)],
                          ids=str)
 @pytest.mark.parametrize("name", ["D", "T", "big_into_small"])
 def test_backward_kernel_variants_agree(name, options):
