@@ -147,29 +147,46 @@ ft_fwd_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const
 #pragma unroll
         for (int h = 0; h < 2; ++h) rows[mt][h] = b_base + mt * 16 + g + 8 * h;
 
-    for (int w = 0; w < s.NW; ++w) {
+    // operands of one bitmask word (two k16 steps): my rows' words and my B fragments; the next word's
+    // operands are fetched before this word's MMAs are issued, so the L1 / L2 latency hides under them
+    struct Operands {
         uint32_t word[2][2];
+        uint4 f[2][3][NB / 2];
+    };
+    auto fetch = [&](Operands &o, int w) {
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int h = 0; h < 2; ++h)
-                word[mt][h] = rows[mt][h] < s.B ? __ldg(bits_s + (size_t)rows[mt][h] * s.NW + w) : 0u;
+                o.word[mt][h] = rows[mt][h] < s.B ? __ldg(bits_s + (size_t)rows[mt][h] * s.NW + w) : 0u;
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int sp = 0; sp < 3; ++sp)
+#pragma unroll
+                for (int nbp = 0; nbp < NB / 2; ++nbp)
+                    o.f[half][sp][nbp] = __ldg(wfrag + ((size_t)((2 * w + half) * 3 + sp) * NBP_ALL + nbp0 + nbp) * 32 + lane);
+    };
+    Operands cur, nxt;
+    fetch(cur, 0);
+    for (int w = 0; w < s.NW; ++w) {
+        if (w + 1 < s.NW) fetch(nxt, w + 1);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            const int kb = 2 * w + half, sh = half * 16 + t * 2;
+            const int sh = half * 16 + t * 2;
             uint32_t a[2][4];
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-                a[mt][0] = bits2_to_bf16x2(word[mt][0] >> sh);
-                a[mt][1] = bits2_to_bf16x2(word[mt][1] >> sh);
-                a[mt][2] = bits2_to_bf16x2(word[mt][0] >> (sh + 8));
-                a[mt][3] = bits2_to_bf16x2(word[mt][1] >> (sh + 8));
+                a[mt][0] = bits2_to_bf16x2(cur.word[mt][0] >> sh);
+                a[mt][1] = bits2_to_bf16x2(cur.word[mt][1] >> sh);
+                a[mt][2] = bits2_to_bf16x2(cur.word[mt][0] >> (sh + 8));
+                a[mt][3] = bits2_to_bf16x2(cur.word[mt][1] >> (sh + 8));
             }
 #pragma unroll
             for (int sp = 0; sp < 3; ++sp)
 #pragma unroll
                 for (int nbp = 0; nbp < NB / 2; ++nbp) {
-                    const uint4 f = __ldg(wfrag + ((size_t)(kb * 3 + sp) * NBP_ALL + nbp0 + nbp) * 32 + lane);
+                    const uint4 f = cur.f[half][sp][nbp];
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt) {
                         mma_bf16(acc[mt][2 * nbp], a[mt], f.x, f.y);
@@ -177,6 +194,7 @@ ft_fwd_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const
                     }
                 }
         }
+        cur = nxt;
     }
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
@@ -201,11 +219,14 @@ template <int NB>
 __global__ void __launch_bounds__(kMmaThreads)
 ft_bwd_dw_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const uint4 *__restrict__ gfrag,
                      float *__restrict__ partial, float *__restrict__ bias_partial, int chunk_blocks) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-    const int w = blockIdx.x * (kMmaThreads / 32) + warp;  // my bitmask word
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int NBP_ALL = s.L1 / 16, col_groups = NBP_ALL / (NB / 2);
+    const int wid = blockIdx.x * (kMmaThreads / 32) + (threadIdx.x >> 5);
+    const int w = wid / col_groups;                      // my bitmask word
+    const int nbp0 = (wid % col_groups) * (NB / 2);      // my first column-block pair
     const int chunk = blockIdx.y;
     const bool active = w < s.NW;
-    const bool do_bias = blockIdx.x == 0 && warp == 0;
+    const bool do_bias = w == 0;
     float acc[2][NB][4], accb[NB][4];
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
@@ -215,10 +236,26 @@ ft_bwd_dw_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, co
     }
     const uint32_t ones[4] = {0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u};
     const int sb_begin = chunk * chunk_blocks, sb_end = min(s.BW, sb_begin + chunk_blocks);  // 32-sample blocks
-    for (int sb = sb_begin; sb < sb_end; ++sb) {
+    struct Operands {
+        uint32_t x;            // my sample's word (lane = sample within the block)
+        uint4 f[2][3][NB / 2];
+    };
+    auto fetch = [&](Operands &o, int sb) {
         const int b = sb * 32 + lane;
-        const uint32_t x = (active && b < s.B) ? __ldg(bits_s + (size_t)b * s.NW + w) : 0u;
-        const uint32_t tr = warp_bit_transpose(x, lane);  // lane L: the 32 samples of position w*32 + L
+        o.x = (active && b < s.B) ? __ldg(bits_s + (size_t)b * s.NW + w) : 0u;
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int sp = 0; sp < 3; ++sp)
+#pragma unroll
+                for (int nbp = 0; nbp < NB / 2; ++nbp)
+                    o.f[half][sp][nbp] = __ldg(gfrag + ((size_t)((2 * sb + half) * 3 + sp) * NBP_ALL + nbp0 + nbp) * 32 + lane);
+    };
+    Operands cur, nxt;
+    if (sb_begin < sb_end) fetch(cur, sb_begin);
+    for (int sb = sb_begin; sb < sb_end; ++sb) {
+        if (sb + 1 < sb_end) fetch(nxt, sb + 1);
+        const uint32_t tr = warp_bit_transpose(cur.x, lane);  // lane L: the 32 samples of position w*32 + L
         uint32_t word[2][2];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
@@ -226,7 +263,7 @@ ft_bwd_dw_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, co
             for (int h = 0; h < 2; ++h) word[mt][h] = __shfl_sync(kFull, tr, mt * 16 + g + 8 * h);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            const int kb = 2 * sb + half, sh = half * 16 + t * 2;
+            const int sh = half * 16 + t * 2;
             uint32_t a[2][4];
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
@@ -239,7 +276,7 @@ ft_bwd_dw_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, co
             for (int sp = 0; sp < 3; ++sp)
 #pragma unroll
                 for (int nbp = 0; nbp < NB / 2; ++nbp) {
-                    const uint4 f = __ldg(gfrag + ((size_t)(kb * 3 + sp) * (NB / 2) + nbp) * 32 + lane);
+                    const uint4 f = cur.f[half][sp][nbp];
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt) {
                         mma_bf16(acc[mt][2 * nbp], a[mt], f.x, f.y);
@@ -251,6 +288,7 @@ ft_bwd_dw_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, co
                     }
                 }
         }
+        cur = nxt;
     }
     if (active) {
         const int cells = s.Gh * s.Gw, c = w / s.CW, cell0 = (w % s.CW) * 32;
@@ -263,13 +301,15 @@ ft_bwd_dw_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, co
                 float *row = partial + ((size_t)chunk * s.P + (size_t)c * cells + cell) * s.L1;
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb)
-                    *reinterpret_cast<float2 *>(row + nb * 8 + t * 2) = make_float2(acc[mt][nb][2 * h], acc[mt][nb][2 * h + 1]);
+                    *reinterpret_cast<float2 *>(row + (nbp0 * 2 + nb) * 8 + t * 2) =
+                        make_float2(acc[mt][nb][2 * h], acc[mt][nb][2 * h + 1]);
             }
     }
     if (do_bias && g == 0)
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb)
-            *reinterpret_cast<float2 *>(bias_partial + (size_t)chunk * s.L1 + nb * 8 + t * 2) = make_float2(accb[nb][0], accb[nb][1]);
+            *reinterpret_cast<float2 *>(bias_partial + (size_t)chunk * s.L1 + (nbp0 * 2 + nb) * 8 + t * 2) =
+                make_float2(accb[nb][0], accb[nb][1]);
 }
 
 // ---- value gradient: gbin[b, pp] = bit(b, pp) ? <Wc[pp], g_ft[b]> : 0 ------------------------------------------
@@ -310,6 +350,13 @@ ft_bwd_gbin_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, 
                 for (int sp = 0; sp < 3; ++sp) a[mt][kb][sp][e] = lo[sp] | (hi[sp] << 16);
             }
     uint32_t word[2][2] = {{0u, 0u}, {0u, 0u}};
+    uint4 fnext[3][KB / 2];
+#pragma unroll
+    for (int sp = 0; sp < 3; ++sp)
+#pragma unroll
+        for (int kbp = 0; kbp < KB / 2; ++kbp)
+            fnext[sp][kbp] = nb_begin < nb_end ? __ldg(wfrag + ((size_t)(nb_begin * 3 + sp) * (KB / 2) + kbp) * 32 + lane)
+                                               : make_uint4(0u, 0u, 0u, 0u);
     for (int nb = nb_begin; nb < nb_end; ++nb) {
         if ((nb & 3) == 0) {
 #pragma unroll
@@ -325,8 +372,11 @@ ft_bwd_gbin_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, 
 #pragma unroll
         for (int sp = 0; sp < 3; ++sp)
 #pragma unroll
-            for (int kbp = 0; kbp < KB / 2; ++kbp)
-                f[sp][kbp] = __ldg(wfrag + ((size_t)(nb * 3 + sp) * (KB / 2) + kbp) * 32 + lane);
+            for (int kbp = 0; kbp < KB / 2; ++kbp) {
+                f[sp][kbp] = fnext[sp][kbp];
+                if (nb + 1 < nb_end)  // the next block's fragments fly while this block's MMAs issue
+                    fnext[sp][kbp] = __ldg(wfrag + ((size_t)((nb + 1) * 3 + sp) * (KB / 2) + kbp) * 32 + lane);
+            }
         // term pairs (split of g, split of W) with i + j <= 2 (0-based): the rest is below 2^-27 relative
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb)
@@ -380,9 +430,9 @@ int launch_ft_bwd_dw_mma(const nnue_shape &s, const uint32_t *bits_s, const floa
     const MmaPlan mp = plan_ft_mma(s);
     int rc = format_rows(s, false, g_ft, s.B, s.BW * 2, gfrag, st);
     if (rc != NNUE_OK) return rc;
-    dim3 grid(ceil_div(s.NW, kMmaThreads / 32), mp.n_chunks);
-    if (s.L1 == 64) ft_bwd_dw_mma_kernel<8><<<grid, kMmaThreads, 0, st>>>(s, bits_s, gfrag, partial, bias_partial, mp.chunk_blocks);
-    else ft_bwd_dw_mma_kernel<4><<<grid, kMmaThreads, 0, st>>>(s, bits_s, gfrag, partial, bias_partial, mp.chunk_blocks);
+    // 2 column blocks (16 columns) per warp: L1 / 16 warps share one bitmask word
+    dim3 grid(ceil_div(s.NW * (s.L1 / 16), kMmaThreads / 32), mp.n_chunks);
+    ft_bwd_dw_mma_kernel<2><<<grid, kMmaThreads, 0, st>>>(s, bits_s, gfrag, partial, bias_partial, mp.chunk_blocks);
     NNUE_CHECK_LAUNCH("ft_bwd_dw_mma_kernel");
     *n_chunks = mp.n_chunks;
     return NNUE_OK;

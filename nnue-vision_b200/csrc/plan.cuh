@@ -267,7 +267,7 @@ struct MmaPlan {
 inline MmaPlan plan_ft_mma(const nnue_shape &s) {
     MmaPlan m{};
     if (!get_option(kOptFtMma) || !dense_shape_ok(s)) return m;
-    int want = ceil_div(12 * kNumSMs, s.NW);  // ~12 warps per SM in flight
+    int want = ceil_div(16 * kNumSMs, s.NW * (s.L1 / 16));  // ~16 warps per SM in flight (L1/16 warps share a word)
     if (want < 1) want = 1;
     m.chunk_blocks = ceil_div(s.BW, want);
     m.n_chunks = ceil_div(s.BW, m.chunk_blocks);
