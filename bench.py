@@ -242,11 +242,13 @@ def int_inference_leg(w, device, seconds):
         ev = engine.NNUEEvaluator(path)
         imgs = torch.randn(B, w["image"], w["image"], 3, generator=torch.Generator().manual_seed(3))
         d_imgs = imgs.to(device)
-        for _ in range(3):
+        # the GPU has been idle while the CPU legs ran: spin it back up to its clocks before timing
+        t_warm = time.perf_counter()
+        while time.perf_counter() - t_warm < 0.5:
             ev.evaluate_logits(d_imgs)
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 20
+        reps = 200
         e0.record()
         for _ in range(reps):
             logits, dens = ev.evaluate_logits(d_imgs)

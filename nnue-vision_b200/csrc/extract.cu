@@ -93,6 +93,125 @@ extract_fwd_kernel(const nnue_shape s, const float *__restrict__ images, const f
     }
 }
 
+// ---- forward, TMA-staged form (CIFAR-sized images) ---------------------------------------------------
+// Same result as extract_fwd_kernel.  A warp owns kExtCH channels of one cell word for the whole kernel and
+// keeps their 3x3x3 taps in registers (no weight traffic at all in the loop); the producer (lane 0 of
+// warp 0) streams each sample's three image planes into a ring of shared-memory stages with bulk TMA
+// copies; out-of-image taps (padding = 1) point at a zeroed pad word behind each plane.  NH CTAs
+// ("roles") cover all (channel group, cell word) units of a sample and walk the same sample stream.
+template <int HWT>
+__global__ void __launch_bounds__(kExtWarps * 32, 1)
+extract_fwd_tma_kernel(const nnue_shape s, const float *__restrict__ images, const float *__restrict__ conv_w,
+                       const float *__restrict__ thr, uint32_t *__restrict__ bits_s, float *__restrict__ xpad,
+                       const ExtPlan pl) {
+    constexpr int CH = kExtCH;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *empty = full + kInMaxStages;
+    float *stages = reinterpret_cast<float *>(smem_raw + kInHeader);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int role = blockIdx.x % pl.NH, q = blockIdx.x / pl.NH;
+    const int HW = HWT ? HWT : s.H * s.W, HWp = HW + 4;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < pl.ST; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], kExtWarps);
+        }
+        mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i < pl.ST * 3 * 4; i += blockDim.x) {
+        const int st = i / 12, pln = (i % 12) / 4, k = i % 4;
+        stages[(size_t)st * pl.stage_floats + pln * HWp + HW + k] = 0.0f;
+    }
+    __syncthreads();
+
+    const int n_mine = s.B > q ? (s.B - q + pl.nq - 1) / pl.nq : 0;
+    auto produce = [&](int ii, int st, uint32_t ph) {
+        if (ii >= pl.ST) mbar_wait(&empty[st], ph);
+        const int b = q + ii * pl.nq;
+        float *stg = stages + (size_t)st * pl.stage_floats;
+        mbar_arrive_expect_tx(&full[st], (uint32_t)(3 * HW) * 4u);
+        const float *img = images + (size_t)b * 3 * HW;
+#pragma unroll
+        for (int pln = 0; pln < 3; ++pln) tma_bulk_g2s(stg + pln * HWp, img + pln * HW, (uint32_t)HW * 4u, &full[st]);
+    };
+    const int ahead = pl.ST - (pl.ST > 2 ? kInLag : 1);
+    if (threadIdx.x == 0)
+        for (int ii = 0; ii < ahead && ii < n_mine; ++ii) produce(ii, ii, 0);
+    int p_st = ahead % pl.ST;
+    uint32_t p_ph = 1u;
+
+    const int cells = s.Gh * s.Gw;
+    const int CG = ceil_div(s.C, CH);
+    const int unit = role * kExtWarps + warp;  // (channel group, cell word)
+    const bool active = unit < CG * s.CW;
+    const int cg = active ? unit / s.CW : 0, j = active ? unit % s.CW : 0;
+    const int c0 = cg * CH;
+    const int cell = j * 32 + lane;
+    const bool valid = active && cell < cells;
+    const int oy = valid ? cell / s.Gw : 0, ox = valid ? cell % s.Gw : 0;
+    int off9[9];
+    {
+        const int y0 = oy * s.stride - 1, x0 = ox * s.stride - 1;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int iy = y0 + kh, ix = x0 + kw;
+                const bool in = valid && (unsigned)iy < (unsigned)s.H && (unsigned)ix < (unsigned)s.W;
+                off9[kh * 3 + kw] = in ? iy * s.W + ix : HW;
+            }
+    }
+    float wk[CH][27], thr_c[CH];
+    bool chan_ok[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        chan_ok[k] = active && c0 + k < s.C;
+        const int c = min(c0 + k, s.C - 1);
+        thr_c[k] = __ldg(thr + c);
+#pragma unroll
+        for (int t = 0; t < 27; ++t) wk[k][t] = __ldg(conv_w + c * 27 + t);
+    }
+
+    int st = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < n_mine; ++i) {
+        if (threadIdx.x == 0 && i + ahead < n_mine) produce(i + ahead, p_st, p_ph);
+        if (++p_st == pl.ST) { p_st = 0; p_ph ^= 1u; }
+        __syncwarp();
+        mbar_wait(&full[st], ph);
+        if (active) {
+            const int b = q + i * pl.nq;
+            const float *stg = stages + (size_t)st * pl.stage_floats;
+            // same accumulation order as conv_tap_sum: taps in OIHW order, one FMA chain per channel
+            float x[CH];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) x[k] = 0.0f;
+#pragma unroll
+            for (int ic = 0; ic < 3; ++ic)
+#pragma unroll
+                for (int t9 = 0; t9 < 9; ++t9) {
+                    const float pt = stg[ic * HWp + off9[t9]];
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) x[k] = fmaf(pt, wk[k][ic * 9 + t9], x[k]);
+                }
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const unsigned word = __ballot_sync(kFull, valid && x[k] > thr_c[k]);
+                if (chan_ok[k]) {  // warp-uniform
+                    const int widx = (c0 + k) * s.CW + j;
+                    if (lane == 0) bits_s[(size_t)b * s.NW + widx] = word;
+                    if (xpad) xpad[(size_t)b * s.PP + (size_t)widx * 32 + lane] = x[k];
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+        if (++st == pl.ST) { st = 0; ph ^= 1u; }
+    }
+}
+
 // Position-major copy of the bitmask: bits_t[pp][bw] holds, for padded position pp, one bit per
 // sample of the 32-sample group bw.  This transpose IS the sort by feature that the weight
 // gradient's segment reduction consumes.  One CTA transposes 8 sample groups x 32 words.
@@ -237,6 +356,14 @@ __global__ void fold_rows_kernel(int n, int nblk, const float *__restrict__ part
 
 static int launch_extract_fwd(const nnue_shape &s, const float *images, const float *conv_w, const float *thr,
                               uint32_t *bits_s, float *xpad, float *conv_out, cudaStream_t st) {
+    const ExtPlan ep = plan_extract_tma(s);
+    if (ep.ok && bits_s && !conv_out) {
+        auto k = s.H * s.W == 1024 ? extract_fwd_tma_kernel<1024> : extract_fwd_tma_kernel<0>;
+        NNUE_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ep.smem));
+        k<<<ep.grid, kExtWarps * 32, ep.smem, st>>>(s, images, conv_w, thr, bits_s, xpad, ep);
+        NNUE_CHECK_LAUNCH("extract_fwd_tma_kernel");
+        return NNUE_OK;
+    }
     const size_t smem = (size_t)s.C * 29 * sizeof(float);
     if (smem > 48 * 1024) return NNUE_ERR_UNSUPPORTED;  // C <= 423 channels
     const long long units = 1LL * s.B * s.CW;

@@ -15,9 +15,12 @@
 // summation order differs from an fp32 FMA chain.  K per accumulator is kept short (one table
 // pass, or one K-chunk of samples folded later in fp32), so accumulation error stays ~1e-7.
 //
-// Operands are pre-formatted into MMA fragment order by small kernels (a lane then loads its
-// B fragments with one coalesced 16-byte load); the bitmask is expanded to bf16 A fragments in
-// registers (two integer instructions per register, amortised over 24 MMAs).
+// Operands are pre-formatted into MMA fragment order by small kernels, column-group major, so that
+// the slice a CTA needs is one contiguous block: it is staged in shared memory with bulk TMA copies
+// once per CTA and a lane then reads its B fragments as conflict-free LDS.128.  The bitmask is
+// expanded to bf16 A fragments in registers (a few integer instructions per register, amortised
+// over 12-24 MMAs).  (A first version loaded fragments straight from L2: ncu showed 14-16 stall
+// cycles per issue on the long scoreboard and 13-19 % issue utilisation, profiles/r1_ncu_v6*.)
 //
 //   mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32, lane = 4 * g + t (g = lane / 4, t = lane % 4):
 //     A (16 x 16): a0 = (row g,     k 2t, 2t+1)   a1 = (row g + 8, k 2t, 2t+1)
@@ -63,7 +66,8 @@ __device__ __forceinline__ int table_row_of(const nnue_shape &s, int pp) {
 // ---- operand formatting ----------------------------------------------------------------------------------
 // B operand with k running over ROWS of a row-major fp32 matrix src[rows][L1] and n over its columns
 // (forward: rows = padded positions of the table; weight gradient: rows = samples of g_ft).
-// out[((kb * 3 + s) * (NB / 2) + nbp) * 32 + lane] = uint4 {b0, b1 of column block 2 nbp, b0, b1 of 2 nbp + 1}.
+// out[((nbp * n_kb + kb) * 3 + s) * 32 + lane] = uint4 {b0, b1 of column block 2 nbp, b0, b1 of 2 nbp + 1}:
+// everything one 16-column group needs is contiguous.
 template <bool TABLE>
 __global__ void mma_format_rows_kernel(const nnue_shape s, const float *__restrict__ src, int nrows, int n_kb,
                                        uint4 *__restrict__ out) {
@@ -94,7 +98,7 @@ __global__ void mma_format_rows_kernel(const nnue_shape s, const float *__restri
     }
 #pragma unroll
     for (int sp = 0; sp < 3; ++sp)
-        out[((size_t)(kb * 3 + sp) * NBP + nbp) * 32 + lane] = make_uint4(packed[sp][0], packed[sp][1], packed[sp][2], packed[sp][3]);
+        out[(((size_t)nbp * n_kb + kb) * 3 + sp) * 32 + lane] = make_uint4(packed[sp][0], packed[sp][1], packed[sp][2], packed[sp][3]);
 }
 
 // B operand with k running over the COLUMNS of the table and n over padded positions (value gradient):
@@ -121,141 +125,132 @@ __global__ void mma_format_cols_kernel(const nnue_shape s, const float *__restri
         out[((size_t)(nb * 3 + sp) * KBP + kbp) * 32 + lane] = make_uint4(packed[sp][0], packed[sp][1], packed[sp][2], packed[sp][3]);
 }
 
+// Stage `bytes` of fragments into shared memory behind a 128-byte mbarrier header; all threads call it.
+__device__ __forceinline__ const uint4 *stage_fragments(unsigned char *smem_raw, const void *src, uint32_t bytes) {
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    tma_stage(smem_raw + 128, src, bytes, bar, 0);
+    return reinterpret_cast<const uint4 *>(smem_raw + 128);
+}
+
+// bits of two rows -> the four A registers of one m16 tile for k half `sh`
+__device__ __forceinline__ void bits_to_afrag(uint32_t (&a)[4], uint32_t w_lo, uint32_t w_hi, int sh) {
+    a[0] = bits2_to_bf16x2(w_lo >> sh);
+    a[1] = bits2_to_bf16x2(w_hi >> sh);
+    a[2] = bits2_to_bf16x2(w_lo >> (sh + 8));
+    a[3] = bits2_to_bf16x2(w_hi >> (sh + 8));
+}
+
 // ---- forward: out[b] = bias + bits[b] . Wc ------------------------------------------------------------------
-// A warp owns 32 samples (two m16 tiles) and NB of the L1 / 8 column blocks (the warps of a CTA share
-// the samples and split the columns, so there are enough warps to fill the machine); K runs over the
-// padded positions, one bitmask word (two k16 steps) at a time.
-template <int NB>
-__global__ void __launch_bounds__(kMmaThreads)
+// A persistent CTA owns one group of 16 columns: its slice of the split table (PP/16 k-steps x 3 terms x
+// 512 B = 96 KB at config D) sits in shared memory; each warp takes 32-sample tiles (two m16 tiles),
+// K runs over the padded positions one bitmask word (two k16 steps) at a time.
+__global__ void __launch_bounds__(kMmaFwdThreads, 1)
 ft_fwd_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const uint4 *__restrict__ wfrag,
                   const float *__restrict__ bias, float *__restrict__ out) {
-    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int NBP_ALL = s.L1 / 16;                       // column-block pairs of the whole row
-    const int col_groups = NBP_ALL / (NB / 2);           // warps that share one sample tile
-    const int wid = blockIdx.x * (kMmaThreads / 32) + (threadIdx.x >> 5);
-    const int b_base = (wid / col_groups) * 32;
-    const int nbp0 = (wid % col_groups) * (NB / 2);      // my first column-block pair
-    if (b_base >= s.B) return;
-    float acc[2][NB][4];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) acc[mt][nb][0] = acc[mt][nb][1] = acc[mt][nb][2] = acc[mt][nb][3] = 0.0f;
-    int rows[2][2];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) rows[mt][h] = b_base + mt * 16 + g + 8 * h;
-
-    // operands of one bitmask word (two k16 steps): my rows' words and my B fragments; the next word's
-    // operands are fetched before this word's MMAs are issued, so the L1 / L2 latency hides under them
-    struct Operands {
-        uint32_t word[2][2];
-        uint4 f[2][3][NB / 2];
-    };
-    auto fetch = [&](Operands &o, int w) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int NBP_ALL = s.L1 / 16, n_kb = s.PP / 16;
+    const int nbp = blockIdx.x % NBP_ALL, cta = blockIdx.x / NBP_ALL, ctas = gridDim.x / NBP_ALL;
+    const uint4 *sf = stage_fragments(smem_raw, wfrag + (size_t)nbp * n_kb * 3 * 32, (uint32_t)n_kb * 3 * 512u) + lane;
+    const int col = nbp * 16 + t * 2;
+    const float2 bv0 = __ldg(reinterpret_cast<const float2 *>(bias + col));
+    const float2 bv1 = __ldg(reinterpret_cast<const float2 *>(bias + col + 8));
+    const int ntiles = ceil_div(s.B, 32), wpc = kMmaFwdThreads / 32;
+    for (int tile = cta * wpc + warp; tile < ntiles; tile += ctas * wpc) {
+        int rows[2][2];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
-                o.word[mt][h] = rows[mt][h] < s.B ? __ldg(bits_s + (size_t)rows[mt][h] * s.NW + w) : 0u;
+            for (int h = 0; h < 2; ++h) rows[mt][h] = tile * 32 + mt * 16 + g + 8 * h;
+        float acc[2][2][4];
 #pragma unroll
-        for (int half = 0; half < 2; ++half)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int sp = 0; sp < 3; ++sp)
+            for (int nb = 0; nb < 2; ++nb) acc[mt][nb][0] = acc[mt][nb][1] = acc[mt][nb][2] = acc[mt][nb][3] = 0.0f;
+        auto fetch = [&](uint32_t (&wd)[2][2], int w) {
 #pragma unroll
-                for (int nbp = 0; nbp < NB / 2; ++nbp)
-                    o.f[half][sp][nbp] = __ldg(wfrag + ((size_t)((2 * w + half) * 3 + sp) * NBP_ALL + nbp0 + nbp) * 32 + lane);
-    };
-    Operands cur, nxt;
-    fetch(cur, 0);
-    for (int w = 0; w < s.NW; ++w) {
-        if (w + 1 < s.NW) fetch(nxt, w + 1);
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int sh = half * 16 + t * 2;
-            uint32_t a[2][4];
+                for (int h = 0; h < 2; ++h)
+                    wd[mt][h] = rows[mt][h] < s.B ? __ldg(bits_s + (size_t)rows[mt][h] * s.NW + w) : 0u;
+        };
+        uint32_t cur[2][2], nxt[2][2];
+        fetch(cur, 0);
+        for (int w = 0; w < s.NW; ++w) {
+            if (w + 1 < s.NW) fetch(nxt, w + 1);  // the next word's bits fly while this word's MMAs issue
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                a[mt][0] = bits2_to_bf16x2(cur.word[mt][0] >> sh);
-                a[mt][1] = bits2_to_bf16x2(cur.word[mt][1] >> sh);
-                a[mt][2] = bits2_to_bf16x2(cur.word[mt][0] >> (sh + 8));
-                a[mt][3] = bits2_to_bf16x2(cur.word[mt][1] >> (sh + 8));
-            }
+            for (int half = 0; half < 2; ++half) {
+                uint32_t a[2][4];
 #pragma unroll
-            for (int sp = 0; sp < 3; ++sp)
+                for (int mt = 0; mt < 2; ++mt) bits_to_afrag(a[mt], cur[mt][0], cur[mt][1], half * 16 + t * 2);
 #pragma unroll
-                for (int nbp = 0; nbp < NB / 2; ++nbp) {
-                    const uint4 f = cur.f[half][sp][nbp];
+                for (int sp = 0; sp < 3; ++sp) {
+                    const uint4 f = sf[((2 * w + half) * 3 + sp) * 32];
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt) {
-                        mma_bf16(acc[mt][2 * nbp], a[mt], f.x, f.y);
-                        mma_bf16(acc[mt][2 * nbp + 1], a[mt], f.z, f.w);
+                        mma_bf16(acc[mt][0], a[mt], f.x, f.y);
+                        mma_bf16(acc[mt][1], a[mt], f.z, f.w);
                     }
                 }
-        }
-        cur = nxt;
-    }
+            }
 #pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
-        const int col = (nbp0 * 2 + nb) * 8 + t * 2;
-        const float2 bv = __ldg(reinterpret_cast<const float2 *>(bias + col));
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) cur[mt][h] = nxt[mt][h];
+        }
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int h = 0; h < 2; ++h)
-                if (rows[mt][h] < s.B)
-                    *reinterpret_cast<float2 *>(out + (size_t)rows[mt][h] * s.L1 + col) =
-                        make_float2(bv.x + acc[mt][nb][2 * h], bv.y + acc[mt][nb][2 * h + 1]);
+                if (rows[mt][h] < s.B) {
+                    float *o = out + (size_t)rows[mt][h] * s.L1 + col;
+                    *reinterpret_cast<float2 *>(o) = make_float2(bv0.x + acc[mt][0][2 * h], bv0.y + acc[mt][0][2 * h + 1]);
+                    *reinterpret_cast<float2 *>(o + 8) = make_float2(bv1.x + acc[mt][1][2 * h], bv1.y + acc[mt][1][2 * h + 1]);
+                }
     }
 }
 
 // ---- weight gradient: dW[p] = sum_b bits[b, p] g_ft[b] --------------------------------------------------------
-// A warp owns one bitmask word (32 positions = two m16 tiles) and one K-chunk of samples; the 32 x 32
-// bit block of (sample, position) is transposed in registers so that k runs over samples.  Output:
-// partial[chunk][p][L1] for the fold kernels of ft.cu (they also resolve the aliasing onto row F-1).
-// Warp 0 of the first word block also multiplies an all-ones tile: its first row is the bias gradient.
-template <int NB>
-__global__ void __launch_bounds__(kMmaThreads)
+// CTA = (block of kMmaDwWarps bitmask words, 16-column group, K-chunk of samples): the chunk's slice of the
+// split g_ft (chunk_blocks x 2 k-steps x 3 terms x 512 B) is staged in shared memory once; a warp owns one
+// word (32 positions = two m16 tiles) and transposes each 32 x 32 bit block of (sample, position) in
+// registers so that k runs over samples.  Output: partial[chunk][p][L1] for the fold kernels of ft.cu
+// (they also resolve the aliasing onto row F-1).  The warp of word 0 also multiplies an all-ones tile:
+// its first row is the bias gradient.
+__global__ void __launch_bounds__(kMmaDwWarps * 32, 2)
 ft_bwd_dw_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const uint4 *__restrict__ gfrag,
                      float *__restrict__ partial, float *__restrict__ bias_partial, int chunk_blocks) {
-    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int NBP_ALL = s.L1 / 16, col_groups = NBP_ALL / (NB / 2);
-    const int wid = blockIdx.x * (kMmaThreads / 32) + (threadIdx.x >> 5);
-    const int w = wid / col_groups;                      // my bitmask word
-    const int nbp0 = (wid % col_groups) * (NB / 2);      // my first column-block pair
-    const int chunk = blockIdx.y;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int n_kb = s.BW * 2;
+    const int w = blockIdx.x * kMmaDwWarps + warp;  // my bitmask word
+    const int nbp = blockIdx.y, chunk = blockIdx.z;
     const bool active = w < s.NW;
     const bool do_bias = w == 0;
-    float acc[2][NB][4], accb[NB][4];
+    const int sb_begin = chunk * chunk_blocks, sb_end = min(s.BW, sb_begin + chunk_blocks);  // 32-sample blocks
+    const uint4 *sf = stage_fragments(smem_raw, gfrag + ((size_t)nbp * n_kb + 2 * sb_begin) * 3 * 32,
+                                      (uint32_t)(sb_end - sb_begin) * 2 * 3 * 512u) + lane;
+    float acc[2][2][4], accb[2][4];
 #pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
+    for (int nb = 0; nb < 2; ++nb) {
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) acc[mt][nb][0] = acc[mt][nb][1] = acc[mt][nb][2] = acc[mt][nb][3] = 0.0f;
         accb[nb][0] = accb[nb][1] = accb[nb][2] = accb[nb][3] = 0.0f;
     }
     const uint32_t ones[4] = {0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u};
-    const int sb_begin = chunk * chunk_blocks, sb_end = min(s.BW, sb_begin + chunk_blocks);  // 32-sample blocks
-    struct Operands {
-        uint32_t x;            // my sample's word (lane = sample within the block)
-        uint4 f[2][3][NB / 2];
-    };
-    auto fetch = [&](Operands &o, int sb) {
+    auto fetch = [&](int sb) -> uint32_t {
         const int b = sb * 32 + lane;
-        o.x = (active && b < s.B) ? __ldg(bits_s + (size_t)b * s.NW + w) : 0u;
-#pragma unroll
-        for (int half = 0; half < 2; ++half)
-#pragma unroll
-            for (int sp = 0; sp < 3; ++sp)
-#pragma unroll
-                for (int nbp = 0; nbp < NB / 2; ++nbp)
-                    o.f[half][sp][nbp] = __ldg(gfrag + ((size_t)((2 * sb + half) * 3 + sp) * NBP_ALL + nbp0 + nbp) * 32 + lane);
+        return (active && sb < sb_end && b < s.B) ? __ldg(bits_s + (size_t)b * s.NW + w) : 0u;
     };
-    Operands cur, nxt;
-    if (sb_begin < sb_end) fetch(cur, sb_begin);
+    uint32_t x = fetch(sb_begin);
     for (int sb = sb_begin; sb < sb_end; ++sb) {
-        if (sb + 1 < sb_end) fetch(nxt, sb + 1);
-        const uint32_t tr = warp_bit_transpose(cur.x, lane);  // lane L: the 32 samples of position w*32 + L
+        const uint32_t xn = fetch(sb + 1);
+        const uint32_t tr = warp_bit_transpose(x, lane);  // lane L: the 32 samples of position w*32 + L
         uint32_t word[2][2];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
@@ -263,33 +258,26 @@ ft_bwd_dw_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, co
             for (int h = 0; h < 2; ++h) word[mt][h] = __shfl_sync(kFull, tr, mt * 16 + g + 8 * h);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            const int sh = half * 16 + t * 2;
             uint32_t a[2][4];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                a[mt][0] = bits2_to_bf16x2(word[mt][0] >> sh);
-                a[mt][1] = bits2_to_bf16x2(word[mt][1] >> sh);
-                a[mt][2] = bits2_to_bf16x2(word[mt][0] >> (sh + 8));
-                a[mt][3] = bits2_to_bf16x2(word[mt][1] >> (sh + 8));
-            }
+            for (int mt = 0; mt < 2; ++mt) bits_to_afrag(a[mt], word[mt][0], word[mt][1], half * 16 + t * 2);
 #pragma unroll
-            for (int sp = 0; sp < 3; ++sp)
+            for (int sp = 0; sp < 3; ++sp) {
+                const uint4 f = sf[((2 * (sb - sb_begin) + half) * 3 + sp) * 32];
 #pragma unroll
-                for (int nbp = 0; nbp < NB / 2; ++nbp) {
-                    const uint4 f = cur.f[half][sp][nbp];
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        mma_bf16(acc[mt][2 * nbp], a[mt], f.x, f.y);
-                        mma_bf16(acc[mt][2 * nbp + 1], a[mt], f.z, f.w);
-                    }
-                    if (do_bias) {  // warp-uniform
-                        mma_bf16(accb[2 * nbp], ones, f.x, f.y);
-                        mma_bf16(accb[2 * nbp + 1], ones, f.z, f.w);
-                    }
+                for (int mt = 0; mt < 2; ++mt) {
+                    mma_bf16(acc[mt][0], a[mt], f.x, f.y);
+                    mma_bf16(acc[mt][1], a[mt], f.z, f.w);
                 }
+                if (do_bias) {  // warp-uniform
+                    mma_bf16(accb[0], ones, f.x, f.y);
+                    mma_bf16(accb[1], ones, f.z, f.w);
+                }
+            }
         }
-        cur = nxt;
+        x = xn;
     }
+    const int col = nbp * 16 + t * 2;
     if (active) {
         const int cells = s.Gh * s.Gw, c = w / s.CW, cell0 = (w % s.CW) * 32;
 #pragma unroll
@@ -298,107 +286,86 @@ ft_bwd_dw_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, co
             for (int h = 0; h < 2; ++h) {
                 const int cell = cell0 + mt * 16 + g + 8 * h;
                 if (cell >= cells) continue;
-                float *row = partial + ((size_t)chunk * s.P + (size_t)c * cells + cell) * s.L1;
-#pragma unroll
-                for (int nb = 0; nb < NB; ++nb)
-                    *reinterpret_cast<float2 *>(row + (nbp0 * 2 + nb) * 8 + t * 2) =
-                        make_float2(acc[mt][nb][2 * h], acc[mt][nb][2 * h + 1]);
+                float *row = partial + ((size_t)chunk * s.P + (size_t)c * cells + cell) * s.L1 + col;
+                *reinterpret_cast<float2 *>(row) = make_float2(acc[mt][0][2 * h], acc[mt][0][2 * h + 1]);
+                *reinterpret_cast<float2 *>(row + 8) = make_float2(acc[mt][1][2 * h], acc[mt][1][2 * h + 1]);
             }
     }
-    if (do_bias && g == 0)
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb)
-            *reinterpret_cast<float2 *>(bias_partial + (size_t)chunk * s.L1 + (nbp0 * 2 + nb) * 8 + t * 2) =
-                make_float2(accb[nb][0], accb[nb][1]);
+    if (do_bias && g == 0) {
+        float *row = bias_partial + (size_t)chunk * s.L1 + col;
+        *reinterpret_cast<float2 *>(row) = make_float2(accb[0][0], accb[0][1]);
+        *reinterpret_cast<float2 *>(row + 8) = make_float2(accb[1][0], accb[1][1]);
+    }
 }
 
 // ---- value gradient: gbin[b, pp] = bit(b, pp) ? <Wc[pp], g_ft[b]> : 0 ------------------------------------------
-// A warp owns 32 samples and 1 / kGbinSplit of the padded positions; the samples' g_ft rows are split
-// into bf16 A fragments once (K = L1) and stay in registers while the warp walks its positions eight
-// at a time.
-constexpr int kGbinSplit = 8;
+// A persistent CTA owns 1 / kGbinSplit of the padded positions: its slice of the split table (column
+// layout) sits in shared memory.  A warp takes 16-sample tiles: the samples' g_ft rows are split into
+// bf16 A fragments once per tile (K = L1) and stay in registers while the warp walks the CTA's
+// positions eight at a time.
 template <int KB>
-__global__ void __launch_bounds__(kMmaThreads)
+__global__ void __launch_bounds__(kMmaGbinThreads, 1)
 ft_bwd_gbin_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const uint4 *__restrict__ wfrag,
                        const float *__restrict__ g_ft, float *__restrict__ gbin) {
-    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int wid = blockIdx.x * (kMmaThreads / 32) + (threadIdx.x >> 5);
-    const int b_base = (wid / kGbinSplit) * 32;
-    if (b_base >= s.B) return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int part = blockIdx.x % kGbinSplit, cta = blockIdx.x / kGbinSplit, ctas = gridDim.x / kGbinSplit;
     // my share of the padded positions, in units of one bitmask word (4 column blocks of 8)
     const int words_per = ceil_div(s.NW, kGbinSplit);
-    const int nb_begin = (wid % kGbinSplit) * words_per * 4, nb_end = min(s.PP / 8, nb_begin + words_per * 4);
-    int rows[2][2];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) rows[mt][h] = b_base + mt * 16 + g + 8 * h;
-    uint32_t a[2][KB][3][4];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    const int nb_begin = min(s.PP / 8, part * words_per * 4), nb_end = min(s.PP / 8, nb_begin + words_per * 4);
+    const uint4 *sf = stage_fragments(smem_raw, wfrag + (size_t)nb_begin * 3 * (KB / 2) * 32,
+                                      (uint32_t)(nb_end - nb_begin) * 3 * (KB / 2) * 512u) + lane;
+    const int ntiles = ceil_div(s.B, 16), wpc = kMmaGbinThreads / 32;
+    for (int tile = cta * wpc + warp; tile < ntiles; tile += ctas * wpc) {
+        const int r0 = tile * 16 + g, r1 = r0 + 8;
+        uint32_t a[KB][3][4];
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {  // a0: (row g, k 2t) a1: (row g+8, k 2t) a2: (row g, k 2t+8) a3: (row g+8, k 2t+8)
-                const int r = rows[mt][e & 1], k0 = kb * 16 + t * 2 + (e >> 1) * 8;
+                const int r = (e & 1) ? r1 : r0, k0 = kb * 16 + t * 2 + (e >> 1) * 8;
                 float2 v = make_float2(0.f, 0.f);
                 if (r < s.B) v = __ldg(reinterpret_cast<const float2 *>(g_ft + (size_t)r * s.L1 + k0));
                 uint32_t lo[3], hi[3];
                 split3(v.x, lo);
                 split3(v.y, hi);
 #pragma unroll
-                for (int sp = 0; sp < 3; ++sp) a[mt][kb][sp][e] = lo[sp] | (hi[sp] << 16);
+                for (int sp = 0; sp < 3; ++sp) a[kb][sp][e] = lo[sp] | (hi[sp] << 16);
             }
-    uint32_t word[2][2] = {{0u, 0u}, {0u, 0u}};
-    uint4 fnext[3][KB / 2];
+        uint32_t word0 = 0u, word1 = 0u;
+        for (int nb = nb_begin; nb < nb_end; ++nb) {
+            if ((nb & 3) == 0) {
+                word0 = r0 < s.B ? __ldg(bits_s + (size_t)r0 * s.NW + (nb >> 2)) : 0u;
+                word1 = r1 < s.B ? __ldg(bits_s + (size_t)r1 * s.NW + (nb >> 2)) : 0u;
+            }
+            // term pairs (split of g, split of W) with i + j <= 2 (0-based): the rest is below 2^-27 relative;
+            // two accumulators (even / odd k16 steps) halve the dependent MMA chain
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-    for (int sp = 0; sp < 3; ++sp)
+            for (int sw = 0; sw < 3; ++sw)
 #pragma unroll
-        for (int kbp = 0; kbp < KB / 2; ++kbp)
-            fnext[sp][kbp] = nb_begin < nb_end ? __ldg(wfrag + ((size_t)(nb_begin * 3 + sp) * (KB / 2) + kbp) * 32 + lane)
-                                               : make_uint4(0u, 0u, 0u, 0u);
-    for (int nb = nb_begin; nb < nb_end; ++nb) {
-        if ((nb & 3) == 0) {
+                for (int kbp = 0; kbp < KB / 2; ++kbp) {
+                    const uint4 f = sf[(((nb - nb_begin) * 3 + sw) * (KB / 2) + kbp) * 32];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+                    for (int sa = 0; sa + sw < 3; ++sa) {
+                        mma_bf16(acc, a[2 * kbp][sa], f.x, f.y);
+                        mma_bf16(acc2, a[2 * kbp + 1][sa], f.z, f.w);
+                    }
+                }
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    word[mt][h] = rows[mt][h] < s.B ? __ldg(bits_s + (size_t)rows[mt][h] * s.NW + (nb >> 2)) : 0u;
+            for (int e = 0; e < 4; ++e) acc[e] += acc2[e];
+            const int off = (nb & 3) * 8 + t * 2;
+            if (r0 < s.B) {
+                const uint32_t m = word0 >> off;
+                *reinterpret_cast<float2 *>(gbin + (size_t)r0 * s.PP + nb * 8 + t * 2) =
+                    make_float2((m & 1u) ? acc[0] : 0.0f, (m & 2u) ? acc[1] : 0.0f);
+            }
+            if (r1 < s.B) {
+                const uint32_t m = word1 >> off;
+                *reinterpret_cast<float2 *>(gbin + (size_t)r1 * s.PP + nb * 8 + t * 2) =
+                    make_float2((m & 1u) ? acc[2] : 0.0f, (m & 2u) ? acc[3] : 0.0f);
+            }
         }
-        float acc[2][4];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.0f;
-        uint4 f[3][KB / 2];
-#pragma unroll
-        for (int sp = 0; sp < 3; ++sp)
-#pragma unroll
-            for (int kbp = 0; kbp < KB / 2; ++kbp) {
-                f[sp][kbp] = fnext[sp][kbp];
-                if (nb + 1 < nb_end)  // the next block's fragments fly while this block's MMAs issue
-                    fnext[sp][kbp] = __ldg(wfrag + ((size_t)((nb + 1) * 3 + sp) * (KB / 2) + kbp) * 32 + lane);
-            }
-        // term pairs (split of g, split of W) with i + j <= 2 (0-based): the rest is below 2^-27 relative
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
-#pragma unroll
-            for (int sa = 0; sa < 3; ++sa)
-#pragma unroll
-                for (int sw = 0; sw + sa < 3; ++sw) {
-                    const uint4 ff = f[sw][kb >> 1];
-                    const uint32_t b0 = (kb & 1) ? ff.z : ff.x, b1 = (kb & 1) ? ff.w : ff.y;
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) mma_bf16(acc[mt], a[mt][kb][sa], b0, b1);
-                }
-        const int off = (nb & 3) * 8 + t * 2;
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-                if (rows[mt][h] < s.B) {
-                    const uint32_t m = word[mt][h] >> off;
-                    *reinterpret_cast<float2 *>(gbin + (size_t)rows[mt][h] * s.PP + nb * 8 + t * 2) =
-                        make_float2((m & 1u) ? acc[mt][2 * h] : 0.0f, (m & 2u) ? acc[mt][2 * h + 1] : 0.0f);
-                }
     }
 }
 
@@ -417,9 +384,13 @@ int launch_ft_fwd_mma(const nnue_shape &s, const uint32_t *bits_s, const float *
     uint4 *wfrag = static_cast<uint4 *>(workspace);
     const int rc = format_rows(s, true, w, s.PP, s.PP / 16, wfrag, st);
     if (rc != NNUE_OK) return rc;
-    // 2 column blocks (16 columns) per warp: L1 / 16 warps share a 32-sample tile
-    const int grid = ceil_div(ceil_div(s.B, 32) * (s.L1 / 16), kMmaThreads / 32);
-    ft_fwd_mma_kernel<2><<<grid, kMmaThreads, 0, st>>>(s, bits_s, wfrag, bias, out);
+    const int groups = s.L1 / 16;
+    const int ntiles = ceil_div(s.B, 32), wpc = kMmaFwdThreads / 32;
+    int ctas = kNumSMs / groups;  // persistent CTAs per column group
+    if (ctas > ceil_div(ntiles, wpc)) ctas = ceil_div(ntiles, wpc);
+    const size_t smem = mma_fwd_smem(s);
+    NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ft_fwd_mma_kernel<<<ctas * groups, kMmaFwdThreads, smem, st>>>(s, bits_s, wfrag, bias, out);
     NNUE_CHECK_LAUNCH("ft_fwd_mma_kernel");
     return NNUE_OK;
 }
@@ -430,9 +401,10 @@ int launch_ft_bwd_dw_mma(const nnue_shape &s, const uint32_t *bits_s, const floa
     const MmaPlan mp = plan_ft_mma(s);
     int rc = format_rows(s, false, g_ft, s.B, s.BW * 2, gfrag, st);
     if (rc != NNUE_OK) return rc;
-    // 2 column blocks (16 columns) per warp: L1 / 16 warps share one bitmask word
-    dim3 grid(ceil_div(s.NW * (s.L1 / 16), kMmaThreads / 32), mp.n_chunks);
-    ft_bwd_dw_mma_kernel<2><<<grid, kMmaThreads, 0, st>>>(s, bits_s, gfrag, partial, bias_partial, mp.chunk_blocks);
+    dim3 grid(ceil_div(s.NW, kMmaDwWarps), s.L1 / 16, mp.n_chunks);
+    const size_t smem = 128 + (size_t)mp.chunk_blocks * 2 * 3 * 512;
+    NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_bwd_dw_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ft_bwd_dw_mma_kernel<<<grid, kMmaDwWarps * 32, smem, st>>>(s, bits_s, gfrag, partial, bias_partial, mp.chunk_blocks);
     NNUE_CHECK_LAUNCH("ft_bwd_dw_mma_kernel");
     *n_chunks = mp.n_chunks;
     return NNUE_OK;
@@ -443,9 +415,13 @@ int launch_ft_bwd_gbin_mma(const nnue_shape &s, const uint32_t *bits_s, const fl
     const long long n = 1LL * (s.PP / 8) * (s.L1 / 32) * 32;
     mma_format_cols_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(s, w, wfrag);
     NNUE_CHECK_LAUNCH("mma_format_cols_kernel");
-    const int grid = ceil_div(ceil_div(s.B, 32) * kGbinSplit, kMmaThreads / 32);
-    if (s.L1 == 64) ft_bwd_gbin_mma_kernel<4><<<grid, kMmaThreads, 0, st>>>(s, bits_s, wfrag, g_ft, gbin);
-    else ft_bwd_gbin_mma_kernel<2><<<grid, kMmaThreads, 0, st>>>(s, bits_s, wfrag, g_ft, gbin);
+    const int ntiles = ceil_div(s.B, 16), wpc = kMmaGbinThreads / 32;
+    int ctas = kNumSMs / kGbinSplit;  // persistent CTAs per position slice
+    if (ctas > ceil_div(ntiles, wpc)) ctas = ceil_div(ntiles, wpc);
+    const size_t smem = mma_gbin_smem(s);
+    auto k = s.L1 == 64 ? ft_bwd_gbin_mma_kernel<4> : ft_bwd_gbin_mma_kernel<2>;
+    NNUE_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<ctas * kGbinSplit, kMmaGbinThreads, smem, st>>>(s, bits_s, wfrag, g_ft, gbin);
     NNUE_CHECK_LAUNCH("ft_bwd_gbin_mma_kernel");
     return NNUE_OK;
 }

@@ -22,15 +22,17 @@ namespace nnue {
 constexpr float kSteSharpness = 10.0f;  // nnue.py:41
 
 // HWT: H*W when known at compile time (plane offsets become LDS immediates), 0 = read it from the shape
-template <int CH, int WARPS, int HWT>
+// XS: the forward stored the pre-threshold activations (xpad, staged next to g_bin) -- otherwise they are
+//     recomputed from the taps and the conv weights
+template <int CH, int WARPS, int HWT, bool XS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 conv_bwd_kernel(const nnue_shape s, const float *__restrict__ images, const float *__restrict__ dval,
-                const float *__restrict__ conv_w, const float *__restrict__ thr, float *__restrict__ partial,
-                const InPlan pl) {
+                const float *__restrict__ xpad, const float *__restrict__ conv_w, const float *__restrict__ thr,
+                float *__restrict__ partial, const InPlan pl) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
     uint64_t *empty = full + kInMaxStages;
-    float *s_cw = reinterpret_cast<float *>(smem_raw + 128);      // [C][28]
+    float *s_cw = reinterpret_cast<float *>(smem_raw + kInHeader);  // [C][28]
     float *s_thr = s_cw + s.C * 28;                                // [C]
     float *red = s_thr + align_up((size_t)s.C, 4);                 // [WARPS][CH][28]
     float *stages = reinterpret_cast<float *>(smem_raw + pl.stage_off);
@@ -66,11 +68,12 @@ conv_bwd_kernel(const nnue_shape s, const float *__restrict__ images, const floa
         if (ii >= pl.ST) mbar_wait(&empty[st], ph);
         const int b = q + ii * pl.nq;
         float *stg = stages + (size_t)st * pl.stage_floats;
-        mbar_arrive_expect_tx(&full[st], (uint32_t)(3 * HW + s.PP) * 4u);
+        mbar_arrive_expect_tx(&full[st], (uint32_t)(3 * HW + (XS ? 2 : 1) * s.PP) * 4u);
         const float *img = images + (size_t)b * 3 * HW;
 #pragma unroll
         for (int pln = 0; pln < 3; ++pln) tma_bulk_g2s(stg + pln * HWp, img + pln * HW, (uint32_t)HW * 4u, &full[st]);
         tma_bulk_g2s(stg + 3 * HWp, dval + (size_t)b * s.PP, (uint32_t)s.PP * 4u, &full[st]);
+        if (XS) tma_bulk_g2s(stg + 3 * HWp + s.PP, xpad + (size_t)b * s.PP, (uint32_t)s.PP * 4u, &full[st]);
     };
     const int ahead = pl.ST - (pl.ST > 2 ? kInLag : 1);  // samples in flight
     if (threadIdx.x == 0)
@@ -130,10 +133,11 @@ conv_bwd_kernel(const nnue_shape s, const float *__restrict__ images, const floa
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
                 gk[k] = chan_ok[k] ? stg[goff[k]] : 0.0f;
-                x[k][0] = x[k][1] = x[k][2] = 0.0f;
+                x[k][0] = (XS && chan_ok[k]) ? stg[goff[k] + s.PP] : 0.0f;
+                x[k][1] = x[k][2] = 0.0f;
             }
-            // one pass over the 27 taps: recompute the conv (one chain per input plane) and accumulate its
-            // weight gradient
+            // one pass over the 27 taps: accumulate the conv weight gradient (and, without stored
+            // activations, recompute the conv: one chain per input plane)
 #pragma unroll
             for (int t9 = 0; t9 < 9; ++t9)
 #pragma unroll
@@ -142,7 +146,7 @@ conv_bwd_kernel(const nnue_shape s, const float *__restrict__ images, const floa
                     const float pt = stg[ic * HWp + off9[t9]];
 #pragma unroll
                     for (int k = 0; k < CH; ++k) {
-                        x[k][ic] = fmaf(pt, cwk[k][t], x[k][ic]);
+                        if (!XS) x[k][ic] = fmaf(pt, cwk[k][t], x[k][ic]);
                         acc[k][t] = fmaf(gk[k], pt, acc[k][t]);
                     }
                 }
@@ -195,10 +199,11 @@ __global__ void input_bwd_fold_kernel(int C, int nblk, const float *__restrict__
 
 template <int CH, int WARPS>
 static int launch_conv_bwd(const nnue_shape &s, const InPlan &pl, const float *images, const float *dval,
-                           const float *conv_w, const float *thr, float *partial, cudaStream_t st) {
-    auto k = s.H * s.W == 1024 ? conv_bwd_kernel<CH, WARPS, 1024> : conv_bwd_kernel<CH, WARPS, 0>;
+                           const float *xpad, const float *conv_w, const float *thr, float *partial, cudaStream_t st) {
+    auto k = xpad ? (s.H * s.W == 1024 ? conv_bwd_kernel<CH, WARPS, 1024, true> : conv_bwd_kernel<CH, WARPS, 0, true>)
+                  : (s.H * s.W == 1024 ? conv_bwd_kernel<CH, WARPS, 1024, false> : conv_bwd_kernel<CH, WARPS, 0, false>);
     NNUE_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    k<<<pl.grid, WARPS * 32, pl.smem, st>>>(s, images, dval, conv_w, thr, partial, pl);
+    k<<<pl.grid, WARPS * 32, pl.smem, st>>>(s, images, dval, xpad, conv_w, thr, partial, pl);
     NNUE_CHECK_LAUNCH("conv_bwd_kernel");
     return NNUE_OK;
 }
@@ -218,9 +223,9 @@ int nnue_ft_bwd_gbin(const nnue_shape *s, const uint32_t *bits_s_d, const float 
     return launch_ft_bwd_dval_dense(*s, bits_s_d, ft_w_d, g_ft_d, gbin_d, static_cast<cudaStream_t>(stream));
 }
 
-int nnue_conv_bwd(const nnue_shape *s, const float *images_d, const float *gbin_d, const float *conv_w_d,
-                  const float *thr_d, float *g_conv_w_d, float *g_thr_d, void *workspace_d, size_t workspace_bytes,
-                  void *stream) {
+int nnue_conv_bwd(const nnue_shape *s, const float *images_d, const float *gbin_d, const float *xpad_d,
+                  const float *conv_w_d, const float *thr_d, float *g_conv_w_d, float *g_thr_d, void *workspace_d,
+                  size_t workspace_bytes, void *stream) {
     if (!s || !images_d || !gbin_d || !conv_w_d || !thr_d || !g_conv_w_d || !g_thr_d || !workspace_d)
         return NNUE_ERR_INVALID_ARG;
     const InPlan pl = plan_input_bwd(*s);
@@ -229,8 +234,8 @@ int nnue_conv_bwd(const nnue_shape *s, const float *images_d, const float *gbin_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float *partial = static_cast<float *>(workspace_d);
     int rc;
-    if (pl.CH == 2) rc = launch_conv_bwd<2, 16>(*s, pl, images_d, gbin_d, conv_w_d, thr_d, partial, st);
-    else rc = launch_conv_bwd<4, 8>(*s, pl, images_d, gbin_d, conv_w_d, thr_d, partial, st);
+    if (pl.CH == 2) rc = launch_conv_bwd<2, 16>(*s, pl, images_d, gbin_d, xpad_d, conv_w_d, thr_d, partial, st);
+    else rc = launch_conv_bwd<4, 8>(*s, pl, images_d, gbin_d, xpad_d, conv_w_d, thr_d, partial, st);
     if (rc != NNUE_OK) return rc;
     input_bwd_fold_kernel<<<ceil_div(s->C * 28, 128), 128, 0, st>>>(s->C, pl.grid, partial, g_conv_w_d, g_thr_d);
     NNUE_CHECK_LAUNCH("input_bwd_fold_kernel");
@@ -252,7 +257,7 @@ int nnue_input_bwd(const nnue_shape *s, const float *images_d, const uint32_t *b
         float *gbin = reinterpret_cast<float *>(ws);
         const int rc = nnue_ft_bwd_gbin(s, bits_s_d, ft_w_d, g_ft_d, gbin, stream);
         if (rc != NNUE_OK) return rc;
-        return nnue_conv_bwd(s, images_d, gbin, conv_w_d, thr_d, g_conv_w_d, g_thr_d, ws + plane,
+        return nnue_conv_bwd(s, images_d, gbin, nullptr, conv_w_d, thr_d, g_conv_w_d, g_thr_d, ws + plane,
                              workspace_bytes - plane, stream);
     }
     // General shapes: recompute the pre-threshold activations into scratch, then the index-driven pair.

@@ -195,14 +195,15 @@ inline size_t ws_extract_bwd(const nnue_shape &s) { return (size_t)exb_grid_x(s)
 
 // ---- input gradient: dense value gradient (ft.cu) + conv gradient from TMA-staged images (input_bwd.cu) ----
 // conv-gradient variant 0: 16 warps x 2 channels of a cell word per warp; 1: 8 warps x 4 channels
-constexpr int kInMaxStages = 8;
+constexpr int kInMaxStages = 16;  // ring depth: HBM latency under load is ~1 us, a sample is consumed in ~0.3 us
+constexpr int kInHeader = 256;    // bytes of mbarriers in front of the ring (2 x kInMaxStages x 8)
 constexpr int kInLag = 2;        // the producer refills a stage this many samples after its release
 constexpr size_t kMaxSmemOptin = 227 * 1024;  // sm_100: opt-in dynamic shared memory per CTA
 struct InPlan {
     bool fused;
     int CH, WARPS;     // channels of one cell word owned by a warp; warps per CTA (lane 0 of warp 0 is the TMA producer)
     int NH, nq, grid, ST;
-    int stage_floats;  // 3 x (H*W + 4 pad) image planes | dval row [PP], padded to 128 B
+    int stage_floats;  // 3 x (H*W + 4 pad) image planes | g_bin row [PP] | activation row [PP], padded to 128 B
     int stage_off;     // byte offset of stage 0 in dynamic shared memory
     size_t smem;
 };
@@ -215,11 +216,11 @@ inline InPlan plan_input_bwd(const nnue_shape &s) {
     const int units = ceil_div(s.C, p.CH) * s.CW;
     p.NH = ceil_div(units, p.WARPS);
     if (p.NH > 8) return p;
-    p.stage_floats = (int)align_up((size_t)(3 * (HW + 4) + s.PP), 32);
-    p.stage_off = (int)align_up(128 + ((size_t)s.C * 28 + align_up((size_t)s.C, 4) + 32 * 28) * 4, 128);
+    p.stage_floats = (int)align_up((size_t)(3 * (HW + 4) + 2 * s.PP), 32);  // g_bin row + optional activation row
+    p.stage_off = (int)align_up(kInHeader + ((size_t)s.C * 28 + align_up((size_t)s.C, 4) + 32 * 28) * 4, 128);
     const size_t room = kMaxSmemOptin - (size_t)p.stage_off;
     int ST = (int)(room / ((size_t)p.stage_floats * 4));
-    if (ST > 6) ST = 6;
+    if (ST > kInMaxStages) ST = kInMaxStages;
     if (ST < 2) return p;
     p.ST = ST;
     p.nq = kNumSMs / p.NH;
@@ -227,6 +228,35 @@ inline InPlan plan_input_bwd(const nnue_shape &s) {
     p.grid = p.nq * p.NH;
     p.smem = (size_t)p.stage_off + (size_t)ST * p.stage_floats * 4;
     p.fused = true;
+    return p;
+}
+
+// ---- extraction forward, TMA-staged form (extract.cu) -------------------------------------------------
+constexpr int kExtWarps = 8;   // warps per CTA (lane 0 of warp 0 is the TMA producer)
+constexpr int kExtCH = 4;      // channels of one cell word owned by a warp (their taps live in registers)
+struct ExtPlan {
+    bool ok;
+    int NH, nq, grid, ST;
+    int stage_floats;  // 3 x (H*W + 4 pad) image planes, padded to 128 B
+    size_t smem;
+};
+inline ExtPlan plan_extract_tma(const nnue_shape &s) {
+    ExtPlan p{};
+    const long long HW = 1LL * s.H * s.W;
+    if (!get_option(kOptExtractTma) || HW % 4 || HW > 16384) return p;
+    const int units = ceil_div(s.C, kExtCH) * s.CW;
+    p.NH = ceil_div(units, kExtWarps);
+    if (p.NH > 8) return p;
+    p.stage_floats = (int)align_up((size_t)(3 * (HW + 4)), 32);
+    int ST = (int)((kMaxSmemOptin - kInHeader) / ((size_t)p.stage_floats * 4));
+    if (ST > kInMaxStages) ST = kInMaxStages;
+    if (ST < 2) return p;
+    p.ST = ST;
+    p.nq = kNumSMs / p.NH;
+    if (p.nq > s.B) p.nq = s.B;
+    p.grid = p.nq * p.NH;
+    p.smem = kInHeader + (size_t)ST * p.stage_floats * 4;
+    p.ok = true;
     return p;
 }
 
@@ -259,22 +289,30 @@ inline size_t ws_input_bwd(const nnue_shape &s) {
 int extract_xpad(const nnue_shape &s, const float *images, const float *conv_w, const float *thr, float *xpad,
                  cudaStream_t st);
 // ---- feature-transformer contractions on the tensor cores (ft_mma.cu) ------------------------------
-constexpr int kMmaThreads = 128;
+constexpr int kMmaFwdThreads = 512;   // forward: 16 warps per persistent CTA
+constexpr int kMmaGbinThreads = 512;  // value gradient: 16 warps per persistent CTA
+constexpr int kMmaDwWarps = 8;        // weight gradient: words (warps) per CTA, two CTAs per SM
+constexpr int kGbinSplit = 8;         // value gradient: position slices (one persistent CTA group each)
 struct MmaPlan {
     bool ok;
     int n_chunks, chunk_blocks;  // weight gradient: K-chunks of `chunk_blocks` 32-sample blocks
 };
+inline size_t mma_fwd_smem(const nnue_shape &s) { return 128 + (size_t)(s.PP / 16) * 3 * 512; }
+inline size_t mma_gbin_smem(const nnue_shape &s) {
+    return 128 + (size_t)ceil_div(s.NW, kGbinSplit) * 4 * 3 * (s.L1 / 32) * 512;
+}
 inline MmaPlan plan_ft_mma(const nnue_shape &s) {
     MmaPlan m{};
     if (!get_option(kOptFtMma) || !dense_shape_ok(s)) return m;
-    int want = ceil_div(16 * kNumSMs, s.NW * (s.L1 / 16));  // ~16 warps per SM in flight (L1/16 warps share a word)
+    if (mma_fwd_smem(s) > kMaxSmemOptin || mma_gbin_smem(s) > kMaxSmemOptin) return m;  // table slice must fit
+    // two resident CTAs per SM, two waves
+    const int ctas_per_chunk = ceil_div(s.NW, kMmaDwWarps) * (s.L1 / 16);
+    int want = ceil_div(4 * kNumSMs, ctas_per_chunk);
     if (want < 1) want = 1;
     m.chunk_blocks = ceil_div(s.BW, want);
+    if (m.chunk_blocks > 32) m.chunk_blocks = 32;  // 96 KB of fragments per CTA at most
     m.n_chunks = ceil_div(s.BW, m.chunk_blocks);
-    while ((size_t)m.n_chunks * s.P * s.L1 * 4 > ((size_t)256 << 20) && m.n_chunks > 1) {
-        m.chunk_blocks *= 2;
-        m.n_chunks = ceil_div(s.BW, m.chunk_blocks);
-    }
+    if ((size_t)m.n_chunks * s.P * s.L1 * 4 > ((size_t)1 << 30)) return m;
     m.ok = true;
     return m;
 }

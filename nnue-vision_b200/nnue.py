@@ -255,6 +255,11 @@ class _NNUEForward(torch.autograd.Function):
         return (None, None, None, None) + tuple(g)
 
 
+# Training keeps the pre-threshold conv activations ([B, PP] fp32) for the threshold gradient instead of
+# recomputing them in the backward (measured faster on B200; set False to trade the time for the memory).
+STORE_ACTIVATIONS = True
+
+
 def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_out=None, marks=None):
     """One whole training step of the hot path -- forward, mean cross-entropy, every parameter gradient --
     in seven launches: extract, feature transformer, fused head step (forward + loss + backward), the two
@@ -271,9 +276,11 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
     g_thr, g_conv_w, g_ft_w, g_ft_b, g_w1, g_b1, g_w2, g_b2, g_w3, g_b3 = grads
     bits_s = _empty((shape.B, shape.NW), torch.int32, images)
     bits_t = _empty((shape.PP, shape.BW), torch.int32, images) if L.nnue_wants_transposed_bits(sp) else None
+    # the dense conv-gradient kernel takes the pre-threshold activations from the forward when asked to
+    xpad = _empty((shape.B, shape.PP), torch.float32, images) if STORE_ACTIVATIONS and L.nnue_input_bwd_is_dense(sp) else None
     _mark(marks, "start")
-    check(L.nnue_extract_fwd(sp, dptr(images), dptr(conv_w), dptr(thr), dptr(bits_s), dptr(bits_t), None, None, None,
-                             st))
+    check(L.nnue_extract_fwd(sp, dptr(images), dptr(conv_w), dptr(thr), dptr(bits_s), dptr(bits_t), dptr(xpad), None,
+                             None, st))
     _mark(marks, "extract_fwd")
     ft_out = _empty((shape.B, shape.L1), torch.float32, images)
     ws_bytes = _lib.workspace_bytes(shape)
@@ -290,7 +297,7 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
         check(L.nnue_ft_bwd(sp, dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(gbin), dptr(ws),
                             ws_bytes, st))
         _mark(marks, "ft_bwd")
-        check(L.nnue_conv_bwd(sp, dptr(images), dptr(gbin), dptr(conv_w), dptr(thr), dptr(g_conv_w), dptr(g_thr),
+        check(L.nnue_conv_bwd(sp, dptr(images), dptr(gbin), dptr(xpad), dptr(conv_w), dptr(thr), dptr(g_conv_w), dptr(g_thr),
                               dptr(ws), ws_bytes, st))
         _mark(marks, "conv_bwd")
         return loss_out, grads
@@ -301,7 +308,7 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
         gbin = _empty((shape.B, shape.PP), torch.float32, images)
         check(L.nnue_ft_bwd_gbin(sp, dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(gbin), st))
         _mark(marks, "ft_bwd_gbin")
-        check(L.nnue_conv_bwd(sp, dptr(images), dptr(gbin), dptr(conv_w), dptr(thr), dptr(g_conv_w), dptr(g_thr),
+        check(L.nnue_conv_bwd(sp, dptr(images), dptr(gbin), dptr(xpad), dptr(conv_w), dptr(thr), dptr(g_conv_w), dptr(g_thr),
                               dptr(ws), ws_bytes, st))
         _mark(marks, "conv_bwd")
     else:

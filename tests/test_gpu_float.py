@@ -194,7 +194,10 @@ def test_ft_forward_staging_modes_agree(mode):
     assert_close(out[torch.as_tensor(~amb).cuda()], ref["ft_out"][torch.as_tensor(~amb)], "ft_out")
 
 
-@pytest.mark.parametrize("options", [dict(ft_mma=0), dict(ft_mma=0, ft_bwd_both=0), dict(ft_mma=0, ft_bwd_dw_owner=0), dict(ft_mma=0, input_bwd_fused=0), dict(input_bwd_variant=0),
+OPTION_DEFAULTS = {"extract_tma": 0}
+
+
+@pytest.mark.parametrize("options", [dict(extract_tma=1), dict(ft_mma=0), dict(ft_mma=0, ft_bwd_both=0), dict(ft_mma=0, ft_bwd_dw_owner=0), dict(ft_mma=0, input_bwd_fused=0), dict(input_bwd_variant=0),
                                      dict(head_fused=0), dict(ft_mma=0, ft_bwd_dw_owner=0, input_bwd_fused=0, head_fused=0)],
                          ids=str)
 @pytest.mark.parametrize("name", ["D", "T", "big_into_small"])
@@ -218,7 +221,7 @@ def test_backward_kernel_variants_agree(name, options):
         torch.cuda.synchronize()
     finally:
         for k in options:
-            lib.set_option(k, 1)
+            lib.set_option(k, OPTION_DEFAULTS.get(k, 1))
     assert_close(loss, ref["loss"], "loss")
     for k, g in ref["grads"].items():
         assert_close(dict(model.named_parameters())[k].grad, g, "grad " + k)
