@@ -12,6 +12,7 @@ synthetic CIFAR-shaped input, config `train_nnue_default.py` at batch 16384 per 
 Prints ONE JSON line on rank 0.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -50,6 +51,14 @@ def parse_args():
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="library tuning knob (nnue_set_option), e.g. --opt input_bwd_variant=1")
     return ap.parse_args()
+
+
+def tensor_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    try:
+        return float(json.loads(p.read_text())["bf16_tflops_sustained"])
+    except Exception:
+        return 1400.0  # fallback (B200_PROFILING.md: sustained bf16)
 
 
 def peaks():
@@ -378,25 +387,43 @@ def run_b200(args):
     nnz_total = int(sum(int(torch.bitwise_and(bits >> k, 1).sum()) for k in range(32)))
     L1, F = w["L1"], shape.F
     img_bytes = B * 3 * w["image"] * w["image"] * 4
-    algo = {  # algorithmic bytes per launch, SURVEY.md section 8(d)
-        "ft_fwd": nnz_total * L1 * 4 + B * L1 * 4 + nnz_total * 4,
-        "ft_bwd_dw": nnz_total * L1 * 4 + F * L1 * 4,
-        # both FT gradients in one kernel: g_ft rows per active position for dW + table rows for dval + outputs
-        "ft_bwd": 2 * nnz_total * L1 * 4 + F * L1 * 4 + B * L1 * 4 + B * shape.PP * 4,
-        # value gradient: W row reads per active position + g_ft read + g_bin write
-        "ft_bwd_gbin": nnz_total * L1 * 4 + B * L1 * 4 + B * shape.PP * 4,
-        # conv / threshold gradient: image read + g_bin read
-        "conv_bwd": img_bytes + B * shape.PP * 4,
+    row_bytes = B * shape.PP * 4  # one fp32 value per (sample, padded position): g_bin, stored activations
+    # algorithmic bytes per launch
+    algo = {
+        "extract_fwd": img_bytes + B * shape.NW * 4 + row_bytes,          # images -> bitmask + stored activations
+        "ft_fwd": nnz_total * L1 * 4 + B * L1 * 4 + nnz_total * 4,        # row reads + out + indices
+        "ft_bwd_dw": nnz_total * L1 * 4 + F * L1 * 4,                      # g_ft row per active pair + dW
+        "ft_bwd_gbin": nnz_total * L1 * 4 + B * L1 * 4 + row_bytes,       # table row per active pair + g_ft + g_bin
+        "ft_bwd": 2 * nnz_total * L1 * 4 + F * L1 * 4 + B * L1 * 4 + row_bytes,
+        "conv_bwd": img_bytes + 2 * row_bytes,                            # images + g_bin + stored activations
         "input_bwd": nnz_total * L1 * 4 + B * L1 * 4 + img_bytes + B * shape.NW * 4,
-        "extract_fwd": img_bytes + B * shape.NW * 4,
+        "head_train": 2 * B * L1 * 4,
     }
+    # tensor-core work actually issued by the bf16-split contractions (2 * M * N * K * number of term products)
+    mma_flops = {"ft_fwd": 2.0 * B * shape.PP * L1 * 3, "ft_bwd_dw": 2.0 * B * shape.PP * L1 * 3,
+                 "ft_bwd_gbin": 2.0 * B * shape.PP * L1 * 6}
+    kernel_of = {"extract_fwd": "extract_fwd_fixed_kernel", "ft_fwd": "ft_fwd_mma_kernel", "head_train": "head_train_kernel",
+                 "ft_bwd_dw": "ft_bwd_dw_mma_kernel", "ft_bwd_gbin": "ft_bwd_gbin_mma_kernel", "conv_bwd": "conv_bwd_kernel"}
+    traffic = {}
+    tp = ROOT / "profiles" / "traffic.json"  # dram bytes per launch from the committed ncu --set full capture
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text())
+        except Exception:
+            traffic = {}
     peak, peak_src = peaks()
+    tpeak = tensor_peak()
     roofs = {}
-    for k, b in algo.items():
+    for k, nbytes in algo.items():
         if k in stages and stages[k] > 0:
-            ach = b / (stages[k] * 1e-3) / 1e9
+            ach = nbytes / (stages[k] * 1e-3) / 1e9
+            kern = kernel_of.get(k)
             roofs[k] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                        "traffic": None, "ms": stages[k], "algorithmic_bytes": b}
+                        "traffic": traffic.get(kern), "ms": stages[k], "algorithmic_bytes": nbytes, "kernel": kern}
+            if k in mma_flops and _lib.lib().nnue_ft_uses_mma(ctypes.byref(shape)):
+                tf = mma_flops[k] / (stages[k] * 1e-3) / 1e12
+                roofs[k]["tensor"] = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                                      "note": "bf16 mma.sync, 3 (6) exact split-term products per fp32 product"}
     dominant = max(roofs, key=lambda k: roofs[k]["ms"]) if roofs else None
 
     line = {
@@ -416,8 +443,10 @@ def run_b200(args):
         "stages_ms": stages,
     }
     if dominant:
-        line["roofline"] = dict(roofs[dominant], kernel=dominant, peak_source=peak_src,
-                                note="table (205 KB) is shared-memory/L2 resident at this config: algorithmic bytes are on-chip traffic and may exceed the HBM peak; see profiles/ for ncu dram bytes")
+        line["roofline"] = dict(roofs[dominant], stage=dominant, peak_source=peak_src,
+                                note="stage = one C-ABI call = the named kernel + its small fold; feature-transformer stages "
+                                     "work on a 205 KB table that is on-chip, so their algorithmic bytes are not HBM bytes "
+                                     "(roofline_all carries their tensor-pipe figures); traffic = ncu dram bytes per launch")
         line["roofline_all"] = roofs
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_training(w, args.cpu_seconds)

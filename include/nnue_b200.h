@@ -76,6 +76,8 @@ unsigned long long nnue_launch_count(int reset);
  *   "input_bwd_fused" 1 (default) = dense value-gradient + conv-gradient kernels where the shape
  *                     allows, 0 = always the index-driven kernel pair.
  *   "input_bwd_variant" conv-gradient kernel: 0 = 16 warps x 2 channels, 1 (default) = 8 warps x 4.
+ *   "extract_fixed"   1 (default) = extraction forward specialised on the channel count (4/8/16/32) with one
+ *                     cell word per warp, 0 = the generic kernel.
  *   "extract_tma"     1 = TMA-staged extraction forward for CIFAR-sized images, 0 (default) = direct loads
  *                     (measured faster at config D: profiles/).
  *   "ft_mma"          1 (default) = tensor-core (bf16-split, fp32-exact products) feature-transformer
@@ -220,6 +222,7 @@ int nnue_wants_transposed_bits(const nnue_shape *s);
  * gbin_d [B][PP] as nnue_ft_bwd_gbin.  A lane keeps its table row and that row's gradient in registers.
  */
 int nnue_ft_bwd_is_fused(const nnue_shape *s);
+int nnue_ft_uses_mma(const nnue_shape *s);  /* 1 when the tensor-core contractions serve this shape */
 int nnue_ft_bwd(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w_d, const float *g_ft_d,
                 float *g_w_d, float *g_b_d, float *gbin_d, void *workspace_d, size_t workspace_bytes,
                 void *stream);
@@ -260,7 +263,8 @@ int nnue_extract_bwd(const nnue_shape *s, const float *images_d, const uint32_t 
 int nnue_input_bwd_is_dense(const nnue_shape *s);  /* 1 when the two dense kernels below serve this shape */
 /* dense half 1: g_bin[b,p] = bit(b,p) ? <W[min(p,F-1)], g_ft[b]> : 0, gbin_d [B][PP] f32 */
 int nnue_ft_bwd_gbin(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w_d,
-                     const float *g_ft_d, float *gbin_d, void *stream);
+                     const float *g_ft_d, float *gbin_d, void *workspace_d, size_t workspace_bytes,
+                     void *stream);  /* with a workspace: tensor-core form; workspace_d may be NULL */
 /* dense half 2: g_conv_w = conv2d_weight(images, g_bin); g_thr from the pre-threshold activations:
  * xpad_d [B][PP] as written by nnue_extract_fwd, or NULL to recompute them from the image taps */
 int nnue_conv_bwd(const nnue_shape *s, const float *images_d, const float *gbin_d, const float *xpad_d,

@@ -1121,6 +1121,31 @@ int nnue_ft_bwd_indexed(int B, int K, int F, int L1, const int64_t *idx_d, const
     return NNUE_OK;
 }
 
+// tensor-core weight/bias gradient; workspace layout: wfrag (value gradient) | gfrag | bias partials | partials | alias
+static int ft_bwd_dw_mma_path(const nnue_shape *s, const uint32_t *bits_s_d, const float *g_ft_d, float *g_w_d, float *g_b_d,
+                              void *workspace_d, size_t workspace_bytes, cudaStream_t st) {
+    if (workspace_bytes < ws_ft_bwd_mma(*s)) return NNUE_ERR_WORKSPACE;
+    const MmaPlan mp = plan_ft_mma(*s);
+    char *ws = static_cast<char *>(workspace_d) + align_up(mma_wfrag_bytes(*s), 256);
+    uint4 *gfrag = reinterpret_cast<uint4 *>(ws); ws += align_up(mma_gfrag_bytes(*s), 256);
+    float *bias_partial = reinterpret_cast<float *>(ws); ws += align_up((size_t)mp.n_chunks * s->L1 * 4, 256);
+    float *partial = reinterpret_cast<float *>(ws);
+    float *alias = partial + (size_t)mp.n_chunks * s->P * s->L1;
+    int n_chunks = 0;
+    const int rc = launch_ft_bwd_dw_mma(*s, bits_s_d, g_ft_d, gfrag, partial, bias_partial, &n_chunks, st);
+    if (rc != NNUE_OK) return rc;
+    fold_partials_kernel<<<ceil_div(s->L1, 128), 128, 0, st>>>(s->L1, n_chunks, bias_partial, g_b_d);
+    NNUE_CHECK_LAUNCH("fold_partials_kernel");
+    const long long n = 1LL * (s->P > s->F - 1 ? s->P : s->F - 1) * (s->L1 / 4);
+    ft_bwd_dw_fold_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(*s, n_chunks, partial, g_w_d, alias);
+    NNUE_CHECK_LAUNCH("ft_bwd_dw_fold_kernel");
+    ft_bwd_dw_fold_last_kernel<<<ceil_div(s->L1 / 4, 32), 256, 0, st>>>(*s, alias, g_w_d);
+    NNUE_CHECK_LAUNCH("ft_bwd_dw_fold_last_kernel");
+    return NNUE_OK;
+}
+
+int nnue_ft_uses_mma(const nnue_shape *s) { return s && plan_ft_mma(*s).ok ? 1 : 0; }
+
 int nnue_ft_bwd_is_fused(const nnue_shape *s) {
     return s && (plan_ft_mma(*s).ok || plan_ft_bwd_both(*s).ok) && plan_input_bwd(*s).fused ? 1 : 0;
 }
@@ -1129,26 +1154,11 @@ int nnue_ft_bwd(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w
                 float *g_b_d, float *gbin_d, void *workspace_d, size_t workspace_bytes, void *stream) {
     if (!s || !bits_s_d || !ft_w_d || !g_ft_d || !g_w_d || !g_b_d || !gbin_d || !workspace_d) return NNUE_ERR_INVALID_ARG;
     if (plan_ft_mma(*s).ok) {  // tensor-core path
-        if (workspace_bytes < ws_ft_bwd_mma(*s)) return NNUE_ERR_WORKSPACE;
-        cudaStream_t st = static_cast<cudaStream_t>(stream);
-        const MmaPlan mp = plan_ft_mma(*s);
-        char *ws = static_cast<char *>(workspace_d);
-        uint4 *wfrag = reinterpret_cast<uint4 *>(ws); ws += align_up(mma_wfrag_bytes(*s), 256);
-        uint4 *gfrag = reinterpret_cast<uint4 *>(ws); ws += align_up(mma_gfrag_bytes(*s), 256);
-        float *bias_partial = reinterpret_cast<float *>(ws); ws += align_up((size_t)mp.n_chunks * s->L1 * 4, 256);
-        float *partial = reinterpret_cast<float *>(ws);
-        float *alias = partial + (size_t)mp.n_chunks * s->P * s->L1;
-        int n_chunks = 0;
-        int rc = launch_ft_bwd_dw_mma(*s, bits_s_d, g_ft_d, gfrag, partial, bias_partial, &n_chunks, st);
+        const int rc = ft_bwd_dw_mma_path(s, bits_s_d, g_ft_d, g_w_d, g_b_d, workspace_d, workspace_bytes,
+                                          static_cast<cudaStream_t>(stream));
         if (rc != NNUE_OK) return rc;
-        fold_partials_kernel<<<ceil_div(s->L1, 128), 128, 0, st>>>(s->L1, n_chunks, bias_partial, g_b_d);
-        NNUE_CHECK_LAUNCH("fold_partials_kernel");
-        const long long n = 1LL * (s->P > s->F - 1 ? s->P : s->F - 1) * (s->L1 / 4);
-        ft_bwd_dw_fold_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(*s, n_chunks, partial, g_w_d, alias);
-        NNUE_CHECK_LAUNCH("ft_bwd_dw_fold_kernel");
-        ft_bwd_dw_fold_last_kernel<<<ceil_div(s->L1 / 4, 32), 256, 0, st>>>(*s, alias, g_w_d);
-        NNUE_CHECK_LAUNCH("ft_bwd_dw_fold_last_kernel");
-        return launch_ft_bwd_gbin_mma(*s, bits_s_d, ft_w_d, g_ft_d, wfrag, gbin_d, st);
+        return launch_ft_bwd_gbin_mma(*s, bits_s_d, ft_w_d, g_ft_d, static_cast<uint4 *>(workspace_d), gbin_d,
+                                      static_cast<cudaStream_t>(stream));
     }
     const FbPlan fb = plan_ft_bwd_both(*s);
     if (!fb.ok) return NNUE_ERR_UNSUPPORTED;
@@ -1176,8 +1186,10 @@ int nnue_wants_transposed_bits(const nnue_shape *s) { return s && plan_ft_bwd_dw
 int nnue_ft_bwd_dw(const nnue_shape *s, const uint32_t *bits_s_d, const uint32_t *bits_t_d, const float *g_ft_d,
                    float *g_w_d, float *g_b_d, void *workspace_d, size_t workspace_bytes, void *stream) {
     if (!s || !g_ft_d || !g_w_d || !g_b_d || !workspace_d) return NNUE_ERR_INVALID_ARG;
-    if (workspace_bytes < ws_ft_bwd_dw(*s)) return NNUE_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (plan_ft_mma(*s).ok && bits_s_d)
+        return ft_bwd_dw_mma_path(s, bits_s_d, g_ft_d, g_w_d, g_b_d, workspace_d, workspace_bytes, st);
+    if (workspace_bytes < ws_ft_bwd_dw(*s)) return NNUE_ERR_WORKSPACE;
     const OwnPlan own = plan_ft_bwd_dw_owner(*s);
     if (own.ok) {
         if (!bits_s_d) return NNUE_ERR_INVALID_ARG;

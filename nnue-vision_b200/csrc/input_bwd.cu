@@ -217,9 +217,12 @@ extern "C" {
 int nnue_input_bwd_is_dense(const nnue_shape *s) { return s && plan_input_bwd(*s).fused ? 1 : 0; }
 
 int nnue_ft_bwd_gbin(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w_d, const float *g_ft_d,
-                     float *gbin_d, void *stream) {
+                     float *gbin_d, void *workspace_d, size_t workspace_bytes, void *stream) {
     if (!s || !bits_s_d || !ft_w_d || !g_ft_d || !gbin_d) return NNUE_ERR_INVALID_ARG;
     if (!plan_input_bwd(*s).fused) return NNUE_ERR_UNSUPPORTED;
+    if (plan_ft_mma(*s).ok && workspace_d && workspace_bytes >= mma_wfrag_bytes(*s))  // tensor-core contraction
+        return launch_ft_bwd_gbin_mma(*s, bits_s_d, ft_w_d, g_ft_d, static_cast<uint4 *>(workspace_d), gbin_d,
+                                      static_cast<cudaStream_t>(stream));
     return launch_ft_bwd_dval_dense(*s, bits_s_d, ft_w_d, g_ft_d, gbin_d, static_cast<cudaStream_t>(stream));
 }
 
@@ -255,7 +258,7 @@ int nnue_input_bwd(const nnue_shape *s, const float *images_d, const uint32_t *b
     const InPlan pl = plan_input_bwd(*s);
     if (pl.fused) {
         float *gbin = reinterpret_cast<float *>(ws);
-        const int rc = nnue_ft_bwd_gbin(s, bits_s_d, ft_w_d, g_ft_d, gbin, stream);
+        const int rc = nnue_ft_bwd_gbin(s, bits_s_d, ft_w_d, g_ft_d, gbin, nullptr, 0, stream);
         if (rc != NNUE_OK) return rc;
         return nnue_conv_bwd(s, images_d, gbin, nullptr, conv_w_d, thr_d, g_conv_w_d, g_thr_d, ws + plane,
                              workspace_bytes - plane, stream);

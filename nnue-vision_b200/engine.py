@@ -29,8 +29,8 @@ class NNUEEvaluator:
         self.close()
 
     def close(self):
-        if getattr(self, "_h", None) and self._h.value:
-            _lib.lib().nnue_q_free(self._h)
+        if getattr(self, "_h", None) and self._h.value and _lib is not None and _lib._lib is not None:
+            _lib.lib().nnue_q_free(self._h)  # (module globals are already gone at interpreter shutdown)
             self._h = ctypes.c_void_p()
 
     def load_model(self, path) -> bool:

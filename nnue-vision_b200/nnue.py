@@ -292,7 +292,17 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
                             dptr(w3), dptr(b3), dptr(loss_out), dptr(g_ft), dptr(g_w1), dptr(g_b1), dptr(g_w2),
                             dptr(g_b2), dptr(g_w3), dptr(g_b3), dptr(ws), ws_bytes, st))
     _mark(marks, "head_train")
-    if L.nnue_ft_bwd_is_fused(sp):  # small tables: both feature-transformer gradients in one pass over g_ft
+    if L.nnue_ft_uses_mma(sp) and L.nnue_input_bwd_is_dense(sp):  # small tables: tensor-core contractions
+        check(L.nnue_ft_bwd_dw(sp, dptr(bits_s), None, dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(ws), ws_bytes, st))
+        _mark(marks, "ft_bwd_dw")
+        gbin = _empty((shape.B, shape.PP), torch.float32, images)
+        check(L.nnue_ft_bwd_gbin(sp, dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(gbin), dptr(ws), ws_bytes, st))
+        _mark(marks, "ft_bwd_gbin")
+        check(L.nnue_conv_bwd(sp, dptr(images), dptr(gbin), dptr(xpad), dptr(conv_w), dptr(thr), dptr(g_conv_w), dptr(g_thr),
+                              dptr(ws), ws_bytes, st))
+        _mark(marks, "conv_bwd")
+        return loss_out, grads
+    if L.nnue_ft_bwd_is_fused(sp):  # both feature-transformer gradients in one CUDA-core pass over g_ft
         gbin = _empty((shape.B, shape.PP), torch.float32, images)
         check(L.nnue_ft_bwd(sp, dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(gbin), dptr(ws),
                             ws_bytes, st))
@@ -306,7 +316,7 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
     _mark(marks, "ft_bwd_dw")
     if L.nnue_input_bwd_is_dense(sp):
         gbin = _empty((shape.B, shape.PP), torch.float32, images)
-        check(L.nnue_ft_bwd_gbin(sp, dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(gbin), st))
+        check(L.nnue_ft_bwd_gbin(sp, dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(gbin), None, 0, st))
         _mark(marks, "ft_bwd_gbin")
         check(L.nnue_conv_bwd(sp, dptr(images), dptr(gbin), dptr(xpad), dptr(conv_w), dptr(thr), dptr(g_conv_w), dptr(g_thr),
                               dptr(ws), ws_bytes, st))

@@ -48,6 +48,25 @@ def main():
     print(out)
     if len(sys.argv) > 2:
         open(sys.argv[2], 'w').write(out + '\n')
+    if len(sys.argv) > 3:  # traffic.json: kernel function name -> dram bytes (read + write) per launch
+        import json
+        import re
+        traffic = {}
+        ir, iw = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+        unit_r, unit_w = rows[1][ir], rows[1][iw]
+        scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+        for r in rows[2:]:
+            m = re.search(r'(\w+)\s*(<|\()', r[hdr.index('Kernel Name')].replace('void ', '').replace('nnue::', ''))
+            if m:
+                traffic[m.group(1)] = float(r[ir].replace(',', '')) * scale.get(unit_r, 1.0) + \
+                    float(r[iw].replace(',', '')) * scale.get(unit_w, 1.0)
+        old = {}
+        try:
+            old = json.load(open(sys.argv[3]))
+        except Exception:
+            pass
+        old.update(traffic)
+        json.dump(old, open(sys.argv[3], 'w'), indent=1, sort_keys=True)
 
 
 if __name__ == '__main__':
