@@ -66,8 +66,8 @@ __device__ __forceinline__ int table_row_of(const nnue_shape &s, int pp) {
 // ---- operand formatting ----------------------------------------------------------------------------------
 // B operand with k running over ROWS of a row-major fp32 matrix src[rows][L1] and n over its columns
 // (forward: rows = padded positions of the table; weight gradient: rows = samples of g_ft).
-// out[((nbp * n_kb + kb) * 3 + s) * 32 + lane] = uint4 {b0, b1 of column block 2 nbp, b0, b1 of 2 nbp + 1}:
-// everything one 16-column group needs is contiguous.
+// out[(((grp * n_kb + kb) * 3 + s) * kMmaGP + q) * 32 + lane] = uint4 {b0, b1 of column block 2 nbp, b0, b1 of
+// 2 nbp + 1} with nbp = grp * kMmaGP + q: everything one 32-column group needs is contiguous.
 template <bool TABLE>
 __global__ void mma_format_rows_kernel(const nnue_shape s, const float *__restrict__ src, int nrows, int n_kb,
                                        uint4 *__restrict__ out) {
@@ -98,7 +98,8 @@ __global__ void mma_format_rows_kernel(const nnue_shape s, const float *__restri
     }
 #pragma unroll
     for (int sp = 0; sp < 3; ++sp)
-        out[(((size_t)nbp * n_kb + kb) * 3 + sp) * 32 + lane] = make_uint4(packed[sp][0], packed[sp][1], packed[sp][2], packed[sp][3]);
+        out[((((size_t)(nbp / kMmaGP) * n_kb + kb) * 3 + sp) * kMmaGP + nbp % kMmaGP) * 32 + lane] =
+            make_uint4(packed[sp][0], packed[sp][1], packed[sp][2], packed[sp][3]);
 }
 
 // B operand with k running over the COLUMNS of the table and n over padded positions (value gradient):
@@ -146,78 +147,64 @@ __device__ __forceinline__ void bits_to_afrag(uint32_t (&a)[4], uint32_t w_lo, u
 }
 
 // ---- forward: out[b] = bias + bits[b] . Wc ------------------------------------------------------------------
-// A persistent CTA owns one group of 16 columns: its slice of the split table (PP/16 k-steps x 3 terms x
-// 512 B = 96 KB at config D) sits in shared memory; each warp takes 32-sample tiles (two m16 tiles),
-// K runs over the padded positions one bitmask word (two k16 steps) at a time.
+// A persistent CTA owns one group of 32 columns: its slice of the split table (PP/16 k-steps x 3 terms x
+// 1 KB = 192 KB at config D) sits in shared memory; each warp takes 16-sample tiles (one m16 tile),
+// K runs over the padded positions one bitmask word (two k16 steps) at a time.  Every A fragment built
+// from the bitmask feeds 12 MMAs (the integer pipe that expands bits to bf16 is the scarce resource:
+// ncu on the 16-column version showed math-pipe throttle, not tensor-pipe, as the top stall).
 __global__ void __launch_bounds__(kMmaFwdThreads, 1)
 ft_fwd_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const uint4 *__restrict__ wfrag,
                   const float *__restrict__ bias, float *__restrict__ out) {
+    constexpr int GP = kMmaGP, NB = 2 * GP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-    const int NBP_ALL = s.L1 / 16, n_kb = s.PP / 16;
-    const int nbp = blockIdx.x % NBP_ALL, cta = blockIdx.x / NBP_ALL, ctas = gridDim.x / NBP_ALL;
-    const uint4 *sf = stage_fragments(smem_raw, wfrag + (size_t)nbp * n_kb * 3 * 32, (uint32_t)n_kb * 3 * 512u) + lane;
-    const int col = nbp * 16 + t * 2;
-    const float2 bv0 = __ldg(reinterpret_cast<const float2 *>(bias + col));
-    const float2 bv1 = __ldg(reinterpret_cast<const float2 *>(bias + col + 8));
-    const int ntiles = ceil_div(s.B, 32), wpc = kMmaFwdThreads / 32;
+    const int groups = s.L1 / (16 * GP), n_kb = s.PP / 16;
+    const int grp = blockIdx.x % groups, cta = blockIdx.x / groups, ctas = gridDim.x / groups;
+    const uint4 *sf = stage_fragments(smem_raw, wfrag + (size_t)grp * n_kb * 3 * GP * 32, (uint32_t)n_kb * 3 * GP * 512u) + lane;
+    const int col0 = grp * 16 * GP + t * 2;
+    // 16-sample tiles (one m16): with 32-sample tiles only half of the warps of the machine would have work
+    const int ntiles = ceil_div(s.B, 16), wpc = kMmaFwdThreads / 32;
     for (int tile = cta * wpc + warp; tile < ntiles; tile += ctas * wpc) {
-        int rows[2][2];
+        const int r0 = tile * 16 + g, r1 = r0 + 8;
+        float acc[NB][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) rows[mt][h] = tile * 32 + mt * 16 + g + 8 * h;
-        float acc[2][2][4];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int nb = 0; nb < 2; ++nb) acc[mt][nb][0] = acc[mt][nb][1] = acc[mt][nb][2] = acc[mt][nb][3] = 0.0f;
-        auto fetch = [&](uint32_t (&wd)[2][2], int w) {
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    wd[mt][h] = rows[mt][h] < s.B ? __ldg(bits_s + (size_t)rows[mt][h] * s.NW + w) : 0u;
-        };
-        uint32_t cur[2][2], nxt[2][2];
-        fetch(cur, 0);
+        for (int nb = 0; nb < NB; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.0f;
+        const uint32_t *p0 = bits_s + (size_t)min(r0, s.B - 1) * s.NW, *p1 = bits_s + (size_t)min(r1, s.B - 1) * s.NW;
+        uint32_t c0 = r0 < s.B ? __ldg(p0) : 0u, c1 = r1 < s.B ? __ldg(p1) : 0u;
         for (int w = 0; w < s.NW; ++w) {
-            if (w + 1 < s.NW) fetch(nxt, w + 1);  // the next word's bits fly while this word's MMAs issue
+            // the next word's bits fly while this word's MMAs issue
+            const uint32_t n0 = (w + 1 < s.NW && r0 < s.B) ? __ldg(p0 + w + 1) : 0u;
+            const uint32_t n1 = (w + 1 < s.NW && r1 < s.B) ? __ldg(p1 + w + 1) : 0u;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                uint32_t a[2][4];
+                uint32_t a[4];
+                bits_to_afrag(a, c0, c1, half * 16 + t * 2);
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) bits_to_afrag(a[mt], cur[mt][0], cur[mt][1], half * 16 + t * 2);
+                for (int sp = 0; sp < 3; ++sp)
 #pragma unroll
-                for (int sp = 0; sp < 3; ++sp) {
-                    const uint4 f = sf[((2 * w + half) * 3 + sp) * 32];
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        mma_bf16(acc[mt][0], a[mt], f.x, f.y);
-                        mma_bf16(acc[mt][1], a[mt], f.z, f.w);
+                    for (int q = 0; q < GP; ++q) {
+                        const uint4 f = sf[(((2 * w + half) * 3 + sp) * GP + q) * 32];
+                        mma_bf16(acc[2 * q], a, f.x, f.y);
+                        mma_bf16(acc[2 * q + 1], a, f.z, f.w);
                     }
-                }
             }
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) cur[mt][h] = nxt[mt][h];
+            c0 = n0;
+            c1 = n1;
         }
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-                if (rows[mt][h] < s.B) {
-                    float *o = out + (size_t)rows[mt][h] * s.L1 + col;
-                    *reinterpret_cast<float2 *>(o) = make_float2(bv0.x + acc[mt][0][2 * h], bv0.y + acc[mt][0][2 * h + 1]);
-                    *reinterpret_cast<float2 *>(o + 8) = make_float2(bv1.x + acc[mt][1][2 * h], bv1.y + acc[mt][1][2 * h + 1]);
-                }
+        for (int nb = 0; nb < NB; ++nb) {
+            const float2 bv = __ldg(reinterpret_cast<const float2 *>(bias + col0 + nb * 8));
+            if (r0 < s.B)
+                *reinterpret_cast<float2 *>(out + (size_t)r0 * s.L1 + col0 + nb * 8) = make_float2(bv.x + acc[nb][0], bv.y + acc[nb][1]);
+            if (r1 < s.B)
+                *reinterpret_cast<float2 *>(out + (size_t)r1 * s.L1 + col0 + nb * 8) = make_float2(bv.x + acc[nb][2], bv.y + acc[nb][3]);
+        }
     }
 }
 
 // ---- weight gradient: dW[p] = sum_b bits[b, p] g_ft[b] --------------------------------------------------------
-// CTA = (block of kMmaDwWarps bitmask words, 16-column group, K-chunk of samples): the chunk's slice of the
-// split g_ft (chunk_blocks x 2 k-steps x 3 terms x 512 B) is staged in shared memory once; a warp owns one
+// CTA = (block of kMmaDwWarps bitmask words, 32-column group, K-chunk of samples): the chunk's slice of the
+// split g_ft (chunk_blocks x 2 k-steps x 3 terms x 1 KB) is staged in shared memory once; a warp owns one
 // word (32 positions = two m16 tiles) and transposes each 32 x 32 bit block of (sample, position) in
 // registers so that k runs over samples.  Output: partial[chunk][p][L1] for the fold kernels of ft.cu
 // (they also resolve the aliasing onto row F-1).  The warp of word 0 also multiplies an all-ones tile:
@@ -225,19 +212,20 @@ ft_fwd_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const
 __global__ void __launch_bounds__(kMmaDwWarps * 32, 2)
 ft_bwd_dw_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const uint4 *__restrict__ gfrag,
                      float *__restrict__ partial, float *__restrict__ bias_partial, int chunk_blocks) {
+    constexpr int GP = kMmaGP, NB = 2 * GP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int n_kb = s.BW * 2;
     const int w = blockIdx.x * kMmaDwWarps + warp;  // my bitmask word
-    const int nbp = blockIdx.y, chunk = blockIdx.z;
+    const int grp = blockIdx.y, chunk = blockIdx.z;
     const bool active = w < s.NW;
     const bool do_bias = w == 0;
     const int sb_begin = chunk * chunk_blocks, sb_end = min(s.BW, sb_begin + chunk_blocks);  // 32-sample blocks
-    const uint4 *sf = stage_fragments(smem_raw, gfrag + ((size_t)nbp * n_kb + 2 * sb_begin) * 3 * 32,
-                                      (uint32_t)(sb_end - sb_begin) * 2 * 3 * 512u) + lane;
-    float acc[2][2][4], accb[2][4];
+    const uint4 *sf = stage_fragments(smem_raw, gfrag + ((size_t)grp * n_kb + 2 * sb_begin) * 3 * GP * 32,
+                                      (uint32_t)(sb_end - sb_begin) * 2 * 3 * GP * 512u) + lane;
+    float acc[2][NB][4], accb[NB][4];
 #pragma unroll
-    for (int nb = 0; nb < 2; ++nb) {
+    for (int nb = 0; nb < NB; ++nb) {
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) acc[mt][nb][0] = acc[mt][nb][1] = acc[mt][nb][2] = acc[mt][nb][3] = 0.0f;
         accb[nb][0] = accb[nb][1] = accb[nb][2] = accb[nb][3] = 0.0f;
@@ -262,22 +250,24 @@ ft_bwd_dw_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, co
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) bits_to_afrag(a[mt], word[mt][0], word[mt][1], half * 16 + t * 2);
 #pragma unroll
-            for (int sp = 0; sp < 3; ++sp) {
-                const uint4 f = sf[((2 * (sb - sb_begin) + half) * 3 + sp) * 32];
+            for (int sp = 0; sp < 3; ++sp)
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    mma_bf16(acc[mt][0], a[mt], f.x, f.y);
-                    mma_bf16(acc[mt][1], a[mt], f.z, f.w);
+                for (int q = 0; q < GP; ++q) {
+                    const uint4 f = sf[(((2 * (sb - sb_begin) + half) * 3 + sp) * GP + q) * 32];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        mma_bf16(acc[mt][2 * q], a[mt], f.x, f.y);
+                        mma_bf16(acc[mt][2 * q + 1], a[mt], f.z, f.w);
+                    }
+                    if (do_bias) {  // warp-uniform
+                        mma_bf16(accb[2 * q], ones, f.x, f.y);
+                        mma_bf16(accb[2 * q + 1], ones, f.z, f.w);
+                    }
                 }
-                if (do_bias) {  // warp-uniform
-                    mma_bf16(accb[0], ones, f.x, f.y);
-                    mma_bf16(accb[1], ones, f.z, f.w);
-                }
-            }
         }
         x = xn;
     }
-    const int col = nbp * 16 + t * 2;
+    const int col0 = grp * 16 * GP + t * 2;
     if (active) {
         const int cells = s.Gh * s.Gw, c = w / s.CW, cell0 = (w % s.CW) * 32;
 #pragma unroll
@@ -286,15 +276,16 @@ ft_bwd_dw_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, co
             for (int h = 0; h < 2; ++h) {
                 const int cell = cell0 + mt * 16 + g + 8 * h;
                 if (cell >= cells) continue;
-                float *row = partial + ((size_t)chunk * s.P + (size_t)c * cells + cell) * s.L1 + col;
-                *reinterpret_cast<float2 *>(row) = make_float2(acc[mt][0][2 * h], acc[mt][0][2 * h + 1]);
-                *reinterpret_cast<float2 *>(row + 8) = make_float2(acc[mt][1][2 * h], acc[mt][1][2 * h + 1]);
+                float *row = partial + ((size_t)chunk * s.P + (size_t)c * cells + cell) * s.L1 + col0;
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb)
+                    *reinterpret_cast<float2 *>(row + nb * 8) = make_float2(acc[mt][nb][2 * h], acc[mt][nb][2 * h + 1]);
             }
     }
     if (do_bias && g == 0) {
-        float *row = bias_partial + (size_t)chunk * s.L1 + col;
-        *reinterpret_cast<float2 *>(row) = make_float2(accb[0][0], accb[0][1]);
-        *reinterpret_cast<float2 *>(row + 8) = make_float2(accb[1][0], accb[1][1]);
+        float *row = bias_partial + (size_t)chunk * s.L1 + col0;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) *reinterpret_cast<float2 *>(row + nb * 8) = make_float2(accb[nb][0], accb[nb][1]);
     }
 }
 
@@ -384,8 +375,8 @@ int launch_ft_fwd_mma(const nnue_shape &s, const uint32_t *bits_s, const float *
     uint4 *wfrag = static_cast<uint4 *>(workspace);
     const int rc = format_rows(s, true, w, s.PP, s.PP / 16, wfrag, st);
     if (rc != NNUE_OK) return rc;
-    const int groups = s.L1 / 16;
-    const int ntiles = ceil_div(s.B, 32), wpc = kMmaFwdThreads / 32;
+    const int groups = s.L1 / (16 * kMmaGP);
+    const int ntiles = ceil_div(s.B, 16), wpc = kMmaFwdThreads / 32;
     int ctas = kNumSMs / groups;  // persistent CTAs per column group
     if (ctas > ceil_div(ntiles, wpc)) ctas = ceil_div(ntiles, wpc);
     const size_t smem = mma_fwd_smem(s);
@@ -401,8 +392,8 @@ int launch_ft_bwd_dw_mma(const nnue_shape &s, const uint32_t *bits_s, const floa
     const MmaPlan mp = plan_ft_mma(s);
     int rc = format_rows(s, false, g_ft, s.B, s.BW * 2, gfrag, st);
     if (rc != NNUE_OK) return rc;
-    dim3 grid(ceil_div(s.NW, kMmaDwWarps), s.L1 / 16, mp.n_chunks);
-    const size_t smem = 128 + (size_t)mp.chunk_blocks * 2 * 3 * 512;
+    dim3 grid(ceil_div(s.NW, kMmaDwWarps), s.L1 / (16 * kMmaGP), mp.n_chunks);
+    const size_t smem = 128 + (size_t)mp.chunk_blocks * 2 * 3 * kMmaGP * 512;
     NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_bwd_dw_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ft_bwd_dw_mma_kernel<<<grid, kMmaDwWarps * 32, smem, st>>>(s, bits_s, gfrag, partial, bias_partial, mp.chunk_blocks);
     NNUE_CHECK_LAUNCH("ft_bwd_dw_mma_kernel");

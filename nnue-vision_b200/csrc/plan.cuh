@@ -289,6 +289,7 @@ inline size_t ws_input_bwd(const nnue_shape &s) {
 int extract_xpad(const nnue_shape &s, const float *images, const float *conv_w, const float *thr, float *xpad,
                  cudaStream_t st);
 // ---- feature-transformer contractions on the tensor cores (ft_mma.cu) ------------------------------
+constexpr int kMmaGP = 2;              // column-block pairs per warp: a warp's tile is 32 columns wide
 constexpr int kMmaFwdThreads = 512;   // forward: 16 warps per persistent CTA
 constexpr int kMmaGbinThreads = 512;  // value gradient: 16 warps per persistent CTA
 constexpr int kMmaDwWarps = 8;        // weight gradient: words (warps) per CTA, two CTAs per SM
@@ -297,7 +298,7 @@ struct MmaPlan {
     bool ok;
     int n_chunks, chunk_blocks;  // weight gradient: K-chunks of `chunk_blocks` 32-sample blocks
 };
-inline size_t mma_fwd_smem(const nnue_shape &s) { return 128 + (size_t)(s.PP / 16) * 3 * 512; }
+inline size_t mma_fwd_smem(const nnue_shape &s) { return 128 + (size_t)(s.PP / 16) * 3 * kMmaGP * 512; }
 inline size_t mma_gbin_smem(const nnue_shape &s) {
     return 128 + (size_t)ceil_div(s.NW, kGbinSplit) * 4 * 3 * (s.L1 / 32) * 512;
 }
@@ -306,11 +307,11 @@ inline MmaPlan plan_ft_mma(const nnue_shape &s) {
     if (!get_option(kOptFtMma) || !dense_shape_ok(s)) return m;
     if (mma_fwd_smem(s) > kMaxSmemOptin || mma_gbin_smem(s) > kMaxSmemOptin) return m;  // table slice must fit
     // two resident CTAs per SM, two waves
-    const int ctas_per_chunk = ceil_div(s.NW, kMmaDwWarps) * (s.L1 / 16);
-    int want = ceil_div(4 * kNumSMs, ctas_per_chunk);
+    const int ctas_per_chunk = ceil_div(s.NW, kMmaDwWarps) * (s.L1 / (16 * kMmaGP));
+    int want = ceil_div(2 * kNumSMs, ctas_per_chunk);  // two resident CTAs per SM, one wave
     if (want < 1) want = 1;
     m.chunk_blocks = ceil_div(s.BW, want);
-    if (m.chunk_blocks > 32) m.chunk_blocks = 32;  // 96 KB of fragments per CTA at most
+    if (m.chunk_blocks > 16) m.chunk_blocks = 16;  // 96 KB of fragments per CTA at most (two CTAs per SM)
     m.n_chunks = ceil_div(s.BW, m.chunk_blocks);
     if ((size_t)m.n_chunks * s.P * s.L1 * 4 > ((size_t)1 << 30)) return m;
     m.ok = true;
