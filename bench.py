@@ -73,18 +73,20 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks + throttle reasons sampled every 50 ms.  It is started early (nvidia-smi needs a
+    moment to come up) and `window()` marks the loaded region -- warm-up, timed steps, end-to-end steps --
+    whose samples `summary()` reports."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -93,11 +95,16 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def __exit__(self, *exc):
         if self.proc:
-            time.sleep(0.25)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -107,7 +114,11 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = (self.t1 if self.t1 is not None else float("inf")) + 0.06  # a sample reports the preceding interval
+        for ts, r in self.rows:
+            if not (t0 <= ts <= t1):
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -117,7 +128,8 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "window": "warm-up + timed steps + end-to-end steps"}
 
 
 def build_model(w, device, seed=42):
@@ -305,6 +317,7 @@ def run_b200(args):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    clocks = ClockSampler(local_rank).__enter__()  # started now: nvidia-smi takes a moment to come up
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=device)
     w = dict(WORKLOADS[args.workload])
@@ -325,17 +338,17 @@ def run_b200(args):
     sets = [synthetic_batch(w, B, seed=1000 * rank + i, device=device) for i in range(n_sets)]
     global_batch = B * world
 
+    clocks.begin()
     for i in range(max(args.warmup, 3)):
         dp.step(*sets[i % n_sets], global_batch=global_batch)
     barrier(world)
     _lib.lib().nnue_launch_count(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        e0.record()
-        for i in range(args.steps):
-            loss = dp.step(*sets[i % n_sets], global_batch=global_batch)
-        e1.record()
-        barrier(world)
+    e0.record()
+    for i in range(args.steps):
+        loss = dp.step(*sets[i % n_sets], global_batch=global_batch)
+    e1.record()
+    barrier(world)
     launches = int(_lib.lib().nnue_launch_count(0))
     ms_total = max_over_ranks(e0.elapsed_time(e1), world, device)
     value = args.steps * global_batch / (ms_total * 1e-3)
@@ -379,6 +392,8 @@ def run_b200(args):
     barrier(world)
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, device)
     e2e_value = args.steps * global_batch / (e2e_ms * 1e-3)
+    clocks.end()
+    clocks.__exit__()
     h2d = int(host_sets[0][0].numel() * 4 + host_sets[0][1].numel() * 8) * world
 
     # ---- per-stage device times and the roofline of the dominant kernel
