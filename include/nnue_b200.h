@@ -276,6 +276,30 @@ int nnue_input_bwd(const nnue_shape *s, const float *images_d, const uint32_t *b
                    void *stream);
 
 /* ------------------------------------------------------------------------- *
+ *  Optimizer step over flat buffers (the step either side of the path)       *
+ * ------------------------------------------------------------------------- */
+
+/*
+ * torch.nn.utils.clip_grad_norm_ + optimizer.step() of train.py:363-366, 457-471 on ONE flat fp32
+ * buffer of n parameters (parameters, gradients and state are views of flat buffers).
+ *   nnue_opt_grad_sqnorm: sqnorm_d[0] = sum g^2 (deterministic two-stage sum; workspace from
+ *                         nnue_opt_workspace_bytes).  Needed only when max_norm > 0.
+ *   nnue_opt_sgd_step:    torch.optim.SGD(lr, momentum, weight_decay) (dampening 0, no nesterov); gradients
+ *                         are first scaled in place by min(1, max_norm / (sqrt(sqnorm) + 1e-6)) when
+ *                         max_norm > 0; first_step != 0 initialises the momentum buffer with the gradient.
+ *   nnue_opt_adam_step:   torch.optim.Adam(lr, (beta1, beta2), eps, weight_decay) (L2 decay, no amsgrad);
+ *                         step counts from 1.
+ */
+size_t nnue_opt_workspace_bytes(long long n);
+int nnue_opt_grad_sqnorm(long long n, const float *g_d, float *sqnorm_d, void *workspace_d,
+                         size_t workspace_bytes, void *stream);
+int nnue_opt_sgd_step(long long n, float *p_d, float *g_d, float *buf_d, float lr, float momentum,
+                      float weight_decay, float max_norm, const float *sqnorm_d, int first_step, void *stream);
+int nnue_opt_adam_step(long long n, float *p_d, float *g_d, float *m_d, float *v_d, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int step, float max_norm,
+                       const float *sqnorm_d, void *stream);
+
+/* ------------------------------------------------------------------------- *
  *  Quantized integer inference path (bit-exact vs serialize.py + engine)     *
  * ------------------------------------------------------------------------- */
 

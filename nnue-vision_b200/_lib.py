@@ -53,6 +53,11 @@ SIGNATURES = {
     "nnue_input_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 9 + [sz, vp]),
     "nnue_ft_bwd_dval": (ctypes.c_int, [SHAPE_P] + [vp] * 8 + [sz, vp]),
     "nnue_extract_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 5 + [sz, vp]),
+    "nnue_opt_workspace_bytes": (sz, [ctypes.c_longlong]),
+    "nnue_opt_grad_sqnorm": (ctypes.c_int, [ctypes.c_longlong, vp, vp, vp, sz, vp]),
+    "nnue_opt_sgd_step": (ctypes.c_int, [ctypes.c_longlong, vp, vp, vp, f32, f32, f32, f32, vp, ctypes.c_int, vp]),
+    "nnue_opt_adam_step": (ctypes.c_int, [ctypes.c_longlong, vp, vp, vp, vp, f32, f32, f32, f32, f32, ctypes.c_int, f32,
+                                          vp, vp]),
     "nnue_q_load": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(vp)]),
     "nnue_q_load_memory": (ctypes.c_int, [vp, sz, ctypes.POINTER(vp)]),
     "nnue_q_free": (None, [vp]),

@@ -52,6 +52,82 @@ class FlatGradBuffer:
         return self.flat.numel()
 
 
+class FlatParamBuffer:
+    """Makes the gradient-bearing parameters views of ONE contiguous fp32 buffer (same order as
+    FlatGradBuffer), so that the optimizer update is a single elementwise pass.  `state_dict()` keys,
+    shapes and values are unchanged; only the storage moves."""
+
+    def __init__(self, named_params, device):
+        self.names = [n for n in GRAD_PARAM_NAMES if n in named_params]
+        self.params = [named_params[n] for n in self.names]
+        sizes = [p.numel() for p in self.params]
+        self.flat = torch.empty(sum(sizes), dtype=torch.float32, device=device)
+        off = 0
+        with torch.no_grad():
+            for p, n in zip(self.params, sizes):
+                view = self.flat[off:off + n].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                off += n
+
+    def numel(self):
+        return self.flat.numel()
+
+
+class FusedOptimizer:
+    """clip_grad_norm_ + optimizer.step() of the reference's loop (train.py:363-366, 457-471) as two or
+    three launches over flat buffers: parameters (FlatParamBuffer), gradients (the DataParallelStep's
+    FlatGradBuffer, already all-reduced) and optimizer state.
+
+        step = DataParallelStep(model)
+        opt = FusedOptimizer(step, "sgd", lr=0.01, momentum=0.9, weight_decay=2e-4, max_grad_norm=1.0)
+        loss = step.step(images, labels); opt.step()
+
+    Semantics are torch's (`torch.optim.SGD` / `torch.optim.Adam` with L2 weight decay,
+    `torch.nn.utils.clip_grad_norm_` with norm 2); tests/test_gpu_optim.py checks them against torch.
+    The parameter the reference's optimizer never touches (`nnue2score`, no gradient) is left alone."""
+
+    def __init__(self, dp_step, optimizer_type="sgd", lr=0.01, momentum=0.9, weight_decay=0.0, max_grad_norm=0.0,
+                 betas=(0.9, 0.999), eps=1e-8):
+        from . import _lib
+        if optimizer_type not in ("sgd", "adam"):
+            raise ValueError(f"optimizer_type must be 'sgd' or 'adam', got {optimizer_type!r}")
+        self._lib = _lib
+        self.kind, self.lr, self.momentum, self.weight_decay = optimizer_type, float(lr), float(momentum), float(weight_decay)
+        self.max_grad_norm, self.betas, self.eps = float(max_grad_norm), (float(betas[0]), float(betas[1])), float(eps)
+        self.grads = dp_step.buf
+        device = self.grads.flat.device
+        if not self.grads.flat.is_cuda:
+            raise _lib.NnueError("FusedOptimizer runs on CUDA only (no CPU fallback)")
+        self.params = FlatParamBuffer(dict(dp_step.model.named_parameters()), device)
+        assert self.params.names == self.grads.names
+        self.n = self.params.numel()
+        self.state1 = torch.zeros(self.n, dtype=torch.float32, device=device)  # momentum buffer / exp_avg
+        self.state2 = torch.zeros(self.n, dtype=torch.float32, device=device) if optimizer_type == "adam" else None
+        self.sqnorm = torch.zeros(1, dtype=torch.float32, device=device)
+        self.ws = torch.empty(int(_lib.lib().nnue_opt_workspace_bytes(self.n)), dtype=torch.uint8, device=device)
+        self.steps = 0
+
+    def grad_norm(self):
+        """Total gradient 2-norm as a 0-d device tensor (what clip_grad_norm_ returns)."""
+        return self.sqnorm.sqrt().reshape(())
+
+    def step(self):
+        L, d, st = self._lib.lib(), self._lib.dptr, self._lib.stream_ptr()
+        g = self.grads.flat[: self.n]
+        if self.max_grad_norm > 0:
+            self._lib.check(L.nnue_opt_grad_sqnorm(self.n, d(g), d(self.sqnorm), d(self.ws), self.ws.numel(), st))
+        self.steps += 1
+        if self.kind == "sgd":
+            self._lib.check(L.nnue_opt_sgd_step(self.n, d(self.params.flat), d(g), d(self.state1), self.lr, self.momentum,
+                                                self.weight_decay, self.max_grad_norm, d(self.sqnorm),
+                                                1 if self.steps == 1 else 0, st))
+        else:
+            self._lib.check(L.nnue_opt_adam_step(self.n, d(self.params.flat), d(g), d(self.state1), d(self.state2),
+                                                 self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                                 self.steps, self.max_grad_norm, d(self.sqnorm), st))
+
+
 def _cuda_local_step(model):
     """The B200 hot path: forward, fused CE, backward -- every kernel through the C ABI."""
     from . import _lib, nnue as _nnue
