@@ -130,3 +130,45 @@ def test_load_errors(tmp_path):
     from nnue_vision_b200 import _lib
     with pytest.raises(_lib.NnueError):  # 64x48 image: raster would overrun the feature buffer
         ev.evaluate_logits(torch.zeros(1, 48, 200, 3).cuda())
+
+
+def test_evaluate_compiled_model_matches_per_sample_engine(oracle_built):
+    """evaluate.evaluate_compiled_model (evaluate.py:90-400 of the reference): same metrics and density as
+    evaluating every sample on its own through the CPU engine, as the reference's subprocess loop does."""
+    from pathlib import Path
+    from nnue_vision_b200 import evaluate, nnue, serialize
+    from oracle import int_oracle
+    torch.manual_seed(11)
+    model = nnue.NNUE(nnue.GridFeatureSet(10, 8), 64, 32, 8, num_classes=10, input_size=32)
+    g = torch.Generator().manual_seed(2)
+    loader = [(torch.randn(n, 3, 32, 32, generator=g), torch.randint(0, 10, (n,), generator=g)) for n in (37, 64, 5)]
+    metrics = evaluate.evaluate_compiled_model(model, loader, "nnue")
+    assert set(metrics) == {"acc", "f1", "precision", "recall", "ms_per_sample", "latent_density"}
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        path = Path(td) / "m.nnue"
+        serialize.serialize_model(model, path)
+        cpu = int_oracle.RefEngine(path) if int_oracle.RefEngine.available() else int_oracle.IntOracle(path)
+        logits, dens = [], []
+        for images, _ in loader:
+            l, d = cpu.eval_batch(images.numpy().reshape(images.shape[0], 32, 32, 3))
+            logits.append(torch.as_tensor(l)); dens.append(torch.as_tensor(d))
+    ref = evaluate.compute_metrics(torch.cat(logits), torch.cat([t for _, t in loader]))
+    for k in ("acc", "f1", "precision", "recall"):
+        assert metrics[k] == ref[k], k
+    assert abs(metrics["latent_density"] - float(torch.cat(dens).mean())) < 1e-7
+    assert metrics["ms_per_sample"] > 0
+    with pytest.raises(ValueError):
+        evaluate.evaluate_compiled_model(model, loader, "etinynet")
+
+
+def test_evaluate_model_float_path():
+    from nnue_vision_b200 import evaluate, nnue
+    torch.manual_seed(12)
+    model = nnue.NNUE(nnue.GridFeatureSet(8, 4), 64, 4, 8, num_classes=10, input_size=32).cuda()
+    g = torch.Generator().manual_seed(3)
+    loader = [(torch.randn(16, 3, 32, 32, generator=g), torch.randint(0, 10, (16,), generator=g)) for _ in range(3)]
+    loss, metrics = evaluate.evaluate_model(model, loader)
+    with torch.no_grad():
+        ref = sum(float(torch.nn.functional.cross_entropy(model(x.cuda()), y.cuda())) for x, y in loader) / 3
+    assert abs(loss - ref) < 1e-6 and 0.0 <= metrics["acc"] <= 1.0
