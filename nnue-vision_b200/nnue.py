@@ -260,6 +260,17 @@ class _NNUEForward(torch.autograd.Function):
 STORE_ACTIVATIONS = True
 
 
+OVERLAP_TABLE_GRADIENT = True
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_out=None, marks=None):
     """One whole training step of the hot path -- forward, mean cross-entropy, every parameter gradient --
     in seven launches: extract, feature transformer, fused head step (forward + loss + backward), the two
@@ -293,14 +304,27 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
                             dptr(g_b2), dptr(g_w3), dptr(g_b3), dptr(ws), ws_bytes, st))
     _mark(marks, "head_train")
     if L.nnue_ft_uses_mma(sp) and L.nnue_input_bwd_is_dense(sp):  # small tables: tensor-core contractions
-        check(L.nnue_ft_bwd_dw(sp, dptr(bits_s), None, dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(ws), ws_bytes, st))
-        _mark(marks, "ft_bwd_dw")
+        # The table gradient depends only on g_ft and nothing downstream depends on it, while the value gradient
+        # and the conv gradient that follow are latency-bound and leave issue slots free: outside the per-stage
+        # timing mode it runs on a side stream next to them (it uses its own part of the workspace).
+        side = _side_stream(images.device) if (marks is None and OVERLAP_TABLE_GRADIENT) else None
+        if side is not None:
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                check(L.nnue_ft_bwd_dw(sp, dptr(bits_s), None, dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(ws), ws_bytes,
+                                       ctypes.c_void_p(side.cuda_stream)))
+        else:
+            check(L.nnue_ft_bwd_dw(sp, dptr(bits_s), None, dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(ws), ws_bytes, st))
+            _mark(marks, "ft_bwd_dw")
         gbin = _empty((shape.B, shape.PP), torch.float32, images)
         check(L.nnue_ft_bwd_gbin(sp, dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(gbin), dptr(ws), ws_bytes, st))
         _mark(marks, "ft_bwd_gbin")
         check(L.nnue_conv_bwd(sp, dptr(images), dptr(gbin), dptr(xpad), dptr(conv_w), dptr(thr), dptr(g_conv_w), dptr(g_thr),
                               dptr(ws), ws_bytes, st))
         _mark(marks, "conv_bwd")
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)  # the step's gradients are complete on the caller's stream
         return loss_out, grads
     if L.nnue_ft_bwd_is_fused(sp):  # both feature-transformer gradients in one CUDA-core pass over g_ft
         gbin = _empty((shape.B, shape.PP), torch.float32, images)
