@@ -323,38 +323,47 @@ ft_bwd_gbin_mma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, 
 #pragma unroll
                 for (int sp = 0; sp < 3; ++sp) a[kb][sp][e] = lo[sp] | (hi[sp] << 16);
             }
-        uint32_t word0 = 0u, word1 = 0u;
-        for (int nb = nb_begin; nb < nb_end; ++nb) {
-            if ((nb & 3) == 0) {
-                word0 = r0 < s.B ? __ldg(bits_s + (size_t)r0 * s.NW + (nb >> 2)) : 0u;
-                word1 = r1 < s.B ? __ldg(bits_s + (size_t)r1 * s.NW + (nb >> 2)) : 0u;
-            }
-            // term pairs (split of g, split of W) with i + j <= 2 (0-based): the rest is below 2^-27 relative;
-            // two accumulators (even / odd k16 steps) halve the dependent MMA chain
-            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        // One bitmask word (four column blocks of 8 positions) per pass.  Consecutive MMAs share their A
+        // operand (the same g_ft fragment against the four blocks' table fragments): without operand reuse
+        // HMMA runs at half rate on the register-file bandwidth (ncu: math-pipe throttle at 50 % tensor-pipe
+        // utilisation with one block per pass).
+        for (int nb = nb_begin; nb < nb_end; nb += 4) {
+            const int wi = nb >> 2;
+            const uint32_t word0 = r0 < s.B ? __ldg(bits_s + (size_t)r0 * s.NW + wi) : 0u;
+            const uint32_t word1 = r1 < s.B ? __ldg(bits_s + (size_t)r1 * s.NW + wi) : 0u;
+            float acc[4][4];
 #pragma unroll
-            for (int sw = 0; sw < 3; ++sw)
+            for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.0f;
 #pragma unroll
-                for (int kbp = 0; kbp < KB / 2; ++kbp) {
-                    const uint4 f = sf[(((nb - nb_begin) * 3 + sw) * (KB / 2) + kbp) * 32];
+            for (int kbp = 0; kbp < KB / 2; ++kbp) {
+                uint4 f[4][3];
 #pragma unroll
-                    for (int sa = 0; sa + sw < 3; ++sa) {
-                        mma_bf16(acc, a[2 * kbp][sa], f.x, f.y);
-                        mma_bf16(acc2, a[2 * kbp + 1][sa], f.z, f.w);
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int sw = 0; sw < 3; ++sw) f[u][sw] = sf[(((nb + u - nb_begin) * 3 + sw) * (KB / 2) + kbp) * 32];
+                // term pairs (split of g, split of W) with i + j <= 2 (0-based): the rest is below 2^-27 relative
+#pragma unroll
+                for (int sa = 0; sa < 3; ++sa)
+#pragma unroll
+                    for (int sw = 0; sa + sw < 3; ++sw) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) mma_bf16(acc[u], a[2 * kbp][sa], f[u][sw].x, f[u][sw].y);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) mma_bf16(acc[u], a[2 * kbp + 1][sa], f[u][sw].z, f[u][sw].w);
                     }
-                }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[e] += acc2[e];
-            const int off = (nb & 3) * 8 + t * 2;
-            if (r0 < s.B) {
-                const uint32_t m = word0 >> off;
-                *reinterpret_cast<float2 *>(gbin + (size_t)r0 * s.PP + nb * 8 + t * 2) =
-                    make_float2((m & 1u) ? acc[0] : 0.0f, (m & 2u) ? acc[1] : 0.0f);
             }
-            if (r1 < s.B) {
-                const uint32_t m = word1 >> off;
-                *reinterpret_cast<float2 *>(gbin + (size_t)r1 * s.PP + nb * 8 + t * 2) =
-                    make_float2((m & 1u) ? acc[2] : 0.0f, (m & 2u) ? acc[3] : 0.0f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int off = u * 8 + t * 2;
+                float *o = gbin + (size_t)(nb + u) * 8 + t * 2;
+                if (r0 < s.B) {
+                    const uint32_t m = word0 >> off;
+                    *reinterpret_cast<float2 *>(o + (size_t)r0 * s.PP) = make_float2((m & 1u) ? acc[u][0] : 0.0f, (m & 2u) ? acc[u][1] : 0.0f);
+                }
+                if (r1 < s.B) {
+                    const uint32_t m = word1 >> off;
+                    *reinterpret_cast<float2 *>(o + (size_t)r1 * s.PP) = make_float2((m & 1u) ? acc[u][2] : 0.0f, (m & 2u) ? acc[u][3] : 0.0f);
+                }
             }
         }
     }

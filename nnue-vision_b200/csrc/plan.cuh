@@ -291,7 +291,7 @@ int extract_xpad(const nnue_shape &s, const float *images, const float *conv_w, 
 // ---- feature-transformer contractions on the tensor cores (ft_mma.cu) ------------------------------
 constexpr int kMmaGP = 2;              // column-block pairs per warp: a warp's tile is 32 columns wide
 constexpr int kMmaFwdThreads = 512;   // forward: 16 warps per persistent CTA
-constexpr int kMmaGbinThreads = 512;  // value gradient: 16 warps per persistent CTA
+constexpr int kMmaGbinThreads = 384;  // value gradient: 12 warps per persistent CTA (up to 168 registers each)
 constexpr int kMmaDwWarps = 8;        // weight gradient: words (warps) per CTA, two CTAs per SM
 constexpr int kGbinSplit = 8;         // value gradient: position slices (one persistent CTA group each)
 struct MmaPlan {
