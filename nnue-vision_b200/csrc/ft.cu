@@ -1076,6 +1076,8 @@ int nnue_ft_fwd(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w
     if (!s || !bits_s_d || !ft_w_d || !ft_b_d || !ft_out_d) return NNUE_ERR_INVALID_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // small tables with scratch available: tensor-core contraction (ft_mma.cu); otherwise the row gather
+    if (ft_umma_ok(*s) && workspace_d && workspace_bytes >= umma_wtiles_bytes(*s))  // tcgen05 / TMEM form
+        return launch_ft_fwd_umma(*s, bits_s_d, ft_w_d, ft_b_d, ft_out_d, workspace_d, st);
     if (plan_ft_mma(*s).ok && workspace_d && workspace_bytes >= ws_ft_fwd(*s))
         return launch_ft_fwd_mma(*s, bits_s_d, ft_w_d, ft_b_d, ft_out_d, workspace_d, st);
     const ColPlan cp = col_plan(s->L1);

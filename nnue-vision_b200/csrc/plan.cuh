@@ -81,6 +81,12 @@ struct OwnPlan {
     size_t smem;
 };
 inline bool dense_shape_ok(const nnue_shape &s) { return s.L1 == 64 || s.L1 == 32; }
+// tcgen05 / TMEM forward (ft_umma.cu): L1 == 64, positions a multiple of 64
+inline bool ft_umma_ok(const nnue_shape &s) { return get_option(kOptFtUmma) && s.L1 == 64 && s.PP % 64 == 0; }
+inline size_t umma_wtiles_bytes(const nnue_shape &s) { return (size_t)s.PP * 64 * 2 * 3; }
+int launch_ft_fwd_umma(const nnue_shape &s, const uint32_t *bits_s, const float *w, const float *bias, float *out,
+                       void *workspace, cudaStream_t st);
+
 inline OwnPlan plan_ft_bwd_dw_owner(const nnue_shape &s) {
     OwnPlan o{};
     if (!get_option(kOptDwOwner) || !dense_shape_ok(s)) return o;
@@ -319,7 +325,10 @@ inline MmaPlan plan_ft_mma(const nnue_shape &s) {
 }
 inline size_t mma_wfrag_bytes(const nnue_shape &s) { return (size_t)(s.PP / 16) * 3 * (s.L1 / 16) * 32 * 16; }
 inline size_t mma_gfrag_bytes(const nnue_shape &s) { return (size_t)(s.BW * 2) * 3 * (s.L1 / 16) * 32 * 16; }
-inline size_t ws_ft_fwd(const nnue_shape &s) { return plan_ft_mma(s).ok ? mma_wfrag_bytes(s) : 0; }
+inline size_t ws_ft_fwd(const nnue_shape &s) {
+    const size_t a = plan_ft_mma(s).ok ? mma_wfrag_bytes(s) : 0, b = ft_umma_ok(s) ? umma_wtiles_bytes(s) : 0;
+    return a > b ? a : b;
+}
 inline size_t ws_ft_bwd_mma(const nnue_shape &s) {
     const MmaPlan m = plan_ft_mma(s);
     if (!m.ok) return 0;
