@@ -419,6 +419,10 @@ def run_b200(args):
                  "ft_bwd_gbin": 2.0 * B * shape.PP * L1 * 6}
     kernel_of = {"extract_fwd": "extract_fwd_fixed_kernel", "ft_fwd": "ft_fwd_mma_kernel", "head_train": "head_train_kernel",
                  "ft_bwd_dw": "ft_bwd_dw_mma_kernel", "ft_bwd_gbin": "ft_bwd_gbin_mma_kernel", "conv_bwd": "conv_bwd_kernel"}
+    umma = bool(_lib.lib().nnue_ft_uses_umma(ctypes.byref(shape)))
+    if umma:  # tcgen05 / TMEM contractions (ft_umma.cu)
+        kernel_of.update({"ft_fwd": "ft_bitgemm_umma_kernel<0>", "ft_bwd_dw": "ft_bitgemm_umma_kernel<1>",
+                          "ft_bwd_gbin": "ft_gbin_umma_kernel"})
     traffic = {}
     tp = ROOT / "profiles" / "traffic.json"  # dram bytes per launch from the committed ncu --set full capture
     if tp.exists():
@@ -438,7 +442,8 @@ def run_b200(args):
             if k in mma_flops and _lib.lib().nnue_ft_uses_mma(ctypes.byref(shape)):
                 tf = mma_flops[k] / (stages[k] * 1e-3) / 1e12
                 roofs[k]["tensor"] = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
-                                      "note": "bf16 mma.sync, 3 (6) exact split-term products per fp32 product"}
+                                      "note": ("bf16 tcgen05.mma (UMMA, TMEM accumulators)" if umma else "bf16 mma.sync") +
+                                              ", 3 (6) exact split-term products per fp32 product"}
     dominant = max(roofs, key=lambda k: roofs[k]["ms"]) if roofs else None
 
     line = {

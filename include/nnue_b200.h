@@ -82,6 +82,8 @@ unsigned long long nnue_launch_count(int reset);
  *                     (measured faster at config D: profiles/).
  *   "ft_mma"          1 (default) = tensor-core (bf16-split, fp32-exact products) feature-transformer
  *                     contractions for small tables, 0 = CUDA-core kernels only.
+ *   "ft_umma"         1 (default) = tcgen05 / TMEM (UMMA) feature-transformer contractions for every L1 that is
+ *                     a multiple of 64, 0 = the warp-level MMA / CUDA-core families.
  *   "ft_bwd_both"     1 (default) = one kernel for both feature-transformer gradients (small tables).
  *   "head_fused"      1 (default) = one-kernel head training step for small stacks, 0 = layer kernels.
  */
@@ -223,6 +225,7 @@ int nnue_wants_transposed_bits(const nnue_shape *s);
  */
 int nnue_ft_bwd_is_fused(const nnue_shape *s);
 int nnue_ft_uses_mma(const nnue_shape *s);  /* 1 when the tensor-core contractions serve this shape */
+int nnue_ft_uses_umma(const nnue_shape *s); /* 1 when they are the tcgen05 / TMEM kernels of ft_umma.cu (L1 a multiple of 64) */
 int nnue_ft_bwd(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w_d, const float *g_ft_d,
                 float *g_w_d, float *g_b_d, float *gbin_d, void *workspace_d, size_t workspace_bytes,
                 void *stream);

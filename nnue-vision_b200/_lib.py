@@ -49,6 +49,7 @@ SIGNATURES = {
     "nnue_input_bwd_is_dense": (ctypes.c_int, [SHAPE_P]),
     "nnue_ft_bwd_gbin": (ctypes.c_int, [SHAPE_P, vp, vp, vp, vp, vp, sz, vp]),
     "nnue_ft_uses_mma": (ctypes.c_int, [SHAPE_P]),
+    "nnue_ft_uses_umma": (ctypes.c_int, [SHAPE_P]),
     "nnue_conv_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 8 + [sz, vp]),
     "nnue_input_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 9 + [sz, vp]),
     "nnue_ft_bwd_dval": (ctypes.c_int, [SHAPE_P] + [vp] * 8 + [sz, vp]),

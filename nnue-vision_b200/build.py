@@ -32,7 +32,7 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    cmd = [NVCC, "-O3", "-std=c++17", *ARCH_FLAGS, "-lineinfo", "-Xcompiler", "-fPIC,-Wall", "-shared",
+    cmd = [NVCC, "-O3", "-std=c++17", "-t", "8", *ARCH_FLAGS, "-lineinfo", "-Xcompiler", "-fPIC,-Wall", "-shared",
            "-I", str(ROOT / "include"), "-I", str(CSRC), "-o", str(LIB), *map(str, sources())]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

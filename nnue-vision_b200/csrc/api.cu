@@ -12,7 +12,7 @@ void note_cuda_error(cudaError_t e, const char *what) {
 }
 static unsigned long long g_launches = 0;
 void note_launch() { __atomic_fetch_add(&g_launches, 1ULL, __ATOMIC_RELAXED); }
-static int g_options[kNumOptions] = {/*ft_fwd_staging=*/1, /*ft_bwd_dw_owner=*/1, /*input_bwd_fused=*/1, /*input_bwd_variant=*/1, /*head_fused=*/1, /*ft_bwd_both=*/1, /*ft_mma=*/1, /*extract_tma=*/0, /*extract_fixed=*/1, /*ft_umma=*/0};
+static int g_options[kNumOptions] = {/*ft_fwd_staging=*/1, /*ft_bwd_dw_owner=*/1, /*input_bwd_fused=*/1, /*input_bwd_variant=*/1, /*head_fused=*/1, /*ft_bwd_both=*/1, /*ft_mma=*/1, /*extract_tma=*/0, /*extract_fixed=*/1, /*ft_umma=*/1};
 int get_option(int which) { return which >= 0 && which < kNumOptions ? g_options[which] : 0; }
 }  // namespace nnue
 
@@ -87,6 +87,7 @@ size_t nnue_workspace_bytes(const nnue_shape *s) {
     v = nnue::ws_ft_bwd_both(*s); if (v > m) m = v;
     v = nnue::ws_ft_bwd_mma(*s); if (v > m) m = v;
     v = nnue::ws_ft_fwd(*s); if (v > m) m = v;
+    v = nnue::ws_ft_bwd_umma(*s); if (v > m) m = v;
     v = nnue::ws_ce(s->B); if (v > m) m = v;
     return m + 256;
 }

@@ -1076,7 +1076,7 @@ int nnue_ft_fwd(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w
     if (!s || !bits_s_d || !ft_w_d || !ft_b_d || !ft_out_d) return NNUE_ERR_INVALID_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // small tables with scratch available: tensor-core contraction (ft_mma.cu); otherwise the row gather
-    if (ft_umma_ok(*s) && workspace_d && workspace_bytes >= umma_wtiles_bytes(*s))  // tcgen05 / TMEM form
+    if (ft_umma_ok(*s) && workspace_d && workspace_bytes >= umma_kt_bytes((size_t)s->PP, *s))  // tcgen05 / TMEM form
         return launch_ft_fwd_umma(*s, bits_s_d, ft_w_d, ft_b_d, ft_out_d, workspace_d, st);
     if (plan_ft_mma(*s).ok && workspace_d && workspace_bytes >= ws_ft_fwd(*s))
         return launch_ft_fwd_mma(*s, bits_s_d, ft_w_d, ft_b_d, ft_out_d, workspace_d, st);
@@ -1146,15 +1146,30 @@ static int ft_bwd_dw_mma_path(const nnue_shape *s, const uint32_t *bits_s_d, con
     return NNUE_OK;
 }
 
-int nnue_ft_uses_mma(const nnue_shape *s) { return s && plan_ft_mma(*s).ok ? 1 : 0; }
+// tcgen05 weight/bias gradient; it owns the second region of the workspace (after the value gradient's operands)
+static int ft_bwd_dw_umma_path(const nnue_shape *s, const uint32_t *bits_s_d, const float *g_ft_d, float *g_w_d, float *g_b_d,
+                               void *workspace_d, size_t workspace_bytes, cudaStream_t st) {
+    if (workspace_bytes < ws_ft_bwd_umma(*s)) return NNUE_ERR_WORKSPACE;
+    return launch_ft_bwd_dw_umma(*s, bits_s_d, g_ft_d, static_cast<char *>(workspace_d) + ws_ft_gbin_umma(*s), g_w_d, g_b_d, st);
+}
+
+int nnue_ft_uses_umma(const nnue_shape *s) { return s && ft_umma_ok(*s) ? 1 : 0; }
+
+int nnue_ft_uses_mma(const nnue_shape *s) { return s && (ft_umma_ok(*s) || plan_ft_mma(*s).ok) ? 1 : 0; }
 
 int nnue_ft_bwd_is_fused(const nnue_shape *s) {
-    return s && (plan_ft_mma(*s).ok || plan_ft_bwd_both(*s).ok) && plan_input_bwd(*s).fused ? 1 : 0;
+    return s && (ft_umma_ok(*s) || plan_ft_mma(*s).ok || plan_ft_bwd_both(*s).ok) && plan_input_bwd(*s).fused ? 1 : 0;
 }
 
 int nnue_ft_bwd(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w_d, const float *g_ft_d, float *g_w_d,
                 float *g_b_d, float *gbin_d, void *workspace_d, size_t workspace_bytes, void *stream) {
     if (!s || !bits_s_d || !ft_w_d || !g_ft_d || !g_w_d || !g_b_d || !gbin_d || !workspace_d) return NNUE_ERR_INVALID_ARG;
+    if (ft_umma_ok(*s)) {  // tcgen05 path
+        const int rc = ft_bwd_dw_umma_path(s, bits_s_d, g_ft_d, g_w_d, g_b_d, workspace_d, workspace_bytes,
+                                           static_cast<cudaStream_t>(stream));
+        if (rc != NNUE_OK) return rc;
+        return launch_ft_bwd_gbin_umma(*s, bits_s_d, ft_w_d, g_ft_d, workspace_d, gbin_d, static_cast<cudaStream_t>(stream));
+    }
     if (plan_ft_mma(*s).ok) {  // tensor-core path
         const int rc = ft_bwd_dw_mma_path(s, bits_s_d, g_ft_d, g_w_d, g_b_d, workspace_d, workspace_bytes,
                                           static_cast<cudaStream_t>(stream));
@@ -1183,12 +1198,14 @@ int nnue_ft_bwd(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w
     return NNUE_OK;
 }
 
-int nnue_wants_transposed_bits(const nnue_shape *s) { return s && plan_ft_bwd_dw_owner(*s).ok ? 0 : 1; }
+int nnue_wants_transposed_bits(const nnue_shape *s) { return s && (ft_umma_ok(*s) || plan_ft_bwd_dw_owner(*s).ok) ? 0 : 1; }
 
 int nnue_ft_bwd_dw(const nnue_shape *s, const uint32_t *bits_s_d, const uint32_t *bits_t_d, const float *g_ft_d,
                    float *g_w_d, float *g_b_d, void *workspace_d, size_t workspace_bytes, void *stream) {
     if (!s || !g_ft_d || !g_w_d || !g_b_d || !workspace_d) return NNUE_ERR_INVALID_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (ft_umma_ok(*s) && bits_s_d)
+        return ft_bwd_dw_umma_path(s, bits_s_d, g_ft_d, g_w_d, g_b_d, workspace_d, workspace_bytes, st);
     if (plan_ft_mma(*s).ok && bits_s_d)
         return ft_bwd_dw_mma_path(s, bits_s_d, g_ft_d, g_w_d, g_b_d, workspace_d, workspace_bytes, st);
     if (workspace_bytes < ws_ft_bwd_dw(*s)) return NNUE_ERR_WORKSPACE;

@@ -1,19 +1,29 @@
-// ft_umma.cu -- the feature-transformer forward on the 5th-generation tensor cores (tcgen05 / TMEM).
+// ft_umma.cu -- the three feature-transformer contractions on the 5th-generation tensor cores
+// (tcgen05.mma issued by one thread, accumulators in tensor memory, operands fed by bulk TMA).
 //
-// Same arithmetic contract as ft_mma.cu: out = bias + bits . (W1 + W2 + W3), the bitmask exact in bf16,
-// the table split exactly into three bf16 terms, exact products, fp32 accumulation -- but issued as
-// tcgen05.mma (UMMA) 128 x 64 x 16 tiles by ONE thread, with the accumulator in tensor memory:
+// Same arithmetic contract as ft_mma.cu: the bitmask operand is exact in bf16 (0.0 / 1.0), an fp32
+// operand is split exactly into three bf16 terms, bf16 x bf16 products are exact in fp32 and the
+// accumulation is fp32 -- only the summation order differs from an fp32 FMA chain.  Any L1 that is a
+// multiple of 64 is served (config D: 64, the reference's "real" config: 1024).
 //
-//   * CTA = one tile of 128 samples x all 64 columns; K = padded positions, 64 per pipeline stage.
-//   * A operand (the bitmask as bf16): eight producer warps expand 32 bits -> 64 B per (sample, word) and
-//     store them as the canonical K-major / no-swizzle UMMA layout (8 x 16-byte core matrices);
-//     every bit is expanded exactly once per step (the warp-level MMA path re-expands it per column
-//     group and per lane: ncu showed that integer work, not the tensor pipe, as its limit).
-//   * B operand (the split table, pre-formatted in the same canonical layout by a small kernel): one
-//     bulk TMA copy of 24 KB per stage (4 k-steps x 3 terms x 2 KB).
-//   * One elected thread of the issuer warp waits for both, issues 12 UMMAs per stage and commits
-//     them to the stage's `empty` mbarrier; after the last stage it commits to `done`.
-//   * Epilogue: warps 0-3 read their 32 TMEM lanes (tcgen05.ld 32x32b), add the bias and store rows.
+//   forward          out[b, n]   = bias[n] + sum_pp bit[b, pp] W[row(pp), n]      M = samples,   K = positions
+//   weight gradient  dW[pp, n]   = sum_b bit[b, pp] g[b, n]                        M = positions, K = samples
+//   value gradient   gbin[b, pp] = bit[b, pp] ? sum_k g[b, k] W[row(pp), k] : 0    M = samples,   K = L1
+//
+// Forward and weight gradient are ONE kernel (`ft_bitgemm_umma_kernel`): a CTA owns a 128-row M tile and a
+// 64-column N tile; the three bf16 terms of the fp32 operand are stacked along N (UMMA 128 x 192 x 16) and
+// summed in fp32 in the epilogue.  The A operand is expanded from the bitmask by four producer warps
+// straight into the canonical K-major shared-memory layout, every bit exactly once per CTA (for the
+// weight gradient each 32 x 32 (sample, position) bit block is transposed in registers first so that k
+// runs over samples); the B operand is pre-formatted by a small kernel and arrives by bulk TMA.
+// The value gradient (`ft_gbin_umma_kernel`) is a TMA-fed GEMM of the pre-split g_ft against the
+// pre-split table with the six term pairs (i, j), i + j <= 4, per k-step (UMMA 128 x 256 x 16) and a
+// masked epilogue.  Two CTAs are resident per SM (<= 110 KB shared, 256 TMEM columns each), so one CTA's
+// epilogue overlaps the other's main loop.
+//
+// Warp roles: warp 0 lane 0 = TMA producer, warp 1 = TMEM owner, lane 0 issues the UMMAs, warps 2.. = bitmask
+// expansion (two groups of four warps on alternating stages: the expansion is latency-bound, not bandwidth-bound),
+// then the epilogue (warp w reads TMEM lanes 32 (w % 4) .. + 31).
 //
 // Canonical K-major layout without swizzle, element (row r, k) of a [rows x 16] bf16 tile:
 //   byte = (k / 8) * LBO + (r / 8) * SBO + (r % 8) * 16 + (k % 8) * 2,  SBO = 128, LBO = rows * 16.
@@ -24,19 +34,29 @@
 
 namespace nnue {
 
-constexpr int kUmmaM = 128;          // samples per CTA tile (UMMA M)
-constexpr int kUmmaN = 64;           // columns (UMMA N) = L1
-constexpr int kUmmaKStage = 64;      // positions per pipeline stage (two bitmask words, four k16 steps)
-constexpr int kUmmaStages = 4;
-constexpr int kUmmaProducerWarps = 8;
-constexpr int kUmmaThreads = (kUmmaProducerWarps + 1) * 32;
-constexpr uint32_t kUmmaABytes = kUmmaM * kUmmaKStage * 2;         // 16 KB: four [128 x 16] tiles
-constexpr uint32_t kUmmaBBytes = 3 * 4 * kUmmaN * 16 * 2;          // 24 KB: (k-step, term) tiles of 2 KB
-constexpr uint32_t kUmmaTmemCols = 64;
+constexpr int kUM = 128;                                 // rows of every M tile (UMMA M)
+constexpr int kBgThreads = 320;                          // bit GEMM: TMA warp, issuer warp, two groups of four producer warps
+constexpr int kGbThreads = 192;                          // value gradient: TMA warp, issuer warp, four epilogue warps
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, K-major both, N = 64, M = 128
-constexpr uint32_t kUmmaIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((kUmmaN >> 3) << 17) | ((kUmmaM >> 4) << 24);
+// ---- bit GEMM (forward / weight gradient) ----
+constexpr int kBgStages = 5;
+constexpr uint32_t kBgABytes = kUM * 32 * 2;             // one bitmask word per row: two [128 x 16] tiles
+constexpr uint32_t kBgNRows = 3 * kUmmaNCols;            // 192: the three terms of 64 columns stacked along N
+constexpr uint32_t kBgBTile = kBgNRows * 32;             // 6 KB: one [192 x 16] tile
+constexpr uint32_t kBgBBytes = 2 * kBgBTile;             // two k-steps per stage
+constexpr uint32_t kBgTmemCols = 256;
+// ---- value gradient ----
+constexpr int kGbStages = 3;
+constexpr uint32_t kGbATile = kUM * 32;                  // 4 KB  [128 x 16]
+constexpr uint32_t kGbBTile = kUmmaGbinN * 32;           // 8 KB  [256 x 16]
+constexpr uint32_t kGbABytes = 3 * kGbATile, kGbBBytes = 3 * kGbBTile;
+constexpr uint32_t kGbTmemCols = 256;
+constexpr int kGbRowPitch = 132;                         // floats per staged epilogue row (128 + 4: 16-byte aligned, conflict-free)
 
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major
+__host__ __device__ constexpr uint32_t umma_idesc(uint32_t M, uint32_t N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), no swizzle, version 1 (sm_100)
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
@@ -56,166 +76,491 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// 16 consecutive fp32 accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // row of the table hit by padded position pp, or -1 for padding cells (same rule as ft_mma.cu)
 __device__ __forceinline__ int umma_table_row(const nnue_shape &s, int pp) {
+    if (pp >= s.PP) return -1;
     const int w = pp >> 5, c = w / s.CW, cell = (w % s.CW) * 32 + (pp & 31);
     if (c >= s.C || cell >= s.Gh * s.Gw) return -1;
-    return min(c * s.Gh * s.Gw + cell, s.F - 1);
+    return min(c * s.Gh * s.Gw + cell, s.F - 1);  // clamp of nnue.py:701
 }
-
-// B operand: out[stage][k-step (4)][term (3)] tiles of [64 columns x 16 positions] bf16 in the canonical layout
-__global__ void umma_format_table_kernel(const nnue_shape s, const float *__restrict__ w, uint16_t *__restrict__ out) {
-    const long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x;  // one (position, column)
-    if (i >= 1LL * s.PP * kUmmaN) return;
-    const int pp = (int)(i / kUmmaN), n = (int)(i % kUmmaN);
-    const int row = umma_table_row(s, pp);
-    float r = row >= 0 ? __ldg(w + (size_t)row * s.L1 + n) : 0.0f;
-    const int kstep = pp / 16, k = pp % 16;
-    const size_t elem = (size_t)(k / 8) * (kUmmaN * 8) + (size_t)(n / 8) * 64 + (n % 8) * 8 + (k % 8);  // in bf16 units
+// eight fp32 values -> the three bf16 terms, each packed as one 16-byte chunk (k % 8 ascending)
+__device__ __forceinline__ void split3x8(const float (&v)[8], uint4 (&o)[3]) {
+    uint32_t h[3][8];
 #pragma unroll
-    for (int sp = 0; sp < 3; ++sp) {
-        const __nv_bfloat16 b = __float2bfloat16_rn(r);
-        out[((size_t)kstep * 3 + sp) * (kUmmaN * 16) + elem] = __bfloat16_as_ushort(b);
-        r -= __bfloat162float(b);
+    for (int j = 0; j < 8; ++j) {
+        float r = v[j];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const __nv_bfloat16 b = __float2bfloat16_rn(r);
+            h[t][j] = (uint32_t)__bfloat16_as_ushort(b);
+            r -= __bfloat162float(b);
+        }
     }
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+        o[t] = make_uint4(h[t][0] | (h[t][1] << 16), h[t][2] | (h[t][3] << 16), h[t][4] | (h[t][5] << 16), h[t][6] | (h[t][7] << 16));
 }
 
-__global__ void __launch_bounds__(kUmmaThreads, 1)
-ft_fwd_umma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const uint16_t *__restrict__ wtiles,
-                   const float *__restrict__ bias, float *__restrict__ out) {
+// ---- operand formatting ------------------------------------------------------------------------------------
+// "K over rows": src[K rows][L1] fp32 -> tiles [nt = L1 / 64][ks] of [192 x 16] with N row = term * 64 + column % 64
+// and k = source row (TABLE: padded position through the clamp rule; else sample).  A thread packs eight
+// consecutive k of one column.
+template <bool TABLE>
+__global__ void umma_format_kt_kernel(const nnue_shape s, const float *__restrict__ src, int nrows, int n_ks,
+                                      unsigned char *__restrict__ out) {
+    const long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2LL * n_ks * s.L1) return;
+    const int col = (int)(i % s.L1), kc = (int)(i / s.L1);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = kc * 8 + j;
+        const int row = TABLE ? umma_table_row(s, k) : (k < nrows ? k : -1);
+        v[j] = row >= 0 ? __ldg(src + (size_t)row * s.L1 + col) : 0.0f;
+    }
+    uint4 o[3];
+    split3x8(v, o);
+    const int nt = col / kUmmaNCols, c = col % kUmmaNCols, ks = kc >> 1;
+    unsigned char *tile = out + ((size_t)nt * n_ks + ks) * kBgBTile + (uint32_t)(kc & 1) * (kBgNRows * 16) + (uint32_t)(c >> 3) * 128 +
+                          (uint32_t)(c & 7) * 16;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) *reinterpret_cast<uint4 *>(tile + (uint32_t)t * (kUmmaNCols / 8) * 128) = o[t];
+}
+// "K over columns": src[rows][L1] fp32 -> tiles [rt][ks = L1 / 16][term] of [RT x 16] with k = source column.
+// TABLE: row = padded position through the clamp rule, zero rows for padding.
+template <bool TABLE, int RT>
+__global__ void umma_format_rows_kernel(const nnue_shape s, const float *__restrict__ src, int nrows, int n_rt,
+                                        unsigned char *__restrict__ out) {
+    const int kcs = s.L1 / 8, n_ks = s.L1 / 16;
+    const long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 1LL * n_rt * RT * kcs) return;
+    const int kc = (int)(i % kcs), r = (int)(i / kcs);
+    const int row = TABLE ? umma_table_row(s, r) : (r < nrows ? r : -1);
+    float v[8];
+    if (row >= 0) {
+        const float4 lo = __ldg(reinterpret_cast<const float4 *>(src + (size_t)row * s.L1 + kc * 8));
+        const float4 hi = __ldg(reinterpret_cast<const float4 *>(src + (size_t)row * s.L1 + kc * 8) + 1);
+        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+    }
+    uint4 o[3];
+    split3x8(v, o);
+    const int rt = r / RT, rr = r % RT, ks = kc >> 1;
+    unsigned char *tile = out + ((size_t)rt * n_ks + ks) * 3 * (RT * 32) + (uint32_t)(kc & 1) * (RT * 16) + (uint32_t)(rr >> 3) * 128 +
+                          (uint32_t)(rr & 7) * 16;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) *reinterpret_cast<uint4 *>(tile + (uint32_t)t * (RT * 32)) = o[t];
+}
+
+// eight bits -> eight bf16 (0.0 / 1.0), k ascending
+__device__ __forceinline__ uint4 bits8_to_bf16x8(uint32_t byte) {
+    uint4 v;
+    v.x = ((byte & 1u) ? 0x3F80u : 0u) | ((byte & 2u) ? 0x3F800000u : 0u);
+    v.y = ((byte & 4u) ? 0x3F80u : 0u) | ((byte & 8u) ? 0x3F800000u : 0u);
+    v.z = ((byte & 16u) ? 0x3F80u : 0u) | ((byte & 32u) ? 0x3F800000u : 0u);
+    v.w = ((byte & 64u) ? 0x3F80u : 0u) | ((byte & 128u) ? 0x3F800000u : 0u);
+    return v;
+}
+
+// ---- forward / weight gradient ---------------------------------------------------------------------------------
+// grid = (M tiles, L1 / 64, K chunks).  DW = false: M = samples, stage j = bitmask word j of the sample rows,
+// out = ft_out [B][L1] (+ bias).  DW = true: M = padded positions (bitmask words 4 x .. 4 x + 3), stage j = the
+// 32-sample block chunk * chunk_blocks + j, out = partial[chunk][P + 1][L1] (row P = bias gradient) for the fold kernels.
+template <bool DW>
+__global__ void __launch_bounds__(kBgThreads, 2)
+ft_bitgemm_umma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const unsigned char *__restrict__ btiles,
+                       const float *__restrict__ bias, float *__restrict__ out, int chunk_blocks) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    uint64_t *full_a = reinterpret_cast<uint64_t *>(smem_raw);       // [ST] producers -> issuer
-    uint64_t *full_b = full_a + kUmmaStages;                         // [ST] TMA -> issuer
-    uint64_t *empty = full_b + kUmmaStages;                          // [ST] UMMA commit -> producers / TMA
-    uint64_t *done = empty + kUmmaStages;                            // accumulator complete
+    uint64_t *full_a = reinterpret_cast<uint64_t *>(smem_raw);     // [ST] producer warps -> issuer
+    uint64_t *full_b = full_a + kBgStages;                         // [ST] TMA -> issuer
+    uint64_t *empty = full_b + kBgStages;                          // [ST] UMMA commit -> producers / TMA
+    uint64_t *done = empty + kBgStages;                            // accumulator complete
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
-    unsigned char *sa = smem_raw + 1024;                             // [ST][16 KB]
-    unsigned char *sb = sa + kUmmaStages * kUmmaABytes;              // [ST][24 KB]
+    unsigned char *sa = smem_raw + 1024;                           // [ST][8 KB]
+    unsigned char *sb = sa + kBgStages * kBgABytes;                // [ST][12 KB]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b0 = blockIdx.x * kUmmaM;
-    const int n_stage = s.PP / kUmmaKStage;
+    const int mt = blockIdx.x, nt = blockIdx.y, chunk = blockIdx.z;
+    int first, n_stage, n_ks_total;
+    if (DW) {
+        first = chunk * chunk_blocks;
+        n_stage = min(s.BW, first + chunk_blocks) - first;
+        n_ks_total = 2 * s.BW;
+    } else {
+        first = 0;
+        n_stage = s.NW;
+        n_ks_total = 2 * s.NW;
+    }
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kUmmaStages; ++i) {
-            mbar_init(&full_a[i], kUmmaProducerWarps);
+        for (int i = 0; i < kBgStages; ++i) {
+            mbar_init(&full_a[i], 4);
             mbar_init(&full_b[i], 1);
             mbar_init(&empty[i], 1);
         }
         mbar_init(done, 1);
         mbar_fence_init();
     }
-    if (warp == kUmmaProducerWarps) {  // the issuer warp owns the tensor-memory allocation
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kUmmaTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    if (warp == 1) tmem_alloc<kBgTmemCols>(tmem_slot);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_acc = *tmem_slot;
 
-    if (warp < kUmmaProducerWarps) {
-        // ---- A producers: thread = (sample row m, word half wh) of the stage ----
-        const int m = threadIdx.x & (kUmmaM - 1), wh = threadIdx.x >> 7;  // 256 threads: 128 rows x 2 words
-        const int b = b0 + m;
-        const uint32_t *brow = bits_s + (size_t)min(b, s.B - 1) * s.NW;
-        // my four 16-byte chunks inside a stage: word wh -> k-steps 2 wh, 2 wh + 1; chunk (k-step, k half)
-        unsigned char *dst0 = sa + (uint32_t)(2 * wh) * (kUmmaM * 32) + (uint32_t)(m / 8) * 128 + (uint32_t)(m % 8) * 16;
-        for (int st_i = 0; st_i < n_stage; ++st_i) {
-            const int st = st_i % kUmmaStages;
-            if (st_i >= kUmmaStages) mbar_wait(&empty[st], ((st_i / kUmmaStages) - 1) & 1);
-            const uint32_t word = b < s.B ? __ldg(brow + st_i * 2 + wh) : 0u;
-            unsigned char *dst = dst0 + (uint32_t)st * kUmmaABytes;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {  // chunk c: bits 8c .. 8c+7 -> k-step c / 2, k half c % 2
-                const uint32_t byte = (word >> (8 * c)) & 0xFFu;
-                uint4 v;
-                v.x = ((byte & 1u) ? 0x3F80u : 0u) | ((byte & 2u) ? 0x3F800000u : 0u);
-                v.y = ((byte & 4u) ? 0x3F80u : 0u) | ((byte & 8u) ? 0x3F800000u : 0u);
-                v.z = ((byte & 16u) ? 0x3F80u : 0u) | ((byte & 32u) ? 0x3F800000u : 0u);
-                v.w = ((byte & 64u) ? 0x3F80u : 0u) | ((byte & 128u) ? 0x3F800000u : 0u);
-                *reinterpret_cast<uint4 *>(dst + (uint32_t)(c / 2) * (kUmmaM * 32) + (uint32_t)(c % 2) * (kUmmaM * 16)) = v;
-            }
-            fence_async_smem();  // my generic-proxy stores must be visible to the tensor core's async-proxy reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full_a[st]);
-        }
-        // ---- epilogue: warps 0-3 own TMEM lanes 32 w .. 32 w + 31 (= sample rows) ----
-        if (warp < 4) {
-            mbar_wait(done, 0);
-            tcgen05_fence_after();
-            const int row = b0 + warp * 32 + lane;
-            float *orow = out + (size_t)row * s.L1;
-#pragma unroll
-            for (int c0 = 0; c0 < kUmmaN; c0 += 16) {
-                uint32_t v[16];
-                const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < s.B) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + c0) + q);
-                        reinterpret_cast<float4 *>(orow + c0)[q] =
-                            make_float4(bv.x + __uint_as_float(v[4 * q]), bv.y + __uint_as_float(v[4 * q + 1]),
-                                        bv.z + __uint_as_float(v[4 * q + 2]), bv.w + __uint_as_float(v[4 * q + 3]));
-                    }
-                }
+    if (warp == 0) {
+        if (lane == 0) {  // ---- TMA: the B tiles of every stage ----
+            const unsigned char *src = btiles + ((size_t)nt * n_ks_total + 2 * (size_t)first) * kBgBTile;
+            for (int j = 0; j < n_stage; ++j) {
+                const int st = j % kBgStages;
+                if (j >= kBgStages) mbar_wait(&empty[st], ((j / kBgStages) - 1) & 1);
+                mbar_arrive_expect_tx(&full_b[st], kBgBBytes);
+                tma_bulk_g2s(sb + (uint32_t)st * kBgBBytes, src + (size_t)j * kBgBBytes, kBgBBytes, &full_b[st]);
             }
         }
-    } else if (lane == 0) {
-        // ---- issuer: TMA for B, then the UMMAs of each stage ----
-        const int ahead = kUmmaStages - 1;
-        auto load_b = [&](int ii) {
-            const int st = ii % kUmmaStages;
-            if (ii >= kUmmaStages) mbar_wait(&empty[st], ((ii / kUmmaStages) - 1) & 1);
-            mbar_arrive_expect_tx(&full_b[st], kUmmaBBytes);
-            tma_bulk_g2s(sb + (uint32_t)st * kUmmaBBytes, reinterpret_cast<const unsigned char *>(wtiles) + (size_t)ii * kUmmaBBytes,
-                         kUmmaBBytes, &full_b[st]);
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---- issuer: two UMMAs (128 x 192 x 16) per stage ----
+            constexpr uint32_t idesc = umma_idesc(kUM, kBgNRows);
+            for (int j = 0; j < n_stage; ++j) {
+                const int st = j % kBgStages;
+                const uint32_t ph = (j / kBgStages) & 1;
+                mbar_wait(&full_a[st], ph);
+                mbar_wait(&full_b[st], ph);
+                tcgen05_fence_after();
+                const uint32_t a_base = smem_u32(sa + (uint32_t)st * kBgABytes), b_base = smem_u32(sb + (uint32_t)st * kBgBBytes);
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                    umma_bf16(tmem_acc, umma_smem_desc(a_base + (uint32_t)ks * (kUM * 32), kUM * 16, 128),
+                              umma_smem_desc(b_base + (uint32_t)ks * kBgBTile, kBgNRows * 16, 128), idesc, (j | ks) ? 1u : 0u);
+                umma_commit(&empty[st]);  // arrives when the UMMAs above have read their shared-memory operands
+            }
+            umma_commit(done);
+        }
+    } else {
+        // ---- A producers: warp quadrant q owns tile rows 32 q .. 32 q + 31, lane = row (after the transpose);
+        //      group grp takes the stages j = grp, grp + 2, ... ----
+        const int q = warp & 3, row = q * 32 + lane, grp = (warp - 2) >> 2;
+        const int wi = mt * 4 + q;  // DW: my bitmask word
+        // DW: one padding row of the M tiles is all ones, so that its output row is the column sum of g_ft (bias gradient)
+        const bool ones_row = DW && (mt * kUM + row == umma_bias_pp(s));
+        auto load = [&](int j) -> uint32_t {
+            if (j >= n_stage) return 0u;
+            if (DW) {
+                const int b = (first + j) * 32 + lane;
+                return (wi < s.NW && b < s.B) ? __ldg(bits_s + (size_t)b * s.NW + wi) : 0u;
+            }
+            const int b = mt * kUM + row;
+            return b < s.B ? __ldg(bits_s + (size_t)b * s.NW + j) : 0u;
         };
-        for (int ii = 0; ii < ahead && ii < n_stage; ++ii) load_b(ii);
-        for (int st_i = 0; st_i < n_stage; ++st_i) {
-            const int st = st_i % kUmmaStages;
-            const uint32_t ph = (st_i / kUmmaStages) & 1;
-            mbar_wait(&full_a[st], ph);
-            mbar_wait(&full_b[st], ph);
-            tcgen05_fence_after();
-            const uint32_t a_base = smem_u32(sa + (uint32_t)st * kUmmaABytes), b_base = smem_u32(sb + (uint32_t)st * kUmmaBBytes);
+        unsigned char *dst0 = sa + (uint32_t)row * 16;
+        uint32_t pre[4];
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t adesc = umma_smem_desc(a_base + (uint32_t)ks * (kUmmaM * 32), kUmmaM * 16, 128);
+        for (int u = 0; u < 4; ++u) pre[u] = load(grp + 2 * u);
+        for (int j0 = grp; j0 < n_stage; j0 += 8) {
 #pragma unroll
-                for (int sp = 0; sp < 3; ++sp) {
-                    const uint64_t bdesc = umma_smem_desc(b_base + (uint32_t)(ks * 3 + sp) * (kUmmaN * 32), kUmmaN * 16, 128);
-                    umma_bf16(tmem_acc, adesc, bdesc, kUmmaIdesc, (st_i | ks | sp) ? 1u : 0u);
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 2 * u;
+                if (j < n_stage) {  // warp-uniform
+                    const int st = j % kBgStages;
+                    if (j >= kBgStages) mbar_wait(&empty[st], ((j / kBgStages) - 1) & 1);
+                    uint32_t word = pre[u];
+                    pre[u] = load(j + 8);
+                    if (DW) {
+                        word = warp_bit_transpose(word, lane);  // lane L: the 32 samples of position 32 wi + L
+                        if (ones_row) word = 0xFFFFFFFFu;       // (samples past B are zero rows of the B operand)
+                    }
+                    unsigned char *dst = dst0 + (uint32_t)st * kBgABytes;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)  // chunk c: k 8c .. 8c+7 -> k-step c / 2, k half c % 2
+                        *reinterpret_cast<uint4 *>(dst + (uint32_t)(c >> 1) * (kUM * 32) + (uint32_t)(c & 1) * (kUM * 16)) =
+                            bits8_to_bf16x8((word >> (8 * c)) & 0xFFu);
+                    fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_a[st]);
                 }
             }
-            umma_commit(&empty[st]);  // arrives when the UMMAs above have read their shared-memory operands
-            if (st_i + ahead < n_stage) load_b(st_i + ahead);  // (waits for the commit of the previous stage)
         }
-        umma_commit(done);
+        // ---- epilogue: (term 2 + term 1) + term 0 per column; group grp takes 32 of the 64 columns of its rows ----
+        mbar_wait(done, 0);
+        tcgen05_fence_after();
+        const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16);
+        float *orow = nullptr;
+        if (DW) {
+            const int pp = mt * kUM + row, w = pp >> 5, cells = s.Gh * s.Gw;
+            if (ones_row) {
+                orow = out + ((size_t)chunk * (s.P + 1) + s.P) * s.L1 + nt * kUmmaNCols;
+            } else if (w < s.NW) {
+                const int c = w / s.CW, cell = (w % s.CW) * 32 + (pp & 31);
+                if (cell < cells) orow = out + ((size_t)chunk * (s.P + 1) + (size_t)c * cells + cell) * s.L1 + nt * kUmmaNCols;
+            }
+        } else {
+            const int b = mt * kUM + row;
+            if (b < s.B) orow = out + (size_t)b * s.L1 + nt * kUmmaNCols;
+        }
+#pragma unroll
+        for (int cc = 0; cc < kUmmaNCols / 2; cc += 16) {
+            const int c0 = grp * (kUmmaNCols / 2) + cc;
+            float t0[16], t1[16], t2[16];
+            tmem_ld16(tbase + (uint32_t)c0, t0);
+            tmem_ld16(tbase + (uint32_t)(kUmmaNCols + c0), t1);
+            tmem_ld16(tbase + (uint32_t)(2 * kUmmaNCols + c0), t2);
+            tmem_ld_wait();
+            if (orow) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    float4 r = make_float4((t2[4 * v] + t1[4 * v]) + t0[4 * v], (t2[4 * v + 1] + t1[4 * v + 1]) + t0[4 * v + 1],
+                                           (t2[4 * v + 2] + t1[4 * v + 2]) + t0[4 * v + 2], (t2[4 * v + 3] + t1[4 * v + 3]) + t0[4 * v + 3]);
+                    if (!DW) r = f4_add(r, __ldg(reinterpret_cast<const float4 *>(bias + nt * kUmmaNCols + c0) + v));
+                    reinterpret_cast<float4 *>(orow + c0)[v] = r;
+                }
+            }
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == kUmmaProducerWarps) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(kUmmaTmemCols) : "memory");
+    if (warp == 1) tmem_dealloc<kBgTmemCols>(tmem_acc);
+}
+
+// ---- value gradient -----------------------------------------------------------------------------------------------
+// grid = (256-position N tiles, 128-sample M tiles).  K = L1 in k-steps of 16: a stage holds the three terms of the
+// g_ft tile (12 KB) and of the table tile (24 KB); six UMMAs (128 x 256 x 16) per stage.
+__global__ void __launch_bounds__(kGbThreads, 2)
+ft_gbin_umma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const unsigned char *__restrict__ atiles,
+                    const unsigned char *__restrict__ btiles, float *__restrict__ gbin) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *empty = full + kGbStages;
+    uint64_t *done = empty + kGbStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
+    unsigned char *sa = smem_raw + 1024;
+    unsigned char *sb = sa + kGbStages * kGbABytes;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nt = blockIdx.x, mt = blockIdx.y, n_ks = s.L1 / 16;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kGbStages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<kGbTmemCols>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const unsigned char *asrc = atiles + (size_t)mt * n_ks * kGbABytes, *bsrc = btiles + (size_t)nt * n_ks * kGbBBytes;
+            for (int j = 0; j < n_ks; ++j) {
+                const int st = j % kGbStages;
+                if (j >= kGbStages) mbar_wait(&empty[st], ((j / kGbStages) - 1) & 1);
+                mbar_arrive_expect_tx(&full[st], kGbABytes + kGbBBytes);
+                tma_bulk_g2s(sa + (uint32_t)st * kGbABytes, asrc + (size_t)j * kGbABytes, kGbABytes, &full[st]);
+                tma_bulk_g2s(sb + (uint32_t)st * kGbBBytes, bsrc + (size_t)j * kGbBBytes, kGbBBytes, &full[st]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(kUM, kUmmaGbinN);
+            for (int j = 0; j < n_ks; ++j) {
+                const int st = j % kGbStages;
+                mbar_wait(&full[st], (j / kGbStages) & 1);
+                tcgen05_fence_after();
+                const uint32_t a_base = smem_u32(sa + (uint32_t)st * kGbABytes), b_base = smem_u32(sb + (uint32_t)st * kGbBBytes);
+                // term pairs (split of g, split of W) with i + j <= 2 (0-based): the rest is below 2^-27 relative
+#pragma unroll
+                for (int ta = 0; ta < 3; ++ta)
+#pragma unroll
+                    for (int tw = 0; ta + tw < 3; ++tw)
+                        umma_bf16(tmem_acc, umma_smem_desc(a_base + (uint32_t)ta * kGbATile, kUM * 16, 128),
+                                  umma_smem_desc(b_base + (uint32_t)tw * kGbBTile, kUmmaGbinN * 16, 128), idesc, (j | ta | tw) ? 1u : 0u);
+                umma_commit(&empty[st]);
+            }
+            umma_commit(done);
+        }
+    } else {
+        // ---- epilogue: mask with the sample's bits, transpose through shared memory (the operand ring is idle
+        //      once `done` fires) so that every global store instruction writes 512 contiguous bytes of one row ----
+        const int q = warp & 3, b = mt * kUM + q * 32 + lane;
+        uint32_t mw[kUmmaGbinN / 32];
+#pragma unroll
+        for (int i = 0; i < kUmmaGbinN / 32; ++i) {
+            const int w = nt * (kUmmaGbinN / 32) + i;
+            mw[i] = (b < s.B && w < s.NW) ? __ldg(bits_s + (size_t)b * s.NW + w) : 0u;
+        }
+        mbar_wait(done, 0);
+        tcgen05_fence_after();
+        const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16);
+        float *stg = reinterpret_cast<float *>(smem_raw + 1024) + q * (32 * kGbRowPitch);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                float v[2][16];
+                tmem_ld16(tbase + (uint32_t)(half * 128 + c0), v[0]);
+                tmem_ld16(tbase + (uint32_t)(half * 128 + c0 + 16), v[1]);
+                tmem_ld_wait();
+                const uint32_t m = mw[(half * 128 + c0) >> 5];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float *x = &v[u >> 2][4 * (u & 3)];
+                    const uint32_t mm = m >> (4 * u);
+                    *reinterpret_cast<float4 *>(stg + lane * kGbRowPitch + c0 + 4 * u) =
+                        make_float4(mm & 1u ? x[0] : 0.0f, mm & 2u ? x[1] : 0.0f, mm & 4u ? x[2] : 0.0f, mm & 8u ? x[3] : 0.0f);
+                }
+            }
+            __syncwarp();
+            const int pp = nt * kUmmaGbinN + half * 128 + lane * 4;
+            if (pp < s.PP) {
+                float *o = gbin + (size_t)(mt * kUM + q * 32) * s.PP + pp;
+                const int nrow = min(32, s.B - (mt * kUM + q * 32));
+#pragma unroll 8
+                for (int r = 0; r < nrow; ++r)
+                    *reinterpret_cast<float4 *>(o + (size_t)r * s.PP) = *reinterpret_cast<const float4 *>(stg + r * kGbRowPitch + lane * 4);
+            }
+            __syncwarp();
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<kGbTmemCols>(tmem_acc);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+constexpr size_t kBgSmem = 1024 + (size_t)kBgStages * (kBgABytes + kBgBBytes);
+constexpr size_t kGbSmem = 1024 + (size_t)kGbStages * (kGbABytes + kGbBBytes);
+
+// out = bias + bits . W;  workspace: the table as [L1 / 64][PP / 16] tiles (umma_kt_bytes(PP, L1))
+int launch_ft_fwd_umma(const nnue_shape &s, const uint32_t *bits_s, const float *w, const float *bias, float *out,
+                       void *workspace, cudaStream_t st) {
+    unsigned char *wt = static_cast<unsigned char *>(workspace);
+    const int n_ks = 2 * s.NW;
+    const long long n = 2LL * n_ks * s.L1;
+    umma_format_kt_kernel<true><<<(int)((n + 255) / 256), 256, 0, st>>>(s, w, s.PP, n_ks, wt);
+    NNUE_CHECK_LAUNCH("umma_format_kt_kernel");
+    NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_bitgemm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmem));
+    ft_bitgemm_umma_kernel<false><<<dim3(ceil_div(s.B, kUM), s.L1 / kUmmaNCols, 1), kBgThreads, kBgSmem, st>>>(s, bits_s, wt, bias, out, 0);
+    NNUE_CHECK_LAUNCH("ft_bitgemm_umma_kernel");
+    return NNUE_OK;
+}
+
+// Fold stage 1: every position p sums its partials over the K chunks (loads batched eight deep: the loop is
+// latency-bound).  Positions below F-1 are table rows and go straight to g_w; positions >= F-1 all alias onto the
+// last row (the clamp of nnue.py:701) and are parked in `alias` [P-(F-1)][L1] for stage 2; rows in [P, F-1) get
+// zeros; the extra row P of every partial block is the bias gradient.
+__global__ void __launch_bounds__(256)
+umma_dw_fold_kernel(const nnue_shape s, int n_chunks, const float *__restrict__ partial, float *__restrict__ g_w,
+                    float *__restrict__ g_b, float *__restrict__ alias) {
+    const int v4 = s.L1 / 4;
+    const int nrows = max(s.P, s.F - 1);
+    const long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 1LL * (nrows + 1) * v4) return;
+    const int r = (int)(i / v4), c4 = (int)(i % v4);
+    const int p = r == nrows ? s.P : r;  // row of the partial blocks
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r == nrows || r < s.P) {
+        const float4 *src = reinterpret_cast<const float4 *>(partial + (size_t)p * s.L1) + c4;
+        const size_t pitch = (size_t)(s.P + 1) * v4;
+        int c = 0;
+        for (; c + 8 <= n_chunks; c += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (size_t)(c + u) * pitch);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = f4_add(acc, v[u]);
+        }
+        for (; c < n_chunks; ++c) acc = f4_add(acc, __ldg(src + (size_t)c * pitch));
+    }
+    if (r == nrows) reinterpret_cast<float4 *>(g_b)[c4] = acc;
+    else if (r < s.F - 1) reinterpret_cast<float4 *>(g_w + (size_t)r * s.L1)[c4] = acc;
+    else reinterpret_cast<float4 *>(alias + (size_t)(r - (s.F - 1)) * s.L1)[c4] = acc;
+}
+// Fold stage 2: g_w[F-1] = sum of the parked rows, 32 slices per column combined in a fixed order.
+__global__ void __launch_bounds__(1024)
+umma_dw_fold_last_kernel(const nnue_shape s, const float *__restrict__ alias, float *__restrict__ g_w) {
+    __shared__ float4 red[1024];
+    const int v4 = s.L1 / 4;
+    const int nalias = max(0, s.P - (s.F - 1));
+    const int col = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int c4 = blockIdx.x * 32 + col;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < v4)
+#pragma unroll 4
+        for (int i = sl; i < nalias; i += 32)
+            acc = f4_add(acc, __ldg(reinterpret_cast<const float4 *>(alias + (size_t)i * s.L1) + c4));
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (sl == 0 && c4 < v4) {
+        for (int k = 1; k < 32; ++k) acc = f4_add(acc, red[k * 32 + col]);
+        reinterpret_cast<float4 *>(g_w + (size_t)(s.F - 1) * s.L1)[c4] = acc;
     }
 }
 
-int launch_ft_fwd_umma(const nnue_shape &s, const uint32_t *bits_s, const float *w, const float *bias, float *out,
-                       void *workspace, cudaStream_t st) {
-    uint16_t *wtiles = static_cast<uint16_t *>(workspace);
-    const long long n = 1LL * s.PP * kUmmaN;
-    umma_format_table_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(s, w, wtiles);
-    NNUE_CHECK_LAUNCH("umma_format_table_kernel");
-    const size_t smem = 1024 + (size_t)kUmmaStages * (kUmmaABytes + kUmmaBBytes);
-    NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ft_fwd_umma_kernel<<<ceil_div(s.B, kUmmaM), kUmmaThreads, smem, st>>>(s, bits_s, wtiles, bias, out);
-    NNUE_CHECK_LAUNCH("ft_fwd_umma_kernel");
+// g_w = bits^T . g_ft, g_b = column sums of g_ft.  `ws`: split g_ft^T tiles | partial[chunk][P + 1][L1] | alias rows
+// (ws_ft_dw_umma bytes)
+int launch_ft_bwd_dw_umma(const nnue_shape &s, const uint32_t *bits_s, const float *g_ft, void *ws, float *g_w, float *g_b,
+                          cudaStream_t st) {
+    const UmmaDwPlan p = plan_ft_dw_umma(s);
+    unsigned char *gt = static_cast<unsigned char *>(ws);
+    float *partial = reinterpret_cast<float *>(gt + align_up(umma_kt_bytes((size_t)s.BW * 32, s), 256));
+    float *alias = partial + (size_t)p.n_chunks * (s.P + 1) * s.L1;
+    const int n_ks = 2 * s.BW;
+    long long n = 2LL * n_ks * s.L1;
+    umma_format_kt_kernel<false><<<(int)((n + 255) / 256), 256, 0, st>>>(s, g_ft, s.B, n_ks, gt);
+    NNUE_CHECK_LAUNCH("umma_format_kt_kernel");
+    NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_bitgemm_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmem));
+    const int m_rows = umma_bias_pp(s) + 1 > s.PP ? s.PP + 1 : s.PP;  // the all-ones row may need one more M tile
+    ft_bitgemm_umma_kernel<true><<<dim3(ceil_div(m_rows, kUM), s.L1 / kUmmaNCols, p.n_chunks), kBgThreads, kBgSmem, st>>>(
+        s, bits_s, gt, nullptr, partial, p.chunk_blocks);
+    NNUE_CHECK_LAUNCH("ft_bitgemm_umma_kernel");
+    n = 1LL * ((s.P > s.F - 1 ? s.P : s.F - 1) + 1) * (s.L1 / 4);
+    umma_dw_fold_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(s, p.n_chunks, partial, g_w, g_b, alias);
+    NNUE_CHECK_LAUNCH("umma_dw_fold_kernel");
+    umma_dw_fold_last_kernel<<<ceil_div(s.L1 / 4, 32), 1024, 0, st>>>(s, alias, g_w);
+    NNUE_CHECK_LAUNCH("umma_dw_fold_last_kernel");
+    return NNUE_OK;
+}
+
+// gbin = bits ? g_ft . W^T : 0;  workspace: split g_ft tiles | split table tiles (ws_ft_gbin_umma)
+int launch_ft_bwd_gbin_umma(const nnue_shape &s, const uint32_t *bits_s, const float *w, const float *g_ft, void *workspace,
+                            float *gbin, cudaStream_t st) {
+    const int n_mt = ceil_div(s.B, kUM), n_nt = ceil_div(s.PP, kUmmaGbinN);
+    unsigned char *at = static_cast<unsigned char *>(workspace);
+    unsigned char *bt = at + align_up((size_t)n_mt * kUM * s.L1 * 6, 256);
+    long long n = 1LL * n_mt * kUM * (s.L1 / 8);
+    umma_format_rows_kernel<false, kUM><<<(int)((n + 255) / 256), 256, 0, st>>>(s, g_ft, s.B, n_mt, at);
+    NNUE_CHECK_LAUNCH("umma_format_rows_kernel");
+    n = 1LL * n_nt * kUmmaGbinN * (s.L1 / 8);
+    umma_format_rows_kernel<true, kUmmaGbinN><<<(int)((n + 255) / 256), 256, 0, st>>>(s, w, s.PP, n_nt, bt);
+    NNUE_CHECK_LAUNCH("umma_format_rows_kernel");
+    NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_gbin_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGbSmem));
+    ft_gbin_umma_kernel<<<dim3(n_nt, n_mt), kGbThreads, kGbSmem, st>>>(s, bits_s, at, bt, gbin);
+    NNUE_CHECK_LAUNCH("ft_gbin_umma_kernel");
     return NNUE_OK;
 }
 

@@ -220,6 +220,9 @@ int nnue_ft_bwd_gbin(const nnue_shape *s, const uint32_t *bits_s_d, const float 
                      float *gbin_d, void *workspace_d, size_t workspace_bytes, void *stream) {
     if (!s || !bits_s_d || !ft_w_d || !g_ft_d || !gbin_d) return NNUE_ERR_INVALID_ARG;
     if (!plan_input_bwd(*s).fused) return NNUE_ERR_UNSUPPORTED;
+    if (ft_umma_ok(*s) && workspace_d && workspace_bytes >= ws_ft_gbin_umma(*s))  // tcgen05 contraction
+        return launch_ft_bwd_gbin_umma(*s, bits_s_d, ft_w_d, g_ft_d, workspace_d, gbin_d, static_cast<cudaStream_t>(stream));
+    if (ft_umma_ok(*s) && !dense_shape_ok(*s)) return NNUE_ERR_WORKSPACE;  // no CUDA-core form for this L1
     if (plan_ft_mma(*s).ok && workspace_d && workspace_bytes >= mma_wfrag_bytes(*s))  // tensor-core contraction
         return launch_ft_bwd_gbin_mma(*s, bits_s_d, ft_w_d, g_ft_d, static_cast<uint4 *>(workspace_d), gbin_d,
                                       static_cast<cudaStream_t>(stream));
@@ -258,7 +261,9 @@ int nnue_input_bwd(const nnue_shape *s, const float *images_d, const uint32_t *b
     const InPlan pl = plan_input_bwd(*s);
     if (pl.fused) {
         float *gbin = reinterpret_cast<float *>(ws);
-        const int rc = nnue_ft_bwd_gbin(s, bits_s_d, ft_w_d, g_ft_d, gbin, nullptr, 0, stream);
+        const bool umma = ft_umma_ok(*s);  // its operand scratch sits behind the plane; the conv gradient reuses it afterwards
+        const int rc = nnue_ft_bwd_gbin(s, bits_s_d, ft_w_d, g_ft_d, gbin, umma ? ws + plane : nullptr,
+                                        umma ? workspace_bytes - plane : 0, stream);
         if (rc != NNUE_OK) return rc;
         return nnue_conv_bwd(s, images_d, gbin, nullptr, conv_w_d, thr_d, g_conv_w_d, g_thr_d, ws + plane,
                              workspace_bytes - plane, stream);

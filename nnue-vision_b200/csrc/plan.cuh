@@ -81,11 +81,51 @@ struct OwnPlan {
     size_t smem;
 };
 inline bool dense_shape_ok(const nnue_shape &s) { return s.L1 == 64 || s.L1 == 32; }
-// tcgen05 / TMEM forward (ft_umma.cu): L1 == 64, positions a multiple of 64
-inline bool ft_umma_ok(const nnue_shape &s) { return get_option(kOptFtUmma) && s.L1 == 64 && s.PP % 64 == 0; }
-inline size_t umma_wtiles_bytes(const nnue_shape &s) { return (size_t)s.PP * 64 * 2 * 3; }
+// ---- tcgen05 / TMEM contractions (ft_umma.cu): any L1 that is a multiple of 64 -----------------------------
+constexpr int kUmmaNCols = 64;    // forward / weight gradient: table columns per CTA (x 3 terms = UMMA N 192)
+constexpr int kUmmaGbinN = 256;   // value gradient: padded positions per CTA (UMMA N)
+inline bool ft_umma_ok(const nnue_shape &s) { return get_option(kOptFtUmma) && s.L1 >= 64 && s.L1 % 64 == 0; }
+// split-bf16 tiles of a [K rows][L1] operand, K a multiple of 32: 3 terms x 2 bytes per element
+inline size_t umma_kt_bytes(size_t K, const nnue_shape &s) { return K * s.L1 * 6; }
+struct UmmaDwPlan {
+    int chunk_blocks, n_chunks;  // K-chunks of `chunk_blocks` 32-sample blocks, one partial buffer each
+};
+inline UmmaDwPlan plan_ft_dw_umma(const nnue_shape &s) {
+    UmmaDwPlan p{};
+    const long long tiles = 1LL * ceil_div(s.PP, 128) * (s.L1 / kUmmaNCols);
+    long long want = (2LL * kNumSMs + tiles - 1) / tiles;  // two resident CTAs per SM, one wave
+    const long long per_chunk = 1LL * (s.P + 1) * s.L1 * 4;
+    long long cap = (256LL << 20) / (per_chunk > 0 ? per_chunk : 1);  // partial buffers capped at 256 MiB
+    if (cap < 1) cap = 1;
+    if (want > cap) want = cap;
+    if (want > s.BW) want = s.BW;
+    if (want < 1) want = 1;
+    p.chunk_blocks = ceil_div(s.BW, (int)want);
+    p.n_chunks = ceil_div(s.BW, p.chunk_blocks);
+    return p;
+}
+// the padded position whose A row is all ones in the weight-gradient GEMM (its output row = the bias gradient):
+// the first padding cell of channel 0, or one row past the last M tile when the cell words have no padding
+__host__ __device__ inline int umma_bias_pp(const nnue_shape &s) { return (s.Gh * s.Gw) % 32 ? s.Gh * s.Gw : s.PP; }
+// value gradient scratch: split g_ft tiles [ceil(B/128)][L1/16][3][128 x 16] | split table tiles [ceil(PP/256)][L1/16][3][256 x 16]
+inline size_t ws_ft_gbin_umma(const nnue_shape &s) {
+    if (!ft_umma_ok(s)) return 0;
+    return align_up((size_t)ceil_div(s.B, 128) * 128 * s.L1 * 6, 256) + align_up((size_t)ceil_div(s.PP, kUmmaGbinN) * kUmmaGbinN * s.L1 * 6, 256);
+}
+// weight gradient scratch: split g_ft^T tiles | partial[chunk][P + 1][L1] | rows parked for the aliased last row
+inline size_t ws_ft_dw_umma(const nnue_shape &s) {
+    if (!ft_umma_ok(s)) return 0;
+    const size_t alias_rows = (size_t)(s.P > s.F - 1 ? s.P - (s.F - 1) : 0);
+    return align_up(umma_kt_bytes((size_t)s.BW * 32, s), 256) + ((size_t)plan_ft_dw_umma(s).n_chunks * (s.P + 1) + alias_rows) * s.L1 * 4;
+}
+// the two gradients may run concurrently on two streams: disjoint regions, value gradient first
+inline size_t ws_ft_bwd_umma(const nnue_shape &s) { return ws_ft_gbin_umma(s) + align_up(ws_ft_dw_umma(s), 256); }
 int launch_ft_fwd_umma(const nnue_shape &s, const uint32_t *bits_s, const float *w, const float *bias, float *out,
                        void *workspace, cudaStream_t st);
+int launch_ft_bwd_dw_umma(const nnue_shape &s, const uint32_t *bits_s, const float *g_ft, void *ws, float *g_w, float *g_b,
+                          cudaStream_t st);
+int launch_ft_bwd_gbin_umma(const nnue_shape &s, const uint32_t *bits_s, const float *w, const float *g_ft, void *workspace,
+                            float *gbin, cudaStream_t st);
 
 inline OwnPlan plan_ft_bwd_dw_owner(const nnue_shape &s) {
     OwnPlan o{};
@@ -216,7 +256,7 @@ struct InPlan {
 inline InPlan plan_input_bwd(const nnue_shape &s) {
     InPlan p{};
     const long long HW = 1LL * s.H * s.W;
-    if (!get_option(kOptInputFused) || !dense_shape_ok(s) || HW % 4 || HW > 16384) return p;
+    if (!get_option(kOptInputFused) || !(dense_shape_ok(s) || ft_umma_ok(s)) || HW % 4 || HW > 16384) return p;
     p.CH = get_option(kOptInputVariant) == 1 ? 4 : 2;
     p.WARPS = 32 / p.CH;
     const int units = ceil_div(s.C, p.CH) * s.CW;
@@ -287,7 +327,11 @@ inline size_t ws_head_bwd(const nnue_shape &s) {
 }
 inline size_t ws_input_bwd(const nnue_shape &s) {
     const InPlan p = plan_input_bwd(s);
-    if (p.fused) return align_up((size_t)s.B * s.PP * 4, 256) + (size_t)p.grid * s.C * 28 * 4;
+    if (p.fused) {  // gbin plane | max(conv-gradient partials, value-gradient operand scratch)
+        size_t rest = (size_t)p.grid * s.C * 28 * 4;
+        if (ws_ft_gbin_umma(s) > rest) rest = ws_ft_gbin_umma(s);
+        return align_up((size_t)s.B * s.PP * 4, 256) + rest;
+    }
     const size_t a = ws_ft_bwd_dval(s), b = ws_extract_bwd(s);
     return 2 * align_up((size_t)s.B * s.PP * 4, 256) + (a > b ? a : b);
 }
@@ -326,7 +370,7 @@ inline MmaPlan plan_ft_mma(const nnue_shape &s) {
 inline size_t mma_wfrag_bytes(const nnue_shape &s) { return (size_t)(s.PP / 16) * 3 * (s.L1 / 16) * 32 * 16; }
 inline size_t mma_gfrag_bytes(const nnue_shape &s) { return (size_t)(s.BW * 2) * 3 * (s.L1 / 16) * 32 * 16; }
 inline size_t ws_ft_fwd(const nnue_shape &s) {
-    const size_t a = plan_ft_mma(s).ok ? mma_wfrag_bytes(s) : 0, b = ft_umma_ok(s) ? umma_wtiles_bytes(s) : 0;
+    const size_t a = plan_ft_mma(s).ok ? mma_wfrag_bytes(s) : 0, b = ft_umma_ok(s) ? umma_kt_bytes((size_t)s.PP, s) : 0;
     return a > b ? a : b;
 }
 inline size_t ws_ft_bwd_mma(const nnue_shape &s) {
