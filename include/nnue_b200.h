@@ -76,6 +76,8 @@ unsigned long long nnue_launch_count(int reset);
  *   "input_bwd_fused" 1 (default) = dense value-gradient + conv-gradient kernels where the shape
  *                     allows, 0 = always the index-driven kernel pair.
  *   "input_bwd_variant" conv-gradient kernel: 0 = 16 warps x 2 channels, 1 (default) = 8 warps x 4.
+ *   "input_bwd_swizzle" 1 (default) = the conv-gradient kernel stages 32 x 32 images with one tensor-map TMA copy in
+ *                     the 128-byte swizzle mode (bank-conflict-free tap reads), 0 = dense rows by 1-D bulk copies.
  *   "extract_fixed"   1 (default) = extraction forward specialised on the channel count (4/8/16/32) with one
  *                     cell word per warp, 0 = the generic kernel.
  *   "extract_tma"     1 = TMA-staged extraction forward for CIFAR-sized images, 0 (default) = direct loads

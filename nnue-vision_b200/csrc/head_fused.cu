@@ -375,7 +375,15 @@ __global__ void head_train_fold_kernel(int nblk, const float *__restrict__ parti
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e > Lay::pLoss) return;
     float v = 0.0f;
-    for (int k = 0; k < nblk; ++k) v += partial[(size_t)k * Lay::pTotal + e];
+    int k = 0;
+    for (; k + 16 <= nblk; k += 16) {  // loads batched sixteen deep (the loop is latency-bound); same summation order
+        float t[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) t[u] = __ldg(partial + (size_t)(k + u) * Lay::pTotal + e);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v += t[u];
+    }
+    for (; k < nblk; ++k) v += __ldg(partial + (size_t)k * Lay::pTotal + e);
     const int h = L1 / 2;
     if (e < Lay::pB1) {
         const int o = e / L1P, sl = e % L1P;

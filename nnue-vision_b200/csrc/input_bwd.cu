@@ -14,6 +14,9 @@
 // shared-memory stages with bulk TMA copies (full / empty mbarriers); consumers read image taps as
 // LDS.32 and share them between their CH channels.  Out-of-image taps (padding = 1) are redirected
 // to a zeroed pad word behind each plane, so the inner loop has no predicates.
+#include <cuda.h>
+#include <string.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 #include "plan.cuh"
 
@@ -21,15 +24,33 @@ namespace nnue {
 
 constexpr float kSteSharpness = 10.0f;  // nnue.py:41
 
+// ---- swizzled staging of 32 x 32 images (SWZ) -------------------------------------------------------------------
+// With a dense 32-word row pitch every image row starts in bank 0, so the lanes of a cell word (three raster rows
+// of 11 cells at config D) hit each bank three times on every tap load (ncu: 56 % of the kernel's shared-memory
+// wavefronts were conflicts).  The SWZ variant fetches a sample with ONE 3-D tensor-map TMA copy in the 128-byte
+// swizzle mode: box = 32 columns x 40 rows x 3 planes starting at row -1, so that 16-byte chunk c of box row r lands
+// at chunk c ^ (r & 7) -- rows three apart no longer share banks -- and the out-of-bounds rows (image rows -1 and
+// 32 .. 38) arrive zero-filled, which also provides the padding taps.  Per-lane tap offsets absorb the swizzle.
+constexpr int kSwzRows = 40;                         // box rows per plane (a multiple of the 8-row swizzle atom)
+constexpr int kSwzPlane = kSwzRows * 32;             // floats per staged plane
+constexpr uint32_t kSwzImgBytes = 3 * kSwzPlane * 4; // 15360 bytes per sample (12288 fetched, the rest zero fill)
+
+__device__ __forceinline__ void tma_tensor3d_g2s(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // HWT: H*W when known at compile time (plane offsets become LDS immediates), 0 = read it from the shape
 // XS: the forward stored the pre-threshold activations (xpad, staged next to g_bin) -- otherwise they are
 //     recomputed from the taps and the conv weights
-template <int CH, int WARPS, int HWT, bool XS>
+template <int CH, int WARPS, int HWT, bool XS, bool SWZ>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 conv_bwd_kernel(const nnue_shape s, const float *__restrict__ images, const float *__restrict__ dval,
                 const float *__restrict__ xpad, const float *__restrict__ conv_w, const float *__restrict__ thr,
-                float *__restrict__ partial, const InPlan pl) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+                float *__restrict__ partial, const InPlan pl, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
     uint64_t *empty = full + kInMaxStages;
     float *s_cw = reinterpret_cast<float *>(smem_raw + kInHeader);  // [C][28]
@@ -39,7 +60,7 @@ conv_bwd_kernel(const nnue_shape s, const float *__restrict__ images, const floa
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int role = blockIdx.x % pl.NH, q = blockIdx.x / pl.NH;
-    const int HW = HWT ? HWT : s.H * s.W, HWp = HW + 4;
+    const int HW = HWT ? HWT : s.H * s.W, HWp = SWZ ? kSwzPlane : HW + 4;  // HWp: floats between staged planes
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < pl.ST; ++i) {
@@ -54,7 +75,7 @@ conv_bwd_kernel(const nnue_shape s, const float *__restrict__ images, const floa
     }
     for (int i = threadIdx.x; i < s.C; i += blockDim.x) s_thr[i] = thr[i];
     // the 4 pad words behind every image plane stay zero for the whole kernel (TMA never writes them)
-    for (int i = threadIdx.x; i < pl.ST * 3 * 4; i += blockDim.x) {
+    if (!SWZ) for (int i = threadIdx.x; i < pl.ST * 3 * 4; i += blockDim.x) {
         const int st = i / 12, pln = (i % 12) / 4, k = i % 4;
         stages[(size_t)st * pl.stage_floats + pln * HWp + HW + k] = 0.0f;
     }
@@ -68,10 +89,15 @@ conv_bwd_kernel(const nnue_shape s, const float *__restrict__ images, const floa
         if (ii >= pl.ST) mbar_wait(&empty[st], ph);
         const int b = q + ii * pl.nq;
         float *stg = stages + (size_t)st * pl.stage_floats;
-        mbar_arrive_expect_tx(&full[st], (uint32_t)(3 * HW + (XS ? 2 : 1) * s.PP) * 4u);
-        const float *img = images + (size_t)b * 3 * HW;
+        if (SWZ) {
+            mbar_arrive_expect_tx(&full[st], kSwzImgBytes + (uint32_t)((XS ? 2 : 1) * s.PP) * 4u);
+            tma_tensor3d_g2s(stg, &tmap, 0, -1, 3 * b, &full[st]);
+        } else {
+            mbar_arrive_expect_tx(&full[st], (uint32_t)(3 * HW + (XS ? 2 : 1) * s.PP) * 4u);
+            const float *img = images + (size_t)b * 3 * HW;
 #pragma unroll
-        for (int pln = 0; pln < 3; ++pln) tma_bulk_g2s(stg + pln * HWp, img + pln * HW, (uint32_t)HW * 4u, &full[st]);
+            for (int pln = 0; pln < 3; ++pln) tma_bulk_g2s(stg + pln * HWp, img + pln * HW, (uint32_t)HW * 4u, &full[st]);
+        }
         tma_bulk_g2s(stg + 3 * HWp, dval + (size_t)b * s.PP, (uint32_t)s.PP * 4u, &full[st]);
         if (XS) tma_bulk_g2s(stg + 3 * HWp + s.PP, xpad + (size_t)b * s.PP, (uint32_t)s.PP * 4u, &full[st]);
     };
@@ -101,7 +127,12 @@ conv_bwd_kernel(const nnue_shape s, const float *__restrict__ images, const floa
             for (int kw = 0; kw < 3; ++kw) {
                 const int iy = y0 + kh, ix = x0 + kw;
                 const bool in = valid && (unsigned)iy < (unsigned)s.H && (unsigned)ix < (unsigned)s.W;
-                off9[kh * 3 + kw] = in ? iy * s.W + ix : HW;
+                if (SWZ) {  // box row iy + 1; out-of-image taps read box row 0 (image row -1: zero fill)
+                    const int r = iy + 1;
+                    off9[kh * 3 + kw] = in ? r * 32 + ((((ix >> 2) ^ (r & 7)) << 2) | (ix & 3)) : 0;
+                } else {
+                    off9[kh * 3 + kw] = in ? iy * s.W + ix : HW;
+                }
             }
     }
     float acc[CH][27], dth[CH], thr_c[CH];
@@ -191,19 +222,73 @@ __global__ void input_bwd_fold_kernel(int C, int nblk, const float *__restrict__
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= C * 28) return;
     float v = 0.0f;
-    for (int k = 0; k < nblk; ++k) v += partial[(size_t)k * C * 28 + i];
+    int k = 0;
+    for (; k + 16 <= nblk; k += 16) {  // loads batched sixteen deep (the loop is latency-bound); same summation order
+        float t[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) t[u] = __ldg(partial + (size_t)(k + u) * C * 28 + i);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v += t[u];
+    }
+    for (; k < nblk; ++k) v += __ldg(partial + (size_t)k * C * 28 + i);
     const int c = i / 28, t = i % 28;
     if (t < 27) g_conv_w[c * 27 + t] = v;
     else g_thr[c] = v;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// images [B][3][32][32] fp32 as a 3-D tensor (x, y, plane), box 32 x 40 x 3, 128-byte swizzle, zero fill out of bounds
+static bool make_image_tmap(const float *images, int B, CUtensorMap *tm) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {32, 32, (cuuint64_t)B * 3};
+    const cuuint64_t strides[2] = {128, 4096};
+    const cuuint32_t box[3] = {32, (cuuint32_t)kSwzRows, 3};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(images), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int CH, int WARPS>
 static int launch_conv_bwd(const nnue_shape &s, const InPlan &pl, const float *images, const float *dval,
                            const float *xpad, const float *conv_w, const float *thr, float *partial, cudaStream_t st) {
-    auto k = xpad ? (s.H * s.W == 1024 ? conv_bwd_kernel<CH, WARPS, 1024, true> : conv_bwd_kernel<CH, WARPS, 0, true>)
-                  : (s.H * s.W == 1024 ? conv_bwd_kernel<CH, WARPS, 1024, false> : conv_bwd_kernel<CH, WARPS, 0, false>);
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    if (s.H == 32 && s.W == 32 && get_option(kOptInputSwizzle) && make_image_tmap(images, s.B, &tm)) {
+        // swizzled staging: stage = 3 planes of 40 rows (1024-byte aligned) | g_bin row | activation row
+        InPlan p2 = pl;
+        p2.stage_off = (int)align_up((size_t)pl.stage_off, 1024);
+        p2.stage_floats = (int)(align_up((size_t)kSwzImgBytes + 2 * (size_t)s.PP * 4, 1024) / 4);
+        int ST = (int)((kMaxSmemOptin - (size_t)p2.stage_off) / ((size_t)p2.stage_floats * 4));
+        if (ST > kInMaxStages) ST = kInMaxStages;
+        if (ST >= 3) {
+            p2.ST = ST;
+            p2.smem = (size_t)p2.stage_off + (size_t)ST * p2.stage_floats * 4;
+            auto k = xpad ? conv_bwd_kernel<CH, WARPS, 1024, true, true> : conv_bwd_kernel<CH, WARPS, 1024, false, true>;
+            NNUE_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2.smem));
+            k<<<p2.grid, WARPS * 32, p2.smem, st>>>(s, images, dval, xpad, conv_w, thr, partial, p2, tm);
+            NNUE_CHECK_LAUNCH("conv_bwd_kernel");
+            return NNUE_OK;
+        }
+    }
+    auto k = xpad ? (s.H * s.W == 1024 ? conv_bwd_kernel<CH, WARPS, 1024, true, false> : conv_bwd_kernel<CH, WARPS, 0, true, false>)
+                  : (s.H * s.W == 1024 ? conv_bwd_kernel<CH, WARPS, 1024, false, false> : conv_bwd_kernel<CH, WARPS, 0, false, false>);
     NNUE_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    k<<<pl.grid, WARPS * 32, pl.smem, st>>>(s, images, dval, xpad, conv_w, thr, partial, pl);
+    k<<<pl.grid, WARPS * 32, pl.smem, st>>>(s, images, dval, xpad, conv_w, thr, partial, pl, tm);
     NNUE_CHECK_LAUNCH("conv_bwd_kernel");
     return NNUE_OK;
 }

@@ -132,3 +132,111 @@ def serialize_model(model, output_path) -> None:
         write_conv_layer(f, q["conv_layer"])
         write_feature_transformer(f, q["feature_transformer"])
         write_classifier(f, q["classifier"])
+
+
+# ---- reader ---------------------------------------------------------------
+# The reference only parses `.nnue` files in C++ (NNUEEvaluator::load_model, nnue_engine.cpp:544-657,
+# ConvLayer / FeatureTransformer / LayerStack::load_from_stream :11-46, :161-186, :283-380).  The reader
+# below applies the same checks in the same order and returns the payloads as numpy arrays, so that a
+# file can be inspected, turned back into a float model, or re-written byte for byte.
+class NnueFormatError(ValueError):
+    pass
+
+
+def _take(buf, off, fmt):
+    n = struct.calcsize(fmt)
+    if off + n > len(buf):
+        raise NnueFormatError("truncated .nnue file")
+    return struct.unpack_from(fmt, buf, off), off + n
+
+
+def _take_array(buf, off, dtype, count):
+    n = np.dtype(dtype).itemsize * count
+    if off + n > len(buf):
+        raise NnueFormatError("truncated .nnue file")
+    return np.frombuffer(buf, dtype=dtype, count=count, offset=off).copy(), off + n
+
+
+def read_nnue(path) -> Dict[str, Any]:
+    """Parse a format-v2 `.nnue` file into
+    {"metadata": {...}, "conv_layer": {...}, "feature_transformer": {...}, "layer_stacks": [ {...}, ... ]}
+    with integer payloads exactly as stored (conv int8 [OC,IC,KH,KW], FT int16 [F,L1], dense int8)."""
+    buf = Path(path).read_bytes()
+    if buf[:4] != b"NNUE":
+        raise NnueFormatError("bad magic")
+    (version, F, L1, L2, L3, n_buckets), off = _take(buf, 4, "<IIIIII")
+    if version != 2:
+        raise NnueFormatError(f"unsupported version {version}")
+    (nnue2score, quantized_one, threshold), off = _take(buf, off, "<fff")
+    (layer_type,), off = _take(buf, off, "<I")
+    if layer_type != 0:
+        raise NnueFormatError("conv layer type must be 0")
+    (conv_scale, OC, IC, KH, KW), off = _take(buf, off, "<fIIII")
+    conv_w, off = _take_array(buf, off, "i1", OC * IC * KH * KW)
+    (nb,), off = _take(buf, off, "<I")
+    conv_b, off = _take_array(buf, off, "<i4", nb)
+    if OC == 0 or F == 0 or F % OC:
+        raise NnueFormatError("invalid feature/channel configuration")
+    G = int(np.sqrt(F // OC))
+    if G * G * OC != F:
+        raise NnueFormatError("invalid feature grid calculation")
+    (ft_scale, ftF, ftL1), off = _take(buf, off, "<fII")
+    ft_w, off = _take_array(buf, off, "<i2", ftF * ftL1)
+    (nb,), off = _take(buf, off, "<I")
+    ft_b, off = _take_array(buf, off, "<i4", nb)
+    if ftF != F or ftL1 != L1:
+        raise NnueFormatError("feature transformer architecture mismatch")
+    stacks = []
+    for _ in range(n_buckets):
+        (s1, s2, so, sf), off = _take(buf, off, "<ffff")
+        blocks = []
+        for _ in range(4):  # L1 (+1 row), L1-fact, L2 (2*L2 inputs), output
+            (n_out, n_in), off = _take(buf, off, "<II")
+            w, off = _take_array(buf, off, "i1", n_out * n_in)
+            (nb,), off = _take(buf, off, "<I")
+            b, off = _take_array(buf, off, "<i4", nb)
+            blocks.append((w.reshape(n_out, n_in), b))
+        (w1, b1), (wf, bf), (w2, b2), (wo, bo) = blocks
+        if w1.shape != (L2 + 1, L1) or w2.shape != (L3, 2 * L2) or wo.shape[1] != L3:
+            raise NnueFormatError("layer stack architecture mismatch")
+        stacks.append({"l1_scale": s1, "l2_scale": s2, "output_scale": so, "l1_fact_scale": sf,
+                       "l1_weight": w1, "l1_bias": b1, "l1_fact_weight": wf, "l1_fact_bias": bf,
+                       "l2_weight": w2, "l2_bias": b2, "output_weight": wo, "output_bias": bo})
+    return {
+        "metadata": {"version": version, "num_features": F, "L1": L1, "L2": L2, "L3": L3, "num_ls_buckets": n_buckets,
+                     "nnue2score": nnue2score, "quantized_one": quantized_one, "visual_threshold": threshold,
+                     "grid_size": G, "num_features_per_square": OC,
+                     "num_classes": int(stacks[0]["output_weight"].shape[0]) if stacks else 0},
+        "conv_layer": {"weight": conv_w.reshape(OC, IC, KH, KW), "bias": conv_b, "scale": conv_scale},
+        "feature_transformer": {"weight": ft_w.reshape(F, L1), "bias": ft_b, "scale": ft_scale},
+        "layer_stacks": stacks,
+        "trailing_bytes": len(buf) - off,
+    }
+
+
+def load_nnue_as_model(path, input_size=32, layer_stack_index=0):
+    """Float `NNUE` whose parameters are the de-quantised contents of a `.nnue` file (payload / scale).
+    Serialising it again reproduces the file byte for byte when the file came from `serialize_model`
+    (integers up to 2**24 survive the division by 64 and the multiplication back exactly).  The file
+    keeps only the channel mean of the threshold (nnue.py:556-558); it is replicated per channel."""
+    from .nnue import NNUE, GridFeatureSet
+    q = read_nnue(path)
+    md = q["metadata"]
+    st = q["layer_stacks"][layer_stack_index]
+    model = NNUE(GridFeatureSet(md["grid_size"], md["num_features_per_square"]), md["L1"], md["L2"], md["L3"],
+                 num_classes=md["num_classes"], input_size=input_size)
+    L2 = md["L2"]
+    lin = [m for m in model.classifier.classifier if isinstance(m, torch.nn.Linear)]
+    with torch.no_grad():
+        model.conv.weight.copy_(torch.from_numpy(q["conv_layer"]["weight"].astype(np.float32) / q["conv_layer"]["scale"]))
+        model.input.weight.copy_(torch.from_numpy(q["feature_transformer"]["weight"].astype(np.float32) / q["feature_transformer"]["scale"]))
+        model.input.bias.copy_(torch.from_numpy(q["feature_transformer"]["bias"].astype(np.float32) / q["feature_transformer"]["scale"]))
+        lin[0].weight.copy_(torch.from_numpy(st["l1_weight"][:L2].astype(np.float32) / st["l1_scale"]))
+        lin[0].bias.copy_(torch.from_numpy(st["l1_bias"][:L2].astype(np.float32) / st["l1_scale"]))
+        lin[1].weight.copy_(torch.from_numpy(st["l2_weight"][:, :L2].astype(np.float32) / st["l2_scale"]))
+        lin[1].bias.copy_(torch.from_numpy(st["l2_bias"].astype(np.float32) / st["l2_scale"]))
+        lin[2].weight.copy_(torch.from_numpy(st["output_weight"].astype(np.float32) / st["output_scale"]))
+        lin[2].bias.copy_(torch.from_numpy(st["output_bias"].astype(np.float32) / st["output_scale"]))
+        model.nnue2score.fill_(md["nnue2score"])
+        model.visual_threshold.fill_(md["visual_threshold"])
+    return model

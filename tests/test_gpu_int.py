@@ -172,3 +172,37 @@ def test_evaluate_model_float_path():
     with torch.no_grad():
         ref = sum(float(torch.nn.functional.cross_entropy(model(x.cuda()), y.cuda())) for x, y in loader) / 3
     assert abs(loss - ref) < 1e-6 and 0.0 <= metrics["acc"] <= 1.0
+
+
+def test_layer_stack_buckets_select_their_own_stack(oracle_built, tmp_path):
+    """N-bucket files (num_ls_buckets > 1, nnue_engine.cpp:619-635): `layer_stack_index` picks the stack, an
+    index past the end falls back to stack 0 (nnue_engine.cpp:705-707).  Each bucket is checked bit-exactly
+    against the oracle on a one-bucket file that holds only that stack (rebuilt with serialize.read_nnue)."""
+    import struct
+    from nnue_vision_b200 import serialize
+    G, C, L1, L2, L3, NC, H = 8, 4, 64, 8, 8, 10, 32
+    rng = np.random.default_rng(77)
+    path = tmp_path / "three.nnue"
+    write_random_nnue(path, rng, G, C, L1, L2, L3, NC, wild=True, n_buckets=3)
+    q = serialize.read_nnue(path)
+    assert q["metadata"]["num_ls_buckets"] == 3 and q["trailing_bytes"] == 0
+    blob = path.read_bytes()
+    stack_bytes = 16 + sum(8 + w.size + 4 + 4 * b.size for w, b in (
+        (q["layer_stacks"][0][k + "_weight"], q["layer_stacks"][0][k + "_bias"]) for k in ("l1", "l1_fact", "l2", "output")))
+    head_end = len(blob) - 3 * stack_bytes
+    imgs = rng.standard_normal((33, H, H, 3)).astype(np.float32)
+    ev = _engine().NNUEEvaluator(path)
+    assert ev.num_layer_stacks == 3
+    outs = []
+    for bucket in range(3):
+        single = tmp_path / f"only{bucket}.nnue"
+        single.write_bytes(blob[:24] + struct.pack("<I", 1) + blob[28:head_end] +
+                           blob[head_end + bucket * stack_bytes: head_end + (bucket + 1) * stack_bytes])
+        ol, od = oracle_built.IntOracle(single).eval_batch(imgs, threads=2)
+        logits, dens = ev.evaluate_logits(torch.as_tensor(imgs).cuda(), layer_stack_index=bucket)
+        np.testing.assert_array_equal(logits.cpu().numpy(), ol)
+        np.testing.assert_array_equal(dens.cpu().numpy(), od)
+        outs.append(ol)
+    assert not np.array_equal(outs[0], outs[1]) and not np.array_equal(outs[1], outs[2])
+    past_end, _ = ev.evaluate_logits(torch.as_tensor(imgs).cuda(), layer_stack_index=7)
+    np.testing.assert_array_equal(past_end.cpu().numpy(), outs[0])

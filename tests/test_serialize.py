@@ -1,6 +1,7 @@
 """Host logic of the drop-in boundary: module surface, state_dict layout and the .nnue writer,
 checked against files and tensors produced by the reference itself (tests/golden)."""
 import io
+import struct
 
 import numpy as np
 import pytest
@@ -130,3 +131,53 @@ def test_cpu_forward_raises_instead_of_falling_back():
         m(torch.zeros(2, 3, 32, 32))
     with pytest.raises(_lib.NnueError):
         m.input(torch.zeros(2, 3, dtype=torch.long), torch.ones(2, 3))
+
+
+# ---- reader ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_reader_parses_reference_written_files(name):
+    """read_nnue on the files the reference's serialize.py wrote: header fields and payloads match the
+    quantised golden state."""
+    from nnue_vision_b200 import serialize
+    rec = load_golden(name)
+    q = serialize.read_nnue(GOLDEN / f"{name}.nnue")
+    cfg, md = rec["cfg"], q["metadata"]
+    assert (md["grid_size"], md["num_features_per_square"], md["L1"], md["L2"], md["L3"], md["num_classes"]) == (
+        cfg["grid"], cfg["C"], cfg["L1"], cfg["L2"], cfg["L3"], cfg["NC"])
+    assert md["num_ls_buckets"] == 1 and md["quantized_one"] == 127.0 and q["trailing_bytes"] == 0
+    st = golden_state(rec, clipped=True)
+    np.testing.assert_array_equal(q["feature_transformer"]["weight"],
+                                  np.clip(np.round(st["input.weight"] * 64.0), -127, 127).astype(np.int16))
+    np.testing.assert_array_equal(q["conv_layer"]["weight"],
+                                  np.clip(np.round(st["conv.weight"] * 64.0), -127, 127).astype(np.int8))
+    s0 = q["layer_stacks"][0]
+    assert not s0["l1_weight"][-1].any() and not s0["l2_weight"][:, cfg["L2"]:].any()
+    np.testing.assert_array_equal(s0["l1_fact_weight"], np.eye(cfg["L1"], dtype=np.int8) * 127)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_nnue_file_round_trips_through_float_model(name, tmp_path):
+    """.nnue -> float model -> .nnue is byte-identical (the quantiser is idempotent on de-quantised values)."""
+    from nnue_vision_b200 import serialize
+    rec = load_golden(name)
+    src = GOLDEN / f"{name}.nnue"
+    model = serialize.load_nnue_as_model(src, input_size=rec["cfg"]["model_input"])
+    out = tmp_path / "again.nnue"
+    serialize.serialize_model(model, out)
+    a, b = out.read_bytes(), src.read_bytes()
+    # every payload byte survives; the header threshold is the fp32 MEAN of the per-channel values
+    # (nnue.py:556-558), which may round in the last bit when re-averaged over C equal entries
+    assert a[:36] == b[:36] and a[40:] == b[40:]
+    ta, tb = struct.unpack("<f", a[36:40])[0], struct.unpack("<f", b[36:40])[0]
+    assert abs(ta - tb) <= 2e-7 * max(abs(tb), 1e-30)
+
+
+def test_reader_rejects_malformed_files(tmp_path):
+    from nnue_vision_b200 import serialize
+    good = (GOLDEN / "test_cfg.nnue").read_bytes()
+    for name, blob in (("magic", b"XXXX" + good[4:]), ("version", good[:4] + b"\x03\x00\x00\x00" + good[8:]),
+                       ("short", good[: len(good) // 2])):
+        p = tmp_path / f"{name}.nnue"
+        p.write_bytes(blob)
+        with pytest.raises(serialize.NnueFormatError):
+            serialize.read_nnue(p)
