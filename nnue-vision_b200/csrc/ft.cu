@@ -1046,6 +1046,39 @@ static int launch_ft_bwd_dval(const nnue_shape &s, const uint32_t *bits, const f
     return NNUE_OK;
 }
 
+// g_thr[c] = -sum_{b, cell} g_bin[b, c, cell] * k * sig * (1 - sig), sig = sigmoid(k (x - thr[c]))   (nnue.py:36-52)
+// over dense [B][PP] rows (g_bin is zero at inactive positions).  CTA = (channel, chunk of samples); per-thread
+// sums, a fixed-order block reduction, partial[chunk][C] for fold_partials_kernel.
+__global__ void __launch_bounds__(256)
+thr_grad_kernel(const nnue_shape s, const float *__restrict__ gbin, const float *__restrict__ xpad,
+                const float *__restrict__ thr, float *__restrict__ partial, int rows_per_chunk) {
+    __shared__ float red[256];
+    const int c = blockIdx.x, chunk = blockIdx.y;
+    const int b0 = chunk * rows_per_chunk, b1 = min(s.B, b0 + rows_per_chunk);
+    const int cw32 = s.CW * 32, cells = s.Gh * s.Gw;
+    const float thr_c = __ldg(thr + c);
+    float acc = 0.0f;
+    const long long n = 1LL * max(0, b1 - b0) * cw32;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const int b = b0 + (int)(i / cw32), cell = (int)(i % cw32);
+        if (cell >= cells) continue;
+        const size_t at = (size_t)b * s.PP + (size_t)c * cw32 + cell;
+        const float g = __ldg(gbin + at);
+        if (g != 0.0f) {
+            const float z = kSteSharpnessFt * (__ldg(xpad + at) - thr_c);
+            const float sgm = __fdividef(1.0f, 1.0f + __expf(-z));
+            acc = fmaf(-g, kSteSharpnessFt * sgm * (1.0f - sgm), acc);
+        }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(size_t)chunk * s.C + c] = red[0];
+}
+
 int launch_ft_bwd_dval_dense(const nnue_shape &s, const uint32_t *bits_s, const float *ft_w, const float *g_ft,
                              float *dval, cudaStream_t st) {
     const DvPlan pl = plan_ft_bwd_dval_dense(s);
@@ -1278,6 +1311,17 @@ int nnue_ft_bwd_dval(const nnue_shape *s, const uint32_t *bits_s_d, const float 
         return NNUE_ERR_INVALID_ARG;
     if (workspace_bytes < ws_ft_bwd_dval(*s)) return NNUE_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (ft_umma_ok(*s)) {  // tcgen05 contraction for the dense masked rows, then the threshold-gradient reduction
+        const int rc = launch_ft_bwd_gbin_umma(*s, bits_s_d, ft_w_d, g_ft_d, workspace_d, dval_d, st);
+        if (rc != NNUE_OK) return rc;
+        float *part = reinterpret_cast<float *>(static_cast<char *>(workspace_d) + ws_ft_gbin_umma(*s));
+        const int nch = thr_chunks(*s), rpc = ceil_div(s->B, nch);
+        thr_grad_kernel<<<dim3(s->C, nch), 256, 0, st>>>(*s, dval_d, xpad_d, thr_d, part, rpc);
+        NNUE_CHECK_LAUNCH("thr_grad_kernel");
+        fold_partials_kernel<<<ceil_div(s->C, 128), 128, 0, st>>>(s->C, nch, part, g_thr_d);
+        NNUE_CHECK_LAUNCH("fold_partials_kernel");
+        return NNUE_OK;
+    }
     float *thr_partial = static_cast<float *>(workspace_d);
     const ColPlan cp = col_plan(s->L1);
     const int grid = dval_grid(*s);

@@ -214,7 +214,18 @@ inline int dval_grid(const nnue_shape &s) {
     if (grid < kNumSMs) grid = kNumSMs;  // the staged variant always runs kNumSMs CTAs
     return (int)grid;
 }
-inline size_t ws_ft_bwd_dval(const nnue_shape &s) { return (size_t)dval_grid(s) * s.C * 4; }
+// tcgen05 form of the general value gradient: dense masked g_bin by ft_gbin_umma_kernel, then a threshold-gradient
+// reduction over (g_bin, activations) in `thr_chunks` sample chunks per channel
+inline int thr_chunks(const nnue_shape &s) {
+    int n = ceil_div(4 * kNumSMs, s.C);
+    if (n > s.B) n = s.B;
+    return n < 1 ? 1 : n;
+}
+inline size_t ws_ft_bwd_dval(const nnue_shape &s) {
+    const size_t a = (size_t)dval_grid(s) * s.C * 4;
+    const size_t b = ft_umma_ok(s) ? ws_ft_gbin_umma(s) + (size_t)thr_chunks(s) * s.C * 4 : 0;
+    return a > b ? a : b;
+}
 
 // ---- extraction backward -----------------------------------------------------------------
 constexpr int kExbCCH = 2;      // channels per warp (register accumulators: 2 x 27 + 2)
