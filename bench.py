@@ -238,6 +238,9 @@ def run_reference(args):
 def stage_breakdown(dp, images, labels, reps=5):
     """Average device time of each C-ABI stage, from CUDA events recorded on the launching stream."""
     totals = {}
+    for _ in range(3):  # the eager, marked path has its own allocations to warm (the timed loop replays a graph)
+        dp.step(images, labels, marks=[])
+    torch.cuda.synchronize()
     for _ in range(reps):
         marks = []
         dp.step(images, labels, marks=marks)

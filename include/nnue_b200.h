@@ -66,6 +66,9 @@ const char *nnue_last_cuda_error(void);
 
 /* Kernels this library has launched in this process so far (optionally reset to 0). */
 unsigned long long nnue_launch_count(int reset);
+/* Account for kernels launched on the library's behalf without passing through it: a host that replays a captured
+ * CUDA graph of these calls adds the graph's kernel count per replay.  Returns the new total. */
+unsigned long long nnue_launch_count_add(unsigned long long n);
 
 /*
  * Tuning knobs (process-wide; defaults work).  Keys:

@@ -40,6 +40,10 @@ unsigned long long nnue_launch_count(int reset) {
     return v;
 }
 
+unsigned long long nnue_launch_count_add(unsigned long long n) {
+    return __atomic_add_fetch(&nnue::g_launches, n, __ATOMIC_RELAXED);
+}
+
 int nnue_b200_abi_version(void) { return NNUE_B200_ABI_VERSION; }
 
 const char *nnue_error_string(int code) {

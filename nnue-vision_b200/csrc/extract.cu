@@ -105,14 +105,17 @@ constexpr int kExtConstChannels = 32;
 __constant__ float c_ext_w[kExtConstChannels * 27];
 __constant__ float c_ext_thr[kExtConstChannels];
 
-template <int CT>
-__global__ void __launch_bounds__(kExtThreads)
+// PLANE = H*W when known at compile time (32 x 32 images: 1024), else 0.  With a fixed plane size a lane keeps nine
+// 64-bit tap POINTERS and advances them once per sample; the three planes of a tap are then LDG immediates.  (ncu on
+// the offset form: 9.8 M of 40 M executed instructions were 64-bit address arithmetic, 5.5 per load, at 70 % issue.)
+template <int CT, int PLANE>
+__global__ void __launch_bounds__(kExtThreads, 2)
 extract_fwd_fixed_kernel(const nnue_shape s, const float *__restrict__ images, uint32_t *__restrict__ bits_s,
                          float *__restrict__ xpad) {
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (kExtThreads / 32) + (threadIdx.x >> 5), nw = gridDim.x * (kExtThreads / 32);
     const int j = gw % s.CW;                       // my cell word (needs nw % CW == 0)
-    const int cells = s.Gh * s.Gw, plane = s.H * s.W;
+    const int cells = s.Gh * s.Gw, plane = PLANE ? PLANE : s.H * s.W;
     const int cell = j * 32 + lane;
     const bool valid = cell < cells;
     const int oy = valid ? cell / s.Gw : 0, ox = valid ? cell % s.Gw : 0;
@@ -130,17 +133,31 @@ extract_fwd_fixed_kernel(const nnue_shape s, const float *__restrict__ images, u
                 okm |= (in ? 1u : 0u) << (kh * 3 + kw);
             }
     }
-    // the next sample's taps are in flight while this sample's channels are computed
-    auto fetch = [&](float (&p)[27], int b) {
-        const float *img = images + (size_t)b * 3 * plane;
-#pragma unroll
-        for (int ic = 0; ic < 3; ++ic)
-#pragma unroll
-            for (int t9 = 0; t9 < 9; ++t9) p[ic * 9 + t9] = __ldg(img + ic * plane + off9[t9]);
-    };
     const int step = nw / s.CW;
-    float nxt[27];
     int b = gw / s.CW;
+    const float *tap[9];  // PLANE only: my nine taps of the sample being fetched (plane 0)
+    if (PLANE) {
+#pragma unroll
+        for (int t9 = 0; t9 < 9; ++t9) tap[t9] = images + (size_t)min(b, s.B - 1) * 3 * PLANE + off9[t9];
+    }
+    // the next sample's taps are in flight while this sample's channels are computed
+    auto fetch = [&](float (&p)[27], int bb) {
+        if (PLANE) {  // (bb is the sample the tap pointers stand on)
+#pragma unroll
+            for (int ic = 0; ic < 3; ++ic)
+#pragma unroll
+                for (int t9 = 0; t9 < 9; ++t9) p[ic * 9 + t9] = __ldg(tap[t9] + ic * PLANE);
+#pragma unroll
+            for (int t9 = 0; t9 < 9; ++t9) tap[t9] += (size_t)step * 3 * PLANE;
+        } else {
+            const float *img = images + (size_t)bb * 3 * plane;
+#pragma unroll
+            for (int ic = 0; ic < 3; ++ic)
+#pragma unroll
+                for (int t9 = 0; t9 < 9; ++t9) p[ic * 9 + t9] = __ldg(img + ic * plane + off9[t9]);
+        }
+    };
+    float nxt[27];
     if (b < s.B) fetch(nxt, b);
     for (; b < s.B; b += step) {
         float patch[27];
@@ -441,11 +458,12 @@ static int launch_extract_fwd(const nnue_shape &s, const float *images, const fl
         if ((1LL * grid * wpb) % s.CW == 0) {
             NNUE_CUDA_TRY(cudaMemcpyToSymbolAsync(c_ext_w, conv_w, (size_t)s.C * 27 * 4, 0, cudaMemcpyDeviceToDevice, st));
             NNUE_CUDA_TRY(cudaMemcpyToSymbolAsync(c_ext_thr, thr, (size_t)s.C * 4, 0, cudaMemcpyDeviceToDevice, st));
+            const bool p32 = s.H * s.W == 1024;  // 32 x 32 images: tap-pointer form
             switch (s.C) {
-                case 4: extract_fwd_fixed_kernel<4><<<grid, kExtThreads, 0, st>>>(s, images, bits_s, xpad); break;
-                case 8: extract_fwd_fixed_kernel<8><<<grid, kExtThreads, 0, st>>>(s, images, bits_s, xpad); break;
-                case 16: extract_fwd_fixed_kernel<16><<<grid, kExtThreads, 0, st>>>(s, images, bits_s, xpad); break;
-                default: extract_fwd_fixed_kernel<32><<<grid, kExtThreads, 0, st>>>(s, images, bits_s, xpad); break;
+                case 4: (p32 ? extract_fwd_fixed_kernel<4, 1024> : extract_fwd_fixed_kernel<4, 0>)<<<grid, kExtThreads, 0, st>>>(s, images, bits_s, xpad); break;
+                case 8: (p32 ? extract_fwd_fixed_kernel<8, 1024> : extract_fwd_fixed_kernel<8, 0>)<<<grid, kExtThreads, 0, st>>>(s, images, bits_s, xpad); break;
+                case 16: (p32 ? extract_fwd_fixed_kernel<16, 1024> : extract_fwd_fixed_kernel<16, 0>)<<<grid, kExtThreads, 0, st>>>(s, images, bits_s, xpad); break;
+                default: (p32 ? extract_fwd_fixed_kernel<32, 1024> : extract_fwd_fixed_kernel<32, 0>)<<<grid, kExtThreads, 0, st>>>(s, images, bits_s, xpad); break;
             }
             NNUE_CHECK_LAUNCH("extract_fwd_fixed_kernel");
             return NNUE_OK;

@@ -158,7 +158,8 @@ class DataParallelStep:
     on CPU with the gloo backend; the default is the CUDA hot path.
     """
 
-    def __init__(self, model, process_group=None, local_step: Optional[Callable] = None, device=None):
+    def __init__(self, model, process_group=None, local_step: Optional[Callable] = None, device=None,
+                 cuda_graphs: Optional[bool] = None, max_graphs: int = 8):
         self.model = model
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
@@ -167,6 +168,53 @@ class DataParallelStep:
         self.buf = FlatGradBuffer(named, device)
         self.buf.attach()
         self._local = local_step if local_step is not None else _cuda_local_step(model)
+        # The step is ~20 short launches on two streams: replaying it as ONE CUDA graph removes the host launch cost
+        # and the gaps between dependent kernels.  A graph is captured per (input buffers, parameter storages, shape)
+        # the second time that combination is seen -- training loops that cycle a few device staging buffers hit the
+        # cache -- and everything it allocates comes from one shared pool.
+        if cuda_graphs is None:
+            cuda_graphs = local_step is None and torch.device(device).type == "cuda"
+        self.cuda_graphs = bool(cuda_graphs)
+        self.max_graphs = int(max_graphs)
+        self._graphs = {}   # key -> [hits, CUDAGraph or None, (images, labels) kept alive]
+        self._pool = None
+
+    def _graph_key(self, images, labels, inv_count):
+        return (images.data_ptr(), labels.data_ptr(), tuple(images.shape), images.dtype, labels.dtype, inv_count,
+                tuple(p.data_ptr() for p in self.model.parameters()))
+
+    def _run_local(self, images, labels, inv_count):
+        ok = (self.cuda_graphs and images.is_cuda and labels.is_cuda and images.is_contiguous() and labels.is_contiguous()
+              and images.dtype == torch.float32)
+        if not ok:
+            self._local(images, labels, inv_count, self.buf)
+            return
+        key = self._graph_key(images, labels, inv_count)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= self.max_graphs:  # drop the least recently used entry
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = [1, None, (images, labels)]
+            self._local(images, labels, inv_count, self.buf)
+            return
+        self._graphs[key] = self._graphs.pop(key)  # most recently used last
+        ent[0] += 1
+        if ent[1] is None:
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()
+            from . import _lib
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(images.device)
+            n0 = int(_lib.lib().nnue_launch_count(0))
+            with torch.cuda.graph(g, pool=self._pool):
+                self._local(images, labels, inv_count, self.buf)
+            ent[1] = g
+            ent.append(int(_lib.lib().nnue_launch_count(0)) - n0)  # kernels in the graph
+            self._count_add = _lib.lib().nnue_launch_count_add
+            g.replay()  # (the capture pass launched nothing but was counted: it stands for this replay)
+            return
+        ent[1].replay()
+        self._count_add(ent[3])  # keep nnue_launch_count() meaning "kernels launched", replayed or not
 
     def step(self, images, labels, global_batch: Optional[int] = None, marks=None):
         if global_batch is None:
@@ -174,7 +222,7 @@ class DataParallelStep:
         if marks is not None:
             self._local(images, labels, 1.0 / float(global_batch), self.buf, marks)
         else:
-            self._local(images, labels, 1.0 / float(global_batch), self.buf)
+            self._run_local(images, labels, 1.0 / float(global_batch))
         if self.world > 1:
             dist.all_reduce(self.buf.flat, op=dist.ReduceOp.SUM, group=self.group)
         return self.buf.loss.reshape(())
