@@ -249,13 +249,28 @@ q_infer_kernel(const QParams q) {
                 const bool on = valid && oc < 64 && (float)v > q.threshold;
                 unsigned word = __ballot_sync(kFull, on);
                 n_active += __popc(word);
+                // Rows of the set bits, four at a time: the loads of a group are issued together (the one-at-a-time loop
+                // stalled on every row: ncu, long-scoreboard on the add) and the index math stays in 32 bits
+                // (F * L1p / 2 < 2^31 is checked at load).  Addition mod 2^16 is order-independent.
+                const unsigned fbase = ((unsigned)cell0 * (unsigned)q.OC + (unsigned)oc) * (unsigned)nwords + (unsigned)lane;
+                const unsigned fstep = (unsigned)q.OC * (unsigned)nwords;
                 while (word) {
-                    const int k = __ffs(word) - 1;
-                    word &= word - 1;
-                    const uint32_t *row = ftw32 + ((size_t)(cell0 + k) * q.OC + oc) * nwords;
+                    int k[4];
 #pragma unroll
-                    for (int i = 0; i < MAXW; ++i)
-                        if (i * 32 + lane < nwords) acc[i] = __vadd2(acc[i], __ldg(row + i * 32 + lane));
+                    for (int u = 0; u < 4; ++u) {
+                        k[u] = word ? __ffs(word) - 1 : -1;
+                        word &= word - 1;  // (0 & 0xffffffff stays 0)
+                    }
+#pragma unroll
+                    for (int i = 0; i < MAXW; ++i) {
+                        if (i * 32 + lane < nwords) {
+                            uint32_t v[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) v[u] = k[u] >= 0 ? __ldg(ftw32 + fbase + (unsigned)k[u] * fstep + i * 32) : 0u;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) acc[i] = __vadd2(acc[i], v[u]);
+                        }
+                    }
                 }
             }
         }
