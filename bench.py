@@ -441,7 +441,7 @@ def run_b200(args):
             ach = nbytes / (stages[k] * 1e-3) / 1e9
             kern = kernel_of.get(k)
             roofs[k] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                        "traffic": traffic.get(kern), "ms": stages[k], "algorithmic_bytes": nbytes, "kernel": kern}
+                        "traffic": traffic.get(kern.split("<")[0]) if kern else None, "ms": stages[k], "algorithmic_bytes": nbytes, "kernel": kern}
             if k in mma_flops and _lib.lib().nnue_ft_uses_mma(ctypes.byref(shape)):
                 tf = mma_flops[k] / (stages[k] * 1e-3) / 1e12
                 roofs[k]["tensor"] = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
