@@ -451,7 +451,11 @@ int nnue_head_train(const nnue_shape *s, const float *ft_out_d, const int64_t *l
     float *act1 = carve(B * s->L2 * 4), *act2 = carve(B * s->L3 * 4), *logits = carve(B * s->NC * 4);
     float *g_logits = carve(B * s->NC * 4), *per = carve(B * 4);
     const size_t rest = workspace_bytes - (size_t)(ws - static_cast<char *>(workspace_d));
-    int rc = nnue_head_fwd(s, ft_out_d, w1_d, b1_d, w2_d, b2_d, w3_d, b3_d, act1, act2, logits, stream);
+    // (the forward's tensor-core scratch sits behind the backward's: both fit in ws_head_train)
+    const size_t fwd_ws = ws_head_umma_fwd(*s);
+    void *fwd_scratch = fwd_ws && rest >= ws_head_bwd(*s) + fwd_ws ? ws + align_up(ws_head_bwd(*s), 256) : nullptr;
+    int rc = head_fwd_ws(s, ft_out_d, w1_d, b1_d, w2_d, b2_d, w3_d, b3_d, act1, act2, logits, fwd_scratch,
+                         fwd_scratch ? fwd_ws : 0, static_cast<cudaStream_t>(stream));
     if (rc != NNUE_OK) return rc;
     rc = nnue_ce_fwd_bwd(s->B, s->NC, logits, labels_d, inv_count, nullptr, loss_d, per, g_logits, nullptr, 0, stream);
     if (rc != NNUE_OK) return rc;

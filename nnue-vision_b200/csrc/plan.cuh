@@ -326,7 +326,46 @@ inline int gemm_splits(int M, int N, int K, int BM, int BN) {
     if (want > max_by_k) want = max_by_k;
     return want < 1 ? 1 : (int)want;
 }
-// split-K partials of the three weight(+bias) gradients, then g_act2, g_act1, g_l0
+// ---- layer 1 of wide stacks on the tensor cores (gemm_umma.cu) ---------------------------------------------------
+// The 1024 -> 128 layer of the reference's "real" config is a dense contraction at the benchmark batch (13 GFLOP per
+// step); the config-D stack (64 -> 32 -> 8 -> 10) is not and keeps the fused FMA kernel.
+inline bool head_umma_ok(const nnue_shape &s) {
+    return get_option(kOptHeadUmma) && s.L1 >= 256 && s.L1 % 16 == 0 && s.L2 >= 16 && s.L2 <= 256 && s.B >= 256;
+}
+inline int head_umma_nt(const nnue_shape &s) { return s.L2 <= 128 ? 128 : 256; }  // B-tile rows of the forward GEMM
+inline size_t ugemm_tile_bytes(int rows, int RT, int K) { return (size_t)ceil_div(rows, RT) * RT * ceil_div(K, 16) * 16 * 6; }
+inline int head_umma_wgrad_splits(const nnue_shape &s) {
+    const int tiles = ceil_div(s.L1, 256) * ceil_div(s.L2, 128);
+    int want = ceil_div(kNumSMs, tiles);
+    const int n_ks = ceil_div(s.B, 16);
+    if (want > n_ks / 8) want = n_ks / 8;  // at least 8 k-steps per split
+    return want < 1 ? 1 : want;
+}
+// forward scratch: l0 rows tiles | W1 rows tiles
+inline size_t ws_head_umma_fwd(const nnue_shape &s) {
+    if (!head_umma_ok(s)) return 0;
+    return align_up(ugemm_tile_bytes(s.B, 128, s.L1), 256) + align_up(ugemm_tile_bytes(s.L2, head_umma_nt(s), s.L1), 256);
+}
+// backward scratch: g_z1 rows | W1 cols | g_z1 cols | l0 cols | split-K partials [splits][L2][L1] | colsum partials
+inline size_t ws_head_umma_bwd(const nnue_shape &s) {
+    if (!head_umma_ok(s)) return 0;
+    return align_up(ugemm_tile_bytes(s.B, 128, s.L2), 256) + align_up(ugemm_tile_bytes(s.L1, 256, s.L2), 256) +
+           align_up(ugemm_tile_bytes(s.L2, 128, s.B), 256) + align_up(ugemm_tile_bytes(s.L1, 256, s.B), 256) +
+           align_up((size_t)head_umma_wgrad_splits(s) * s.L2 * s.L1 * 4, 256) + align_up((size_t)ceil_div(s.B, 256) * s.L2 * 4, 256);
+}
+int ugemm_format_rows(int RT, const float *src, long long ld, int nrows, int K, int pair_half, unsigned char *out,
+                      cudaStream_t st);
+int ugemm_format_cols(int RT, const float *src, long long ld, int K, int ncols, int pair_half, unsigned char *out,
+                      cudaStream_t st);
+int ugemm_launch(int NT, int M, int N, int K, const unsigned char *at, const unsigned char *bt, float *C, long long ldc,
+                 const float *bias, int relu, const float *mask, long long ldm, int splits, long long c_split_stride,
+                 cudaStream_t st);
+// forward of the stack with optional scratch (head.cu): with ws_head_umma_fwd bytes layer 1 runs on the tensor cores
+int head_fwd_ws(const nnue_shape *s, const float *ft_out_d, const float *w1_d, const float *b1_d, const float *w2_d,
+                const float *b2_d, const float *w3_d, const float *b3_d, float *act1_d, float *act2_d, float *logits_d,
+                void *workspace_d, size_t workspace_bytes, cudaStream_t st);
+
+// split-K partials of the three weight(+bias) gradients, then g_act2, g_act1, g_l0 (+ the tensor-core scratch)
 inline size_t ws_head_bwd(const nnue_shape &s) {
     const size_t B = s.B;
     size_t bytes = 0;
@@ -334,7 +373,7 @@ inline size_t ws_head_bwd(const nnue_shape &s) {
     bytes += align_up((size_t)gemm_splits(s.L3, s.L2 + 1, s.B, 64, 64) * s.L3 * (s.L2 + 1) * 4, 256);
     bytes += align_up((size_t)gemm_splits(s.L2, s.L1 + 1, s.B, 64, 64) * s.L2 * (s.L1 + 1) * 4, 256);
     bytes += align_up(B * s.L3 * 4, 256) + align_up(B * s.L2 * 4, 256) + align_up(B * s.L1 * 4, 256);
-    return bytes;
+    return bytes + ws_head_umma_bwd(s);
 }
 inline size_t ws_input_bwd(const nnue_shape &s) {
     const InPlan p = plan_input_bwd(s);
@@ -412,7 +451,7 @@ inline size_t ws_head_train(const nnue_shape &s) {
     if (head_train_fused_ok(s)) return (size_t)head_train_grid(s) * kHeadPartial * 4;
     const size_t B = s.B;
     return align_up(B * s.L2 * 4, 256) + align_up(B * s.L3 * 4, 256) + 2 * align_up(B * s.NC * 4, 256) +
-           align_up(B * 4, 256) + ws_head_bwd(s);
+           align_up(B * 4, 256) + ws_head_bwd(s) + ws_head_umma_fwd(s);
 }
 inline size_t ws_ce(int B) { return align_up((size_t)B * 4, 256); }
 

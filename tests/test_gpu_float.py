@@ -83,6 +83,9 @@ CFGS = {
     "odd_L1_generic": (dict(grid=6, C=5, L1=50, L2=6, L3=5, NC=3, model_input=30), 30, 37),
     "L1_128": (dict(grid=6, C=16, L1=128, L2=16, L3=32, NC=1000, model_input=64), 64, 50),
     "one_sample": (dict(grid=10, C=8, L1=64, L2=32, L3=8, NC=10, model_input=32), 32, 1),
+    # wide stacks at a batch where layer 1 runs as the split-bf16 tcgen05 GEMM (gemm_umma.cu)
+    "D1k_tensor_head": (dict(grid=10, C=8, L1=1024, L2=128, L3=32, NC=10, model_input=32), 32, 300),
+    "wide_head_ragged": (dict(grid=6, C=16, L1=256, L2=48, L3=16, NC=10, model_input=64), 64, 257),
 }
 
 
@@ -199,10 +202,10 @@ OPTION_DEFAULTS = {"extract_tma": 0}
 
 @pytest.mark.parametrize("options", [dict(extract_tma=1), dict(extract_fixed=0), dict(ft_umma=0), dict(ft_umma=0, ft_mma=0),
                                      dict(ft_umma=0, ft_mma=0, ft_bwd_both=0), dict(ft_umma=0, ft_mma=0, ft_bwd_dw_owner=0),
-                                     dict(ft_umma=0, ft_mma=0, input_bwd_fused=0), dict(input_bwd_fused=0), dict(input_bwd_variant=0), dict(input_bwd_swizzle=0), dict(input_bwd_swizzle=0, input_bwd_variant=0), dict(head_fused=0),
+                                     dict(ft_umma=0, ft_mma=0, input_bwd_fused=0), dict(input_bwd_fused=0), dict(input_bwd_variant=0), dict(input_bwd_swizzle=0), dict(input_bwd_swizzle=0, input_bwd_variant=0), dict(head_fused=0), dict(head_umma=0),
                                      dict(ft_umma=0, ft_mma=0, ft_bwd_dw_owner=0, input_bwd_fused=0, head_fused=0)],
                          ids=str)
-@pytest.mark.parametrize("name", ["D", "T", "big_into_small"])
+@pytest.mark.parametrize("name", ["D", "T", "big_into_small", "D1k_tensor_head"])
 def test_backward_kernel_variants_agree(name, options):
     """The general kernels (transposed-bitmask segment reduction; value-gradient + conv-gradient pair)
     stay correct on the shapes where the row-owner / fused kernels normally run."""
