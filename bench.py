@@ -341,6 +341,11 @@ def run_b200(args):
     sets = [synthetic_batch(w, B, seed=1000 * rank + i, device=device) for i in range(n_sets)]
     global_batch = B * world
 
+    # DataParallelStep replays a CUDA graph per input buffer from the second time it sees the buffer on: prime every
+    # set twice (untimed, before the warm-up steps) so that no capture falls into the warm-up or the timed region
+    for _ in range(2):
+        for imgs, labs in sets:
+            dp.step(imgs, labs, global_batch=global_batch)
     clocks.begin()
     for i in range(max(args.warmup, 3)):
         dp.step(*sets[i % n_sets], global_batch=global_batch)
@@ -388,7 +393,7 @@ def run_b200(args):
             losses.append(float(l))  # D2H read of the step's result
         return losses
 
-    e2e_steps(3)
+    e2e_steps(6)  # (both staging buffers seen twice: their graphs exist before the timed region)
     barrier(world)
     t0 = time.perf_counter()
     e2e_steps(args.steps)

@@ -92,9 +92,10 @@ template <bool TABLE, int RT>
 __global__ void umma_format_rows_kernel(const nnue_shape s, const float *__restrict__ src, int nrows, int n_rt,
                                         unsigned char *__restrict__ out) {
     const int kcs = s.L1 / 8, n_ks = s.L1 / 16;
+    // neighbouring threads take neighbouring rows of the same 8-wide k chunk: contiguous 16-byte outputs in the tile
     const long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 1LL * n_rt * RT * kcs) return;
-    const int kc = (int)(i % kcs), r = (int)(i / kcs);
+    const int r = (int)(i % (n_rt * RT)), kc = (int)(i / (n_rt * RT));
     const int row = TABLE ? umma_table_row(s, r) : (r < nrows ? r : -1);
     float v[8];
     if (row >= 0) {

@@ -45,14 +45,34 @@ __device__ __forceinline__ float pair_load(const float *row, int k, int h) {
 template <int RT>
 __global__ void ugemm_format_rows_kernel(const float *__restrict__ src, long long ld, int nrows, int K, int pair_half,
                                          int n_rt, int n_ks, unsigned char *__restrict__ out) {
+    // neighbouring threads take neighbouring ROWS of the same 8-wide k chunk: their 16-byte outputs are contiguous
+    // in the tile (512 B per warp) and each reads one full 32-byte sector of its row
     const long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 1LL * n_rt * RT * n_ks * 2) return;
-    const int kc = (int)(i % (n_ks * 2)), r = (int)(i / (n_ks * 2));
+    const int NR = n_rt * RT;
+    if (i >= 1LL * NR * n_ks * 2) return;
+    const int r = (int)(i % NR), kc = (int)(i / NR);
     float v[8];
+    if (r < nrows && pair_half == 0 && kc * 8 + 8 <= K && (ld & 3) == 0) {
+        const float4 lo = __ldg(reinterpret_cast<const float4 *>(src + (size_t)r * ld + kc * 8));
+        const float4 hi = __ldg(reinterpret_cast<const float4 *>(src + (size_t)r * ld + kc * 8) + 1);
+        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+    } else if (r < nrows && pair_half > 0 && (pair_half & 7) == 0 && kc * 8 + 8 <= K && (ld & 3) == 0) {
+        // l0 chunk: product of the two halves of the row, or a copy of the first half
+        const int k = kc * 8;
+        const float4 *p = reinterpret_cast<const float4 *>(src + (size_t)r * ld + (k < pair_half ? k : k - pair_half));
+        const float4 lo = __ldg(p), hi = __ldg(p + 1);
+        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+        if (k < pair_half) {
+            const float4 *q = reinterpret_cast<const float4 *>(src + (size_t)r * ld + k + pair_half);
+            const float4 lo2 = __ldg(q), hi2 = __ldg(q + 1);
+            v[0] *= lo2.x; v[1] *= lo2.y; v[2] *= lo2.z; v[3] *= lo2.w; v[4] *= hi2.x; v[5] *= hi2.y; v[6] *= hi2.z; v[7] *= hi2.w;
+        }
+    } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int k = kc * 8 + j;
-        v[j] = (r < nrows && k < K) ? pair_load(src + (size_t)r * ld, k, pair_half) : 0.0f;
+        for (int j = 0; j < 8; ++j) {
+            const int k = kc * 8 + j;
+            v[j] = (r < nrows && k < K) ? pair_load(src + (size_t)r * ld, k, pair_half) : 0.0f;
+        }
     }
     uint4 o[3];
     split3x8(v, o);

@@ -222,7 +222,15 @@ __global__ void head_colsum_partial_kernel(int rows, int cols, const float *__re
     if (c >= cols) return;
     const int r0 = blockIdx.y * 256, r1 = min(rows, r0 + 256);
     float acc = 0.0f;
-    for (int r = r0; r < r1; ++r) acc += __ldg(x + (size_t)r * cols + c);
+    int r = r0;
+    for (; r + 16 <= r1; r += 16) {  // loads batched sixteen deep, same summation order
+        float t[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) t[u] = __ldg(x + (size_t)(r + u) * cols + c);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) acc += t[u];
+    }
+    for (; r < r1; ++r) acc += __ldg(x + (size_t)r * cols + c);
     partial[(size_t)blockIdx.y * cols + c] = acc;
 }
 __global__ void head_fold_kernel(long long n, int nparts, long long stride, const float *__restrict__ partial, float *__restrict__ out) {
