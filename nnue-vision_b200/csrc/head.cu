@@ -117,7 +117,9 @@ static int launch_gemm(GemmArgs g, int splits, cudaStream_t st) {
     } else if (g.N <= 16) {
         gemm_kernel<128, 16, 4, 2><<<dim3(ceil_div(g.M, 128), 1, nz), 256, 0, st>>>(g);
     } else if (g.N <= 32) {
-        gemm_kernel<128, 32, 8, 2><<<dim3(ceil_div(g.M, 128), 1, nz), 256, 0, st>>>(g);
+        // few row tiles (small batches): 32-row tiles put four times as many CTAs on the machine
+        if (ceil_div(g.M, 128) * nz < kNumSMs) gemm_kernel<32, 32, 2, 2><<<dim3(ceil_div(g.M, 32), 1, nz), 256, 0, st>>>(g);
+        else gemm_kernel<128, 32, 8, 2><<<dim3(ceil_div(g.M, 128), 1, nz), 256, 0, st>>>(g);
     } else {
         gemm_kernel<64, 64, 4, 4><<<dim3(ceil_div(g.M, 64), ceil_div(g.N, 64), nz), 256, 0, st>>>(g);
     }
