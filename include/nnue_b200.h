@@ -90,6 +90,8 @@ unsigned long long nnue_launch_count_add(unsigned long long n);
  *   "ft_umma"         1 (default) = tcgen05 / TMEM (UMMA) feature-transformer contractions for every L1 that is
  *                     a multiple of 64, 0 = the warp-level MMA / CUDA-core families.
  *   "ft_bwd_both"     1 (default) = one kernel for both feature-transformer gradients (small tables).
+ *   "q_tc_min_batch"  integer inference: batches of at least this many samples (default 2048; 0 = never) run as
+ *                     bitmask -> tcgen05 accumulate -> layer stack instead of the one fused kernel (L1 % 64 == 0).
  *   "head_umma"       1 (default) = layer 1 of wide stacks (L1 >= 256, 16 <= L2 <= 256) as a split-bf16 tcgen05 GEMM
  *                     (fp32-exact products) wherever scratch is passed, 0 = fp32 FMA GEMM kernels.
  *   "head_fused"      1 (default) = one-kernel head training step for small stacks, 0 = layer kernels.

@@ -45,6 +45,7 @@ constexpr uint32_t kBgABytes = kUM * 32 * 2;             // one bitmask word per
 constexpr uint32_t kBgNRows = 3 * kUmmaNCols;            // 192: the three terms of 64 columns stacked along N
 constexpr uint32_t kBgBTile = kBgNRows * 32;             // 6 KB: one [192 x 16] tile
 constexpr uint32_t kBgBBytes = 2 * kBgBTile;             // two k-steps per stage
+constexpr uint32_t kBgNRowsInt = 2 * kUmmaNCols;         // integer accumulate: high and low byte of the int16 rows (128)
 constexpr uint32_t kBgTmemCols = 256;
 // ---- value gradient ----
 constexpr int kGbStages = 3;
@@ -129,10 +130,15 @@ __device__ __forceinline__ uint4 bits8_to_bf16x8(uint32_t byte) {
 // grid = (M tiles, L1 / 64, K chunks).  DW = false: M = samples, stage j = bitmask word j of the sample rows,
 // out = ft_out [B][L1] (+ bias).  DW = true: M = padded positions (bitmask words 4 x .. 4 x + 3), stage j = the
 // 32-sample block chunk * chunk_blocks + j, out = partial[chunk][P + 1][L1] (row P = bias gradient) for the fold kernels.
-template <bool DW>
+// MODE 2 (integer inference, qinfer.cu): same as the forward but the B operand is the int16 table as TWO exact bf16
+// terms (high byte, signed; low byte, unsigned: UMMA 128 x 128 x 16), bias is int32 [L1] and out is int16 [B][L1]:
+// out = (int16)(bias + 256 * sum_hi + sum_lo), the engine's wrap-around accumulate (simd_scalar.cpp:78-95).
+template <int MODE>
 __global__ void __launch_bounds__(kBgThreads, 2)
 ft_bitgemm_umma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const unsigned char *__restrict__ btiles,
                        const float *__restrict__ bias, float *__restrict__ out, int chunk_blocks) {
+    constexpr bool DW = MODE == 1;
+    constexpr uint32_t NR = MODE == 2 ? kBgNRowsInt : kBgNRows, BTile = NR * 32, BBytes = 2 * BTile;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t *full_a = reinterpret_cast<uint64_t *>(smem_raw);     // [ST] producer warps -> issuer
     uint64_t *full_b = full_a + kBgStages;                         // [ST] TMA -> issuer
@@ -171,28 +177,28 @@ ft_bitgemm_umma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, 
 
     if (warp == 0) {
         if (lane == 0) {  // ---- TMA: the B tiles of every stage ----
-            const unsigned char *src = btiles + ((size_t)nt * n_ks_total + 2 * (size_t)first) * kBgBTile;
+            const unsigned char *src = btiles + ((size_t)nt * n_ks_total + 2 * (size_t)first) * BTile;
             for (int j = 0; j < n_stage; ++j) {
                 const int st = j % kBgStages;
                 if (j >= kBgStages) mbar_wait(&empty[st], ((j / kBgStages) - 1) & 1);
-                mbar_arrive_expect_tx(&full_b[st], kBgBBytes);
-                tma_bulk_g2s(sb + (uint32_t)st * kBgBBytes, src + (size_t)j * kBgBBytes, kBgBBytes, &full_b[st]);
+                mbar_arrive_expect_tx(&full_b[st], BBytes);
+                tma_bulk_g2s(sb + (uint32_t)st * BBytes, src + (size_t)j * BBytes, BBytes, &full_b[st]);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {  // ---- issuer: two UMMAs (128 x 192 x 16) per stage ----
-            constexpr uint32_t idesc = umma_idesc(kUM, kBgNRows);
+            constexpr uint32_t idesc = umma_idesc(kUM, NR);
             for (int j = 0; j < n_stage; ++j) {
                 const int st = j % kBgStages;
                 const uint32_t ph = (j / kBgStages) & 1;
                 mbar_wait(&full_a[st], ph);
                 mbar_wait(&full_b[st], ph);
                 tcgen05_fence_after();
-                const uint32_t a_base = smem_u32(sa + (uint32_t)st * kBgABytes), b_base = smem_u32(sb + (uint32_t)st * kBgBBytes);
+                const uint32_t a_base = smem_u32(sa + (uint32_t)st * kBgABytes), b_base = smem_u32(sb + (uint32_t)st * BBytes);
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks)
                     umma_bf16(tmem_acc, umma_smem_desc(a_base + (uint32_t)ks * (kUM * 32), kUM * 16, 128),
-                              umma_smem_desc(b_base + (uint32_t)ks * kBgBTile, kBgNRows * 16, 128), idesc, (j | ks) ? 1u : 0u);
+                              umma_smem_desc(b_base + (uint32_t)ks * BTile, NR * 16, 128), idesc, (j | ks) ? 1u : 0u);
                 umma_commit(&empty[st]);  // arrives when the UMMAs above have read their shared-memory operands
             }
             umma_commit(done);
@@ -258,6 +264,30 @@ ft_bitgemm_umma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, 
             const int b = mt * kUM + row;
             if (b < s.B) orow = out + (size_t)b * s.L1 + nt * kUmmaNCols;
         }
+        if (MODE == 2) {
+            const int b = mt * kUM + row;
+            int16_t *orow16 = reinterpret_cast<int16_t *>(out) + (size_t)min(b, s.B - 1) * s.L1 + nt * kUmmaNCols;
+            const int32_t *bias32 = reinterpret_cast<const int32_t *>(bias) + nt * kUmmaNCols;
+#pragma unroll
+            for (int cc = 0; cc < kUmmaNCols / 2; cc += 16) {
+                const int c0 = grp * (kUmmaNCols / 2) + cc;
+                float hi[16], lo[16];
+                tmem_ld16(tbase + (uint32_t)c0, hi);
+                tmem_ld16(tbase + (uint32_t)(kUmmaNCols + c0), lo);
+                tmem_ld_wait();
+                uint32_t pk[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int v0 = __ldg(bias32 + c0 + 2 * u) + 256 * __float2int_rn(hi[2 * u]) + __float2int_rn(lo[2 * u]);
+                    const int v1 = __ldg(bias32 + c0 + 2 * u + 1) + 256 * __float2int_rn(hi[2 * u + 1]) + __float2int_rn(lo[2 * u + 1]);
+                    pk[u] = ((uint32_t)v0 & 0xFFFFu) | ((uint32_t)v1 << 16);
+                }
+                if (b < s.B) {
+                    reinterpret_cast<uint4 *>(orow16 + c0)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    reinterpret_cast<uint4 *>(orow16 + c0)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+            }
+        } else
 #pragma unroll
         for (int cc = 0; cc < kUmmaNCols / 2; cc += 16) {
             const int c0 = grp * (kUmmaNCols / 2) + cc;
@@ -402,8 +432,8 @@ int launch_ft_fwd_umma(const nnue_shape &s, const uint32_t *bits_s, const float 
     const long long n = 2LL * n_ks * s.L1;
     umma_format_kt_kernel<true><<<(int)((n + 255) / 256), 256, 0, st>>>(s, w, s.PP, n_ks, wt);
     NNUE_CHECK_LAUNCH("umma_format_kt_kernel");
-    NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_bitgemm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmem));
-    ft_bitgemm_umma_kernel<false><<<dim3(ceil_div(s.B, kUM), s.L1 / kUmmaNCols, 1), kBgThreads, kBgSmem, st>>>(s, bits_s, wt, bias, out, 0);
+    NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_bitgemm_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmem));
+    ft_bitgemm_umma_kernel<0><<<dim3(ceil_div(s.B, kUM), s.L1 / kUmmaNCols, 1), kBgThreads, kBgSmem, st>>>(s, bits_s, wt, bias, out, 0);
     NNUE_CHECK_LAUNCH("ft_bitgemm_umma_kernel");
     return NNUE_OK;
 }
@@ -472,9 +502,9 @@ int launch_ft_bwd_dw_umma(const nnue_shape &s, const uint32_t *bits_s, const flo
     long long n = 2LL * n_ks * s.L1;
     umma_format_kt_kernel<false><<<(int)((n + 255) / 256), 256, 0, st>>>(s, g_ft, s.B, n_ks, gt);
     NNUE_CHECK_LAUNCH("umma_format_kt_kernel");
-    NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_bitgemm_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmem));
+    NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_bitgemm_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmem));
     const int m_rows = umma_bias_pp(s) + 1 > s.PP ? s.PP + 1 : s.PP;  // the all-ones row may need one more M tile
-    ft_bitgemm_umma_kernel<true><<<dim3(ceil_div(m_rows, kUM), s.L1 / kUmmaNCols, p.n_chunks), kBgThreads, kBgSmem, st>>>(
+    ft_bitgemm_umma_kernel<1><<<dim3(ceil_div(m_rows, kUM), s.L1 / kUmmaNCols, p.n_chunks), kBgThreads, kBgSmem, st>>>(
         s, bits_s, gt, nullptr, partial, p.chunk_blocks);
     NNUE_CHECK_LAUNCH("ft_bitgemm_umma_kernel");
     n = 1LL * ((s.P > s.F - 1 ? s.P : s.F - 1) + 1) * (s.L1 / 4);
@@ -482,6 +512,20 @@ int launch_ft_bwd_dw_umma(const nnue_shape &s, const uint32_t *bits_s, const flo
     NNUE_CHECK_LAUNCH("umma_dw_fold_kernel");
     umma_dw_fold_last_kernel<<<ceil_div(s.L1 / 4, 32), 1024, 0, st>>>(s, alias, g_w);
     NNUE_CHECK_LAUNCH("umma_dw_fold_last_kernel");
+    return NNUE_OK;
+}
+
+// Integer accumulate of qinfer.cu: acc16[b] = (int16)(bias + sum over set bits of the int16 table rows).
+// bits [B][NW] (word w = 32 k-indices), tiles [L1 / 64][2 NW][128 x 16] (high / low byte terms, built at load time)
+int launch_q_accumulate_umma(int B, int NW, int L1, const uint32_t *bits, const unsigned char *tiles, const int32_t *bias,
+                             int16_t *acc16, cudaStream_t st) {
+    nnue_shape s{};
+    s.B = B; s.NW = NW; s.L1 = L1; s.PP = 32 * NW; s.BW = ceil_div(B, 32);
+    constexpr size_t smem = 1024 + (size_t)kBgStages * (kBgABytes + 2 * kBgNRowsInt * 32);
+    NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_bitgemm_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ft_bitgemm_umma_kernel<2><<<dim3(ceil_div(B, kUM), L1 / kUmmaNCols, 1), kBgThreads, smem, st>>>(
+        s, bits, tiles, reinterpret_cast<const float *>(bias), reinterpret_cast<float *>(acc16), 0);
+    NNUE_CHECK_LAUNCH("ft_bitgemm_umma_kernel");
     return NNUE_OK;
 }
 

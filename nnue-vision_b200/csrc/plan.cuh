@@ -124,6 +124,8 @@ int launch_ft_fwd_umma(const nnue_shape &s, const uint32_t *bits_s, const float 
                        void *workspace, cudaStream_t st);
 int launch_ft_bwd_dw_umma(const nnue_shape &s, const uint32_t *bits_s, const float *g_ft, void *ws, float *g_w, float *g_b,
                           cudaStream_t st);
+int launch_q_accumulate_umma(int B, int NW, int L1, const uint32_t *bits, const unsigned char *tiles, const int32_t *bias,
+                             int16_t *acc16, cudaStream_t st);
 int launch_ft_bwd_gbin_umma(const nnue_shape &s, const uint32_t *bits_s, const float *w, const float *g_ft, void *workspace,
                             float *gbin, cudaStream_t st);
 

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "plan.cuh"
 
 struct nnue_qmodel {
     int F, L1, L2, L3, NC, OC, G, n_buckets;
@@ -24,6 +25,7 @@ struct nnue_qmodel {
     int32_t *conv_b;   // [OC]
     int16_t *ft_w;     // [F][L1p]
     int16_t *ft_b;     // [L1p]  bias truncated to int16 (simd_scalar.cpp:82-84)
+    int32_t *ft_b32 = nullptr;  // [L1] the same bias as stored (the tensor-core accumulate wraps at the end)
     struct Stack {
         float l1_scale, l2_scale, out_scale;
         int32_t *w1, *b1;  // w1 [K1][L2] dp4a words: inputs 4k..4k+3 of output o
@@ -36,6 +38,13 @@ struct nnue_qmodel {
     mutable float *h_img = nullptr, *h_logits = nullptr, *h_density = nullptr;
     mutable size_t h_cap_img = 0, h_cap_b = 0;
     mutable cudaStream_t h_stream = nullptr;
+    // tensor-core form for large batches (L1 a multiple of 64): the table as high/low-byte bf16 tiles in UMMA order,
+    // K index = oc * CWq * 32 + cell over the whole G x G buffer; per-instance scratch grown on demand
+    unsigned char *tc_tiles = nullptr;
+    int CWq = 0;                            // 32-bit words per channel: ceil(G*G / 32)
+    mutable uint32_t *s_bits = nullptr;     // [B][OC * CWq]
+    mutable int16_t *s_acc = nullptr;       // [B][L1]
+    mutable size_t s_cap = 0;               // samples the scratch holds
 };
 
 namespace nnue {
@@ -125,8 +134,36 @@ static int parse_and_upload(const unsigned char *bytes, size_t n, nnue_qmodel *m
     for (uint32_t i = 0; i < L1; ++i) fbp[i] = (int16_t)fb[i];
     int rc;
     if ((rc = upload(m, cw32, &m->conv_w)) || (rc = upload(m, cb, &m->conv_b)) || (rc = upload(m, fwp, &m->ft_w)) ||
-        (rc = upload(m, fbp, &m->ft_b)))
+        (rc = upload(m, fbp, &m->ft_b)) || (rc = upload(m, fb, &m->ft_b32)))
         return rc;
+
+    if (L1 % 64 == 0 && (uint64_t)OC * ((uint64_t)(G * G + 31) / 32) * 32 * L1 * 4 <= (1ull << 31)) {
+        // tiles [L1 / 64][k-step][128 rows x 16 k] bf16, canonical K-major: row n = term * 64 + column, term 0 = high
+        // byte (signed), term 1 = low byte (unsigned): w = 256 * hi + lo, both exact in bf16
+        const int CWq = (G * G + 31) / 32, NWq = (int)OC * CWq, n_ks = 2 * NWq;
+        std::vector<uint16_t> tiles((size_t)(L1 / 64) * n_ks * 128 * 16, 0);
+        auto bf16_of_int = [](int v) { float f = (float)v; uint32_t u; memcpy(&u, &f, 4); return (uint16_t)(u >> 16); };
+        for (int kk = 0; kk < 32 * NWq; ++kk) {
+            const int oc = (kk >> 5) / CWq, cell = ((kk >> 5) % CWq) * 32 + (kk & 31);
+            if (cell >= G * G) continue;
+            const int16_t *row = &fw[((size_t)cell * OC + oc) * L1];
+            const int ks = kk / 16, k = kk % 16;
+            for (uint32_t col = 0; col < L1; ++col) {
+                const int w = row[col], lo = w & 0xFF, hi = (w - lo) / 256;
+                const size_t tile = ((size_t)(col / 64) * n_ks + ks) * (128 * 16);
+                const int c = (int)(col % 64);
+                for (int t = 0; t < 2; ++t) {
+                    const int n = t * 64 + c;
+                    tiles[tile + (size_t)(k / 8) * (128 * 8) + (size_t)(n / 8) * 64 + (size_t)(n % 8) * 8 + (k % 8)] =
+                        bf16_of_int(t == 0 ? hi : lo);
+                }
+            }
+        }
+        uint16_t *d_tiles = nullptr;
+        if ((rc = upload(m, tiles, &d_tiles))) return rc;
+        m->tc_tiles = reinterpret_cast<unsigned char *>(d_tiles);
+        m->CWq = CWq;
+    }
 
     for (uint32_t b = 0; b < nb; ++b) {
         nnue_qmodel::Stack st{};
@@ -183,6 +220,10 @@ struct QParams {
     const int32_t *w1, *b1, *w2, *b2, *wo, *bo;
     const float *images;
     float *logits, *density;
+    // split form (MODE 1 / 2 of the kernel)
+    int G2, CWq;              // cells of the whole feature buffer (F / OC), bitmask words per channel
+    uint32_t *bits_out;       // MODE 1: [B][OC][CWq]
+    const int16_t *acc_in;    // MODE 2: [B][L1]
 };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return max(lo, min(hi, v)); }
@@ -190,7 +231,10 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return max(lo, mi
 constexpr int kQWarps = 8;
 
 // MAXW: 32-bit accumulator words per lane (L1p/2 <= 32*MAXW)
-template <int MAXW>
+// MODE 0: the whole path in one kernel.  Large batches split it around the tensor-core accumulate
+// (launch_q_accumulate_umma, ft_umma.cu): MODE 1 = conv + threshold -> active-feature bitmask (+ density),
+// MODE 2 = clipped ReLU + pairwise + dense layers from the int16 accumulators.
+template <int MAXW, int MODE>
 __global__ void __launch_bounds__(kQWarps * 32)
 q_infer_kernel(const QParams q) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -220,8 +264,14 @@ q_infer_kernel(const QParams q) {
         for (int i = 0; i < MAXW; ++i) acc[i] = (i * 32 + lane < nwords) ? __ldg(ftb32 + i * 32 + lane) : 0u;
         int n_active = 0;
 
+        if (MODE == 2) {  // accumulators come from the tensor-core kernel
+            const uint32_t *arow = reinterpret_cast<const uint32_t *>(q.acc_in) + (size_t)b * (q.L1 / 2);
+#pragma unroll
+            for (int i = 0; i < MAXW; ++i) acc[i] = (i * 32 + lane < q.L1 / 2) ? __ldg(arow + i * 32 + lane) : 0u;
+        }
         // Q1 + Q2 + Q3: conv cell per lane, ballot per channel, accumulate rows of set bits
-        for (int cell0 = 0; cell0 < cells; cell0 += 32) {
+        // (MODE 1 walks the whole G x G buffer: cells past the conv raster stay 0 and are active iff 0 > threshold)
+        for (int cell0 = 0; MODE != 2 && cell0 < (MODE == 1 ? q.G2 : cells); cell0 += 32) {
             const int cell = cell0 + lane;
             const bool valid = cell < cells;
             const int oy = valid ? cell / q.ow : 0, ox = valid ? cell % q.ow : 0;
@@ -246,9 +296,14 @@ q_infer_kernel(const QParams q) {
 #pragma unroll
                 for (int t = 0; t < 27; ++t) a += xq[t] * w[t];
                 const int v = clampi(a / q.conv_iscale, -127, 127);
-                const bool on = valid && oc < 64 && (float)v > q.threshold;
+                const bool on = valid ? (oc < 64 && (float)v > q.threshold)
+                                      : (MODE == 1 && cell < q.G2 && oc < 64 && 0.0f > q.threshold);
                 unsigned word = __ballot_sync(kFull, on);
                 n_active += __popc(word);
+                if (MODE == 1) {
+                    if (lane == 0) q.bits_out[((size_t)b * q.OC + oc) * q.CWq + (cell0 >> 5)] = word;
+                    continue;
+                }
                 // Rows of the set bits, four at a time: the loads of a group are issued together (the one-at-a-time loop
                 // stalled on every row: ncu, long-scoreboard on the add) and the index math stays in 32 bits
                 // (F * L1p / 2 < 2^31 is checked at load).  Addition mod 2^16 is order-independent.
@@ -274,8 +329,13 @@ q_infer_kernel(const QParams q) {
                 }
             }
         }
+        if (MODE == 1) {
+            if (q.density && lane == 0)
+                q.density[b] = __fdiv_rn(__int2float_rn(n_active), __int2float_rn(q.F));  // nnue_inference.cpp:54
+            continue;
+        }
         // buffer entries past the conv raster stay 0 (nnue_engine.cpp:720): active iff 0 > threshold
-        if (0.0f > q.threshold) {
+        if (MODE == 0 && 0.0f > q.threshold) {
             for (int f = cells * q.OC; f < q.F; ++f) {
                 if (f % q.OC >= 64) continue;
                 ++n_active;
@@ -335,7 +395,7 @@ q_infer_kernel(const QParams q) {
             for (int k = 0; k < q.K3; ++k) a = __dp4a(h24[k], __ldg(q.wo + (size_t)k * q.NC + c), a);
             q.logits[(size_t)b * q.NC + c] = __fdiv_rn(__int2float_rn(a), q.out_scale);
         }
-        if (q.density && lane == 0)
+        if (MODE == 0 && q.density && lane == 0)
             q.density[b] = __fdiv_rn(__int2float_rn(n_active), __int2float_rn(q.F));  // nnue_inference.cpp:54
         __syncwarp();
     }
@@ -364,7 +424,7 @@ static int fill_params(const nnue_qmodel *m, int B, int H, int W, int bucket, QP
     return NNUE_OK;
 }
 
-static int launch_q_infer(const QParams &q, cudaStream_t st) {
+static int launch_q_infer(const QParams &q, int mode, cudaStream_t st) {
     const size_t act = (size_t)q.L1p * 2 + (size_t)(q.K1 + q.K2 + q.K3) * 4;
     const size_t smem = (size_t)q.OC * 29 * 4 + kQWarps * act;
     if (smem > 200 * 1024) return NNUE_ERR_UNSUPPORTED;
@@ -373,7 +433,7 @@ static int launch_q_infer(const QParams &q, cudaStream_t st) {
     const int nwords = q.L1p / 2;
 #define NNUE_QLAUNCH(MAXW)                                                                                   \
     do {                                                                                                     \
-        auto k = q_infer_kernel<MAXW>;                                                                       \
+        auto k = mode == 0 ? q_infer_kernel<MAXW, 0> : mode == 1 ? q_infer_kernel<MAXW, 1> : q_infer_kernel<MAXW, 2>; \
         if (smem > 48 * 1024)                                                                                \
             NNUE_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
         k<<<grid, kQWarps * 32, smem, st>>>(q);                                                              \
@@ -401,6 +461,8 @@ void nnue_q_free(nnue_qmodel *m) {
     if (m->h_logits) cudaFree(m->h_logits);
     if (m->h_density) cudaFree(m->h_density);
     if (m->h_stream) cudaStreamDestroy(m->h_stream);
+    if (m->s_bits) cudaFree(m->s_bits);
+    if (m->s_acc) cudaFree(m->s_acc);
     delete m;
 }
 
@@ -444,7 +506,25 @@ int nnue_q_infer(const nnue_qmodel *m, const float *images_d, int B, int H, int 
     const int rc = fill_params(m, B, H, W, bucket, &q);
     if (rc != NNUE_OK) return rc;
     q.images = images_d; q.logits = logits_d; q.density = density_d;
-    return launch_q_infer(q, static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int min_b = get_option(kOptQTcMinBatch);
+    if (m->tc_tiles && min_b > 0 && B >= min_b) {
+        // large batches: bitmask -> tcgen05 accumulate -> layer stack (three launches, same integers)
+        if ((size_t)B > m->s_cap) {  // grow the per-instance scratch (synchronising; only when the batch grows)
+            if (m->s_bits) { cudaFree(m->s_bits); cudaFree(m->s_acc); m->s_bits = nullptr; m->s_acc = nullptr; m->s_cap = 0; }
+            NNUE_CUDA_TRY(cudaMalloc(&m->s_bits, (size_t)B * m->OC * m->CWq * 4));
+            NNUE_CUDA_TRY(cudaMalloc(&m->s_acc, (size_t)B * m->L1 * 2));
+            m->s_cap = (size_t)B;
+        }
+        q.G2 = m->F / m->OC; q.CWq = m->CWq; q.bits_out = m->s_bits; q.acc_in = m->s_acc;
+        int rc2 = launch_q_infer(q, 1, st);
+        if (rc2 != NNUE_OK) return rc2;
+        rc2 = launch_q_accumulate_umma(B, m->OC * m->CWq, m->L1, m->s_bits, m->tc_tiles,
+                                       reinterpret_cast<const int32_t *>(m->ft_b32), m->s_acc, st);
+        if (rc2 != NNUE_OK) return rc2;
+        return launch_q_infer(q, 2, st);
+    }
+    return launch_q_infer(q, 0, st);
 }
 
 int nnue_q_infer_host(const nnue_qmodel *m, const float *images_h, int B, int H, int W, int bucket, float *logits_h,

@@ -206,3 +206,35 @@ def test_layer_stack_buckets_select_their_own_stack(oracle_built, tmp_path):
     assert not np.array_equal(outs[0], outs[1]) and not np.array_equal(outs[1], outs[2])
     past_end, _ = ev.evaluate_logits(torch.as_tensor(imgs).cuda(), layer_stack_index=7)
     np.testing.assert_array_equal(past_end.cpu().numpy(), outs[0])
+
+
+TC_ARCHS = [a for a in INT_ARCHS if a[2] % 64 == 0]
+
+
+@pytest.mark.parametrize("arch", TC_ARCHS, ids=lambda a: "x".join(map(str, a)))
+@pytest.mark.parametrize("wild", [False, True])
+@pytest.mark.parametrize("thr", [None, -0.5, 127.0])
+def test_tensor_core_accumulate_matches_oracle(oracle_built, tmp_path, arch, wild, thr):
+    """The large-batch form (bitmask -> tcgen05 accumulate of the high/low bytes of the int16 rows -> layer
+    stack) forced onto small batches: full int16 rows and biases (wrap-around), negative thresholds (the
+    cells past the conv raster become active), ragged batches that do not fill a 128-sample tile."""
+    from nnue_vision_b200 import _lib
+    G, C, L1, L2, L3, NC, H = arch
+    rng = np.random.default_rng(abs(hash((arch, wild, thr))) % (2**32))
+    path = tmp_path / "m.nnue"
+    write_random_nnue(path, rng, G, C, L1, L2, L3, NC, wild=wild, threshold=thr)
+    B = 7 if H > 100 else 300
+    imgs = (rng.standard_normal((B, H, H, 3)) * (3.0 if wild else 1.0)).astype(np.float32)
+    ol, od = oracle_built.IntOracle(path).eval_batch(imgs, threads=4)
+    ev = _engine().NNUEEvaluator(path)
+    fl, fd = gpu_eval(ev, imgs)  # fused kernel (batch below the switch-over)
+    _lib.set_option("q_tc_min_batch", 1)
+    try:
+        tl, td = gpu_eval(ev, imgs)
+        tl1, td1 = gpu_eval(ev, imgs[:1])
+    finally:
+        _lib.set_option("q_tc_min_batch", 2048)
+    np.testing.assert_array_equal(fl, ol)
+    np.testing.assert_array_equal(tl, ol)
+    np.testing.assert_array_equal(td, od)
+    np.testing.assert_array_equal(tl1, ol[:1])
