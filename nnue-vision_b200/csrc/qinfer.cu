@@ -274,6 +274,15 @@ q_infer_kernel(const QParams q) {
         for (int cell0 = 0; MODE != 2 && cell0 < (MODE == 1 ? q.G2 : cells); cell0 += 32) {
             const int cell = cell0 + lane;
             const bool valid = cell < cells;
+            if (MODE == 1 && cell0 >= cells) {  // warp-uniform: a block entirely past the raster needs no conv
+                const unsigned word = (0.0f > q.threshold) ? __ballot_sync(kFull, cell < q.G2) : 0u;
+                for (int oc = 0; oc < q.OC; ++oc) {
+                    const unsigned wd = oc < 64 ? word : 0u;
+                    n_active += __popc(wd);
+                    if (lane == 0) q.bits_out[((size_t)b * q.OC + oc) * q.CWq + (cell0 >> 5)] = wd;
+                }
+                continue;
+            }
             const int oy = valid ? cell / q.ow : 0, ox = valid ? cell % q.ow : 0;
             int xq[27];  // [kh][kw][ic], truncated (int32)(pixel * scale), 0 in the padding
 #pragma unroll
@@ -292,9 +301,15 @@ q_infer_kernel(const QParams q) {
             }
             for (int oc = 0; oc < q.OC; ++oc) {
                 int a = s_cb[oc];
-                const int32_t *w = s_cw + oc * 28;
+                const int4 *w4 = reinterpret_cast<const int4 *>(s_cw + oc * 28);  // 28 taps = 7 broadcast LDS.128
 #pragma unroll
-                for (int t = 0; t < 27; ++t) a += xq[t] * w[t];
+                for (int t4 = 0; t4 < 7; ++t4) {
+                    const int4 w = w4[t4];
+                    a += xq[4 * t4] * w.x;
+                    a += xq[4 * t4 + 1] * w.y;
+                    a += xq[4 * t4 + 2] * w.z;
+                    if (t4 < 6) a += xq[4 * t4 + 3] * w.w;
+                }
                 const int v = clampi(a / q.conv_iscale, -127, 127);
                 const bool on = valid ? (oc < 64 && (float)v > q.threshold)
                                       : (MODE == 1 && cell < q.G2 && oc < 64 && 0.0f > q.threshold);

@@ -8,7 +8,7 @@ with tempfile.TemporaryDirectory() as td:
     p = Path(td) / "m.nnue"
     serialize.serialize_model(bench.build_model(w, "cpu"), p)
     ev = engine.NNUEEvaluator(p)
-    for B in (1, 256, 4096, 16384, 65536):
+    for B in ([int(x) for x in sys.argv[1:]] or (1, 256, 4096, 16384, 65536)):
         imgs = torch.randn(B, 32, 32, 3, generator=torch.Generator().manual_seed(3)).cuda()
         for _ in range(3): ev.evaluate_logits(imgs)
         torch.cuda.synchronize()
