@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl"],
+                    help="gradient exchange at N > 1: the library's one-shot all-reduce over NVLink peer memory (auto) or NCCL")
     ap.add_argument("--no-int", action="store_true", help="skip the integer-inference side measurement")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="library tuning knob (nnue_set_option), e.g. --opt input_bwd_variant=1")
@@ -331,7 +333,7 @@ def run_b200(args):
         key, val = kv.split("=")
         _lib.set_option(key, int(val))
     model = build_model(w, device)
-    dp = train.DataParallelStep(model)
+    dp = train.DataParallelStep(model, allreduce=args.exchange)
     if world > 1:  # identical replicas
         for p in model.parameters():
             torch.distributed.broadcast(p.data, src=0)
@@ -460,7 +462,7 @@ def run_b200(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "per_gpu_batch": B, "global_batch": global_batch,
                    "arch": {k: w[k] for k in ("grid", "C", "L1", "L2", "L3", "NC", "input", "image")},
-                   "parallelism": f"dp{world}", "nnz_per_sample": nnz_total / B,
+                   "parallelism": f"dp{world}", "exchange": dp.allreduce, "nnz_per_sample": nnz_total / B,
                    "l2_policy": "inputs larger than L2: 3 image sets x %.0f MB cycled" % (img_bytes / 1e6),
                    "loss_after_timed_steps": final_loss},
         "clocks": clocks.summary(),

@@ -346,6 +346,25 @@ int nnue_q_infer(const nnue_qmodel *m, const float *images_d, int B, int H, int 
 int nnue_q_infer_host(const nnue_qmodel *m, const float *images_h, int B, int H, int W, int bucket,
                       float *logits_h, float *density_h);
 
+/* ------------------------------------------------------------------------- *
+ *  Data-parallel exchange (the reference has no collective)        *
+ * ------------------------------------------------------------------------- */
+
+/*
+ * One-shot all-reduce (sum, in rank order on every rank) of `n` floats over NVLink peer memory.
+ *   peer_bufs_h[world]  host array of DEVICE pointers: rank r's symmetric send buffer (n floats), peer-mapped
+ *   peer_flags_h[world] host array of device pointers: rank r's flag block, int32[2][nnue_allreduce_max_world()],
+ *                       zeroed once before the first call
+ *   counter_d           local device uint32, zero before the first call
+ *   out_d               local result buffer (n floats; not one of the send buffers)
+ *   epoch               1, 2, 3, ... : the same value on every rank for the same step
+ * Every rank must launch the same epoch; the kernel returns only after all peers have read this rank's buffer,
+ * so the buffer may be overwritten by the next work queued on `stream`.
+ */
+int nnue_allreduce_max_world(void);
+int nnue_allreduce_oneshot(int world, int rank, const void *const *peer_bufs_h, void *const *peer_flags_h,
+                           void *counter_d, size_t n, float *out_d, int epoch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,11 +33,12 @@ class FlatGradBuffer:
     """One contiguous fp32 buffer holding every gradient (+ one trailing slot for the loss) with
     per-parameter views; `attach()` makes the views the parameters' `.grad`."""
 
-    def __init__(self, named_params, device):
+    def __init__(self, named_params, device, flat=None):
         self.names = [n for n in GRAD_PARAM_NAMES if n in named_params]
         self.params = [named_params[n] for n in self.names]
         sizes = [p.numel() for p in self.params]
-        self.flat = torch.zeros(sum(sizes) + 1, dtype=torch.float32, device=device)
+        # `flat` may be supplied (e.g. a symmetric-memory tensor the peers can read); at least sum(sizes) + 1 floats
+        self.flat = torch.zeros(sum(sizes) + 1, dtype=torch.float32, device=device) if flat is None else flat
         self.views, off = [], 0
         for p, n in zip(self.params, sizes):
             self.views.append(self.flat[off:off + n].view(p.shape))
@@ -159,7 +160,7 @@ class DataParallelStep:
     """
 
     def __init__(self, model, process_group=None, local_step: Optional[Callable] = None, device=None,
-                 cuda_graphs: Optional[bool] = None, max_graphs: int = 8):
+                 cuda_graphs: Optional[bool] = None, max_graphs: int = 8, allreduce: str = "auto"):
         self.model = model
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
@@ -178,6 +179,54 @@ class DataParallelStep:
         self.max_graphs = int(max_graphs)
         self._graphs = {}   # key -> [hits, CUDAGraph or None, (images, labels) kept alive]
         self._pool = None
+        # Exchange: the library's one-shot all-reduce over NVLink peer memory when the ranks share a node and
+        # symmetric memory is available (the kernels then write a symmetric send buffer and the all-reduce writes
+        # the .grad buffer), otherwise one NCCL / gloo all-reduce on the flat buffer.
+        self.allreduce = "none" if self.world == 1 else "collective"
+        self._send = self.buf
+        if self.world > 1 and local_step is None and torch.device(device).type == "cuda" and allreduce != "nccl":
+            self._setup_oneshot(named, device)
+
+    def _setup_oneshot(self, named, device):
+        import ctypes
+        import sys
+        from . import _lib
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.group if self.group is not None else dist.group.WORLD
+            if self.world > int(_lib.lib().nnue_allreduce_max_world()):
+                return
+            n = self.buf.numel()
+            send = symm.empty(n, dtype=torch.float32, device=device)
+            flags = symm.empty(2 * int(_lib.lib().nnue_allreduce_max_world()), dtype=torch.int32, device=device)
+            send.zero_()
+            flags.zero_()
+            h_send = symm.rendezvous(send, group)
+            h_flags = symm.rendezvous(flags, group)
+            torch.cuda.synchronize(device)
+            dist.barrier(group=self.group)  # every rank's flags are zero before anybody signals
+            self._send = FlatGradBuffer(named, device, flat=send)
+            self._ar = dict(
+                rank=int(h_send.rank), n=n, epoch=0, keep=(send, flags, h_send, h_flags),
+                bufs=(ctypes.c_void_p * self.world)(*[int(x) for x in h_send.buffer_ptrs]),
+                flags=(ctypes.c_void_p * self.world)(*[int(x) for x in h_flags.buffer_ptrs]),
+                counter=torch.zeros(1, dtype=torch.int32, device=device))
+            self.allreduce = "oneshot_p2p"
+        except Exception as e:  # no peer access / no symmetric memory on this system: the collective stays
+            print(f"nnue_vision_b200: one-shot all-reduce unavailable ({type(e).__name__}: {e}); using the collective",
+                  file=sys.stderr)
+            self._send = self.buf
+
+    def _exchange(self):
+        if self.allreduce == "oneshot_p2p":
+            from . import _lib
+            a = self._ar
+            a["epoch"] += 1
+            _lib.check(_lib.lib().nnue_allreduce_oneshot(
+                self.world, a["rank"], a["bufs"], a["flags"], _lib.dptr(a["counter"]), a["n"], _lib.dptr(self.buf.flat),
+                a["epoch"], _lib.stream_ptr()))
+        else:
+            dist.all_reduce(self.buf.flat, op=dist.ReduceOp.SUM, group=self.group)
 
     def _graph_key(self, images, labels, inv_count):
         return (images.data_ptr(), labels.data_ptr(), tuple(images.shape), images.dtype, labels.dtype, inv_count,
@@ -187,7 +236,7 @@ class DataParallelStep:
         ok = (self.cuda_graphs and images.is_cuda and labels.is_cuda and images.is_contiguous() and labels.is_contiguous()
               and images.dtype == torch.float32)
         if not ok:
-            self._local(images, labels, inv_count, self.buf)
+            self._local(images, labels, inv_count, self._send)
             return
         key = self._graph_key(images, labels, inv_count)
         ent = self._graphs.get(key)
@@ -195,7 +244,7 @@ class DataParallelStep:
             if len(self._graphs) >= self.max_graphs:  # drop the least recently used entry
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = [1, None, (images, labels)]
-            self._local(images, labels, inv_count, self.buf)
+            self._local(images, labels, inv_count, self._send)
             return
         self._graphs[key] = self._graphs.pop(key)  # most recently used last
         ent[0] += 1
@@ -207,7 +256,7 @@ class DataParallelStep:
             torch.cuda.synchronize(images.device)
             n0 = int(_lib.lib().nnue_launch_count(0))
             with torch.cuda.graph(g, pool=self._pool):
-                self._local(images, labels, inv_count, self.buf)
+                self._local(images, labels, inv_count, self._send)
             ent[1] = g
             ent.append(int(_lib.lib().nnue_launch_count(0)) - n0)  # kernels in the graph
             self._count_add = _lib.lib().nnue_launch_count_add
@@ -220,9 +269,9 @@ class DataParallelStep:
         if global_batch is None:
             global_batch = images.shape[0] * self.world  # equal shards
         if marks is not None:
-            self._local(images, labels, 1.0 / float(global_batch), self.buf, marks)
+            self._local(images, labels, 1.0 / float(global_batch), self._send, marks)
         else:
             self._run_local(images, labels, 1.0 / float(global_batch))
         if self.world > 1:
-            dist.all_reduce(self.buf.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self._exchange()
         return self.buf.loss.reshape(())
