@@ -237,7 +237,7 @@ constexpr int kQWarps = 8;
 template <int MAXW, int MODE>
 __global__ void __launch_bounds__(kQWarps * 32)
 q_infer_kernel(const QParams q) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     int32_t *s_cw = reinterpret_cast<int32_t *>(smem_raw);       // [OC][28]
     int32_t *s_cb = s_cw + q.OC * 28;                             // [OC]
     const int act_bytes = q.L1p * 2 + q.K1 * 4 + q.K2 * 4 + q.K3 * 4;
@@ -300,16 +300,18 @@ q_infer_kernel(const QParams q) {
                 }
             }
             for (int oc = 0; oc < q.OC; ++oc) {
-                int a = s_cb[oc];
+                // four independent partial sums (integer addition is associative: same result, 4x shorter IMAD chains)
+                int a = s_cb[oc], a1 = 0, a2 = 0, a3 = 0;
                 const int4 *w4 = reinterpret_cast<const int4 *>(s_cw + oc * 28);  // 28 taps = 7 broadcast LDS.128
 #pragma unroll
                 for (int t4 = 0; t4 < 7; ++t4) {
                     const int4 w = w4[t4];
                     a += xq[4 * t4] * w.x;
-                    a += xq[4 * t4 + 1] * w.y;
-                    a += xq[4 * t4 + 2] * w.z;
-                    if (t4 < 6) a += xq[4 * t4 + 3] * w.w;
+                    a1 += xq[4 * t4 + 1] * w.y;
+                    a2 += xq[4 * t4 + 2] * w.z;
+                    if (t4 < 6) a3 += xq[4 * t4 + 3] * w.w;
                 }
+                a += (a1 + a2) + a3;
                 const int v = clampi(a / q.conv_iscale, -127, 127);
                 const bool on = valid ? (oc < 64 && (float)v > q.threshold)
                                       : (MODE == 1 && cell < q.G2 && oc < 64 && 0.0f > q.threshold);
