@@ -351,19 +351,21 @@ int nnue_q_infer_host(const nnue_qmodel *m, const float *images_h, int B, int H,
  * ------------------------------------------------------------------------- */
 
 /*
- * One-shot all-reduce (sum, in rank order on every rank) of `n` floats over NVLink peer memory.
- *   peer_bufs_h[world]  host array of DEVICE pointers: rank r's symmetric send buffer (n floats), peer-mapped
- *   peer_flags_h[world] host array of device pointers: rank r's flag block, int32[2][nnue_allreduce_max_world()],
+ * One-shot all-reduce (sum, in rank order on every rank, in place) of `n` floats over NVLink peer memory.
+ *   peer_recv_h[world]  host array of DEVICE pointers: rank r's symmetric receive area of
+ *                       nnue_allreduce_recv_floats(world, n) floats, peer-mapped on every rank
+ *   peer_flags_h[world] host array of device pointers: rank r's flag block, int32[nnue_allreduce_max_world()],
  *                       zeroed once before the first call
  *   counter_d           local device uint32, zero before the first call
- *   out_d               local result buffer (n floats; not one of the send buffers)
+ *   buf_d               local buffer of n floats (n % 4 == 0, 16-byte aligned): input and result
  *   epoch               1, 2, 3, ... : the same value on every rank for the same step
- * Every rank must launch the same epoch; the kernel returns only after all peers have read this rank's buffer,
- * so the buffer may be overwritten by the next work queued on `stream`.
+ * Every rank must launch the same epoch sequence.  The kernel pushes the local values into every rank's receive
+ * area (posted NVLink stores), publishes the epoch, waits for the peers' and sums its own area.
  */
 int nnue_allreduce_max_world(void);
-int nnue_allreduce_oneshot(int world, int rank, const void *const *peer_bufs_h, void *const *peer_flags_h,
-                           void *counter_d, size_t n, float *out_d, int epoch, void *stream);
+size_t nnue_allreduce_recv_floats(int world, size_t n);
+int nnue_allreduce_oneshot(int world, int rank, void *const *peer_recv_h, void *const *peer_flags_h,
+                           void *counter_d, size_t n, float *buf_d, int epoch, void *stream);
 
 #ifdef __cplusplus
 }

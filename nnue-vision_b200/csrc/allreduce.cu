@@ -1,22 +1,23 @@
 // allreduce.cu -- one-shot all-reduce (sum) of the flat gradient buffer over NVLink peer memory.
 //
 // The data-parallel step exchanges ONE small buffer per step (54 K floats at config D: latency-bound).
-// Every rank keeps a symmetric "send" buffer that its gradient kernels write; this kernel then
-//   1. tells every peer that the local buffer is complete (release store of the step's epoch into the peer's flag
-//      slot, system scope) and waits until all peers have said the same,
-//   2. reads all `world` buffers through peer pointers (P2P loads over NVLink / NVSwitch) and writes their sum, taken
-//      in rank order on every rank -- bit-identical results everywhere, run to run -- into the local result buffer,
-//   3. (last CTA) tells every peer that its reads are done and waits for the peers' reads of the local buffer, so the
-//      next step may overwrite it as soon as this kernel has completed.
-// One launch, no host synchronisation, no NCCL call on the path.
+// Push form: every rank owns a symmetric receive area of 2 (epoch parity) x world slots.  One launch
+//   1. copies the local buffer into slot [parity][rank] of EVERY rank (posted stores over NVLink / NVSwitch: one-way
+//      latency, no read round trip),
+//   2. when all CTAs have pushed, publishes the step's epoch in every peer's flag slot (release, system scope) and
+//      waits until all peers' epochs have arrived,
+//   3. sums the `world` local slots in rank order -- bit-identical results on every rank, run to run -- in place.
+// The parity double-buffering makes a trailing barrier unnecessary: a slot is rewritten two steps later, and a rank
+// can only get there after every peer has published the epoch in between, which it does after finishing its sums.
+// No host synchronisation, no NCCL call on the path.
 #include "common.cuh"
 
 namespace nnue {
 
 constexpr int kArMaxWorld = 16;
 struct ArPeers {
-    const float *buf[kArMaxWorld];
-    int *flags[kArMaxWorld];  // per rank: int[2][kArMaxWorld] -- [0][r] "r's buffer is ready", [1][r] "r has read mine"
+    float *recv[kArMaxWorld];  // rank r's receive area: float[2][world][n]
+    int *flags[kArMaxWorld];   // rank r's flags: int[kArMaxWorld], flags[s] = last epoch whose data from rank s is complete
 };
 
 __device__ __forceinline__ void st_release_sys(int *p, int v) {
@@ -27,55 +28,46 @@ __device__ __forceinline__ int ld_acquire_sys(const int *p) {
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ float4 ld_peer_f4(const float4 *p) {
+__device__ __forceinline__ float4 ld_sys_f4(const float4 *p) {
     float4 v;
     asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ float ld_peer_f(const float *p) {
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void st_sys_f4(float4 *p, float4 v) {
+    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// n4 = float4 elements (the buffer is padded to a multiple of 4 floats); every CTA owns the same index range in the
+// push and in the sum, so the sum may overwrite `buf` in place
 __global__ void __launch_bounds__(512)
-allreduce_oneshot_kernel(const ArPeers p, int rank, int world, size_t n, float *__restrict__ out, int epoch,
-                         unsigned *__restrict__ counter) {
+allreduce_push_kernel(const ArPeers p, int rank, int world, size_t n4, float4 *__restrict__ buf, int epoch,
+                      unsigned *__restrict__ counter) {
     __shared__ bool last;
-    // 1. my buffer is complete (written by earlier kernels of this stream): publish, then wait for every peer
-    if (blockIdx.x == 0 && threadIdx.x < world) {
-        __threadfence_system();
-        st_release_sys(p.flags[threadIdx.x] + rank, epoch);
+    const size_t stride = (size_t)gridDim.x * blockDim.x, first = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t slot0 = (size_t)(epoch & 1) * world * n4;
+    // 1. push my values into slot [parity][rank] of every rank
+    for (size_t i = first; i < n4; i += stride) {
+        const float4 v = buf[i];
+        for (int r = 0; r < world; ++r) st_sys_f4(reinterpret_cast<float4 *>(p.recv[r]) + slot0 + (size_t)rank * n4 + i, v);
+    }
+    // 2. all CTAs pushed -> publish the epoch to every peer; then wait for every peer's epoch
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x < world) st_release_sys(p.flags[threadIdx.x] + rank, epoch);
+        if (threadIdx.x == 0) *counter = 0u;
     }
     if (threadIdx.x < world)
         while (ld_acquire_sys(p.flags[rank] + threadIdx.x) < epoch) {}
     __syncthreads();
-    // 2. sum in rank order
-    const size_t n4 = n / 4, stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        float4 acc = ld_peer_f4(reinterpret_cast<const float4 *>(p.buf[0]) + i);
-        for (int r = 1; r < world; ++r) acc = f4_add(acc, ld_peer_f4(reinterpret_cast<const float4 *>(p.buf[r]) + i));
-        reinterpret_cast<float4 *>(out)[i] = acc;
-    }
-    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        float acc = ld_peer_f(p.buf[0] + i);
-        for (int r = 1; r < world; ++r) acc += ld_peer_f(p.buf[r] + i);
-        out[i] = acc;
-    }
-    // 3. the last CTA to finish tells the peers that this rank's reads are done and waits for theirs
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        last = atomicAdd(counter, 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (last) {
-        if (threadIdx.x < world) {
-            st_release_sys(p.flags[threadIdx.x] + kArMaxWorld + rank, epoch);
-            while (ld_acquire_sys(p.flags[rank] + kArMaxWorld + threadIdx.x) < epoch) {}
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) *counter = 0u;
+    // 3. sum my slots in rank order
+    const float4 *mine = reinterpret_cast<const float4 *>(p.recv[rank]) + slot0;
+    for (size_t i = first; i < n4; i += stride) {
+        float4 acc = ld_sys_f4(mine + i);
+        for (int r = 1; r < world; ++r) acc = f4_add(acc, ld_sys_f4(mine + (size_t)r * n4 + i));
+        buf[i] = acc;
     }
 }
 
@@ -87,22 +79,24 @@ extern "C" {
 
 int nnue_allreduce_max_world(void) { return kArMaxWorld; }
 
-int nnue_allreduce_oneshot(int world, int rank, const void *const *peer_bufs_h, void *const *peer_flags_h, void *counter_d,
-                           size_t n, float *out_d, int epoch, void *stream) {
-    if (world < 1 || world > kArMaxWorld || rank < 0 || rank >= world || !peer_bufs_h || !peer_flags_h || !counter_d ||
-        !out_d || n < 1 || epoch < 1)
+size_t nnue_allreduce_recv_floats(int world, size_t n) { return 2 * (size_t)world * ((n + 3) / 4 * 4); }
+
+int nnue_allreduce_oneshot(int world, int rank, void *const *peer_recv_h, void *const *peer_flags_h, void *counter_d,
+                           size_t n, float *buf_d, int epoch, void *stream) {
+    if (world < 1 || world > kArMaxWorld || rank < 0 || rank >= world || !peer_recv_h || !peer_flags_h || !counter_d ||
+        !buf_d || n < 1 || epoch < 1 || (n & 3) || (reinterpret_cast<uintptr_t>(buf_d) & 15))
         return NNUE_ERR_INVALID_ARG;
     ArPeers p{};
     for (int r = 0; r < world; ++r) {
-        p.buf[r] = static_cast<const float *>(peer_bufs_h[r]);
+        p.recv[r] = static_cast<float *>(peer_recv_h[r]);
         p.flags[r] = static_cast<int *>(peer_flags_h[r]);
-        if (!p.buf[r] || !p.flags[r]) return NNUE_ERR_INVALID_ARG;
+        if (!p.recv[r] || !p.flags[r]) return NNUE_ERR_INVALID_ARG;
     }
-    size_t want = (n / 4 + 511) / 512;
-    int grid = (int)(want < 1 ? 1 : want > 64 ? 64 : want);  // every CTA spins on the flags: keep them co-resident
-    allreduce_oneshot_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(stream)>>>(
-        p, rank, world, n, out_d, epoch, static_cast<unsigned *>(counter_d));
-    NNUE_CHECK_LAUNCH("allreduce_oneshot_kernel");
+    const size_t n4 = n / 4, want = (n4 + 511) / 512;
+    const int grid = (int)(want < 1 ? 1 : want > 64 ? 64 : want);  // every CTA spins on the flags: keep them co-resident
+    allreduce_push_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(stream)>>>(
+        p, rank, world, n4, reinterpret_cast<float4 *>(buf_d), epoch, static_cast<unsigned *>(counter_d));
+    NNUE_CHECK_LAUNCH("allreduce_push_kernel");
     return NNUE_OK;
 }
 

@@ -38,7 +38,8 @@ class FlatGradBuffer:
         self.params = [named_params[n] for n in self.names]
         sizes = [p.numel() for p in self.params]
         # `flat` may be supplied (e.g. a symmetric-memory tensor the peers can read); at least sum(sizes) + 1 floats
-        self.flat = torch.zeros(sum(sizes) + 1, dtype=torch.float32, device=device) if flat is None else flat
+        total = (sum(sizes) + 1 + 3) // 4 * 4  # padded to whole float4s (the one-shot all-reduce moves 16-byte words)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device) if flat is None else flat
         self.views, off = [], 0
         for p, n in zip(self.params, sizes):
             self.views.append(self.flat[off:off + n].view(p.shape))
@@ -180,10 +181,8 @@ class DataParallelStep:
         self._graphs = {}   # key -> [hits, CUDAGraph or None, (images, labels) kept alive]
         self._pool = None
         # Exchange: the library's one-shot all-reduce over NVLink peer memory when the ranks share a node and
-        # symmetric memory is available (the kernels then write a symmetric send buffer and the all-reduce writes
-        # the .grad buffer), otherwise one NCCL / gloo all-reduce on the flat buffer.
+        # symmetric memory is available (in place on the flat buffer), otherwise one NCCL / gloo all-reduce.
         self.allreduce = "none" if self.world == 1 else "collective"
-        self._send = self.buf
         if self.world > 1 and local_step is None and torch.device(device).type == "cuda" and allreduce != "nccl":
             self._setup_oneshot(named, device)
 
@@ -193,29 +192,28 @@ class DataParallelStep:
         from . import _lib
         try:
             import torch.distributed._symmetric_memory as symm
+            L = _lib.lib()
             group = self.group if self.group is not None else dist.group.WORLD
-            if self.world > int(_lib.lib().nnue_allreduce_max_world()):
+            if self.world > int(L.nnue_allreduce_max_world()):
                 return
-            n = self.buf.numel()
-            send = symm.empty(n, dtype=torch.float32, device=device)
-            flags = symm.empty(2 * int(_lib.lib().nnue_allreduce_max_world()), dtype=torch.int32, device=device)
-            send.zero_()
+            n = self.buf.numel()  # (FlatGradBuffer pads its buffer to a multiple of 4 floats)
+            recv = symm.empty(int(L.nnue_allreduce_recv_floats(self.world, n)), dtype=torch.float32, device=device)
+            flags = symm.empty(int(L.nnue_allreduce_max_world()), dtype=torch.int32, device=device)
+            recv.zero_()
             flags.zero_()
-            h_send = symm.rendezvous(send, group)
+            h_recv = symm.rendezvous(recv, group)
             h_flags = symm.rendezvous(flags, group)
             torch.cuda.synchronize(device)
-            dist.barrier(group=self.group)  # every rank's flags are zero before anybody signals
-            self._send = FlatGradBuffer(named, device, flat=send)
+            dist.barrier(group=self.group)  # every rank's flags are zero before anybody publishes an epoch
             self._ar = dict(
-                rank=int(h_send.rank), n=n, epoch=0, keep=(send, flags, h_send, h_flags),
-                bufs=(ctypes.c_void_p * self.world)(*[int(x) for x in h_send.buffer_ptrs]),
+                rank=int(h_recv.rank), n=n, epoch=0, keep=(recv, flags, h_recv, h_flags),
+                recv=(ctypes.c_void_p * self.world)(*[int(x) for x in h_recv.buffer_ptrs]),
                 flags=(ctypes.c_void_p * self.world)(*[int(x) for x in h_flags.buffer_ptrs]),
                 counter=torch.zeros(1, dtype=torch.int32, device=device))
             self.allreduce = "oneshot_p2p"
         except Exception as e:  # no peer access / no symmetric memory on this system: the collective stays
             print(f"nnue_vision_b200: one-shot all-reduce unavailable ({type(e).__name__}: {e}); using the collective",
                   file=sys.stderr)
-            self._send = self.buf
 
     def _exchange(self):
         if self.allreduce == "oneshot_p2p":
@@ -223,7 +221,7 @@ class DataParallelStep:
             a = self._ar
             a["epoch"] += 1
             _lib.check(_lib.lib().nnue_allreduce_oneshot(
-                self.world, a["rank"], a["bufs"], a["flags"], _lib.dptr(a["counter"]), a["n"], _lib.dptr(self.buf.flat),
+                self.world, a["rank"], a["recv"], a["flags"], _lib.dptr(a["counter"]), a["n"], _lib.dptr(self.buf.flat),
                 a["epoch"], _lib.stream_ptr()))
         else:
             dist.all_reduce(self.buf.flat, op=dist.ReduceOp.SUM, group=self.group)
@@ -236,7 +234,7 @@ class DataParallelStep:
         ok = (self.cuda_graphs and images.is_cuda and labels.is_cuda and images.is_contiguous() and labels.is_contiguous()
               and images.dtype == torch.float32)
         if not ok:
-            self._local(images, labels, inv_count, self._send)
+            self._local(images, labels, inv_count, self.buf)
             return
         key = self._graph_key(images, labels, inv_count)
         ent = self._graphs.get(key)
@@ -244,7 +242,7 @@ class DataParallelStep:
             if len(self._graphs) >= self.max_graphs:  # drop the least recently used entry
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = [1, None, (images, labels)]
-            self._local(images, labels, inv_count, self._send)
+            self._local(images, labels, inv_count, self.buf)
             return
         self._graphs[key] = self._graphs.pop(key)  # most recently used last
         ent[0] += 1
@@ -256,7 +254,7 @@ class DataParallelStep:
             torch.cuda.synchronize(images.device)
             n0 = int(_lib.lib().nnue_launch_count(0))
             with torch.cuda.graph(g, pool=self._pool):
-                self._local(images, labels, inv_count, self._send)
+                self._local(images, labels, inv_count, self.buf)
             ent[1] = g
             ent.append(int(_lib.lib().nnue_launch_count(0)) - n0)  # kernels in the graph
             self._count_add = _lib.lib().nnue_launch_count_add
@@ -269,7 +267,7 @@ class DataParallelStep:
         if global_batch is None:
             global_batch = images.shape[0] * self.world  # equal shards
         if marks is not None:
-            self._local(images, labels, 1.0 / float(global_batch), self._send, marks)
+            self._local(images, labels, 1.0 / float(global_batch), self.buf, marks)
         else:
             self._run_local(images, labels, 1.0 / float(global_batch))
         if self.world > 1:

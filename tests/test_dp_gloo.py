@@ -89,7 +89,9 @@ def test_two_rank_step_equals_single_process_step(tmp_path, shard_sizes):
     got = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
     assert np.array_equal(got[0]["flat"], got[1]["flat"]), "all ranks must hold the same reduced buffer"
     scale = np.abs(expect).max()
-    np.testing.assert_allclose(got[0]["flat"], expect, rtol=1e-5, atol=1e-5 * scale)
+    # (the buffer is padded to whole float4s behind the loss slot; the padding stays zero)
+    np.testing.assert_allclose(got[0]["flat"][: len(expect)], expect, rtol=1e-5, atol=1e-5 * scale)
+    assert len(got[0]["flat"]) % 4 == 0 and not got[0]["flat"][len(expect):].any()
     assert abs(got[0]["loss"] - float(ref["loss"])) < 1e-5 * abs(float(ref["loss"]))
 
 
@@ -98,7 +100,8 @@ def test_flat_buffer_layout_follows_reference_parameter_order():
     model = _model()
     buf = train.FlatGradBuffer(dict(model.named_parameters()), "cpu")
     assert buf.names == list(train.GRAD_PARAM_NAMES)
-    assert buf.numel() == sum(p.numel() for n, p in model.named_parameters() if n != "nnue2score") + 1
+    n_real = sum(p.numel() for n, p in model.named_parameters() if n != "nnue2score") + 1  # gradients + the loss slot
+    assert buf.numel() == (n_real + 3) // 4 * 4  # padded to whole float4s
     off = 0
     for n, v in zip(buf.names, buf.views):
         assert v.data_ptr() == buf.flat.data_ptr() + 4 * off and v.shape == dict(model.named_parameters())[n].shape
