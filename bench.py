@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "oneshot", "nccl"],
                     help="gradient exchange at N > 1: the library's one-shot all-reduce over NVLink peer memory (auto) or NCCL")
     ap.add_argument("--no-int", action="store_true", help="skip the integer-inference side measurement")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",

@@ -30,7 +30,7 @@ def _worker(rank, world, port, out):
         mine = slice(rank * per, (rank + 1) * per)
         x, y = images[mine].cuda(), labels[mine].cuda()
         res = {}
-        for kind in ("auto", "nccl"):
+        for kind in ("oneshot", "nccl"):
             dp = train.DataParallelStep(model, allreduce=kind)
             losses = []
             for _ in range(4):  # eager, capture, replays: the exchange follows each of them
@@ -43,7 +43,7 @@ def _worker(rank, world, port, out):
             ref_loss = float(ref.step(images.cuda(), labels.cuda()))
             torch.cuda.synchronize()
             res["ref"] = ("none", [ref_loss], ref.buf.flat.clone())
-        flat = res["auto"][2]
+        flat = res["oneshot"][2]
         others = [torch.empty_like(flat) for _ in range(world)]
         dist.all_gather(others, flat)
         same_everywhere = all(torch.equal(o, flat) for o in others)
@@ -60,7 +60,7 @@ def test_one_shot_allreduce_matches_nccl_and_full_batch(tmp_path):
     out = str(tmp_path / "res.pt")
     mp.spawn(_worker, args=(world, 29641, out), nprocs=world, join=True)
     res = torch.load(out)
-    kind, losses, flat = res["auto"]
+    kind, losses, flat = res["oneshot"]
     assert res["same"], "ranks disagree"
     assert all(l == losses[0] for l in losses), "the step is deterministic: every repeat gives the same loss"
     nk, nlosses, nflat = res["nccl"]
