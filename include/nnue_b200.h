@@ -346,6 +346,21 @@ int nnue_q_infer(const nnue_qmodel *m, const float *images_d, int B, int H, int 
 int nnue_q_infer_host(const nnue_qmodel *m, const float *images_h, int B, int H, int W, int bucket,
                       float *logits_h, float *density_h);
 
+/*
+ * Incremental accumulators over S independent streams -- the batched form of NNUEEvaluator::refresh_accumulator /
+ * update_features / evaluate_incremental / save_ / restore_accumulator (nnue_engine.cpp:739-821,
+ * nnue_engine.h:583-594).  acc_d is caller-owned int16 [S][L1] (save / restore = copies of it).
+ *   refresh != 0: acc = (int16)bias + rows(added)            (refresh_accumulator)
+ *   refresh == 0: acc = acc - rows(removed) + rows(added)    (update_features), int16 wrap-around
+ * Feature lists are CSR: *_off_d int32 [S + 1], *_idx_d int32 [nnz]; either pair may be NULL (no features);
+ * indices outside [0, F) are ignored as the engine does.
+ */
+int nnue_q_acc_apply(const nnue_qmodel *m, int S, int refresh, const int32_t *add_off_d, const int32_t *add_idx_d,
+                     const int32_t *rem_off_d, const int32_t *rem_idx_d, int16_t *acc_d, void *stream);
+/* score_d[s] = LayerStack::forward(clipped acc[s]) -- the single score evaluate_incremental returns
+ * (nnue_engine.cpp:382-478, 775-787).  NNUE_ERR_UNSUPPORTED when the file lacks bias L2 of the combined layer. */
+int nnue_q_acc_score(const nnue_qmodel *m, int S, const int16_t *acc_d, int bucket, float *score_d, void *stream);
+
 /* ------------------------------------------------------------------------- *
  *  Data-parallel exchange (the reference has no collective)        *
  * ------------------------------------------------------------------------- */

@@ -69,6 +69,8 @@ SIGNATURES = {
     "nnue_q_free": (None, [vp]),
     "nnue_q_dims": (ctypes.c_int, [vp, vp, ctypes.POINTER(f32)]),
     "nnue_q_infer": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp]),
+    "nnue_q_acc_apply": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]),
+    "nnue_q_acc_score": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.c_int, vp, vp]),
     "nnue_q_infer_host": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]),
 }
 

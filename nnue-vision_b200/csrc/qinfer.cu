@@ -31,6 +31,16 @@ struct nnue_qmodel {
         int32_t *w1, *b1;  // w1 [K1][L2] dp4a words: inputs 4k..4k+3 of output o
         int32_t *w2, *b2;  // w2 [K2][L3]
         int32_t *wo, *bo;  // wo [K3][NC]
+        // raw blocks for the single-score LayerStack::forward behind evaluate_incremental (nnue_engine.cpp:382-478);
+        // null when the file lacks what that path indexes (bias L2 of the combined layer)
+        float l1_fact_scale;
+        int8_t *w1_raw = nullptr;    // [(L2 + 1)][L1]
+        int32_t *b1_raw = nullptr;   // [L2 + 1]
+        int8_t *wf_row = nullptr;    // row L2 of the L1-factoriser weights [L1]
+        int32_t bf_L2 = 0;           // its bias
+        int8_t *w2_raw = nullptr;    // [L3][2 * L2]
+        int8_t *wo_row = nullptr;    // output row 0 [L3]
+        int32_t bo0 = 0;
     };
     std::vector<Stack> stacks;
     std::vector<void *> allocs;
@@ -168,7 +178,7 @@ static int parse_and_upload(const unsigned char *bytes, size_t n, nnue_qmodel *m
     for (uint32_t b = 0; b < nb; ++b) {
         nnue_qmodel::Stack st{};
         st.l1_scale = r.f32(); st.l2_scale = r.f32(); st.out_scale = r.f32();
-        (void)r.f32();  // l1_fact_scale
+        st.l1_fact_scale = r.f32();
         uint32_t rows = r.u32(), cols = r.u32();
         if (!r.ok || rows != L2 + 1 || cols != L1 || L2 < 1 || L3 < 1) return NNUE_ERR_FORMAT;
         std::vector<int8_t> w1((size_t)rows * cols);
@@ -177,11 +187,13 @@ static int parse_and_upload(const unsigned char *bytes, size_t n, nnue_qmodel *m
         if (!r.ok || nbias < L2) return NNUE_ERR_FORMAT;
         std::vector<int32_t> b1(nbias);
         if (!r.take(b1.data(), (size_t)nbias * 4)) return NNUE_ERR_FORMAT;
-        rows = r.u32(); cols = r.u32();  // L1 factoriser: unused by the multiclass head
+        rows = r.u32(); cols = r.u32();  // L1 factoriser: unused by the multiclass head, row L2 feeds the single score
         if (!r.ok || cols != L1 || rows <= L2) return NNUE_ERR_FORMAT;
-        if (!r.skip((size_t)rows * cols)) return NNUE_ERR_FORMAT;
+        std::vector<int8_t> wf((size_t)rows * cols);
+        if (!r.take(wf.data(), wf.size())) return NNUE_ERR_FORMAT;
         nbias = r.u32();
-        if (!r.skip((size_t)nbias * 4)) return NNUE_ERR_FORMAT;
+        std::vector<int32_t> bfv(r.ok ? nbias : 0);
+        if (!r.take(bfv.data(), (size_t)nbias * 4)) return NNUE_ERR_FORMAT;
         rows = r.u32(); cols = r.u32();
         if (!r.ok || cols != 2 * L2 || rows != L3) return NNUE_ERR_FORMAT;
         std::vector<int8_t> w2((size_t)rows * cols);
@@ -204,6 +216,16 @@ static int parse_and_upload(const unsigned char *bytes, size_t n, nnue_qmodel *m
             (rc = upload(m, pack_dp4a(w2, (int)L3, (int)L2, (int)(2 * L2)), &st.w2)) || (rc = upload(m, b2, &st.b2)) ||
             (rc = upload(m, pack_dp4a(wo, m->NC, (int)L3, (int)L3), &st.wo)) || (rc = upload(m, bo, &st.bo)))
             return rc;
+        if (b1.size() >= (size_t)L2 + 1 && bfv.size() > (size_t)L2) {
+            std::vector<int32_t> b1x(b1.begin(), b1.begin() + L2 + 1);
+            std::vector<int8_t> wfr(wf.begin() + (size_t)L2 * L1, wf.begin() + (size_t)(L2 + 1) * L1);
+            std::vector<int8_t> wor(wo.begin(), wo.begin() + L3);
+            if ((rc = upload(m, w1, &st.w1_raw)) || (rc = upload(m, b1x, &st.b1_raw)) || (rc = upload(m, wfr, &st.wf_row)) ||
+                (rc = upload(m, w2, &st.w2_raw)) || (rc = upload(m, wor, &st.wo_row)))
+                return rc;
+            st.bf_L2 = bfv[L2];
+            st.bo0 = bo[0];
+        }
         m->stacks.push_back(st);
     }
     return NNUE_OK;
@@ -542,6 +564,135 @@ int nnue_q_infer(const nnue_qmodel *m, const float *images_d, int B, int H, int 
         return launch_q_infer(q, 2, st);
     }
     return launch_q_infer(q, 0, st);
+}
+
+}  // extern "C"
+
+namespace nnue {
+
+// ---- incremental accumulators (NNUEEvaluator::refresh_accumulator / update_features / evaluate_incremental,
+//      nnue_engine.cpp:739-821), batched over S independent streams -----------------------------------------------
+// acc [S][L1] int16.  A warp owns a stream: refresh starts from (int16)bias, otherwise from the stored accumulator;
+// rows of `removed` are subtracted and rows of `added` are added with int16 wrap-around (simd_scalar.cpp:97-113);
+// indices outside [0, F) are ignored (nnue_engine.cpp:215, 234).
+__global__ void __launch_bounds__(256)
+q_acc_apply_kernel(int S, int F, int L1, int L1p, const int16_t *__restrict__ ft_w, const int16_t *__restrict__ ft_b, int refresh,
+                   const int32_t *__restrict__ add_off, const int32_t *__restrict__ add_idx,
+                   const int32_t *__restrict__ rem_off, const int32_t *__restrict__ rem_idx, int16_t *__restrict__ acc) {
+    const int lane = threadIdx.x & 31;
+    const int s = (int)((1LL * blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (s >= S) return;
+    int16_t *row = acc + (size_t)s * L1;
+    for (int c0 = lane; c0 < L1; c0 += 32) {  // a lane owns columns lane, lane + 32, ...
+        int v = refresh ? (int)ft_b[c0] : (int)row[c0];
+        if (rem_off)
+            for (int k = rem_off[s]; k < rem_off[s + 1]; ++k) {
+                const int f = rem_idx[k];
+                if (f >= 0 && f < F) v -= (int)__ldg(ft_w + (size_t)f * L1p + c0);
+            }
+        if (add_off)
+            for (int k = add_off[s]; k < add_off[s + 1]; ++k) {
+                const int f = add_idx[k];
+                if (f >= 0 && f < F) v += (int)__ldg(ft_w + (size_t)f * L1p + c0);
+            }
+        row[c0] = (int16_t)v;  // exact int arithmetic, then the wrap the engine's int16 adds perform step by step
+    }
+}
+
+struct QLegacy {
+    int L1, L2, L3, qone;
+    float l1_scale, l2_scale, out_scale, l1_fact_scale;
+    const int8_t *w1, *wf, *w2, *wo;
+    const int32_t *b1, *b2;
+    int32_t bf, bo0;
+};
+__device__ __forceinline__ int dense_out(int acc, float scale) {  // simd_scalar.cpp:131-133: float divide, truncate, 0..127
+    return max(0, min(127, __float2int_rz(__fdiv_rn(__int2float_rn(acc), scale))));
+}
+// simd_avx2.cpp:114-152 -- the form LayerStack::forward takes on every AVX2 host (nnue_engine.cpp:393-397, 453-457),
+// i.e. what the reference engine computes wherever it is built today: the accumulator vector starts as
+// set1_epi32(bias) and all eight lanes are summed, so the bias counts EIGHT times, and the quotient is an integer
+// division.  Reproduced as is (oracle/_ref is that build; tests/test_oracle_int.py pins the restatement against it).
+__device__ __forceinline__ int dense_out_avx2(int dot, int bias, float scale) {
+    const int iscale = (int)scale;
+    return max(0, min(127, (8 * bias + dot) / (iscale ? iscale : 1)));
+}
+// score[s] = LayerStack::forward(clipped accumulator) (nnue_engine.cpp:382-478): combined layer (L2 + 1 outputs),
+// row L2 of the factoriser, squared / linear expansion, L2 layer over 2 * L2 inputs, output row 0; a warp per stream
+__global__ void __launch_bounds__(256)
+q_acc_score_kernel(int S, const QLegacy q, const int16_t *__restrict__ acc, float *__restrict__ score) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = blockIdx.x * (blockDim.x >> 5) + warp;
+    int16_t *in = reinterpret_cast<int16_t *>(smem_raw) + (size_t)warp * (q.L1 + 3 * q.L2 + q.L3 + 8);
+    int16_t *comb = in + q.L1;          // [L2 + 1]
+    int16_t *expd = comb + q.L2 + 1;    // [2 * L2]
+    int16_t *l2o = expd + 2 * q.L2;     // [L3]
+    if (s >= S) return;
+    for (int i = lane; i < q.L1; i += 32) in[i] = (int16_t)max(0, min(q.qone, (int)acc[(size_t)s * q.L1 + i]));
+    __syncwarp();
+    for (int o = lane; o <= q.L2; o += 32) {
+        int a = 0;
+        for (int i = 0; i < q.L1; ++i) a += (int)in[i] * (int)__ldg(q.w1 + (size_t)o * q.L1 + i);
+        comb[o] = (int16_t)dense_out_avx2(a, q.b1[o], q.l1_scale);
+    }
+    int af = 0;  // factoriser row L2: lanes split the inputs
+    for (int i = lane; i < q.L1; i += 32) af += (int)in[i] * (int)__ldg(q.wf + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) af += __shfl_xor_sync(kFull, af, o);
+    __syncwarp();
+    for (int i = lane; i < q.L2; i += 32) {
+        const int c = comb[i];
+        expd[i] = (int16_t)max(0, min(127, (c * c * 127) / 128));
+        expd[i + q.L2] = (int16_t)c;
+    }
+    __syncwarp();
+    for (int o = lane; o < q.L3; o += 32) {
+        int a = 0;
+        for (int i = 0; i < 2 * q.L2; ++i) a += (int)expd[i] * (int)__ldg(q.w2 + (size_t)o * 2 * q.L2 + i);
+        l2o[o] = (int16_t)dense_out_avx2(a, q.b2[o], q.l2_scale);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int a = q.bo0;
+        for (int j = 0; j < q.L3; ++j) a += (int)l2o[j] * (int)__ldg(q.wo + j);
+        const float l3c = __fdiv_rn(__int2float_rn(a), q.out_scale);
+        const float l1f = __fdiv_rn(__int2float_rn(dense_out(q.bf + af, q.l1_fact_scale)), q.l1_fact_scale);
+        const float l1c = __fdiv_rn(__int2float_rn((int)comb[q.L2]), q.l1_scale);
+        score[s] = __fadd_rn(__fadd_rn(l3c, l1f), l1c);  // nnue_engine.cpp:477
+    }
+}
+
+}  // namespace nnue
+
+extern "C" {
+
+int nnue_q_acc_apply(const nnue_qmodel *m, int S, int refresh, const int32_t *add_off_d, const int32_t *add_idx_d,
+                     const int32_t *rem_off_d, const int32_t *rem_idx_d, int16_t *acc_d, void *stream) {
+    if (!m || S < 1 || !acc_d || (add_off_d && !add_idx_d) || (rem_off_d && !rem_idx_d)) return NNUE_ERR_INVALID_ARG;
+    q_acc_apply_kernel<<<ceil_div(S, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        S, m->F, m->L1, m->L1p, m->ft_w, m->ft_b, refresh ? 1 : 0, add_off_d, add_idx_d, rem_off_d, rem_idx_d, acc_d);
+    NNUE_CHECK_LAUNCH("q_acc_apply_kernel");
+    return NNUE_OK;
+}
+
+int nnue_q_acc_score(const nnue_qmodel *m, int S, const int16_t *acc_d, int bucket, float *score_d, void *stream) {
+    if (!m || S < 1 || !acc_d || !score_d || bucket < 0) return NNUE_ERR_INVALID_ARG;
+    if (bucket >= m->n_buckets) bucket = 0;  // nnue_engine.cpp:741-743
+    const nnue_qmodel::Stack &st = m->stacks[(size_t)bucket];
+    if (!st.w1_raw) return NNUE_ERR_UNSUPPORTED;
+    QLegacy q{};
+    q.L1 = m->L1; q.L2 = m->L2; q.L3 = m->L3; q.qone = (int)(int16_t)m->quantized_one;
+    q.l1_scale = st.l1_scale; q.l2_scale = st.l2_scale; q.out_scale = st.out_scale; q.l1_fact_scale = st.l1_fact_scale;
+    q.w1 = st.w1_raw; q.wf = st.wf_row; q.w2 = st.w2_raw; q.wo = st.wo_row; q.b1 = st.b1_raw; q.b2 = st.b2;
+    q.bf = st.bf_L2; q.bo0 = st.bo0;
+    const size_t smem = 8 * (size_t)(q.L1 + 3 * q.L2 + q.L3 + 8) * 2;
+    if (smem > 200 * 1024) return NNUE_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024)
+        NNUE_CUDA_TRY(cudaFuncSetAttribute(q_acc_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    q_acc_score_kernel<<<ceil_div(S, 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(S, q, acc_d, score_d);
+    NNUE_CHECK_LAUNCH("q_acc_score_kernel");
+    return NNUE_OK;
 }
 
 int nnue_q_infer_host(const nnue_qmodel *m, const float *images_h, int B, int H, int W, int bucket, float *logits_h,

@@ -22,6 +22,10 @@ class NNUEEvaluator:
         self.num_features = self.l1_size = self.l2_size = self.l3_size = 0
         self.num_classes = self.num_channels_per_square = self.grid_size = self.num_layer_stacks = 0
         self.visual_threshold = 0.0
+        # incremental-accumulator state (nnue_engine.h:583-594), over S independent streams
+        self._acc = self._backup = None
+        self._last_features = None
+        self._dirty, self._incremental = True, True
         if path is not None and not self.load_model(path):
             raise _lib.NnueError(f"cannot load {path}")
 
@@ -48,6 +52,8 @@ class NNUEEvaluator:
         (self.num_features, self.l1_size, self.l2_size, self.l3_size, self.num_classes,
          self.num_channels_per_square, self.grid_size, self.num_layer_stacks) = (int(v) for v in dims)
         self.visual_threshold = float(thr.value)
+        self._acc = self._backup = self._last_features = None
+        self._dirty = True
         return True
 
     def _require(self):
@@ -82,3 +88,91 @@ class NNUEEvaluator:
                                            int(layer_stack_index), logits.ctypes.data_as(ctypes.c_void_p),
                                            density.ctypes.data_as(ctypes.c_void_p)))
         return logits, density
+
+    # ---- incremental accumulators (NNUEEvaluator::refresh_accumulator / update_features / evaluate_incremental /
+    #      save_ / restore_accumulator, nnue_engine.cpp:739-821), batched over S independent streams ---------------
+    # A flat list of feature indices addresses ONE stream (the reference's interface, a Python float comes back);
+    # a list of lists addresses S streams at once (a CUDA tensor [S] comes back).
+    @staticmethod
+    def _streams(features):
+        single = len(features) == 0 or not isinstance(features[0], (list, tuple, np.ndarray))
+        lists = [list(map(int, features))] if single else [list(map(int, f)) for f in features]
+        return single, lists
+
+    @staticmethod
+    def _csr(lists, device):
+        off = np.zeros(len(lists) + 1, np.int32)
+        np.cumsum([len(l) for l in lists], out=off[1:])
+        idx = np.fromiter((f for l in lists for f in l), np.int32, count=int(off[-1])) if off[-1] else np.zeros(1, np.int32)
+        return torch.from_numpy(off).to(device), torch.from_numpy(idx).to(device)
+
+    def _device(self):
+        return torch.device("cuda", torch.cuda.current_device())
+
+    def refresh_accumulator(self, features):
+        """acc = (int16)bias + sum of the listed rows, for every stream (nnue_engine.cpp:804-815)."""
+        self._require()
+        _, lists = self._streams(features)
+        dev = self._device()
+        S = len(lists)
+        if self._acc is None or self._acc.shape[0] != S or self._acc.device != dev:
+            self._acc = torch.empty((S, self.l1_size), dtype=torch.int16, device=dev)
+        off, idx = self._csr(lists, dev)
+        check(_lib.lib().nnue_q_acc_apply(self._h, S, 1, dptr(off), dptr(idx), None, None, dptr(self._acc), stream_ptr()))
+
+    def update_features(self, added, removed):
+        """acc -= rows(removed); acc += rows(added) with int16 wrap-around (nnue_engine.cpp:818-821)."""
+        self._require()
+        if self._acc is None:
+            raise _lib.NnueError("update_features before refresh_accumulator")
+        _, la = self._streams(added)
+        _, lr = self._streams(removed)
+        S = self._acc.shape[0]
+        if len(la) != S or len(lr) != S:
+            raise ValueError(f"expected feature lists for {S} streams")
+        dev = self._acc.device
+        ao, ai = self._csr(la, dev)
+        ro, ri = self._csr(lr, dev)
+        check(_lib.lib().nnue_q_acc_apply(self._h, S, 0, dptr(ao), dptr(ai), dptr(ro), dptr(ri), dptr(self._acc), stream_ptr()))
+
+    def evaluate_incremental(self, current_features, layer_stack_index: int = 0):
+        """The engine's chess-style entry point (nnue_engine.cpp:739-787): refresh when dirty / disabled, otherwise
+        apply the difference to the previous call's features; then clipped ReLU + the single-score layer stack."""
+        self._require()
+        single, cur = self._streams(current_features)
+        stale = (not self._incremental or self._dirty or self._acc is None or self._last_features is None
+                 or len(self._last_features) != len(cur))
+        if stale:
+            self.refresh_accumulator(cur)
+            self._last_features, self._dirty = cur, False
+        else:
+            added, removed = [], []
+            for last, now in zip(self._last_features, cur):
+                sl, sn = set(last), set(now)
+                removed.append([f for f in last if f not in sn])  # std::find per element: multiplicities are kept
+                added.append([f for f in now if f not in sl])
+            if any(added) or any(removed):
+                self.update_features(added, removed)
+                self._last_features = cur
+        S = self._acc.shape[0]
+        score = torch.empty((S,), dtype=torch.float32, device=self._acc.device)
+        check(_lib.lib().nnue_q_acc_score(self._h, S, dptr(self._acc), int(layer_stack_index), dptr(score), stream_ptr()))
+        return float(score[0]) if single else score
+
+    def save_accumulator(self):
+        if self._acc is not None:
+            self._backup = self._acc.clone()
+
+    def restore_accumulator(self):
+        if self._backup is not None and self._acc is not None and self._backup.shape == self._acc.shape:
+            self._acc.copy_(self._backup)
+
+    def enable_incremental(self, enable: bool = True):
+        self._incremental = bool(enable)
+
+    def mark_dirty(self):
+        self._dirty = True
+
+    def get_accumulator(self):
+        """The int16 accumulators [S][L1] (device tensor; for inspection and tests)."""
+        return self._acc

@@ -147,5 +147,55 @@ class RefEngine:
         return logits, dens
 
 
+    # ---- incremental surface of the reference engine (ref_driver.cpp: evaluate_incremental / mark_dirty) ----
+    def eval_incremental(self, features):
+        f = np.ascontiguousarray(features, np.int32)
+        self._lib.ref_eval_incremental.restype = ctypes.c_float
+        self._lib.ref_eval_incremental.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        return float(self._lib.ref_eval_incremental(self._h, _ptr(f) if len(f) else None, int(len(f))))
+
+    def mark_dirty(self):
+        self._lib.ref_mark_dirty.argtypes = [ctypes.c_void_p]
+        self._lib.ref_mark_dirty(self._h)
+
+
+def legacy_score(q, features, bucket=0):
+    """numpy restatement of NNUEEvaluator::evaluate_incremental after a full refresh: accumulator
+    (nnue_engine.cpp:804-815, simd_scalar.cpp:97-104), clipped ReLU (:775-779) and the single-score
+    LayerStack::forward (:382-478).  `q` is the dict of nnue_vision_b200.serialize.read_nnue (file parsing only)."""
+    md, ft, st = q["metadata"], q["feature_transformer"], q["layer_stacks"][bucket]
+    F, L1, L2 = md["num_features"], md["L1"], md["L2"]
+    acc = ft["bias"].astype(np.int64)
+    acc = acc.astype(np.int16).astype(np.int64)
+    for f in features:
+        if 0 <= f < F:
+            acc = acc + ft["weight"][f].astype(np.int64)
+    acc = ((acc + 32768) % 65536 - 32768)                      # int16 wrap-around of the running sums
+    x = np.clip(acc, 0, int(np.int16(md["quantized_one"])))     # clipped ReLU
+
+    def dense(w, b, v, scale):                                  # simd_scalar.cpp:116-136 (float divide, truncate)
+        a = b.astype(np.int64) + w.astype(np.int64) @ v
+        return np.clip(np.trunc(a.astype(np.float32) / np.float32(scale)).astype(np.int64), 0, 127)
+
+    def dense_avx2(w, b, v, scale):
+        # simd_avx2.cpp:114-152, the form LayerStack::forward takes on every AVX2 host (nnue_engine.cpp:393-397,
+        # 453-457): the accumulator vector starts as set1_epi32(bias) and ALL EIGHT lanes are summed, so the bias
+        # counts eight times; the quotient is an integer division
+        a = 8 * b.astype(np.int64) + w.astype(np.int64) @ v
+        q_ = np.abs(a) // int(scale) * np.sign(a)                # C++ division truncates toward zero
+        return np.clip(q_, 0, 127)
+
+    comb = dense_avx2(st["l1_weight"], st["l1_bias"][: L2 + 1], x, st["l1_scale"])
+    fact = dense(st["l1_fact_weight"][L2: L2 + 1], st["l1_fact_bias"][L2: L2 + 1], x, st["l1_fact_scale"])
+    l1c = np.float32(comb[L2]) / np.float32(st["l1_scale"])
+    l1f = np.float32(fact[0]) / np.float32(st["l1_fact_scale"])
+    c = comb[:L2]
+    expd = np.concatenate([np.clip((c * c * 127) // 128, 0, 127), c])
+    l2o = dense_avx2(st["l2_weight"], st["l2_bias"], expd, st["l2_scale"])
+    a = int(st["output_bias"][0]) + int(st["output_weight"][0].astype(np.int64) @ l2o)
+    l3c = np.float32(a) / np.float32(st["output_scale"])
+    return float(np.float32(np.float32(l3c + l1f) + l1c))
+
+
 def host_threads():
     return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)

@@ -238,3 +238,63 @@ def test_tensor_core_accumulate_matches_oracle(oracle_built, tmp_path, arch, wil
     np.testing.assert_array_equal(tl, ol)
     np.testing.assert_array_equal(td, od)
     np.testing.assert_array_equal(tl1, ol[:1])
+
+
+@pytest.mark.parametrize("arch", [(8, 4, 64, 4, 8, 10), (10, 8, 64, 32, 8, 10), (5, 3, 30, 5, 7, 3), (6, 16, 128, 16, 32, 1000)],
+                         ids=lambda a: "x".join(map(str, a)))
+@pytest.mark.parametrize("wild", [False, True])
+def test_incremental_accumulator_api_matches_engine(oracle_built, tmp_path, arch, wild):
+    """refresh_accumulator / update_features / evaluate_incremental / save / restore (nnue_engine.cpp:739-821),
+    one stream (the reference's interface) and 33 streams at once, against the restatement that
+    tests/test_oracle_int.py pins to the reference engine -- and against the engine itself where oracle/_ref exists."""
+    from nnue_vision_b200 import serialize
+    G, C, L1, L2, L3, NC = arch
+    rng = np.random.default_rng(abs(hash((arch, wild))) % (2**32))
+    path = tmp_path / "m.nnue"
+    write_random_nnue(path, rng, G, C, L1, L2, L3, NC, wild=wild)
+    q = serialize.read_nnue(path)
+    F = G * G * C
+    ev = _engine().NNUEEvaluator(path)
+    ref = oracle_built.RefEngine(path) if oracle_built.RefEngine.available() else None
+
+    def draw(n):
+        return rng.choice(F, size=min(F, n), replace=False).tolist()
+
+    # one stream: a walk of small changes, each step scored incrementally
+    feats = draw(60)
+    if ref:
+        ref.mark_dirty()
+    for step in range(6):
+        got = ev.evaluate_incremental(feats)
+        assert got == oracle_built.legacy_score(q, feats), f"step {step}"
+        if ref:
+            assert got == ref.eval_incremental(feats)
+        drop = set(feats[:4])
+        feats = [f for f in feats if f not in drop] + [f for f in draw(6) if f not in feats]
+    # the accumulator itself: int16 wrap-around sums
+    acc = ev.get_accumulator().cpu().numpy()[0].astype(np.int64)
+    want = q["feature_transformer"]["bias"].astype(np.int64)
+    last = ev._last_features[0]
+    want = want + q["feature_transformer"]["weight"][last].astype(np.int64).sum(0)
+    np.testing.assert_array_equal(acc, (want + 32768) % 65536 - 32768)
+    # save / restore / mark_dirty / disable
+    ev.save_accumulator()
+    ev.update_features([1, 2, 3], [])
+    ev.restore_accumulator()
+    np.testing.assert_array_equal(ev.get_accumulator().cpu().numpy()[0], acc)
+    ev.update_features([F + 5, -1], [F])  # out-of-range indices are ignored (nnue_engine.cpp:215, 234)
+    np.testing.assert_array_equal(ev.get_accumulator().cpu().numpy()[0], acc)
+    ev.mark_dirty()
+    assert ev.evaluate_incremental(last) == oracle_built.legacy_score(q, last)
+    ev.enable_incremental(False)
+    other = draw(30)
+    assert ev.evaluate_incremental(other) == oracle_built.legacy_score(q, other)
+    ev.enable_incremental(True)
+    # 33 streams at once
+    streams = [draw(int(rng.integers(0, 80))) for _ in range(33)]
+    ev.mark_dirty()
+    for step in range(3):
+        got = ev.evaluate_incremental(streams).cpu().numpy()
+        want = np.array([oracle_built.legacy_score(q, s) for s in streams], np.float32)
+        np.testing.assert_array_equal(got, want)
+        streams = [[f for f in s[2:]] + [f for f in draw(3) if f not in s] for s in streams]

@@ -66,3 +66,32 @@ def test_c_oracle_matches_reference_engine(oracle_built, tmp_path, arch, wild):
     np.testing.assert_array_equal(ol, rl)
     np.testing.assert_array_equal(od, rd)
     assert (ref.F, ref.L1, ref.L2, ref.L3, ref.OC, ref.G) == (orc.F, orc.L1, orc.L2, orc.L3, orc.OC, orc.G)
+
+
+def test_legacy_score_restatement_is_pinned_to_the_reference_engine(oracle_built, tmp_path):
+    """evaluate_incremental's single score (nnue_engine.cpp:739-787, LayerStack::forward :382-478): the numpy
+    restatement equals the reference engine itself (oracle/_ref, an AVX2 build: the eight-fold bias of
+    simd_avx2.cpp:119 is part of what it computes) on random files, full int16 rows included."""
+    from util import write_random_nnue
+    from nnue_vision_b200 import serialize
+    if not oracle_built.RefEngine.available():
+        pytest.skip("oracle/_ref not built (no reference checkout)")
+    rng = np.random.default_rng(3)
+    for (G, C, L1, L2, L3, NC) in [(8, 4, 64, 4, 8, 10), (10, 8, 64, 32, 8, 10), (5, 3, 30, 5, 7, 3), (6, 16, 128, 16, 32, 1000)]:
+        for wild in (False, True):
+            p = tmp_path / "m.nnue"
+            write_random_nnue(p, rng, G, C, L1, L2, L3, NC, wild=wild)
+            q = serialize.read_nnue(p)
+            ref = oracle_built.RefEngine(p)
+            F = G * G * C
+            for _ in range(6):
+                feats = rng.choice(F, size=int(rng.integers(0, min(F, 150))), replace=False).tolist()
+                ref.mark_dirty()
+                assert ref.eval_incremental(feats) == oracle_built.legacy_score(q, feats)
+            # incremental walk: the engine diffs against its previous call; the restatement recomputes from scratch
+            feats = rng.choice(F, size=min(F, 40), replace=False).tolist()
+            ref.mark_dirty()
+            for _ in range(5):
+                assert ref.eval_incremental(feats) == oracle_built.legacy_score(q, feats)
+                drop = set(rng.choice(feats, size=min(len(feats), 5), replace=False).tolist())
+                feats = [f for f in feats if f not in drop] + [int(f) for f in rng.choice(F, size=5) if f not in feats]
