@@ -612,7 +612,7 @@ __device__ __forceinline__ int dense_out(int acc, float scale) {  // simd_scalar
 // simd_avx2.cpp:114-152 -- the form LayerStack::forward takes on every AVX2 host (nnue_engine.cpp:393-397, 453-457),
 // i.e. what the reference engine computes wherever it is built today: the accumulator vector starts as
 // set1_epi32(bias) and all eight lanes are summed, so the bias counts EIGHT times, and the quotient is an integer
-// division.  Reproduced as is (oracle/_ref is that build; tests/test_oracle_int.py pins the restatement against it).
+// division.  Reproduced as is (the parity tests compare against exactly that build of the reference engine).
 __device__ __forceinline__ int dense_out_avx2(int dot, int bias, float scale) {
     const int iscale = (int)scale;
     return max(0, min(127, (8 * bias + dot) / (iscale ? iscale : 1)));
