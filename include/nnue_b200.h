@@ -233,6 +233,18 @@ int nnue_wants_transposed_bits(const nnue_shape *s);
  * gbin_d [B][PP] as nnue_ft_bwd_gbin.  A lane keeps its table row and that row's gradient in registers.
  */
 int nnue_ft_bwd_is_fused(const nnue_shape *s);
+/*
+ * Pre-formatted table tiles for the tcgen05 kernels.  nnue_ft_fwd / nnue_ft_bwd_gbin re-format the table into
+ * split-bf16 tiles on every call; the formatting depends only on the weights, so a training step may do it once, on
+ * another stream, while the images are being extracted, and then call the *_tables forms.
+ *   nnue_ft_tables_bytes: size of the tile buffer, 0 when the tcgen05 kernels do not serve the shape.
+ */
+size_t nnue_ft_tables_bytes(const nnue_shape *s);
+int nnue_ft_format_tables(const nnue_shape *s, const float *ft_w_d, void *tables_d, void *stream);
+int nnue_ft_fwd_tables(const nnue_shape *s, const uint32_t *bits_s_d, const void *tables_d, const float *ft_b_d,
+                       float *ft_out_d, void *stream);
+int nnue_ft_bwd_gbin_tables(const nnue_shape *s, const uint32_t *bits_s_d, const void *tables_d, const float *g_ft_d,
+                            float *gbin_d, void *workspace_d, size_t workspace_bytes, void *stream);
 int nnue_ft_uses_mma(const nnue_shape *s);  /* 1 when the tensor-core contractions serve this shape */
 int nnue_ft_uses_umma(const nnue_shape *s); /* 1 when they are the tcgen05 / TMEM kernels of ft_umma.cu (L1 a multiple of 64) */
 int nnue_ft_bwd(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w_d, const float *g_ft_d,

@@ -54,6 +54,10 @@ SIGNATURES = {
     "nnue_input_bwd_is_dense": (ctypes.c_int, [SHAPE_P]),
     "nnue_ft_bwd_gbin": (ctypes.c_int, [SHAPE_P, vp, vp, vp, vp, vp, sz, vp]),
     "nnue_ft_uses_mma": (ctypes.c_int, [SHAPE_P]),
+    "nnue_ft_tables_bytes": (sz, [SHAPE_P]),
+    "nnue_ft_format_tables": (ctypes.c_int, [SHAPE_P, vp, vp, vp]),
+    "nnue_ft_fwd_tables": (ctypes.c_int, [SHAPE_P, vp, vp, vp, vp, vp]),
+    "nnue_ft_bwd_gbin_tables": (ctypes.c_int, [SHAPE_P, vp, vp, vp, vp, vp, sz, vp]),
     "nnue_ft_uses_umma": (ctypes.c_int, [SHAPE_P]),
     "nnue_conv_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 8 + [sz, vp]),
     "nnue_input_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 9 + [sz, vp]),

@@ -1125,6 +1125,31 @@ int nnue_ft_fwd(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w
     return rc;
 }
 
+// ---- pre-formatted table tiles (tcgen05 shapes): the formatting depends only on the weights and can run beside the
+//      extraction on another stream ----
+size_t nnue_ft_tables_bytes(const nnue_shape *s) { return s ? ft_tables_bytes(*s) : 0; }
+
+int nnue_ft_format_tables(const nnue_shape *s, const float *ft_w_d, void *tables_d, void *stream) {
+    if (!s || !ft_w_d || !tables_d) return NNUE_ERR_INVALID_ARG;
+    if (!ft_umma_ok(*s)) return NNUE_ERR_UNSUPPORTED;
+    return launch_ft_format_tables(*s, ft_w_d, tables_d, 3, static_cast<cudaStream_t>(stream));
+}
+
+int nnue_ft_fwd_tables(const nnue_shape *s, const uint32_t *bits_s_d, const void *tables_d, const float *ft_b_d,
+                       float *ft_out_d, void *stream) {
+    if (!s || !bits_s_d || !tables_d || !ft_b_d || !ft_out_d) return NNUE_ERR_INVALID_ARG;
+    if (!ft_umma_ok(*s)) return NNUE_ERR_UNSUPPORTED;
+    return launch_ft_fwd_umma_tiles(*s, bits_s_d, tables_d, ft_b_d, ft_out_d, static_cast<cudaStream_t>(stream));
+}
+
+int nnue_ft_bwd_gbin_tables(const nnue_shape *s, const uint32_t *bits_s_d, const void *tables_d, const float *g_ft_d,
+                            float *gbin_d, void *workspace_d, size_t workspace_bytes, void *stream) {
+    if (!s || !bits_s_d || !tables_d || !g_ft_d || !gbin_d || !workspace_d) return NNUE_ERR_INVALID_ARG;
+    if (!ft_umma_ok(*s) || !plan_input_bwd(*s).fused) return NNUE_ERR_UNSUPPORTED;
+    if (workspace_bytes < ws_ft_gbin_umma(*s)) return NNUE_ERR_WORKSPACE;
+    return launch_ft_bwd_gbin_umma(*s, bits_s_d, nullptr, g_ft_d, workspace_d, gbin_d, static_cast<cudaStream_t>(stream), tables_d);
+}
+
 int nnue_ft_fwd_indexed(int B, int K, int F, int L1, const int64_t *idx_d, const float *val_d, const float *ft_w_d,
                         const float *ft_b_d, float *ft_out_d, void *stream) {
     if (B < 1 || K < 1 || F < 1 || L1 < 1 || !idx_d || !val_d || !ft_w_d || !ft_b_d || !ft_out_d)

@@ -424,18 +424,43 @@ ft_gbin_umma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, con
 constexpr size_t kBgSmem = 1024 + (size_t)kBgStages * (kBgABytes + kBgBBytes);
 constexpr size_t kGbSmem = 1024 + (size_t)kGbStages * (kGbABytes + kGbBBytes);
 
+// The table in both tile orders, formatted once per step: [forward / kt tiles: umma_kt_bytes(PP)] [value-gradient /
+// rows tiles: ceil(PP / 256) * 256 * L1 * 6].  It depends only on the weights, so a caller may run it on a side stream
+// while the images are being extracted (nnue_ft_format_tables).
+int launch_ft_format_tables(const nnue_shape &s, const float *w, void *tables, int which, cudaStream_t st) {
+    unsigned char *wt = static_cast<unsigned char *>(tables);
+    if (which & 1) {
+        const int n_ks = 2 * s.NW;
+        const long long n = 2LL * n_ks * s.L1;
+        umma_format_kt_kernel<true><<<(int)((n + 255) / 256), 256, 0, st>>>(s, w, s.PP, n_ks, wt);
+        NNUE_CHECK_LAUNCH("umma_format_kt_kernel");
+    }
+    if (which & 2) {
+        const int n_nt = ceil_div(s.PP, kUmmaGbinN);
+        const long long n = 1LL * n_nt * kUmmaGbinN * (s.L1 / 8);
+        umma_format_rows_kernel<true, kUmmaGbinN><<<(int)((n + 255) / 256), 256, 0, st>>>(
+            s, w, s.PP, n_nt, wt + align_up(umma_kt_bytes((size_t)s.PP, s), 256));
+        NNUE_CHECK_LAUNCH("umma_format_rows_kernel");
+    }
+    return NNUE_OK;
+}
+
+// out = bias + bits . W from pre-formatted forward tiles
+int launch_ft_fwd_umma_tiles(const nnue_shape &s, const uint32_t *bits_s, const void *tables, const float *bias, float *out,
+                             cudaStream_t st) {
+    NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_bitgemm_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmem));
+    ft_bitgemm_umma_kernel<0><<<dim3(ceil_div(s.B, kUM), s.L1 / kUmmaNCols, 1), kBgThreads, kBgSmem, st>>>(
+        s, bits_s, static_cast<const unsigned char *>(tables), bias, out, 0);
+    NNUE_CHECK_LAUNCH("ft_bitgemm_umma_kernel");
+    return NNUE_OK;
+}
+
 // out = bias + bits . W;  workspace: the table as [L1 / 64][PP / 16] tiles (umma_kt_bytes(PP, L1))
 int launch_ft_fwd_umma(const nnue_shape &s, const uint32_t *bits_s, const float *w, const float *bias, float *out,
                        void *workspace, cudaStream_t st) {
-    unsigned char *wt = static_cast<unsigned char *>(workspace);
-    const int n_ks = 2 * s.NW;
-    const long long n = 2LL * n_ks * s.L1;
-    umma_format_kt_kernel<true><<<(int)((n + 255) / 256), 256, 0, st>>>(s, w, s.PP, n_ks, wt);
-    NNUE_CHECK_LAUNCH("umma_format_kt_kernel");
-    NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_bitgemm_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmem));
-    ft_bitgemm_umma_kernel<0><<<dim3(ceil_div(s.B, kUM), s.L1 / kUmmaNCols, 1), kBgThreads, kBgSmem, st>>>(s, bits_s, wt, bias, out, 0);
-    NNUE_CHECK_LAUNCH("ft_bitgemm_umma_kernel");
-    return NNUE_OK;
+    const int rc = launch_ft_format_tables(s, w, workspace, 1, st);
+    if (rc != NNUE_OK) return rc;
+    return launch_ft_fwd_umma_tiles(s, bits_s, workspace, bias, out, st);
 }
 
 // Fold stage 1: every position p sums its partials over the K chunks (loads batched eight deep: the loop is
@@ -530,17 +555,22 @@ int launch_q_accumulate_umma(int B, int NW, int L1, const uint32_t *bits, const 
 }
 
 // gbin = bits ? g_ft . W^T : 0;  workspace: split g_ft tiles | split table tiles (ws_ft_gbin_umma)
+// table_tiles != null: the value-gradient table tiles are already formatted (launch_ft_format_tables)
 int launch_ft_bwd_gbin_umma(const nnue_shape &s, const uint32_t *bits_s, const float *w, const float *g_ft, void *workspace,
-                            float *gbin, cudaStream_t st) {
+                            float *gbin, cudaStream_t st, const void *table_tiles) {
     const int n_mt = ceil_div(s.B, kUM), n_nt = ceil_div(s.PP, kUmmaGbinN);
     unsigned char *at = static_cast<unsigned char *>(workspace);
     unsigned char *bt = at + align_up((size_t)n_mt * kUM * s.L1 * 6, 256);
     long long n = 1LL * n_mt * kUM * (s.L1 / 8);
     umma_format_rows_kernel<false, kUM><<<(int)((n + 255) / 256), 256, 0, st>>>(s, g_ft, s.B, n_mt, at);
     NNUE_CHECK_LAUNCH("umma_format_rows_kernel");
-    n = 1LL * n_nt * kUmmaGbinN * (s.L1 / 8);
-    umma_format_rows_kernel<true, kUmmaGbinN><<<(int)((n + 255) / 256), 256, 0, st>>>(s, w, s.PP, n_nt, bt);
-    NNUE_CHECK_LAUNCH("umma_format_rows_kernel");
+    if (table_tiles) {
+        bt = const_cast<unsigned char *>(static_cast<const unsigned char *>(table_tiles)) + align_up(umma_kt_bytes((size_t)s.PP, s), 256);
+    } else {
+        n = 1LL * n_nt * kUmmaGbinN * (s.L1 / 8);
+        umma_format_rows_kernel<true, kUmmaGbinN><<<(int)((n + 255) / 256), 256, 0, st>>>(s, w, s.PP, n_nt, bt);
+        NNUE_CHECK_LAUNCH("umma_format_rows_kernel");
+    }
     NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_gbin_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGbSmem));
     ft_gbin_umma_kernel<<<dim3(n_nt, n_mt), kGbThreads, kGbSmem, st>>>(s, bits_s, at, bt, gbin);
     NNUE_CHECK_LAUNCH("ft_gbin_umma_kernel");

@@ -127,7 +127,15 @@ int launch_ft_bwd_dw_umma(const nnue_shape &s, const uint32_t *bits_s, const flo
 int launch_q_accumulate_umma(int B, int NW, int L1, const uint32_t *bits, const unsigned char *tiles, const int32_t *bias,
                              int16_t *acc16, cudaStream_t st);
 int launch_ft_bwd_gbin_umma(const nnue_shape &s, const uint32_t *bits_s, const float *w, const float *g_ft, void *workspace,
-                            float *gbin, cudaStream_t st);
+                            float *gbin, cudaStream_t st, const void *table_tiles = nullptr);
+// both tile orders of the table in one buffer (forward tiles | value-gradient tiles); which: bit 0 forward, bit 1 value gradient
+inline size_t ft_tables_bytes(const nnue_shape &s) {
+    if (!ft_umma_ok(s)) return 0;
+    return align_up(umma_kt_bytes((size_t)s.PP, s), 256) + align_up((size_t)ceil_div(s.PP, kUmmaGbinN) * kUmmaGbinN * s.L1 * 6, 256);
+}
+int launch_ft_format_tables(const nnue_shape &s, const float *w, void *tables, int which, cudaStream_t st);
+int launch_ft_fwd_umma_tiles(const nnue_shape &s, const uint32_t *bits_s, const void *tables, const float *bias, float *out,
+                             cudaStream_t st);
 
 inline OwnPlan plan_ft_bwd_dw_owner(const nnue_shape &s) {
     OwnPlan o{};

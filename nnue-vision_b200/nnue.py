@@ -13,6 +13,7 @@ gradient, value gradient back into the conv / threshold.  There is no CPU or eag
 fallback: CPU tensors raise.
 """
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -261,6 +262,10 @@ STORE_ACTIVATIONS = True
 
 
 OVERLAP_TABLE_GRADIENT = True
+# Format the table tiles on the side stream while the images are extracted (tcgen05 shapes).  Off by default: at
+# config D the two 4 us formatting kernels running beside the extraction cost more than they save (measured on one
+# box, 200 steps each: 227 us per step with, 216 us without -- the extraction is issue-bound and shares its SMs).
+PREFORMAT_TABLES = os.environ.get("NNUE_PREFORMAT_TABLES", "0") == "1"
 _SIDE_STREAMS = {}
 
 
@@ -289,6 +294,16 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
     bits_t = _empty((shape.PP, shape.BW), torch.int32, images) if L.nnue_wants_transposed_bits(sp) else None
     # the dense conv-gradient kernel takes the pre-threshold activations from the forward when asked to
     xpad = _empty((shape.B, shape.PP), torch.float32, images) if STORE_ACTIVATIONS and L.nnue_input_bwd_is_dense(sp) else None
+    # tcgen05 shapes: the table's split-bf16 tiles depend only on the weights -- outside the per-stage timing mode they
+    # are formatted on the side stream while the images are being extracted
+    tables = None
+    tb = int(L.nnue_ft_tables_bytes(sp)) if (marks is None and PREFORMAT_TABLES and OVERLAP_TABLE_GRADIENT and L.nnue_input_bwd_is_dense(sp)) else 0
+    if tb:
+        tables = _empty((tb,), torch.uint8, images)
+        side0, main0 = _side_stream(images.device), torch.cuda.current_stream()
+        side0.wait_stream(main0)
+        with torch.cuda.stream(side0):
+            check(L.nnue_ft_format_tables(sp, dptr(ft_w), dptr(tables), ctypes.c_void_p(side0.cuda_stream)))
     _mark(marks, "start")
     check(L.nnue_extract_fwd(sp, dptr(images), dptr(conv_w), dptr(thr), dptr(bits_s), dptr(bits_t), dptr(xpad), None,
                              None, st))
@@ -296,7 +311,11 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
     ft_out = _empty((shape.B, shape.L1), torch.float32, images)
     ws_bytes = _lib.workspace_bytes(shape)
     ws = _empty((ws_bytes,), torch.uint8, images)
-    check(L.nnue_ft_fwd(sp, dptr(bits_s), dptr(ft_w), dptr(ft_b), dptr(ft_out), dptr(ws), ws_bytes, st))
+    if tables is not None:
+        torch.cuda.current_stream().wait_stream(side0)
+        check(L.nnue_ft_fwd_tables(sp, dptr(bits_s), dptr(tables), dptr(ft_b), dptr(ft_out), st))
+    else:
+        check(L.nnue_ft_fwd(sp, dptr(bits_s), dptr(ft_w), dptr(ft_b), dptr(ft_out), dptr(ws), ws_bytes, st))
     _mark(marks, "ft_fwd")
     g_ft = _empty((shape.B, shape.L1), torch.float32, images)
     check(L.nnue_head_train(sp, dptr(ft_out), dptr(labels), inv_count, dptr(w1), dptr(b1), dptr(w2), dptr(b2),
@@ -318,7 +337,10 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
             check(L.nnue_ft_bwd_dw(sp, dptr(bits_s), None, dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(ws), ws_bytes, st))
             _mark(marks, "ft_bwd_dw")
         gbin = _empty((shape.B, shape.PP), torch.float32, images)
-        check(L.nnue_ft_bwd_gbin(sp, dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(gbin), dptr(ws), ws_bytes, st))
+        if tables is not None:
+            check(L.nnue_ft_bwd_gbin_tables(sp, dptr(bits_s), dptr(tables), dptr(g_ft), dptr(gbin), dptr(ws), ws_bytes, st))
+        else:
+            check(L.nnue_ft_bwd_gbin(sp, dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(gbin), dptr(ws), ws_bytes, st))
         _mark(marks, "ft_bwd_gbin")
         check(L.nnue_conv_bwd(sp, dptr(images), dptr(gbin), dptr(xpad), dptr(conv_w), dptr(thr), dptr(g_conv_w), dptr(g_thr),
                               dptr(ws), ws_bytes, st))
