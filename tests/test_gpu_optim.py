@@ -72,7 +72,7 @@ def test_flat_parameters_keep_the_state_dict_contract():
     for n in opt.params.names:  # parameters alias the flat buffer, in the reference's registration order
         assert named[n].data_ptr() == opt.params.flat.data_ptr() + 4 * off
         off += named[n].numel()
-    assert off == opt.n == dp.buf.numel() - 1
+    assert off == opt.n and dp.buf.numel() == (off + 1 + 3) // 4 * 4  # gradients + loss slot, padded to whole float4s
     # the model still serialises and still loads reference checkpoints
     model.load_state_dict(before)
     images, labels = _data(32)
