@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: the workload's batch is the GLOBAL batch, split evenly over the GPUs (default: weak)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "oneshot", "nccl"],
                     help="gradient exchange at N > 1: the library's one-shot all-reduce over NVLink peer memory (auto) or NCCL")
     ap.add_argument("--no-int", action="store_true", help="skip the integer-inference side measurement")
@@ -282,6 +284,25 @@ def int_inference_leg(w, device, seconds):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         out["device"] = {"value": B / (ms * 1e-3), "unit": "samples/s", "batch": B, "ms": ms}
+        # BASELINE config "batch sweep 1..65536": device-resident throughput per batch size (images [Bs,32,32,3] views
+        # of one buffer; small batches run the fused kernel, >= 2048 the bitmask -> tcgen05 accumulate -> stack form)
+        sweep = {}
+        big = torch.randn(65536, w["image"], w["image"], 3, generator=torch.Generator().manual_seed(4)).to(device) \
+            if w["image"] <= 64 else None
+        if big is not None:
+            for Bs in (1, 16, 256, 4096, 16384, 65536):
+                x = big[:Bs]
+                for _ in range(3):
+                    ev.evaluate_logits(x)
+                n_rep = 50
+                e0.record()
+                for _ in range(n_rep):
+                    ev.evaluate_logits(x)
+                e1.record()
+                torch.cuda.synchronize()
+                sweep[str(Bs)] = Bs / (e0.elapsed_time(e1) / n_rep * 1e-3)
+            out["device_sweep_samples_per_s"] = sweep
+            del big
         # end to end through host buffers (pinned), copies inside the C call
         pinned = imgs.pin_memory().numpy()
         ev.evaluate_logits_host(pinned)
@@ -328,6 +349,8 @@ def run_b200(args):
     w = dict(WORKLOADS[args.workload])
     if args.batch:
         w["batch"] = args.batch
+    if args.strong:
+        w["batch"] = max(1, w["batch"] // world)
     B = w["batch"]
     for kv in args.opt:
         key, val = kv.split("=")
@@ -458,7 +481,7 @@ def run_b200(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "per_gpu_batch": B, "global_batch": global_batch,
                    "arch": {k: w[k] for k in ("grid", "C", "L1", "L2", "L3", "NC", "input", "image")},
