@@ -341,3 +341,28 @@ def test_large_batch_properties():
         step_grads = cur if step_grads is None else {k: step_grads[k] + cur[k] for k in cur}
     for k in g1:
         assert_close(g1[k], step_grads[k], "shard additivity " + k, rtol=2e-5)
+
+
+def test_preformatted_table_tiles_give_identical_results():
+    """nnue_ft_format_tables + the *_tables entry points (table tiles formatted once, on the side stream) run the same
+    kernels on the same tiles as the per-call formatting: bit-identical loss and gradients."""
+    from nnue_vision_b200 import nnue as nn_mod
+    cfg, model, images, labels = _make("D_staged")
+
+    def run():
+        model.zero_grad()
+        loss = model.loss(images, labels)
+        loss.backward()
+        torch.cuda.synchronize()
+        return loss.detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+
+    l0, g0 = run()
+    old = nn_mod.PREFORMAT_TABLES
+    nn_mod.PREFORMAT_TABLES = True
+    try:
+        l1, g1 = run()
+    finally:
+        nn_mod.PREFORMAT_TABLES = old
+    assert torch.equal(l0, l1)
+    for k in g0:
+        assert torch.equal(g0[k], g1[k]), k
