@@ -256,8 +256,17 @@ class DataParallelStep:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(images.device)
             n0 = int(_lib.lib().nnue_launch_count(0))
-            with torch.cuda.graph(g, pool=self._pool):
+            try:
+                with torch.cuda.graph(g, pool=self._pool):
+                    self._local(images, labels, inv_count, self.buf)
+            except Exception as e:  # a capture that cannot be taken must not cost the step: stay eager for good
+                import sys
+                print(f"nnue_vision_b200: CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+                self.cuda_graphs = False
+                self._graphs.clear()
+                torch.cuda.synchronize(images.device)
                 self._local(images, labels, inv_count, self.buf)
+                return
             ent[1] = g
             ent.append(int(_lib.lib().nnue_launch_count(0)) - n0)  # kernels in the graph
             self._count_add = _lib.lib().nnue_launch_count_add
