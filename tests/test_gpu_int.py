@@ -298,3 +298,21 @@ def test_incremental_accumulator_api_matches_engine(oracle_built, tmp_path, arch
         want = np.array([oracle_built.legacy_score(q, s) for s in streams], np.float32)
         np.testing.assert_array_equal(got, want)
         streams = [[f for f in s[2:]] + [f for f in draw(3) if f not in s] for s in streams]
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_incremental_api_matches_reference_engine_golden(name):
+    """evaluate_incremental against scores the reference engine itself produced on the golden models
+    (tests/golden/incremental.npz): fresh refreshes, an incremental walk, and all fresh lists as one batch of streams."""
+    from util import load_incremental_golden
+    g = load_incremental_golden(name)
+    ev = _engine().NNUEEvaluator(GOLDEN / f"{name}.nnue")
+    for feats, want in zip(g["fresh"], g["fresh_score"]):
+        ev.mark_dirty()
+        assert np.float32(ev.evaluate_incremental(feats)) == want
+    ev.mark_dirty()
+    for feats, want in zip(g["walk"], g["walk_score"]):
+        assert np.float32(ev.evaluate_incremental(feats)) == want
+    ev.mark_dirty()
+    batch = ev.evaluate_incremental([list(f) for f in g["fresh"]]).cpu().numpy()
+    np.testing.assert_array_equal(batch, g["fresh_score"])

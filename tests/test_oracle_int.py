@@ -95,3 +95,16 @@ def test_legacy_score_restatement_is_pinned_to_the_reference_engine(oracle_built
                 assert ref.eval_incremental(feats) == oracle_built.legacy_score(q, feats)
                 drop = set(rng.choice(feats, size=min(len(feats), 5), replace=False).tolist())
                 feats = [f for f in feats if f not in drop] + [int(f) for f in rng.choice(F, size=5) if f not in feats]
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_legacy_score_restatement_matches_reference_engine_golden(name):
+    """The same pin without the compiled engine at hand: committed scores the reference engine produced
+    (tests/golden/incremental.npz, generator make_incremental_golden.py)."""
+    from oracle import int_oracle
+    from util import load_incremental_golden
+    from nnue_vision_b200 import serialize
+    q = serialize.read_nnue(GOLDEN / f"{name}.nnue")
+    g = load_incremental_golden(name)
+    for feats, want in zip(g["fresh"] + g["walk"], list(g["fresh_score"]) + list(g["walk_score"])):
+        assert np.float32(int_oracle.legacy_score(q, feats)) == want

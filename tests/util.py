@@ -87,3 +87,15 @@ INT_ARCHS = [
     (1, 8, 16, 4, 4, 2, 9),       # single-cell grid: stride collapses to H
     (16, 32, 256, 16, 32, 1000, 224),  # engine test shape (tests/test_nnue_engine.cpp:12-16)
 ]
+
+
+def load_incremental_golden(name):
+    """Feature lists and the reference engine's evaluate_incremental scores for one golden model
+    (tests/golden/make_incremental_golden.py)."""
+    z = np.load(GOLDEN / "incremental.npz")
+
+    def unpack(off, idx):
+        return [idx[off[i]:off[i + 1]].tolist() for i in range(len(off) - 1)]
+
+    return {"fresh": unpack(z[f"{name}.fresh_off"], z[f"{name}.fresh_idx"]), "fresh_score": z[f"{name}.fresh_score"],
+            "walk": unpack(z[f"{name}.walk_off"], z[f"{name}.walk_idx"]), "walk_score": z[f"{name}.walk_score"]}
