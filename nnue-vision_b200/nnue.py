@@ -258,7 +258,7 @@ class _NNUEForward(torch.autograd.Function):
 
 # Training keeps the pre-threshold conv activations ([B, PP] fp32) for the threshold gradient instead of
 # recomputing them in the backward (measured faster on B200; set False to trade the time for the memory).
-STORE_ACTIVATIONS = True
+STORE_ACTIVATIONS = os.environ.get("NNUE_STORE_ACTIVATIONS", "1") != "0"
 
 
 OVERLAP_TABLE_GRADIENT = True
