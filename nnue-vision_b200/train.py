@@ -284,4 +284,6 @@ class DataParallelStep:
             self._run_local(images, labels, 1.0 / float(global_batch))
         if self.world > 1:
             self._exchange()
+        # optimizer.zero_grad() sets .grad to None by default: make the views the gradients again (ten assignments)
+        self.buf.attach()
         return self.buf.loss.reshape(())

@@ -120,3 +120,23 @@ def test_single_process_step_issues_no_collective():
     ref = fo.step({k: v.detach() for k, v in model.state_dict().items()}, images, labels, model.conv.stride[0],
                   dtype=torch.float64)
     assert abs(float(loss) - float(ref["loss"])) < 1e-6
+
+
+def test_step_reattaches_gradients_after_zero_grad():
+    """torch's optimizer.zero_grad() drops .grad (set_to_none=True is the default): the next step() must make the
+    flat-buffer views the gradients again, or a torch optimizer would silently see nothing."""
+    from nnue_vision_b200 import train
+    model = _model()
+    images, labels = _batch()
+    dp = train.DataParallelStep(model, local_step=_oracle_local_step(model), device="cpu")
+    dp.step(images, labels)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    opt.zero_grad()
+    named = dict(model.named_parameters())
+    assert all(named[n].grad is None for n in dp.buf.names)
+    before = named["input.weight"].detach().clone()
+    dp.step(images, labels)
+    for n, v in zip(dp.buf.names, dp.buf.views):
+        assert named[n].grad is not None and named[n].grad.data_ptr() == v.data_ptr()
+    opt.step()
+    assert not torch.equal(named["input.weight"], before)
