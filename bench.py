@@ -1,15 +1,20 @@
 #!/usr/bin/env python3
 """bench.py -- NNUE train samples/s (fwd+bwd) on B200, with roofline, CPU baseline and e2e legs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (N=1 default)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME]   # our arm (N=1 default)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        --master-port P bench.py --gpus N --steps K --warmup W     # N > 1: one rank per GPU, NCCL
-    python bench.py --impl reference [...]                         # the reference's CPU path
+        --master-port P bench.py --gpus N --steps K --warmup W               # N > 1: one rank per GPU, NCCL
+    python bench.py --impl reference [...]                                   # the reference's CPU path
 
 A "step" is one pass of the hot path (grid-feature extraction -> feature transformer ->
 pairwise + head -> mean CE -> full backward -> gradient all-reduce when N > 1) over one batch of
-synthetic CIFAR-shaped input, config `train_nnue_default.py` at batch 16384 per GPU (weak scaling).
-Prints ONE JSON line on rank 0.
+synthetic input.  The default workload is config `train_nnue_default.py` at batch 16384 per GPU
+(BASELINE configs[1], weak scaling); `--workload` selects the reference's other configurations
+(T, D1k, I-s, I).  Prints ONE JSON line on rank 0.
+
+Timing: W >= 3 warm-up steps, then `--windows` (default 5) timed windows of EXACTLY K steps each, every
+window bracketed by barrier + synchronize and timed with CUDA events on the launching stream (max over
+ranks); `value` / `ms_per_step` are the MEDIAN window, all windows are listed in `windows_ms`.
 """
 import argparse
 import ctypes
@@ -25,13 +30,22 @@ import torch
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+REF_DIR = ROOT / "baseline" / "_ref"   # the unmodified reference's nnue.py (git-ignored; __graft_entry__.build copies it)
 
-# config/train_nnue_default.py:16-35 of the reference (batch overridden to the BASELINE value)
+# reference configurations; `ref_batch` = samples per step of the CPU reference arm (its cost is
+# linear in the batch: per-sample Python loops, and a dense [F, L1] gradient allocated per sample in the backward)
 WORKLOADS = {
-    "default_cifar_b16384": dict(grid=10, C=8, L1=64, L2=32, L3=8, NC=10, input=32, image=32, batch=16384),
-    "test_cifar_b16": dict(grid=8, C=4, L1=64, L2=4, L3=8, NC=10, input=32, image=32, batch=16),
-    "real_cifar_l1_1024_b16384": dict(grid=10, C=8, L1=1024, L2=128, L3=32, NC=10, input=32, image=32, batch=16384),
-    "imagenet_small_b2048": dict(grid=16, C=32, L1=256, L2=16, L3=32, NC=1000, input=224, image=224, batch=2048),
+    # config/train_nnue_default.py:16-35 (batch overridden to the BASELINE value)
+    "default_cifar_b16384": dict(grid=10, C=8, L1=64, L2=32, L3=8, NC=10, input=32, image=32, batch=16384, ref_batch=256),
+    # config/train_nnue_test.py:9-23
+    "test_cifar_b16": dict(grid=8, C=4, L1=64, L2=4, L3=8, NC=10, input=32, image=32, batch=16, ref_batch=16),
+    # config/train_nnue.py:16-36 (the reference's "real" config)
+    "real_cifar_l1_1024_b16384": dict(grid=10, C=8, L1=1024, L2=128, L3=32, NC=10, input=32, image=32, batch=16384, ref_batch=64),
+    # engine test shape (engine/tests/test_nnue_engine.cpp:12-16) on ImageNet-shaped input, 1000 classes
+    "imagenet_small_b2048": dict(grid=16, C=32, L1=256, L2=16, L3=32, NC=1000, input=224, image=224, batch=2048, ref_batch=16),
+    "imagenet_small_b16384": dict(grid=16, C=32, L1=256, L2=16, L3=32, NC=1000, input=224, image=224, batch=16384, ref_batch=16),
+    # largest grid the integer engine supports (64 channels, nnue_engine.h:243; serialize.py:745): F = 65536, table 268 MB
+    "imagenet_large_b4096": dict(grid=32, C=64, L1=1024, L2=128, L3=32, NC=1000, input=224, image=224, batch=4096, ref_batch=2),
 }
 METRIC = "nnue_train_samples_per_sec_fwd_bwd"
 UNIT = "samples/s"
@@ -42,6 +56,7 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--windows", type=int, default=5, help="timed windows of --steps steps each; the median is reported")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="default_cifar_b16384", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
@@ -52,27 +67,30 @@ def parse_args():
     ap.add_argument("--exchange", default="auto", choices=["auto", "oneshot", "nccl"],
                     help="gradient exchange at N > 1: the library's one-shot all-reduce over NVLink peer memory (auto) or NCCL")
     ap.add_argument("--no-int", action="store_true", help="skip the integer-inference side measurement")
+    ap.add_argument("--no-module-api", action="store_true", help="skip the compute_loss(model, batch); loss.backward() leg")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="library tuning knob (nnue_set_option), e.g. --opt input_bwd_variant=1")
     return ap.parse_args()
 
 
-def tensor_peak():
-    p = ROOT / "MEASURED_PEAKS.json"
+def _peaks_file():
     try:
-        return float(json.loads(p.read_text())["bf16_tflops_sustained"])
+        return json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
     except Exception:
-        return 1400.0  # fallback (B200_PROFILING.md: sustained bf16)
+        return {}
+
+
+def tensor_peak():
+    d = _peaks_file()
+    if "bf16_tflops_sustained" in d:
+        return float(d["bf16_tflops_sustained"]), "measured sustained bf16 (MEASURED_PEAKS.json)"
+    return 1400.0, "fallback (B200_PROFILING.md: sustained bf16)"
 
 
 def peaks():
-    p = ROOT / "MEASURED_PEAKS.json"
-    if p.exists():
-        try:
-            d = json.loads(p.read_text())
-            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-        except Exception:
-            pass
+    d = _peaks_file()
+    if "hbm_gbs" in d:
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
@@ -145,12 +163,26 @@ def build_model(w, device, seed=42):
 
 
 def synthetic_batch(w, B, seed, device=None, pin=False):
+    """N(0,1) images [B,3,H,W] and uniform labels.  CPU tensors come from a CPU generator; for a CUDA
+    device (or a pinned host copy of an ImageNet-sized batch) the values are drawn on the device."""
+    shape = (B, 3, w["image"], w["image"])
+    on_gpu = torch.cuda.is_available() and (pin or (device is not None and torch.device(device).type == "cuda"))
+    if on_gpu:
+        dev = torch.device(device) if device is not None and torch.device(device).type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+        g = torch.Generator(device=dev).manual_seed(seed)
+        images = torch.randn(shape, generator=g, device=dev)
+        labels = torch.randint(0, w["NC"], (B,), generator=g, device=dev)
+        if not pin:
+            return images, labels
+        himg = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        hlab = torch.empty((B,), dtype=torch.long, pin_memory=True)
+        himg.copy_(images); hlab.copy_(labels)
+        torch.cuda.synchronize()
+        return himg, hlab
     g = torch.Generator().manual_seed(seed)
-    images = torch.randn(B, 3, w["image"], w["image"], generator=g)
+    images = torch.randn(shape, generator=g)
     labels = torch.randint(0, w["NC"], (B,), generator=g)
-    if pin:
-        return images.pin_memory(), labels.pin_memory()
-    return images.to(device), labels.to(device)
+    return images, labels
 
 
 def max_over_ranks(ms, world, device):
@@ -167,27 +199,69 @@ def barrier(world):
     torch.cuda.synchronize()
 
 
-def cpu_baseline_training(w, seconds, threads=None):
-    """The oracle's reference-shaped step (per-sample nonzero / gather-sum loops under autograd --
-    the algorithm of nnue.py:601-606, 694-708) timed on the host cores: kind "port"."""
-    from oracle import float_oracle as fo
-    if threads:
+# ---- the reference's CPU implementation of the path ------------------------------------------------------------------
+def _reference_module():
+    """The UNMODIFIED reference nnue.py from baseline/_ref (copied there, git-ignored, by __graft_entry__.build() in the
+    build container; it travels to the GPU box with the snapshot).  None when absent."""
+    if not (REF_DIR / "nnue.py").exists():
+        return None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("reference_nnue", REF_DIR / "nnue.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class ReferenceStepper:
+    """One training step of the reference on the host cores: `F.cross_entropy(model(images), targets.long())` +
+    `loss.backward()` (train.py:250-254, 352-361) on the stock `nnue.NNUE` (kind "reference"); when baseline/_ref is
+    absent, the oracle's restatement of the same per-sample loops (kind "port")."""
+
+    def __init__(self, w, threads):
+        import torch.nn.functional as F
         torch.set_num_threads(threads)
-    B = min(256, w["batch"])
-    torch.manual_seed(42)
-    state = cpu_reference_state(w)
-    images, labels = synthetic_batch(w, B, seed=7, device="cpu")
-    stride = fo.python_stride(w["input"], w["grid"])
-    fo.reference_style_step(state, images, labels, stride)  # warm-up
+        self.B = min(w["ref_batch"], w["batch"])
+        self.images, self.labels = synthetic_batch(w, self.B, seed=7, device="cpu")
+        ref = _reference_module()
+        if ref is not None:
+            self.kind = "reference"
+            torch.manual_seed(42)
+            self.model = ref.NNUE(ref.GridFeatureSet(w["grid"], w["C"]), w["L1"], w["L2"], w["L3"], num_classes=w["NC"],
+                                  input_size=w["input"])
+            self.model.train()
+            self.what = "stock nnue.NNUE forward + F.cross_entropy + backward (baseline/_ref/nnue.py, unmodified)"
+
+            def step():
+                self.model.zero_grad(set_to_none=True)
+                loss = F.cross_entropy(self.model(self.images), self.labels.long())
+                loss.backward()
+                return float(loss.detach())
+        else:
+            from oracle import float_oracle as fo
+            self.kind = "port"
+            state = cpu_reference_state(w)
+            stride = fo.python_stride(w["input"], w["grid"])
+            self.what = "oracle.float_oracle.reference_style_step (baseline/_ref absent)"
+
+            def step():
+                return fo.reference_style_step(state, self.images, self.labels, stride)
+        self.step = step
+
+
+def cpu_baseline_training(w, seconds, threads=None):
+    from oracle.int_oracle import host_threads
+    threads = threads or host_threads()
+    rs = ReferenceStepper(w, threads)
+    rs.step()  # warm-up
     n, t0 = 0, time.perf_counter()
     while True:
-        fo.reference_style_step(state, images, labels, stride)
+        rs.step()
         n += 1
         dt = time.perf_counter() - t0
         if dt > seconds or n >= 200:
             break
-    return {"value": n * B / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} fwd+bwd passes of batch {B} of workload (oracle.float_oracle.reference_style_step), {dt:.1f} s"}
+    return {"value": n * rs.B / dt, "unit": UNIT, "cores": threads, "kind": rs.kind,
+            "sample": f"{n} fwd+bwd passes of batch {rs.B} of the workload: {rs.what}, {dt:.1f} s"}
 
 
 def cpu_reference_state(w):
@@ -200,39 +274,33 @@ def cpu_reference_state(w):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the training path on the host cores.
-    The reference's float path is Python (nnue.py) and cannot travel to the GPU box, so this arm
-    times the oracle's faithful restatement of it (kind "port") with every host thread."""
+    """--impl reference: the reference's own CPU implementation of the training path on the host cores, every host
+    thread, each step a bounded sample (`ref_batch` samples) of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     w = dict(WORKLOADS[args.workload])
     if args.batch:
         w["batch"] = args.batch
-    from oracle import float_oracle as fo
     from oracle.int_oracle import host_threads
     threads = host_threads()
-    torch.set_num_threads(threads)
-    B = min(256, w["batch"])
-    state = cpu_reference_state(w)
-    images, labels = synthetic_batch(w, B, seed=7, device="cpu")
-    stride = fo.python_stride(w["input"], w["grid"])
+    rs = ReferenceStepper(w, threads)
     for _ in range(max(1, min(args.warmup, 3))):
-        fo.reference_style_step(state, images, labels, stride)
+        rs.step()
     steps = max(1, min(args.steps, 40))
     t0 = time.perf_counter()
     for _ in range(steps):
-        fo.reference_style_step(state, images, labels, stride)
+        rs.step()
     dt = time.perf_counter() - t0
-    value = steps * B / dt
+    value = steps * rs.B / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "batch_per_step": B,
-                   "note": "CPU only; each step is a bounded sample (batch 256) of the workload; cost is linear in batch"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{steps} fwd+bwd passes of batch {B} (oracle.float_oracle.reference_style_step)"},
+        "config": {"workload": args.workload, "batch_per_step": rs.B,
+                   "note": "CPU only; each step is a bounded sample of the workload; the reference's cost is linear in the batch"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": rs.kind,
+                         "sample": f"{steps} fwd+bwd passes of batch {rs.B}: {rs.what}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -333,6 +401,75 @@ def int_inference_leg(w, device, seconds):
     return out
 
 
+def touched_image_bytes(w, shape, B):
+    """Bytes of the image rows a 3x3 / pad 1 / stride s conv actually reads: every row for s <= 3, otherwise three rows
+    per raster row (whole rows: DRAM moves 32-byte sectors and the three taps of a cell lie s columns apart)."""
+    H, s = w["image"], int(shape.stride)
+    rows = set()
+    for oy in range(int(shape.Gh)):
+        for k in (-1, 0, 1):
+            y = oy * s + k
+            if 0 <= y < H:
+                rows.add(y)
+    return B * 3 * len(rows) * w["image"] * 4
+
+
+def module_api_leg(model, sets, steps, global_batch):
+    """The drop-in loop of INTEGRATION 2.1(a): loss = compute_loss(model, batch); loss.backward() -- eager launches,
+    gradients accumulated by autograd into .grad, no CUDA graph, no flat buffer."""
+    from nnue_vision_b200 import train
+    for p in model.parameters():
+        p.grad = None
+    for i in range(3):
+        loss = train.compute_loss(model, sets[i % len(sets)])
+        loss.backward()
+        for p in model.parameters():
+            p.grad = None
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(steps):
+        loss = train.compute_loss(model, sets[i % len(sets)])
+        loss.backward()
+        for p in model.parameters():
+            p.grad = None
+    e1.record()
+    torch.cuda.synchronize()
+    host_ms = (time.perf_counter() - t0) * 1e3 / steps
+    ms = e0.elapsed_time(e1) / steps
+    B = sets[0][0].shape[0]
+    return {"api": "module", "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "host_ms_per_step": host_ms,
+            "note": "loss = train.compute_loss(model, batch); loss.backward(); eager launches on one GPU, device-resident inputs"}
+
+
+def exchange_check(dp, world, device):
+    """Untimed: the exchange the timed loop uses against one NCCL all-reduce of the same per-rank values, and the
+    same result on every rank (the driver's GPU test tier has one GPU; this runs wherever bench.py runs with N > 1)."""
+    if world == 1:
+        return None
+    n = dp.buf.numel()
+    saved = dp.buf.flat.clone()
+    g = torch.Generator(device=device).manual_seed(99 + torch.distributed.get_rank())
+    vals = torch.randn(n, generator=g, device=device)
+    ref = vals.clone()
+    torch.distributed.all_reduce(ref)
+    dp.buf.flat.copy_(vals)
+    dp._exchange()
+    torch.cuda.synchronize()
+    got = dp.buf.flat.clone()
+    dp.buf.flat.copy_(saved)
+    err = float((got - ref).abs().max())
+    scale = float(ref.abs().max())
+    # bit-identical on every rank: compare against rank 0's copy
+    r0 = got.clone()
+    torch.distributed.broadcast(r0, src=0)
+    same = torch.tensor([1 if torch.equal(r0, got) else 0], device=device)
+    torch.distributed.all_reduce(same, op=torch.distributed.ReduceOp.MIN)
+    return {"exchange": dp.allreduce, "max_abs_diff_vs_nccl": err, "max_abs_ref": scale,
+            "within_1e-6_rel": bool(err <= 1e-6 * scale), "identical_on_all_ranks": bool(int(same.item()))}
+
+
 def run_b200(args):
     from nnue_vision_b200 import _lib, train
     rank = int(os.environ.get("RANK", "0"))
@@ -361,8 +498,10 @@ def run_b200(args):
         for p in model.parameters():
             torch.distributed.broadcast(p.data, src=0)
 
-    # three input sets (3 x B x 12 KB = 600 MB at CIFAR shape, far above the 126 MB L2), cycled
-    n_sets = 3
+    # input sets cycled so that every step reads images that are not in the 126 MB L2: three sets at CIFAR shape
+    # (3 x B x 12 KB = 600 MB), one set when a single set is already far larger than L2 (ImageNet shapes: GBs)
+    img_bytes = B * 3 * w["image"] * w["image"] * 4
+    n_sets = 3 if img_bytes < (1 << 30) else 1
     sets = [synthetic_batch(w, B, seed=1000 * rank + i, device=device) for i in range(n_sets)]
     global_batch = B * world
 
@@ -371,24 +510,29 @@ def run_b200(args):
     for _ in range(2):
         for imgs, labs in sets:
             dp.step(imgs, labs, global_batch=global_batch)
+    xcheck = exchange_check(dp, world, device)
     clocks.begin()
     for i in range(max(args.warmup, 3)):
         dp.step(*sets[i % n_sets], global_batch=global_batch)
-    barrier(world)
-    _lib.lib().nnue_launch_count(1)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        loss = dp.step(*sets[i % n_sets], global_batch=global_batch)
-    e1.record()
-    barrier(world)
-    launches = int(_lib.lib().nnue_launch_count(0))
-    ms_total = max_over_ranks(e0.elapsed_time(e1), world, device)
+    windows, launches = [], 0
+    for wdw in range(max(1, args.windows)):
+        barrier(world)
+        _lib.lib().nnue_launch_count(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            loss = dp.step(*sets[i % n_sets], global_batch=global_batch)
+        e1.record()
+        barrier(world)
+        launches = int(_lib.lib().nnue_launch_count(0))
+        windows.append(max_over_ranks(e0.elapsed_time(e1), world, device))
+    ms_total = sorted(windows)[len(windows) // 2]
     value = args.steps * global_batch / (ms_total * 1e-3)
     final_loss = float(loss)
 
     # ---- e2e: the user-facing call with HOST buffers; H2D of the step's inputs and D2H of the loss timed
-    host_sets = [synthetic_batch(w, B, seed=2000 * rank + i, pin=True) for i in range(2)]
+    n_host = 2 if img_bytes < (1 << 30) else 1
+    host_sets = [synthetic_batch(w, B, seed=2000 * rank + i, pin=True) for i in range(n_host)]
     dev_img = [torch.empty_like(sets[0][0]) for _ in range(2)]
     dev_lab = [torch.empty_like(sets[0][1]) for _ in range(2)]
     copy_stream = torch.cuda.Stream()
@@ -409,8 +553,8 @@ def run_b200(args):
                 with torch.cuda.stream(copy_stream):
                     if i >= 1:
                         copy_stream.wait_event(done[nxt])
-                    dev_img[nxt].copy_(host_sets[nxt][0], non_blocking=True)
-                    dev_lab[nxt].copy_(host_sets[nxt][1], non_blocking=True)
+                    dev_img[nxt].copy_(host_sets[nxt % n_host][0], non_blocking=True)
+                    dev_lab[nxt].copy_(host_sets[nxt % n_host][1], non_blocking=True)
                     ready[nxt].record()
             torch.cuda.current_stream().wait_event(ready[cur])
             l = dp.step(dev_img[cur], dev_lab[cur], global_batch=global_batch)
@@ -418,92 +562,125 @@ def run_b200(args):
             losses.append(float(l))  # D2H read of the step's result
         return losses
 
-    e2e_steps(6)  # (both staging buffers seen twice: their graphs exist before the timed region)
+    e2e_n = args.steps if img_bytes < (1 << 30) else max(3, min(args.steps, 6))
+    e2e_steps(6 if img_bytes < (1 << 30) else 4)  # (both staging buffers seen twice: their graphs exist before the timed region)
     barrier(world)
     t0 = time.perf_counter()
-    e2e_steps(args.steps)
+    e2e_steps(e2e_n)
     barrier(world)
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, device)
-    e2e_value = args.steps * global_batch / (e2e_ms * 1e-3)
+    e2e_value = e2e_n * global_batch / (e2e_ms * 1e-3)
     clocks.end()
     clocks.__exit__()
     h2d = int(host_sets[0][0].numel() * 4 + host_sets[0][1].numel() * 8) * world
+    del host_sets, dev_img, dev_lab
+
+    # ---- the module API (compute_loss + backward, eager)
+    module_api = None
+    if world == 1 and not args.no_module_api:
+        module_api = module_api_leg(model, sets, min(args.steps, 20), global_batch)
+        dp.buf.attach()
 
     # ---- per-stage device times and the roofline of the dominant kernel
     stages = stage_breakdown(dp, *sets[0])
     shape, bits = model.extract_bits(sets[0][0])
     nnz_total = int(sum(int(torch.bitwise_and(bits >> k, 1).sum()) for k in range(32)))
+    del bits
     L1, F = w["L1"], shape.F
-    img_bytes = B * 3 * w["image"] * w["image"] * 4
+    img_algo = touched_image_bytes(w, shape, B)
     row_bytes = B * shape.PP * 4  # one fp32 value per (sample, padded position): g_bin, stored activations
+    sp = ctypes.byref(shape)
+    L = _lib.lib()
+    dense_in = bool(L.nnue_input_bwd_is_dense(sp))
+    umma = bool(L.nnue_ft_uses_umma(sp))
+    mma = bool(L.nnue_ft_uses_mma(sp))
     # algorithmic bytes per launch
     algo = {
-        "extract_fwd": img_bytes + B * shape.NW * 4 + row_bytes,          # images -> bitmask + stored activations
+        "extract_fwd": img_algo + B * shape.NW * 4 + (row_bytes if dense_in else 0),  # images -> bitmask (+ stored activations)
         "ft_fwd": nnz_total * L1 * 4 + B * L1 * 4 + nnz_total * 4,        # row reads + out + indices
         "ft_bwd_dw": nnz_total * L1 * 4 + F * L1 * 4,                      # g_ft row per active pair + dW
         "ft_bwd_gbin": nnz_total * L1 * 4 + B * L1 * 4 + row_bytes,       # table row per active pair + g_ft + g_bin
         "ft_bwd": 2 * nnz_total * L1 * 4 + F * L1 * 4 + B * L1 * 4 + row_bytes,
-        "conv_bwd": img_bytes + 2 * row_bytes,                            # images + g_bin + stored activations
-        "input_bwd": nnz_total * L1 * 4 + B * L1 * 4 + img_bytes + B * shape.NW * 4,
+        "conv_bwd": img_algo + 2 * row_bytes,                             # images + g_bin + stored activations
+        # general input gradient: activations recomputed and stored, table rows, g_bin written and read, images twice
+        "input_bwd": nnz_total * L1 * 4 + B * L1 * 4 + 2 * img_algo + 4 * row_bytes,
         "head_train": 2 * B * L1 * 4,
     }
     # tensor-core work actually issued by the bf16-split contractions (2 * M * N * K * number of term products)
     mma_flops = {"ft_fwd": 2.0 * B * shape.PP * L1 * 3, "ft_bwd_dw": 2.0 * B * shape.PP * L1 * 3,
-                 "ft_bwd_gbin": 2.0 * B * shape.PP * L1 * 6}
-    kernel_of = {"extract_fwd": "extract_fwd_fixed_kernel", "ft_fwd": "ft_fwd_mma_kernel", "head_train": "head_train_kernel",
-                 "ft_bwd_dw": "ft_bwd_dw_mma_kernel", "ft_bwd_gbin": "ft_bwd_gbin_mma_kernel", "conv_bwd": "conv_bwd_kernel"}
-    umma = bool(_lib.lib().nnue_ft_uses_umma(ctypes.byref(shape)))
+                 "ft_bwd_gbin": 2.0 * B * shape.PP * L1 * 6, "input_bwd": 2.0 * B * shape.PP * L1 * 6}
+    if L.nnue_head_uses_umma(sp):  # layer 1 of wide stacks: forward, input gradient, weight gradient, six term pairs each
+        mma_flops["head_train"] = 3 * 2.0 * B * L1 * w["L2"] * 6
+    kernel_of = {"extract_fwd": "extract_fwd_fixed_kernel" if w["C"] in (4, 8, 16, 32) else "extract_fwd_kernel",
+                 "ft_fwd": "ft_fwd_mma_kernel", "head_train": "head_train_kernel" if L.nnue_head_is_fused(sp) else "ugemm_kernel",
+                 "ft_bwd_dw": "ft_bwd_dw_mma_kernel", "ft_bwd_gbin": "ft_bwd_gbin_mma_kernel", "conv_bwd": "conv_bwd_kernel",
+                 "input_bwd": "extract_bwd_kernel"}
     if umma:  # tcgen05 / TMEM contractions (ft_umma.cu)
         kernel_of.update({"ft_fwd": "ft_bitgemm_umma_kernel<0>", "ft_bwd_dw": "ft_bitgemm_umma_kernel<1>",
-                          "ft_bwd_gbin": "ft_gbin_umma_kernel"})
+                          "ft_bwd_gbin": "ft_gbin_umma_kernel", "input_bwd": "ft_gbin_umma_kernel"})
+    elif not mma:
+        kernel_of.update({"ft_fwd": "ft_gather_fwd_kernel", "ft_bwd_dw": "ft_bwd_dw_kernel", "input_bwd": "ft_gather_dval_kernel"})
+    # dram bytes per launch from the committed ncu --set full captures, keyed by workload then kernel; null when this
+    # workload has no capture (a capture of another workload says nothing about this one)
     traffic = {}
-    tp = ROOT / "profiles" / "traffic.json"  # dram bytes per launch from the committed ncu --set full capture
+    tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text())
+            traffic = json.loads(tp.read_text()).get(args.workload, {})
         except Exception:
             traffic = {}
     peak, peak_src = peaks()
-    tpeak = tensor_peak()
+    tpeak, tpeak_src = tensor_peak()
     roofs = {}
     for k, nbytes in algo.items():
         if k in stages and stages[k] > 0:
-            ach = nbytes / (stages[k] * 1e-3) / 1e9
             kern = kernel_of.get(k)
-            roofs[k] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                        "traffic": traffic.get(kern.split("<")[0]) if kern else None, "ms": stages[k], "algorithmic_bytes": nbytes, "kernel": kern}
-            if k in mma_flops and _lib.lib().nnue_ft_uses_mma(ctypes.byref(shape)):
+            tr = traffic.get(kern.split("<")[0]) if kern else None
+            ach = nbytes / (stages[k] * 1e-3) / 1e9
+            hbm = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": tr,
+                   "ms": stages[k], "algorithmic_bytes": nbytes, "kernel": kern, "peak_source": peak_src}
+            roofs[k] = hbm
+            if k in mma_flops and (mma or k == "head_train"):
                 tf = mma_flops[k] / (stages[k] * 1e-3) / 1e12
-                roofs[k]["tensor"] = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
-                                      "note": ("bf16 tcgen05.mma (UMMA, TMEM accumulators)" if umma else "bf16 mma.sync") +
-                                              ", 3 (6) exact split-term products per fp32 product"}
+                tens = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "traffic": tr,
+                        "ms": stages[k], "algorithmic_flops": mma_flops[k], "kernel": kern, "peak_source": tpeak_src,
+                        "note": ("bf16 tcgen05.mma (UMMA, TMEM accumulators)" if umma or k == "head_train" else "bf16 mma.sync") +
+                                ": flops issued = 2 M N K x 3 (6) exact split-term products per fp32 product"}
+                # a contraction against a table that does not stream from HBM per sample is bound by the tensor pipe
+                roofs[k] = dict(tens, hbm_view={kk: hbm[kk] for kk in ("achieved", "frac", "algorithmic_bytes")})
     dominant = max(roofs, key=lambda k: roofs[k]["ms"]) if roofs else None
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
+        "windows_ms": windows, "windows_note": f"{len(windows)} windows of {args.steps} steps each; value and ms_per_step are the median window",
         "config": {"workload": args.workload, "per_gpu_batch": B, "global_batch": global_batch,
                    "arch": {k: w[k] for k in ("grid", "C", "L1", "L2", "L3", "NC", "input", "image")},
                    "parallelism": f"dp{world}", "exchange": dp.allreduce, "nnz_per_sample": nnz_total / B,
-                   "l2_policy": "inputs larger than L2: 3 image sets x %.0f MB cycled" % (img_bytes / 1e6),
+                   "ft_form": "dense (tcgen05 bit-GEMM)" if umma else ("dense (mma.sync)" if mma else "gather"),
+                   "l2_policy": "inputs larger than L2: %d image set(s) x %.0f MB cycled" % (n_sets, img_bytes / 1e6),
                    "loss_after_timed_steps": final_loss},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * world,
-                "ms_per_step": e2e_ms / args.steps,
+                "ms_per_step": e2e_ms / e2e_n, "steps": e2e_n,
                 "note": "DataParallelStep.step on pinned host batches, H2D double-buffered against compute, loss read back every step"},
         "gpu_launches": launches,
         "stages_ms": stages,
     }
+    if xcheck is not None:
+        line["exchange_check"] = xcheck
+    if module_api is not None:
+        line["module_api"] = module_api
     if dominant:
-        line["roofline"] = dict(roofs[dominant], stage=dominant, peak_source=peak_src,
-                                note="stage = one C-ABI call = the named kernel + its small fold; feature-transformer stages "
-                                     "work on a 205 KB table that is on-chip, so their algorithmic bytes are not HBM bytes "
-                                     "(roofline_all carries their tensor-pipe figures); traffic = ncu dram bytes per launch")
+        line["roofline"] = dict(roofs[dominant], stage=dominant,
+                                note="stage = one C-ABI call = the named kernel + its small helper kernels; algorithmic bytes per "
+                                     "SURVEY 8d (image bytes = rows the conv touches); traffic = ncu dram bytes per launch of the "
+                                     "named kernel from the committed capture of THIS workload (profiles/traffic.json), else null")
         line["roofline_all"] = roofs
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_training(w, args.cpu_seconds)
-        if not args.no_int:
+        if not args.no_int and w["image"] <= 64:
             try:
                 line["int_inference"] = int_inference_leg(w, device, args.cpu_seconds)
             except Exception as e:  # the side measurement must never lose the headline line

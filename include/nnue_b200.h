@@ -89,6 +89,16 @@ unsigned long long nnue_launch_count_add(unsigned long long n);
  *                     contractions for small tables, 0 = CUDA-core kernels only.
  *   "ft_umma"         1 (default) = tcgen05 / TMEM (UMMA) feature-transformer contractions for every L1 that is
  *                     a multiple of 64, 0 = the warp-level MMA / CUDA-core families.
+ *   "input_bwd_rows"  1 (default) = conv / threshold gradients of large images from row-staged tiles
+ *                     (input_bwd_rows.cu), 0 = the direct-gather kernel pair.
+ *   "ft_gather"       1 (default) = index-driven forward / value gradient through the TMA-staged row gather of
+ *                     ft_gather.cu (L1 a multiple of 128), 0 = the direct-load kernels of ft.cu.
+ *   "ft_gather_slab"  columns per CTA of the gather forward (128, 256, 512, 1024; 0 = widest that divides L1).
+ *   "ft_form"         which formulation of the feature transformer serves a shape: 0 (default) = the cost model of
+ *                     plan.cuh (dense bit-GEMM on the tensor cores vs index-driven row gather / segment reduction,
+ *                     compared with measured rates), 1 = always dense, 2 = always gather.
+ *   "ft_density_permille" fraction of active positions the cost model expects, in 1/1000 (default 400: the reference
+ *                     model at initialisation has 330 - 430); the gather form wins below ~20.
  *   "ft_bwd_both"     1 (default) = one kernel for both feature-transformer gradients (small tables).
  *   "q_tc_min_batch"  integer inference: batches of at least this many samples (default 2048; 0 = never) run as
  *                     bitmask -> tcgen05 accumulate -> layer stack instead of the one fused kernel (L1 % 64 == 0).
@@ -210,6 +220,8 @@ int nnue_head_bwd(const nnue_shape *s, const float *g_logits_d, const float *ft_
  * the layer kernels on scratch carved from the workspace.
  *   loss_d [1] = sum_b CE_b * inv_count; g_ft_d [B,L1]; g_w*, g_b* as nnue_head_bwd
  */
+int nnue_head_is_fused(const nnue_shape *s);   /* 1 when nnue_head_train runs the one-kernel form for this shape */
+int nnue_head_uses_umma(const nnue_shape *s);  /* 1 when layer 1 runs as split-bf16 tcgen05 GEMMs (gemm_umma.cu) */
 int nnue_head_train(const nnue_shape *s, const float *ft_out_d, const int64_t *labels_d, float inv_count,
                     const float *w1_d, const float *b1_d, const float *w2_d, const float *b2_d,
                     const float *w3_d, const float *b3_d, float *loss_d, float *g_ft_d, float *g_w1_d,
@@ -298,6 +310,14 @@ int nnue_input_bwd(const nnue_shape *s, const float *images_d, const uint32_t *b
                    const float *ft_w_d, const float *g_ft_d, const float *conv_w_d, const float *thr_d,
                    float *g_conv_w_d, float *g_thr_d, void *workspace_d, size_t workspace_bytes,
                    void *stream);
+/* Same, with the pre-threshold activations the forward stored (xpad_d [B][PP] from nnue_extract_fwd; NULL = recompute
+ * them from the images, which is what nnue_input_bwd does).  nnue_input_bwd_wants_activations: 1 when passing them
+ * saves a pass over the images for this shape (ImageNet-sized input). */
+int nnue_input_bwd_wants_activations(const nnue_shape *s);
+int nnue_input_bwd_stored(const nnue_shape *s, const float *images_d, const uint32_t *bits_s_d, const float *xpad_d,
+                          const float *ft_w_d, const float *g_ft_d, const float *conv_w_d, const float *thr_d,
+                          float *g_conv_w_d, float *g_thr_d, void *workspace_d, size_t workspace_bytes,
+                          void *stream);
 
 /* ------------------------------------------------------------------------- *
  *  Optimizer step over flat buffers (the step either side of the path)       *

@@ -46,6 +46,8 @@ SIGNATURES = {
     "nnue_head_fwd": (ctypes.c_int, [SHAPE_P] + [vp] * 11),
     "nnue_ce_fwd_bwd": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, vp, f32, vp, vp, vp, vp, vp, sz, vp]),
     "nnue_head_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 15 + [sz, vp]),
+    "nnue_head_is_fused": (ctypes.c_int, [SHAPE_P]),
+    "nnue_head_uses_umma": (ctypes.c_int, [SHAPE_P]),
     "nnue_head_train": (ctypes.c_int, [SHAPE_P, vp, vp, f32] + [vp] * 14 + [vp, sz, vp]),
     "nnue_ft_bwd_is_fused": (ctypes.c_int, [SHAPE_P]),
     "nnue_ft_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 7 + [sz, vp]),
@@ -61,6 +63,8 @@ SIGNATURES = {
     "nnue_ft_uses_umma": (ctypes.c_int, [SHAPE_P]),
     "nnue_conv_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 8 + [sz, vp]),
     "nnue_input_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 9 + [sz, vp]),
+    "nnue_input_bwd_wants_activations": (ctypes.c_int, [SHAPE_P]),
+    "nnue_input_bwd_stored": (ctypes.c_int, [SHAPE_P] + [vp] * 10 + [sz, vp]),
     "nnue_ft_bwd_dval": (ctypes.c_int, [SHAPE_P] + [vp] * 8 + [sz, vp]),
     "nnue_extract_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 5 + [sz, vp]),
     "nnue_opt_workspace_bytes": (sz, [ctypes.c_longlong]),

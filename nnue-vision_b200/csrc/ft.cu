@@ -1114,6 +1114,9 @@ int nnue_ft_fwd(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w
     if (plan_ft_mma(*s).ok && workspace_d && workspace_bytes >= ws_ft_fwd(*s))
         return launch_ft_fwd_mma(*s, bits_s_d, ft_w_d, ft_b_d, ft_out_d, workspace_d, st);
     const ColPlan cp = col_plan(s->L1);
+    // tables that do not fit one CTA's shared memory: rows staged through a shared-memory ring by bulk TMA (ft_gather.cu)
+    if (ft_gather_ok(*s) && !use_staging(*s, cp.nchunks, 1LL * s->B * cp.nchunks))
+        return launch_ft_gather_fwd(*s, bits_s_d, ft_w_d, ft_b_d, ft_out_d, workspace_d, workspace_bytes, st);
     if (!cp.LPR) {
         ft_fwd_bits_generic_kernel<<<ceil_div(s->B, kFtThreads / 32), kFtThreads, 0, st>>>(*s, bits_s_d, ft_w_d, ft_b_d,
                                                                                           ft_out_d);
@@ -1349,6 +1352,13 @@ int nnue_ft_bwd_dval(const nnue_shape *s, const uint32_t *bits_s_d, const float 
     }
     float *thr_partial = static_cast<float *>(workspace_d);
     const ColPlan cp = col_plan(s->L1);
+    if (ft_gather_dval_ok(*s) && !use_staging(*s, cp.nchunks, s->B)) {  // rows staged by bulk TMA, dots reduced with shuffles
+        const int rc = launch_ft_gather_dval(*s, bits_s_d, ft_w_d, g_ft_d, xpad_d, thr_d, dval_d, thr_partial, st);
+        if (rc != NNUE_OK) return rc;
+        fold_partials_kernel<<<ceil_div(s->C, 128), 128, 0, st>>>(s->C, ft_gather_dval_grid(*s), thr_partial, g_thr_d);
+        NNUE_CHECK_LAUNCH("fold_partials_kernel");
+        return NNUE_OK;
+    }
     const int grid = dval_grid(*s);
     if (!cp.LPR) {
         ft_bwd_dval_generic_kernel<<<grid, kFtThreads, (size_t)(kFtThreads / 32) * s->C * 4, st>>>(

@@ -412,6 +412,9 @@ using namespace nnue;
 
 extern "C" {
 
+int nnue_head_is_fused(const nnue_shape *s) { return s && head_train_fused_ok(*s) ? 1 : 0; }
+int nnue_head_uses_umma(const nnue_shape *s) { return s && !head_train_fused_ok(*s) && head_umma_ok(*s) ? 1 : 0; }
+
 int nnue_head_train(const nnue_shape *s, const float *ft_out_d, const int64_t *labels_d, float inv_count,
                     const float *w1_d, const float *b1_d, const float *w2_d, const float *b2_d, const float *w3_d,
                     const float *b3_d, float *loss_d, float *g_ft_d, float *g_w1_d, float *g_b1_d, float *g_w2_d,

@@ -233,7 +233,7 @@ __global__ void input_bwd_fold_kernel(int C, int nblk, const float *__restrict__
     for (; k < nblk; ++k) v += __ldg(partial + (size_t)k * C * 28 + i);
     const int c = i / 28, t = i % 28;
     if (t < 27) g_conv_w[c * 27 + t] = v;
-    else g_thr[c] = v;
+    else if (g_thr) g_thr[c] = v;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
@@ -333,9 +333,21 @@ int nnue_conv_bwd(const nnue_shape *s, const float *images_d, const float *gbin_
     return NNUE_OK;
 }
 
+int nnue_input_bwd_wants_activations(const nnue_shape *s) {
+    if (!s) return 0;
+    return plan_input_bwd(*s).fused ? 0 : 1;  // (the dense pair takes them through nnue_conv_bwd)
+}
+
 int nnue_input_bwd(const nnue_shape *s, const float *images_d, const uint32_t *bits_s_d, const float *ft_w_d,
                    const float *g_ft_d, const float *conv_w_d, const float *thr_d, float *g_conv_w_d, float *g_thr_d,
                    void *workspace_d, size_t workspace_bytes, void *stream) {
+    return nnue_input_bwd_stored(s, images_d, bits_s_d, nullptr, ft_w_d, g_ft_d, conv_w_d, thr_d, g_conv_w_d, g_thr_d,
+                                 workspace_d, workspace_bytes, stream);
+}
+
+int nnue_input_bwd_stored(const nnue_shape *s, const float *images_d, const uint32_t *bits_s_d, const float *xpad_d,
+                          const float *ft_w_d, const float *g_ft_d, const float *conv_w_d, const float *thr_d,
+                          float *g_conv_w_d, float *g_thr_d, void *workspace_d, size_t workspace_bytes, void *stream) {
     if (!s || !images_d || !bits_s_d || !ft_w_d || !g_ft_d || !conv_w_d || !thr_d || !g_conv_w_d || !g_thr_d ||
         !workspace_d)
         return NNUE_ERR_INVALID_ARG;
@@ -350,18 +362,44 @@ int nnue_input_bwd(const nnue_shape *s, const float *images_d, const uint32_t *b
         const int rc = nnue_ft_bwd_gbin(s, bits_s_d, ft_w_d, g_ft_d, gbin, umma ? ws + plane : nullptr,
                                         umma ? workspace_bytes - plane : 0, stream);
         if (rc != NNUE_OK) return rc;
-        return nnue_conv_bwd(s, images_d, gbin, nullptr, conv_w_d, thr_d, g_conv_w_d, g_thr_d, ws + plane,
+        return nnue_conv_bwd(s, images_d, gbin, xpad_d, conv_w_d, thr_d, g_conv_w_d, g_thr_d, ws + plane,
                              workspace_bytes - plane, stream);
     }
-    // General shapes: recompute the pre-threshold activations into scratch, then the index-driven pair.
-    float *xpad = reinterpret_cast<float *>(ws);
+    // General shapes.  The pre-threshold activations come from the forward (xpad_d) or are recomputed into scratch; the
+    // value gradient goes to a scratch plane; the conv / threshold gradients are taken from row-staged images
+    // (input_bwd_rows.cu) or, where that kernel does not apply, by the direct-gather kernel of extract.cu.
     float *dval = reinterpret_cast<float *>(ws + plane);
-    void *rest = ws + 2 * plane;
+    char *rest = ws + 2 * plane;
     const size_t rest_bytes = workspace_bytes - 2 * plane;
-    int rc = extract_xpad(*s, images_d, conv_w_d, thr_d, xpad, st);
-    if (rc != NNUE_OK) return rc;
+    int rc;
+    const float *xpad = xpad_d;
+    if (!xpad) {
+        rc = extract_xpad(*s, images_d, conv_w_d, thr_d, reinterpret_cast<float *>(ws), st);
+        if (rc != NNUE_OK) return rc;
+        xpad = reinterpret_cast<const float *>(ws);
+    }
+    const RowsPlan rp = plan_conv_bwd_rows(*s);
+    const size_t part_bytes = (size_t)rp.grid * s->C * 28 * 4;
+    if (rp.ok && ft_umma_ok(*s)) {  // dense value gradient, then ONE pass for both the conv and the threshold gradient
+        rc = launch_ft_bwd_gbin_umma(*s, bits_s_d, ft_w_d, g_ft_d, rest + align_up(part_bytes, 256), dval, st);
+        if (rc != NNUE_OK) return rc;
+        float *partial = reinterpret_cast<float *>(rest);
+        rc = launch_conv_bwd_rows(*s, rp, images_d, bits_s_d, dval, xpad, thr_d, partial, st);
+        if (rc != NNUE_OK) return rc;
+        input_bwd_fold_kernel<<<ceil_div(s->C * 28, 128), 128, 0, st>>>(s->C, rp.grid, partial, g_conv_w_d, g_thr_d);
+        NNUE_CHECK_LAUNCH("input_bwd_fold_kernel");
+        return NNUE_OK;
+    }
     rc = nnue_ft_bwd_dval(s, bits_s_d, ft_w_d, g_ft_d, xpad, thr_d, dval, g_thr_d, rest, rest_bytes, stream);
     if (rc != NNUE_OK) return rc;
+    if (rp.ok) {  // (the index-driven value gradient has already produced the threshold gradient)
+        float *partial = reinterpret_cast<float *>(rest);
+        rc = launch_conv_bwd_rows(*s, rp, images_d, bits_s_d, dval, xpad, thr_d, partial, st);
+        if (rc != NNUE_OK) return rc;
+        input_bwd_fold_kernel<<<ceil_div(s->C * 28, 128), 128, 0, st>>>(s->C, rp.grid, partial, g_conv_w_d, nullptr);
+        NNUE_CHECK_LAUNCH("input_bwd_fold_kernel");
+        return NNUE_OK;
+    }
     return nnue_extract_bwd(s, images_d, bits_s_d, dval, g_conv_w_d, rest, rest_bytes, stream);
 }
 

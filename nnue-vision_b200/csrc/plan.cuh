@@ -84,7 +84,41 @@ inline bool dense_shape_ok(const nnue_shape &s) { return s.L1 == 64 || s.L1 == 3
 // ---- tcgen05 / TMEM contractions (ft_umma.cu): any L1 that is a multiple of 64 -----------------------------
 constexpr int kUmmaNCols = 64;    // forward / weight gradient: table columns per CTA (x 3 terms = UMMA N 192)
 constexpr int kUmmaGbinN = 256;   // value gradient: padded positions per CTA (UMMA N)
-inline bool ft_umma_ok(const nnue_shape &s) { return get_option(kOptFtUmma) && s.L1 >= 64 && s.L1 % 64 == 0; }
+// ---- which formulation of the feature transformer serves a shape ----------------------------------------------------
+// dense : the three contractions as bitmask GEMMs on the tensor cores.  Work is independent of how many positions are
+//         active: 2 B PP L1 flops x (3 + 3 + 6) exact split-bf16 term products per step, plus re-formatting the table
+//         into operand tiles (two passes over it).  The table is re-read once per wave of M tiles, not once per sample.
+// gather: index-driven (nnue.py:686-710): every active (sample, position) pair moves one table row (forward,
+//         value gradient) or one g_ft row (weight gradient): 3 x nnz x L1 x 4 bytes per step, from HBM when the table
+//         is larger than L2 and from L2 otherwise.
+// The model compares the two with rates measured on B200 (profiles/r2_ft_compare_*.json): the tcgen05 kernels sustain
+// ~0.55 of the measured sustained bf16 peak over the three contractions, the gather kernels ~0.65 of the measured HBM
+// copy bandwidth on tables beyond L2 and ~1.2x that bandwidth on L2-resident ones.  With the density the reference
+// model has at initialisation (0.33 - 0.43) the dense form wins at every table size -- a row of L1 floats
+// gathered per ACTIVE position costs more than 12 flops per position and column on a 1.4 PFLOP/s pipe as soon as more
+// than ~2 % of the positions are active.  `ft_density_permille` (default 400) tells the model what to expect;
+// `ft_form` forces a formulation (1 dense, 2 gather).
+constexpr double kTensorPeakFlops = 1384.6e12, kHbmPeakBytes = 6464.9e9, kL2Bytes = 126.0e6;
+struct FtCost {
+    double dense_s, gather_s;
+};
+inline FtCost ft_cost(const nnue_shape &s) {
+    FtCost c{};
+    const double B = s.B, L1 = s.L1, table = (double)s.F * s.L1 * 4.0;
+    const double density = get_option(kOptFtDensity) / 1000.0;
+    c.dense_s = 12.0 * 2.0 * B * (double)s.PP * L1 / (0.55 * kTensorPeakFlops) + 2.0 * (table + 1.5 * table) / (0.8 * kHbmPeakBytes);
+    const double bw = table > 0.75 * kL2Bytes ? 0.65 * kHbmPeakBytes : 1.2 * kHbmPeakBytes;
+    c.gather_s = 3.0 * density * B * (double)s.P * L1 * 4.0 / bw;
+    return c;
+}
+inline bool ft_prefers_dense(const nnue_shape &s) {
+    const int form = get_option(kOptFtForm);
+    if (form == 1) return true;
+    if (form == 2) return false;
+    const FtCost c = ft_cost(s);
+    return c.dense_s <= c.gather_s;
+}
+inline bool ft_umma_ok(const nnue_shape &s) { return get_option(kOptFtUmma) && s.L1 >= 64 && s.L1 % 64 == 0 && ft_prefers_dense(s); }
 // split-bf16 tiles of a [K rows][L1] operand, K a multiple of 32: 3 terms x 2 bytes per element
 inline size_t umma_kt_bytes(size_t K, const nnue_shape &s) { return K * s.L1 * 6; }
 struct UmmaDwPlan {
@@ -136,6 +170,16 @@ inline size_t ft_tables_bytes(const nnue_shape &s) {
 int launch_ft_format_tables(const nnue_shape &s, const float *w, void *tables, int which, cudaStream_t st);
 int launch_ft_fwd_umma_tiles(const nnue_shape &s, const uint32_t *bits_s, const void *tables, const float *bias, float *out,
                              cudaStream_t st);
+
+// ---- TMA-staged row gather (ft_gather.cu): the index-driven forward / value gradient for tables in HBM or L2 ----
+bool ft_gather_ok(const nnue_shape &s);       // forward: L1 a multiple of 128
+bool ft_gather_dval_ok(const nnue_shape &s);  // value gradient: L1 in {128, 256, 512, 1024}, whole cell words per channel
+int ft_gather_dval_grid(const nnue_shape &s);
+size_t ws_ft_gather_fwd(const nnue_shape &s);
+int launch_ft_gather_fwd(const nnue_shape &s, const uint32_t *bits, const float *w, const float *bias, float *out, void *workspace,
+                         size_t workspace_bytes, cudaStream_t st);
+int launch_ft_gather_dval(const nnue_shape &s, const uint32_t *bits, const float *w, const float *g_ft, const float *xpad,
+                          const float *thr, float *dval, float *thr_partial, cudaStream_t st);
 
 inline OwnPlan plan_ft_bwd_dw_owner(const nnue_shape &s) {
     OwnPlan o{};
@@ -298,6 +342,52 @@ inline InPlan plan_input_bwd(const nnue_shape &s) {
     return p;
 }
 
+// ---- conv / threshold gradient from row-staged images (input_bwd_rows.cu): images beyond the whole-image staging ----
+constexpr int kRowsCH = 4;     // channels per warp (4 x 27 accumulators in registers; 2 x 16 warps measured 10 % slower)
+constexpr int kRowsWarps = 8;  // warps per CTA: 32 channels
+struct RowsPlan {
+    bool ok;
+    int NCB, nq, grid;   // channel blocks of 32, unit streams per channel block, CTAs
+    int NR, ST;          // raster rows a cell word can span (one TMA box each), ring depth
+    int WB, tile;        // box width in floats (= W), floats per box (9 WB rounded up to 32)
+    int stage_floats, stage_off;
+    int dx_off;          // floats from a stage's start to its g_bin [32][32] | activations [32][32] | bitmask words [32]
+    size_t smem;
+};
+inline RowsPlan plan_conv_bwd_rows(const nnue_shape &s) {
+    RowsPlan p{};
+    if (!get_option(kOptInputRows) || s.W % 4 || s.CW > 256) return p;  // tensor-map rows need a 16-byte pitch
+    p.WB = s.W;
+    if (p.WB > 256) return p;  // box dimension limit of the TMA unit
+    const int cells = s.Gh * s.Gw;
+    int max_nr = 1;
+    for (int j = 0; j < s.CW; ++j) {
+        const int first = (j * 32) / s.Gw, last = (j * 32 + 31 < cells ? j * 32 + 31 : cells - 1) / s.Gw;
+        if (last - first + 1 > max_nr) max_nr = last - first + 1;
+    }
+    p.NR = max_nr;
+    if (p.NR > kRowsWarps) return p;  // warp r issues the box of raster row r
+    p.tile = (int)align_up((size_t)9 * p.WB, 32);
+    p.dx_off = p.NR * p.tile;
+    p.stage_floats = p.dx_off + 2048 + 32;
+    p.stage_off = (int)align_up((size_t)kInHeader + (size_t)kRowsWarps * kRowsCH * 28 * 4 + (size_t)s.CW * 132, 1024);
+    int ST = (int)((kMaxSmemOptin - (size_t)p.stage_off) / ((size_t)p.stage_floats * 4));
+    if (ST > kInMaxStages) ST = kInMaxStages;
+    if (ST < 3) return p;
+    p.ST = ST;
+    p.NCB = ceil_div(s.C, kRowsWarps * kRowsCH);
+    if (p.NCB > kNumSMs) return p;
+    p.nq = kNumSMs / p.NCB;
+    const long long units = 1LL * s.B * s.CW;
+    if (p.nq > units) p.nq = (int)units;
+    p.grid = p.nq * p.NCB;
+    p.smem = (size_t)p.stage_off + (size_t)ST * p.stage_floats * 4;
+    p.ok = true;
+    return p;
+}
+int launch_conv_bwd_rows(const nnue_shape &s, const RowsPlan &pl, const float *images, const uint32_t *bits_s, const float *dval,
+                         const float *xpad, const float *thr, float *partial, cudaStream_t st);
+
 // ---- extraction forward, TMA-staged form (extract.cu) -------------------------------------------------
 constexpr int kExtWarps = 8;   // warps per CTA (lane 0 of warp 0 is the TMA producer)
 constexpr int kExtCH = 4;      // channels of one cell word owned by a warp (their taps live in registers)
@@ -392,8 +482,13 @@ inline size_t ws_input_bwd(const nnue_shape &s) {
         if (ws_ft_gbin_umma(s) > rest) rest = ws_ft_gbin_umma(s);
         return align_up((size_t)s.B * s.PP * 4, 256) + rest;
     }
-    const size_t a = ws_ft_bwd_dval(s), b = ws_extract_bwd(s);
-    return 2 * align_up((size_t)s.B * s.PP * 4, 256) + (a > b ? a : b);
+    size_t a = ws_ft_bwd_dval(s);
+    const size_t b = ws_extract_bwd(s);
+    if (b > a) a = b;
+    const RowsPlan rp = plan_conv_bwd_rows(s);
+    const size_t rows_ws = align_up((size_t)rp.grid * s.C * 28 * 4, 256) + ws_ft_gbin_umma(s);
+    if (rp.ok && rows_ws > a) a = rows_ws;
+    return 2 * align_up((size_t)s.B * s.PP * 4, 256) + a;
 }
 // pre-threshold conv activations in padded-position layout (extract.cu); used by the general input-gradient path
 int extract_xpad(const nnue_shape &s, const float *images, const float *conv_w, const float *thr, float *xpad,
@@ -414,7 +509,7 @@ inline size_t mma_gbin_smem(const nnue_shape &s) {
 }
 inline MmaPlan plan_ft_mma(const nnue_shape &s) {
     MmaPlan m{};
-    if (!get_option(kOptFtMma) || !dense_shape_ok(s)) return m;
+    if (!get_option(kOptFtMma) || !dense_shape_ok(s) || get_option(kOptFtForm) == 2) return m;
     if (mma_fwd_smem(s) > kMaxSmemOptin || mma_gbin_smem(s) > kMaxSmemOptin) return m;  // table slice must fit
     // two resident CTAs per SM, two waves
     const int ctas_per_chunk = ceil_div(s.NW, kMmaDwWarps) * (s.L1 / (16 * kMmaGP));

@@ -293,7 +293,8 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
     bits_s = _empty((shape.B, shape.NW), torch.int32, images)
     bits_t = _empty((shape.PP, shape.BW), torch.int32, images) if L.nnue_wants_transposed_bits(sp) else None
     # the dense conv-gradient kernel takes the pre-threshold activations from the forward when asked to
-    xpad = _empty((shape.B, shape.PP), torch.float32, images) if STORE_ACTIVATIONS and L.nnue_input_bwd_is_dense(sp) else None
+    xpad = _empty((shape.B, shape.PP), torch.float32, images) if (
+        (STORE_ACTIVATIONS and L.nnue_input_bwd_is_dense(sp)) or L.nnue_input_bwd_wants_activations(sp)) else None
     # tcgen05 shapes: the table's split-bf16 tiles depend only on the weights -- outside the per-stage timing mode they
     # are formatted on the side stream while the images are being extracted
     tables = None
@@ -368,8 +369,8 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
                               dptr(ws), ws_bytes, st))
         _mark(marks, "conv_bwd")
     else:
-        check(L.nnue_input_bwd(sp, dptr(images), dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(conv_w), dptr(thr),
-                               dptr(g_conv_w), dptr(g_thr), dptr(ws), ws_bytes, st))
+        check(L.nnue_input_bwd_stored(sp, dptr(images), dptr(bits_s), dptr(xpad), dptr(ft_w), dptr(g_ft), dptr(conv_w),
+                                      dptr(thr), dptr(g_conv_w), dptr(g_thr), dptr(ws), ws_bytes, st))
         _mark(marks, "input_bwd")
     return loss_out, grads
 

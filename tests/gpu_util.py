@@ -71,3 +71,25 @@ def shape_of(model, images):
     fs = model.feature_set
     return _lib.make_shape(B, H, W, fs.num_features_per_square, fs.grid_size, model.l1_size, model.l2_size,
                            model.l3_size, model.num_classes, model.conv.stride[0])
+
+
+def deambiguate(model, images, eps=1e-4, rounds=8):
+    """Nudges input pixels until no conv activation lies within `eps` of its threshold, so that the fp32 kernels and the
+    fp64 oracle must agree on every bit of the active set.  With 65536 positions per sample (SURVEY config I) nearly
+    every random sample has SOME activation within 1e-5 of its threshold and dropping such samples would leave none."""
+    import torch.nn.functional as F
+    w = model.conv.weight.detach().double().cpu()
+    thr = model.visual_threshold.detach().double().cpu().view(1, -1, 1, 1)
+    s = model.conv.stride[0]
+    img = images.detach().double().cpu().clone()
+    for _ in range(rounds):
+        x = F.conv2d(img, w, None, stride=s, padding=1)
+        near = ((x - thr).abs() < eps).any(dim=1)  # [B, Gh, Gw]
+        idx = near.nonzero()
+        if idx.numel() == 0:
+            break
+        # the centre tap of cell (oy, ox) is pixel (oy*s, ox*s), always inside the image
+        img[idx[:, 0], 0, idx[:, 1] * s, idx[:, 2] * s] += 1e-2
+    else:
+        raise AssertionError("could not move the activations away from their thresholds")
+    return img.float().to(images.device)

@@ -12,7 +12,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from gpu_util import (RTOL, ambiguous_samples, assert_close, build_model, golden_model, model_state_numpy,
+from gpu_util import (RTOL, ambiguous_samples, assert_close, build_model, deambiguate, golden_model, model_state_numpy,
                       oracle_step, shape_of, unpack_bits)
 from oracle import float_oracle as fo
 from util import GOLDEN_CASES
@@ -86,6 +86,8 @@ CFGS = {
     # wide stacks at a batch where layer 1 runs as the split-bf16 tcgen05 GEMM (gemm_umma.cu)
     "D1k_tensor_head": (dict(grid=10, C=8, L1=1024, L2=128, L3=32, NC=10, model_input=32), 32, 300),
     "wide_head_ragged": (dict(grid=6, C=16, L1=256, L2=48, L3=16, NC=10, model_input=64), 64, 257),
+    # SURVEY config I: the largest grid the integer engine supports (F = 65536 rows x 1024 columns = 268 MB, beyond L2)
+    "I_large": (dict(grid=32, C=64, L1=1024, L2=128, L3=32, NC=1000, model_input=224), 224, 6),
 }
 
 
@@ -100,6 +102,8 @@ def _make(name, seed=0):
     with torch.no_grad():
         model.input.bias.copy_(torch.randn(cfg["L1"], generator=g).cuda() * 0.05)
         model.visual_threshold.copy_((torch.rand(cfg["C"], generator=g) * 0.3 - 0.05).cuda())
+    if cfg["grid"] * cfg["grid"] * cfg["C"] >= 16384:  # large feature sets: see gpu_util.deambiguate
+        images = deambiguate(model, images)
     return cfg, model, images, labels
 
 
@@ -197,12 +201,12 @@ def test_ft_forward_staging_modes_agree(mode):
     assert_close(out[torch.as_tensor(~amb).cuda()], ref["ft_out"][torch.as_tensor(~amb)], "ft_out")
 
 
-OPTION_DEFAULTS = {"extract_tma": 0}
+OPTION_DEFAULTS = {"extract_tma": 0, "ft_form": 0}
 
 
 @pytest.mark.parametrize("options", [dict(extract_tma=1), dict(extract_fixed=0), dict(ft_umma=0), dict(ft_umma=0, ft_mma=0),
                                      dict(ft_umma=0, ft_mma=0, ft_bwd_both=0), dict(ft_umma=0, ft_mma=0, ft_bwd_dw_owner=0),
-                                     dict(ft_umma=0, ft_mma=0, input_bwd_fused=0), dict(input_bwd_fused=0), dict(input_bwd_variant=0), dict(input_bwd_swizzle=0), dict(input_bwd_swizzle=0, input_bwd_variant=0), dict(head_fused=0), dict(head_umma=0),
+                                     dict(ft_umma=0, ft_mma=0, input_bwd_fused=0), dict(input_bwd_fused=0), dict(ft_form=2), dict(ft_form=2, input_bwd_fused=0), dict(input_bwd_variant=0), dict(input_bwd_swizzle=0), dict(input_bwd_swizzle=0, input_bwd_variant=0), dict(head_fused=0), dict(head_umma=0),
                                      dict(ft_umma=0, ft_mma=0, ft_bwd_dw_owner=0, input_bwd_fused=0, head_fused=0)],
                          ids=str)
 @pytest.mark.parametrize("name", ["D", "T", "big_into_small", "D1k_tensor_head"])
