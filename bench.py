@@ -415,12 +415,12 @@ def touched_image_bytes(w, shape, B):
 
 
 def module_api_leg(model, sets, steps, global_batch):
-    """The drop-in loop of INTEGRATION 2.1(a): loss = compute_loss(model, batch); loss.backward() -- eager launches,
-    gradients accumulated by autograd into .grad, no CUDA graph, no flat buffer."""
+    """The drop-in loop of INTEGRATION 2.1(a): loss = compute_loss(model, batch); loss.backward() -- gradients
+    accumulated by autograd into .grad (nnue._NNUELoss)."""
     from nnue_vision_b200 import train
     for p in model.parameters():
         p.grad = None
-    for i in range(3):
+    for i in range(3 * len(sets)):  # every input buffer is seen three times: eager, graph capture, replay
         loss = train.compute_loss(model, sets[i % len(sets)])
         loss.backward()
         for p in model.parameters():
@@ -440,7 +440,9 @@ def module_api_leg(model, sets, steps, global_batch):
     ms = e0.elapsed_time(e1) / steps
     B = sets[0][0].shape[0]
     return {"api": "module", "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "host_ms_per_step": host_ms,
-            "note": "loss = train.compute_loss(model, batch); loss.backward(); eager launches on one GPU, device-resident inputs"}
+            "note": "loss = train.compute_loss(model, batch); loss.backward() on one GPU, device-resident inputs: the step replays a "
+                    "CUDA graph into a private flat buffer, one copy hands the gradients to the autograd node, one kernel applies "
+                    "the upstream factor; autograd accumulates into .grad"}
 
 
 def exchange_check(dp, world, device):

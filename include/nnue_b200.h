@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NNUE_B200_ABI_VERSION 2
+#define NNUE_B200_ABI_VERSION 3
 
 enum {
     NNUE_OK = 0,
@@ -334,6 +334,9 @@ int nnue_input_bwd_stored(const nnue_shape *s, const float *images_d, const uint
  *   nnue_opt_adam_step:   torch.optim.Adam(lr, (beta1, beta2), eps, weight_decay) (L2 decay, no amsgrad);
  *                         step counts from 1.
  */
+/* dst[i] = src[i] * *scale_d (a DEVICE scalar): the upstream gradient of the scalar loss applied to the flat buffer
+ * of parameter gradients in one pass (loss.backward() of train.py:352-361 with any upstream factor). */
+int nnue_scale_flat(long long n, const float *src_d, const float *scale_d, float *dst_d, void *stream);
 size_t nnue_opt_workspace_bytes(long long n);
 int nnue_opt_grad_sqnorm(long long n, const float *g_d, float *sqnorm_d, void *workspace_d,
                          size_t workspace_bytes, void *stream);
@@ -372,6 +375,16 @@ int nnue_q_dims(const nnue_qmodel *m, int32_t *dims, float *visual_threshold);
 int nnue_q_infer(const nnue_qmodel *m, const float *images_d, int B, int H, int W, int bucket,
                  float *logits_d, float *density_d, void *stream);
 /*
+ * Same with caller-provided scratch (nnue_q_workspace_bytes(m, B) bytes; 0 when the model has no tensor-core form):
+ * batches of at least "q_tc_min_batch" samples then run as bitmask -> tcgen05 accumulate -> layer stack, three
+ * launches computing the same integers.  Neither call allocates, synchronises or writes to the model, so one model
+ * may serve several streams at once as long as each call has its own scratch; nnue_q_infer (no scratch) always runs
+ * the one-kernel form.
+ */
+size_t nnue_q_workspace_bytes(const nnue_qmodel *m, int B);
+int nnue_q_infer_ws(const nnue_qmodel *m, const float *images_d, int B, int H, int W, int bucket,
+                    float *logits_d, float *density_d, void *workspace_d, size_t workspace_bytes, void *stream);
+/*
  * Same through HOST buffers (the call evaluate.py:126-173 would make instead of one
  * subprocess per sample): H2D, kernel, D2H and a stream synchronise inside the call.
  */
@@ -403,16 +416,17 @@ int nnue_q_acc_score(const nnue_qmodel *m, int S, const int16_t *acc_d, int buck
  *                       nnue_allreduce_recv_floats(world, n) floats, peer-mapped on every rank
  *   peer_flags_h[world] host array of device pointers: rank r's flag block, int32[nnue_allreduce_max_world()],
  *                       zeroed once before the first call
- *   counter_d           local device uint32, zero before the first call
- *   buf_d               local buffer of n floats (n % 4 == 0, 16-byte aligned): input and result
- *   epoch               1, 2, 3, ... : the same value on every rank for the same step
- * Every rank must launch the same epoch sequence.  The kernel pushes the local values into every rank's receive
- * area (posted NVLink stores), publishes the epoch, waits for the peers' and sums its own area.
+ *   state_d             local device uint32[2] {CTA counter, epoch}, zero before the first call; the kernel advances
+ *                       the epoch itself (no per-step host argument: the launch can be captured in a CUDA graph)
+ *   buf_d               local buffer of n floats (n % 4 == 0, 16-byte aligned): input and result; any aligned slice
+ *                       of a larger buffer may be exchanged on its own, with its own recv / flags / state
+ * Every rank must issue the same sequence of calls per (recv, flags, state) set.  The kernel pushes the local values
+ * into every rank's receive area (posted NVLink stores), publishes the epoch, waits for the peers' and sums its own area.
  */
 int nnue_allreduce_max_world(void);
 size_t nnue_allreduce_recv_floats(int world, size_t n);
 int nnue_allreduce_oneshot(int world, int rank, void *const *peer_recv_h, void *const *peer_flags_h,
-                           void *counter_d, size_t n, float *buf_d, int epoch, void *stream);
+                           void *state_d, size_t n, float *buf_d, void *stream);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,9 @@ i32, i64, f32 = ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 vp, sz = ctypes.c_void_p, ctypes.c_size_t
 
 
+ABI_VERSION = 3  # NNUE_B200_ABI_VERSION of include/nnue_b200.h
+
+
 class NnueShape(ctypes.Structure):
     """struct nnue_shape (include/nnue_b200.h)."""
     _fields_ = [(n, i32) for n in (
@@ -34,7 +37,7 @@ SIGNATURES = {
     "nnue_allreduce_max_world": (ctypes.c_int, []),
     "nnue_allreduce_recv_floats": (sz, [ctypes.c_int, sz]),
     "nnue_allreduce_oneshot": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                               ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+                                               ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
     "nnue_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "nnue_shape_init": (ctypes.c_int, [SHAPE_P] + [ctypes.c_int] * 10),
     "nnue_workspace_bytes": (sz, [SHAPE_P]),
@@ -67,6 +70,7 @@ SIGNATURES = {
     "nnue_input_bwd_stored": (ctypes.c_int, [SHAPE_P] + [vp] * 10 + [sz, vp]),
     "nnue_ft_bwd_dval": (ctypes.c_int, [SHAPE_P] + [vp] * 8 + [sz, vp]),
     "nnue_extract_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 5 + [sz, vp]),
+    "nnue_scale_flat": (ctypes.c_int, [ctypes.c_longlong, vp, vp, vp, vp]),
     "nnue_opt_workspace_bytes": (sz, [ctypes.c_longlong]),
     "nnue_opt_grad_sqnorm": (ctypes.c_int, [ctypes.c_longlong, vp, vp, vp, sz, vp]),
     "nnue_opt_sgd_step": (ctypes.c_int, [ctypes.c_longlong, vp, vp, vp, f32, f32, f32, f32, vp, ctypes.c_int, vp]),
@@ -77,6 +81,8 @@ SIGNATURES = {
     "nnue_q_free": (None, [vp]),
     "nnue_q_dims": (ctypes.c_int, [vp, vp, ctypes.POINTER(f32)]),
     "nnue_q_infer": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp]),
+    "nnue_q_workspace_bytes": (sz, [vp, ctypes.c_int]),
+    "nnue_q_infer_ws": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, sz, vp]),
     "nnue_q_acc_apply": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]),
     "nnue_q_acc_score": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.c_int, vp, vp]),
     "nnue_q_infer_host": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]),
@@ -103,7 +109,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError here = header/library mismatch
             fn.restype = res
             fn.argtypes = args
-        if handle.nnue_b200_abi_version() != 2:
+        if handle.nnue_b200_abi_version() != ABI_VERSION:
             raise NnueError("libnnue_b200.so ABI version mismatch; rebuild it")
         _lib = handle
     return _lib
@@ -118,7 +124,9 @@ def check(rc):
 
 
 def set_option(key, value):
+    global _options_epoch
     check(lib().nnue_set_option(key.encode(), int(value)))
+    _options_epoch += 1
 
 
 def make_shape(B, H, W, C, G, L1, L2, L3, NC, stride):
@@ -146,3 +154,22 @@ def dptr(t, dtype=None):
 
 def stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def on_device_of(t):
+    """Context manager: make the device of CUDA tensor `t` the current one for the calls inside (the C side launches
+    on the CURRENT device's current stream and never calls cudaSetDevice, as PyTorch's own ops guard by tensor device:
+    a model moved to cuda:1 must work while cuda:0 is current).  CPU tensors get a null context; they are rejected by
+    the hot-path calls themselves."""
+    if t is not None and getattr(t, "is_cuda", False):
+        return torch.cuda.device(t.device)
+    import contextlib
+    return contextlib.nullcontext()
+
+
+_options_epoch = 0
+
+
+def options_epoch():
+    """Bumped by every set_option(): cached launch plans / captured graphs made under other options are stale."""
+    return _options_epoch

@@ -9,7 +9,11 @@
 //   3. sums the `world` local slots in rank order -- bit-identical results on every rank, run to run -- in place.
 // The parity double-buffering makes a trailing barrier unnecessary: a slot is rewritten two steps later, and a rank
 // can only get there after every peer has published the epoch in between, which it does after finishing its sums.
-// No host synchronisation, no NCCL call on the path.
+// No host synchronisation, no NCCL call on the path.  The step counter (epoch) lives in DEVICE memory and is advanced by
+// the kernel itself, so the launch has no per-step host argument and can sit inside a captured CUDA graph; a call
+// reduces any 16-byte-aligned slice of the buffer, so the step can exchange the gradients that are final early (head,
+// feature transformer) on a side stream while the conv gradient is still running, and only the last few hundred floats
+// at the end (train.py DataParallelStep).
 #include "common.cuh"
 
 namespace nnue {
@@ -39,10 +43,14 @@ __device__ __forceinline__ void st_sys_f4(float4 *p, float4 v) {
 
 // n4 = float4 elements (the buffer is padded to a multiple of 4 floats); every CTA owns the same index range in the
 // push and in the sum, so the sum may overwrite `buf` in place
-__global__ void __launch_bounds__(512)
-allreduce_push_kernel(const ArPeers p, int rank, int world, size_t n4, float4 *__restrict__ buf, int epoch,
-                      unsigned *__restrict__ counter) {
+__global__ void __launch_bounds__(256)
+allreduce_push_kernel(const ArPeers p, int rank, int world, size_t n4, float4 *__restrict__ buf,
+                      unsigned *__restrict__ state) {
     __shared__ bool last;
+    unsigned *counter = state;  // CTAs that have pushed
+    // state[1] = epoch of the previous launch: every CTA reads it before its own arrival on `counter`, the last CTA to
+    // arrive writes the new value -- after every read
+    const int epoch = (int)*reinterpret_cast<volatile unsigned *>(state + 1) + 1;
     const size_t stride = (size_t)gridDim.x * blockDim.x, first = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t slot0 = (size_t)(epoch & 1) * world * n4;
     // 1. push my values into slot [parity][rank] of every rank
@@ -56,8 +64,12 @@ allreduce_push_kernel(const ArPeers p, int rank, int world, size_t n4, float4 *_
     if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1;
     __syncthreads();
     if (last) {
+        __threadfence_system();  // the other CTAs' pushes (ordered before their counter arrivals) before the flags go out
         if (threadIdx.x < world) st_release_sys(p.flags[threadIdx.x] + rank, epoch);
-        if (threadIdx.x == 0) *counter = 0u;
+        if (threadIdx.x == 0) {
+            *counter = 0u;
+            state[1] = (unsigned)epoch;
+        }
     }
     if (threadIdx.x < world)
         while (ld_acquire_sys(p.flags[rank] + threadIdx.x) < epoch) {}
@@ -81,10 +93,10 @@ int nnue_allreduce_max_world(void) { return kArMaxWorld; }
 
 size_t nnue_allreduce_recv_floats(int world, size_t n) { return 2 * (size_t)world * ((n + 3) / 4 * 4); }
 
-int nnue_allreduce_oneshot(int world, int rank, void *const *peer_recv_h, void *const *peer_flags_h, void *counter_d,
-                           size_t n, float *buf_d, int epoch, void *stream) {
-    if (world < 1 || world > kArMaxWorld || rank < 0 || rank >= world || !peer_recv_h || !peer_flags_h || !counter_d ||
-        !buf_d || n < 1 || epoch < 1 || (n & 3) || (reinterpret_cast<uintptr_t>(buf_d) & 15))
+int nnue_allreduce_oneshot(int world, int rank, void *const *peer_recv_h, void *const *peer_flags_h, void *state_d,
+                           size_t n, float *buf_d, void *stream) {
+    if (world < 1 || world > kArMaxWorld || rank < 0 || rank >= world || !peer_recv_h || !peer_flags_h || !state_d ||
+        !buf_d || n < 1 || (n & 3) || (reinterpret_cast<uintptr_t>(buf_d) & 15))
         return NNUE_ERR_INVALID_ARG;
     ArPeers p{};
     for (int r = 0; r < world; ++r) {
@@ -92,10 +104,11 @@ int nnue_allreduce_oneshot(int world, int rank, void *const *peer_recv_h, void *
         p.flags[r] = static_cast<int *>(peer_flags_h[r]);
         if (!p.recv[r] || !p.flags[r]) return NNUE_ERR_INVALID_ARG;
     }
-    const size_t n4 = n / 4, want = (n4 + 511) / 512;
-    const int grid = (int)(want < 1 ? 1 : want > 64 ? 64 : want);  // every CTA spins on the flags: keep them co-resident
-    allreduce_push_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(stream)>>>(
-        p, rank, world, n4, reinterpret_cast<float4 *>(buf_d), epoch, static_cast<unsigned *>(counter_d));
+    // every CTA spins on the flags: few, small CTAs, so that they fit beside a kernel of the step that is still running
+    const size_t n4 = n / 4, want = (n4 + 255) / 256;
+    const int grid = (int)(want < 1 ? 1 : want > 64 ? 64 : want);
+    allreduce_push_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        p, rank, world, n4, reinterpret_cast<float4 *>(buf_d), static_cast<unsigned *>(state_d));
     NNUE_CHECK_LAUNCH("allreduce_push_kernel");
     return NNUE_OK;
 }

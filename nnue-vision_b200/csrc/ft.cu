@@ -1189,7 +1189,7 @@ static int ft_bwd_dw_mma_path(const nnue_shape *s, const uint32_t *bits_s_d, con
                               void *workspace_d, size_t workspace_bytes, cudaStream_t st) {
     if (workspace_bytes < ws_ft_bwd_mma(*s)) return NNUE_ERR_WORKSPACE;
     const MmaPlan mp = plan_ft_mma(*s);
-    char *ws = static_cast<char *>(workspace_d) + align_up(mma_wfrag_bytes(*s), 256);
+    char *ws = static_cast<char *>(workspace_d) + ws_bwd_front_mma(*s);
     uint4 *gfrag = reinterpret_cast<uint4 *>(ws); ws += align_up(mma_gfrag_bytes(*s), 256);
     float *bias_partial = reinterpret_cast<float *>(ws); ws += align_up((size_t)mp.n_chunks * s->L1 * 4, 256);
     float *partial = reinterpret_cast<float *>(ws);
@@ -1211,7 +1211,7 @@ static int ft_bwd_dw_mma_path(const nnue_shape *s, const uint32_t *bits_s_d, con
 static int ft_bwd_dw_umma_path(const nnue_shape *s, const uint32_t *bits_s_d, const float *g_ft_d, float *g_w_d, float *g_b_d,
                                void *workspace_d, size_t workspace_bytes, cudaStream_t st) {
     if (workspace_bytes < ws_ft_bwd_umma(*s)) return NNUE_ERR_WORKSPACE;
-    return launch_ft_bwd_dw_umma(*s, bits_s_d, g_ft_d, static_cast<char *>(workspace_d) + ws_ft_gbin_umma(*s), g_w_d, g_b_d, st);
+    return launch_ft_bwd_dw_umma(*s, bits_s_d, g_ft_d, static_cast<char *>(workspace_d) + ws_bwd_front_umma(*s), g_w_d, g_b_d, st);
 }
 
 int nnue_ft_uses_umma(const nnue_shape *s) { return s && ft_umma_ok(*s) ? 1 : 0; }

@@ -190,7 +190,7 @@ ce_kernel(int B, int NC, const float *__restrict__ logits, const int64_t *__rest
     float se = 0.0f;
     for (int c = lane; c < NC; c += 32) se += expf(row[c] - mx);
     se = warp_sum(se);
-    const int y = (int)labels[b];
+    const int y = min(max((int)labels[b], 0), NC - 1);  // (a target outside [0, NC) must not read out of bounds)
     const float lse = mx + logf(se);
     if (per_sample && lane == 0) per_sample[b] = lse - row[y];
     if (g_logits) {

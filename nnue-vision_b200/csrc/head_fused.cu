@@ -194,7 +194,7 @@ head_train_kernel(const HeadTrainArgs a) {
                 mx = fmaxf(mx, gl[c]);
                 if (c % 4 == 3) NNUE_SCHED_FENCE();
             }
-            const int y = live ? (int)a.labels[b] : 0;
+            const int y = live ? min(max((int)a.labels[b], 0), a.NC - 1) : 0;
             float se = 0.0f, ly = 0.0f;
 #pragma unroll
             for (int c = 0; c < NCP; ++c) {

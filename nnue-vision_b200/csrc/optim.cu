@@ -82,6 +82,14 @@ adam_step_kernel(long long n, float *__restrict__ p, float *__restrict__ g, floa
     }
 }
 
+// dst[i] = src[i] * *scale: the upstream gradient of the scalar loss applied to every parameter gradient in one pass
+// (train.py:352-361: loss.backward() with an arbitrary upstream factor, e.g. (loss * w).backward())
+__global__ void __launch_bounds__(kOptThreads)
+scale_flat_kernel(long long n, const float *__restrict__ src, const float *__restrict__ scale, float *__restrict__ dst) {
+    const float g = __ldg(scale);
+    for (long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 1LL * gridDim.x * blockDim.x) dst[i] = src[i] * g;
+}
+
 static int opt_grid(long long n) {
     long long g = (n + kOptThreads - 1) / kOptThreads;
     if (g > 8LL * kNumSMs) g = 8LL * kNumSMs;
@@ -107,6 +115,13 @@ int nnue_opt_grad_sqnorm(long long n, const float *g_d, float *sqnorm_d, void *w
     NNUE_CHECK_LAUNCH("grad_sqnorm_partial_kernel");
     grad_sqnorm_fold_kernel<<<1, 32, 0, st>>>(grid, partial, sqnorm_d);
     NNUE_CHECK_LAUNCH("grad_sqnorm_fold_kernel");
+    return NNUE_OK;
+}
+
+int nnue_scale_flat(long long n, const float *src_d, const float *scale_d, float *dst_d, void *stream) {
+    if (n < 1 || !src_d || !scale_d || !dst_d) return NNUE_ERR_INVALID_ARG;
+    scale_flat_kernel<<<opt_grid(n), kOptThreads, 0, static_cast<cudaStream_t>(stream)>>>(n, src_d, scale_d, dst_d);
+    NNUE_CHECK_LAUNCH("scale_flat_kernel");
     return NNUE_OK;
 }
 

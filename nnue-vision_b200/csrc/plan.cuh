@@ -152,8 +152,16 @@ inline size_t ws_ft_dw_umma(const nnue_shape &s) {
     const size_t alias_rows = (size_t)(s.P > s.F - 1 ? s.P - (s.F - 1) : 0);
     return align_up(umma_kt_bytes((size_t)s.BW * 32, s), 256) + ((size_t)plan_ft_dw_umma(s).n_chunks * (s.P + 1) + alias_rows) * s.L1 * 4;
 }
-// the two gradients may run concurrently on two streams: disjoint regions, value gradient first
-inline size_t ws_ft_bwd_umma(const nnue_shape &s) { return ws_ft_gbin_umma(s) + align_up(ws_ft_dw_umma(s), 256); }
+// The two gradients may run concurrently on two streams: disjoint regions.  The FIRST region holds the value gradient's
+// operands and, after it, the conv gradient's per-CTA partials ([grid <= kNumSMs][C][28] floats, written at offset 0 by
+// nnue_conv_bwd while the weight gradient may still be running on the side stream): it is sized for the larger of the
+// two, and the weight gradient's region starts behind it.
+inline size_t ws_conv_partials_bound(const nnue_shape &s) { return align_up((size_t)kNumSMs * s.C * 28 * 4, 256); }
+inline size_t ws_bwd_front_umma(const nnue_shape &s) {
+    const size_t a = ws_ft_gbin_umma(s), b = ws_conv_partials_bound(s);
+    return a > b ? a : b;
+}
+inline size_t ws_ft_bwd_umma(const nnue_shape &s) { return ws_bwd_front_umma(s) + align_up(ws_ft_dw_umma(s), 256); }
 int launch_ft_fwd_umma(const nnue_shape &s, const uint32_t *bits_s, const float *w, const float *bias, float *out,
                        void *workspace, cudaStream_t st);
 int launch_ft_bwd_dw_umma(const nnue_shape &s, const uint32_t *bits_s, const float *g_ft, void *ws, float *g_w, float *g_b,
@@ -528,11 +536,17 @@ inline size_t ws_ft_fwd(const nnue_shape &s) {
     const size_t a = plan_ft_mma(s).ok ? mma_wfrag_bytes(s) : 0, b = ft_umma_ok(s) ? umma_kt_bytes((size_t)s.PP, s) : 0;
     return a > b ? a : b;
 }
+// first region of the warp-level MMA backward: the table fragments of the value gradient, then (reused) the conv
+// gradient's per-CTA partials -- see ws_bwd_front_umma
+inline size_t ws_bwd_front_mma(const nnue_shape &s) {
+    const size_t a = align_up(mma_wfrag_bytes(s), 256), b = ws_conv_partials_bound(s);
+    return a > b ? a : b;
+}
 inline size_t ws_ft_bwd_mma(const nnue_shape &s) {
     const MmaPlan m = plan_ft_mma(s);
     if (!m.ok) return 0;
     const size_t alias_rows = (size_t)(s.P > s.F - 1 ? s.P - (s.F - 1) : 0);
-    return align_up(mma_wfrag_bytes(s), 256) + align_up(mma_gfrag_bytes(s), 256) +
+    return ws_bwd_front_mma(s) + align_up(mma_gfrag_bytes(s), 256) +
            align_up((size_t)m.n_chunks * s.L1 * 4, 256) + ((size_t)m.n_chunks * s.P + alias_rows) * s.L1 * 4;
 }
 int launch_ft_fwd_mma(const nnue_shape &s, const uint32_t *bits_s, const float *w, const float *bias, float *out,

@@ -49,12 +49,12 @@ struct nnue_qmodel {
     mutable size_t h_cap_img = 0, h_cap_b = 0;
     mutable cudaStream_t h_stream = nullptr;
     // tensor-core form for large batches (L1 a multiple of 64): the table as high/low-byte bf16 tiles in UMMA order,
-    // K index = oc * CWq * 32 + cell over the whole G x G buffer; per-instance scratch grown on demand
+    // K index = oc * CWq * 32 + cell over the whole G x G buffer.  The device entry points take their scratch from the
+    // caller (nnue_q_workspace_bytes); only nnue_q_infer_host keeps its own (s_ws, with its other host-path buffers)
     unsigned char *tc_tiles = nullptr;
     int CWq = 0;                            // 32-bit words per channel: ceil(G*G / 32)
-    mutable uint32_t *s_bits = nullptr;     // [B][OC * CWq]
-    mutable int16_t *s_acc = nullptr;       // [B][L1]
-    mutable size_t s_cap = 0;               // samples the scratch holds
+    mutable void *s_ws = nullptr;
+    mutable size_t s_cap = 0;               // bytes
 };
 
 namespace nnue {
@@ -73,6 +73,9 @@ struct Reader {
         p += n;
         return true;
     }
+    size_t remaining() const { return ok ? (size_t)(end - p) : 0; }
+    // may a payload of `count` elements of `elem` bytes still follow?  (checked BEFORE anything is allocated for it)
+    bool fits(uint64_t count, uint64_t elem) const { return ok && count <= remaining() / (elem ? elem : 1); }
     uint32_t u32() { uint32_t v = 0; take(&v, 4); return v; }
     float f32() { float v = 0; take(&v, 4); return v; }
 };
@@ -111,10 +114,11 @@ static int parse_and_upload(const unsigned char *bytes, size_t n, nnue_qmodel *m
     (void)r.u32();  // conv layer type
     m->conv_scale = r.f32();
     const uint32_t OC = r.u32(), IC = r.u32(), KH = r.u32(), KW = r.u32();
-    if (!r.ok || IC != 3 || KH != 3 || KW != 3 || OC == 0 || OC > (1u << 20)) return NNUE_ERR_FORMAT;
+    if (!r.ok || IC != 3 || KH != 3 || KW != 3 || OC == 0 || OC > (1u << 20) || !r.fits((uint64_t)OC * 27, 1)) return NNUE_ERR_FORMAT;
+    if (L2 > (1u << 16) || L3 > (1u << 16)) return NNUE_ERR_FORMAT;  // (the engine's layer sizes are small integers)
     std::vector<int8_t> cw((size_t)OC * 27);
     if (!r.take(cw.data(), cw.size())) return NNUE_ERR_FORMAT;
-    if (r.u32() != OC) return NNUE_ERR_FORMAT;
+    if (r.u32() != OC || !r.fits(OC, 4)) return NNUE_ERR_FORMAT;
     std::vector<int32_t> cb(OC);
     if (!r.take(cb.data(), (size_t)OC * 4)) return NNUE_ERR_FORMAT;
     if (F == 0 || F % OC) return NNUE_ERR_FORMAT;
@@ -123,9 +127,10 @@ static int parse_and_upload(const unsigned char *bytes, size_t n, nnue_qmodel *m
     m->ft_scale = r.f32();
     if (r.u32() != F || r.u32() != L1 || !r.ok || L1 == 0) return NNUE_ERR_FORMAT;
     if ((uint64_t)F * L1 > (1ull << 31)) return NNUE_ERR_UNSUPPORTED;
+    if (!r.fits((uint64_t)F * L1, 2)) return NNUE_ERR_FORMAT;  // truncated file: refuse before allocating the table
     std::vector<int16_t> fw((size_t)F * L1);
     if (!r.take(fw.data(), fw.size() * 2)) return NNUE_ERR_FORMAT;
-    if (r.u32() != L1) return NNUE_ERR_FORMAT;
+    if (r.u32() != L1 || !r.fits(L1, 4)) return NNUE_ERR_FORMAT;
     std::vector<int32_t> fb(L1);
     if (!r.take(fb.data(), (size_t)L1 * 4)) return NNUE_ERR_FORMAT;
     if (nb < 1 || nb > 4096) return NNUE_ERR_FORMAT;
@@ -180,36 +185,37 @@ static int parse_and_upload(const unsigned char *bytes, size_t n, nnue_qmodel *m
         st.l1_scale = r.f32(); st.l2_scale = r.f32(); st.out_scale = r.f32();
         st.l1_fact_scale = r.f32();
         uint32_t rows = r.u32(), cols = r.u32();
-        if (!r.ok || rows != L2 + 1 || cols != L1 || L2 < 1 || L3 < 1) return NNUE_ERR_FORMAT;
+        if (!r.ok || rows != L2 + 1 || cols != L1 || L2 < 1 || L3 < 1 || !r.fits((uint64_t)rows * cols, 1)) return NNUE_ERR_FORMAT;
         std::vector<int8_t> w1((size_t)rows * cols);
         if (!r.take(w1.data(), w1.size())) return NNUE_ERR_FORMAT;
         uint32_t nbias = r.u32();
-        if (!r.ok || nbias < L2) return NNUE_ERR_FORMAT;
+        if (!r.ok || nbias < L2 || !r.fits(nbias, 4)) return NNUE_ERR_FORMAT;
         std::vector<int32_t> b1(nbias);
         if (!r.take(b1.data(), (size_t)nbias * 4)) return NNUE_ERR_FORMAT;
         rows = r.u32(); cols = r.u32();  // L1 factoriser: unused by the multiclass head, row L2 feeds the single score
-        if (!r.ok || cols != L1 || rows <= L2) return NNUE_ERR_FORMAT;
+        if (!r.ok || cols != L1 || rows <= L2 || !r.fits((uint64_t)rows * cols, 1)) return NNUE_ERR_FORMAT;
         std::vector<int8_t> wf((size_t)rows * cols);
         if (!r.take(wf.data(), wf.size())) return NNUE_ERR_FORMAT;
         nbias = r.u32();
-        std::vector<int32_t> bfv(r.ok ? nbias : 0);
+        if (!r.fits(nbias, 4)) return NNUE_ERR_FORMAT;
+        std::vector<int32_t> bfv(nbias);
         if (!r.take(bfv.data(), (size_t)nbias * 4)) return NNUE_ERR_FORMAT;
         rows = r.u32(); cols = r.u32();
-        if (!r.ok || cols != 2 * L2 || rows != L3) return NNUE_ERR_FORMAT;
+        if (!r.ok || cols != 2 * L2 || rows != L3 || !r.fits((uint64_t)rows * cols, 1)) return NNUE_ERR_FORMAT;
         std::vector<int8_t> w2((size_t)rows * cols);
         if (!r.take(w2.data(), w2.size())) return NNUE_ERR_FORMAT;
         nbias = r.u32();
-        if (!r.ok || nbias < L3) return NNUE_ERR_FORMAT;
+        if (!r.ok || nbias < L3 || !r.fits(nbias, 4)) return NNUE_ERR_FORMAT;
         std::vector<int32_t> b2(nbias);
         if (!r.take(b2.data(), (size_t)nbias * 4)) return NNUE_ERR_FORMAT;
         rows = r.u32(); cols = r.u32();
-        if (!r.ok || cols != L3 || rows < 1 || rows > (1u << 24)) return NNUE_ERR_FORMAT;
+        if (!r.ok || cols != L3 || rows < 1 || rows > (1u << 24) || !r.fits((uint64_t)rows * cols, 1)) return NNUE_ERR_FORMAT;
         if (b == 0) m->NC = (int)rows;
         else if ((int)rows != m->NC) return NNUE_ERR_FORMAT;
         std::vector<int8_t> wo((size_t)rows * cols);
         if (!r.take(wo.data(), wo.size())) return NNUE_ERR_FORMAT;
         nbias = r.u32();
-        if (!r.ok || nbias < rows) return NNUE_ERR_FORMAT;
+        if (!r.ok || nbias < rows || !r.fits(nbias, 4)) return NNUE_ERR_FORMAT;
         std::vector<int32_t> bo(nbias);
         if (!r.take(bo.data(), (size_t)nbias * 4)) return NNUE_ERR_FORMAT;
         if ((rc = upload(m, pack_dp4a(w1, (int)L2, (int)L1, (int)L1), &st.w1)) || (rc = upload(m, b1, &st.b1)) ||
@@ -500,16 +506,23 @@ void nnue_q_free(nnue_qmodel *m) {
     if (m->h_logits) cudaFree(m->h_logits);
     if (m->h_density) cudaFree(m->h_density);
     if (m->h_stream) cudaStreamDestroy(m->h_stream);
-    if (m->s_bits) cudaFree(m->s_bits);
-    if (m->s_acc) cudaFree(m->s_acc);
+    if (m->s_ws) cudaFree(m->s_ws);
     delete m;
 }
 
 int nnue_q_load_memory(const void *bytes_h, size_t n_bytes, nnue_qmodel **out) {
     if (!bytes_h || !out) return NNUE_ERR_INVALID_ARG;
     *out = nullptr;
-    nnue_qmodel *m = new nnue_qmodel();
-    const int rc = parse_and_upload(static_cast<const unsigned char *>(bytes_h), n_bytes, m);
+    // nothing may unwind through the C boundary: a malformed file answers NNUE_ERR_FORMAT the way
+    // NNUEEvaluator::load_model answers false (nnue_engine.cpp:544-657)
+    nnue_qmodel *m = nullptr;
+    int rc;
+    try {
+        m = new nnue_qmodel();
+        rc = parse_and_upload(static_cast<const unsigned char *>(bytes_h), n_bytes, m);
+    } catch (...) {
+        rc = NNUE_ERR_FORMAT;
+    }
     if (rc != NNUE_OK) { nnue_q_free(m); return rc; }
     *out = m;
     return NNUE_OK;
@@ -521,10 +534,15 @@ int nnue_q_load(const char *path, nnue_qmodel **out) {
     FILE *f = fopen(path, "rb");
     if (!f) return NNUE_ERR_IO;
     std::vector<unsigned char> buf;
-    unsigned char chunk[1 << 16];
-    size_t got;
-    while ((got = fread(chunk, 1, sizeof(chunk), f)) > 0) buf.insert(buf.end(), chunk, chunk + got);
-    const bool err = ferror(f) != 0;
+    bool err = false;
+    try {
+        std::vector<unsigned char> chunk(1 << 20);
+        size_t got;
+        while ((got = fread(chunk.data(), 1, chunk.size(), f)) > 0) buf.insert(buf.end(), chunk.begin(), chunk.begin() + got);
+        err = ferror(f) != 0;
+    } catch (...) {
+        err = true;
+    }
     fclose(f);
     if (err) return NNUE_ERR_IO;
     return nnue_q_load_memory(buf.data(), buf.size(), out);
@@ -538,8 +556,14 @@ int nnue_q_dims(const nnue_qmodel *m, int32_t *dims, float *visual_threshold) {
     return NNUE_OK;
 }
 
-int nnue_q_infer(const nnue_qmodel *m, const float *images_d, int B, int H, int W, int bucket, float *logits_d,
-                 float *density_d, void *stream) {
+// scratch of the split (large-batch) form: bitmask [B][OC * CWq] u32 | accumulators [B][L1] i16
+size_t nnue_q_workspace_bytes(const nnue_qmodel *m, int B) {
+    if (!m || B < 1 || !m->tc_tiles) return 0;
+    return align_up((size_t)B * m->OC * m->CWq * 4, 256) + align_up((size_t)B * m->L1 * 2, 256);
+}
+
+int nnue_q_infer_ws(const nnue_qmodel *m, const float *images_d, int B, int H, int W, int bucket, float *logits_d,
+                    float *density_d, void *workspace_d, size_t workspace_bytes, void *stream) {
     if (!images_d || !logits_d) return NNUE_ERR_INVALID_ARG;
     QParams q{};
     const int rc = fill_params(m, B, H, W, bucket, &q);
@@ -547,23 +571,25 @@ int nnue_q_infer(const nnue_qmodel *m, const float *images_d, int B, int H, int 
     q.images = images_d; q.logits = logits_d; q.density = density_d;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int min_b = get_option(kOptQTcMinBatch);
-    if (m->tc_tiles && min_b > 0 && B >= min_b) {
-        // large batches: bitmask -> tcgen05 accumulate -> layer stack (three launches, same integers)
-        if ((size_t)B > m->s_cap) {  // grow the per-instance scratch (synchronising; only when the batch grows)
-            if (m->s_bits) { cudaFree(m->s_bits); cudaFree(m->s_acc); m->s_bits = nullptr; m->s_acc = nullptr; m->s_cap = 0; }
-            NNUE_CUDA_TRY(cudaMalloc(&m->s_bits, (size_t)B * m->OC * m->CWq * 4));
-            NNUE_CUDA_TRY(cudaMalloc(&m->s_acc, (size_t)B * m->L1 * 2));
-            m->s_cap = (size_t)B;
-        }
-        q.G2 = m->F / m->OC; q.CWq = m->CWq; q.bits_out = m->s_bits; q.acc_in = m->s_acc;
+    if (m->tc_tiles && min_b > 0 && B >= min_b && workspace_d && workspace_bytes >= nnue_q_workspace_bytes(m, B)) {
+        // large batches: bitmask -> tcgen05 accumulate -> layer stack (three launches, same integers) on the caller's scratch
+        uint32_t *s_bits = static_cast<uint32_t *>(workspace_d);
+        int16_t *s_acc = reinterpret_cast<int16_t *>(static_cast<char *>(workspace_d) + align_up((size_t)B * m->OC * m->CWq * 4, 256));
+        q.G2 = m->F / m->OC; q.CWq = m->CWq; q.bits_out = s_bits; q.acc_in = s_acc;
         int rc2 = launch_q_infer(q, 1, st);
         if (rc2 != NNUE_OK) return rc2;
-        rc2 = launch_q_accumulate_umma(B, m->OC * m->CWq, m->L1, m->s_bits, m->tc_tiles,
-                                       reinterpret_cast<const int32_t *>(m->ft_b32), m->s_acc, st);
+        rc2 = launch_q_accumulate_umma(B, m->OC * m->CWq, m->L1, s_bits, m->tc_tiles,
+                                       reinterpret_cast<const int32_t *>(m->ft_b32), s_acc, st);
         if (rc2 != NNUE_OK) return rc2;
         return launch_q_infer(q, 2, st);
     }
     return launch_q_infer(q, 0, st);
+}
+
+// without scratch: the one-kernel form at every batch size (never allocates, never touches the model)
+int nnue_q_infer(const nnue_qmodel *m, const float *images_d, int B, int H, int W, int bucket, float *logits_d,
+                 float *density_d, void *stream) {
+    return nnue_q_infer_ws(m, images_d, B, H, W, bucket, logits_d, density_d, nullptr, 0, stream);
 }
 
 }  // extern "C"
@@ -711,8 +737,14 @@ int nnue_q_infer_host(const nnue_qmodel *m, const float *images_h, int B, int H,
         NNUE_CUDA_TRY(cudaMalloc(&m->h_density, (size_t)B * 4));
         m->h_cap_b = (size_t)B;
     }
+    const size_t ws_bytes = nnue_q_workspace_bytes(m, B);
+    if (ws_bytes > m->s_cap) {
+        if (m->s_ws) { cudaFree(m->s_ws); m->s_ws = nullptr; m->s_cap = 0; }
+        NNUE_CUDA_TRY(cudaMalloc(&m->s_ws, ws_bytes));
+        m->s_cap = ws_bytes;
+    }
     NNUE_CUDA_TRY(cudaMemcpyAsync(m->h_img, images_h, img_bytes, cudaMemcpyHostToDevice, m->h_stream));
-    const int rc = nnue_q_infer(m, m->h_img, B, H, W, bucket, m->h_logits, m->h_density, m->h_stream);
+    const int rc = nnue_q_infer_ws(m, m->h_img, B, H, W, bucket, m->h_logits, m->h_density, m->s_ws, m->s_cap, m->h_stream);
     if (rc != NNUE_OK) return rc;
     NNUE_CUDA_TRY(cudaMemcpyAsync(logits_h, m->h_logits, (size_t)B * m->NC * 4, cudaMemcpyDeviceToHost, m->h_stream));
     if (density_h)

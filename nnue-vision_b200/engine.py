@@ -41,6 +41,8 @@ class NNUEEvaluator:
         """NNUEEvaluator::load_model (nnue_engine.cpp:544-657): False on a missing or malformed file."""
         self.close()
         h = ctypes.c_void_p()
+        # the tables are uploaded to the CURRENT device; evaluate_* checks its inputs against it
+        self.device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
         rc = _lib.lib().nnue_q_load(str(path).encode(), ctypes.byref(h))
         if rc in (-4, -5):  # NNUE_ERR_IO / NNUE_ERR_FORMAT: the engine reports these as `false`
             return False
@@ -56,22 +58,30 @@ class NNUEEvaluator:
         self._dirty = True
         return True
 
-    def _require(self):
+    def _require(self, t=None):
         if not self._h.value:
             raise _lib.NnueError("no model loaded")
+        if t is not None and torch.is_tensor(t) and t.is_cuda and t.device != self.device:
+            raise _lib.NnueError(f"the model was loaded on {self.device} but the input lives on {t.device}: load one "
+                                 "evaluator per device (inference runs per GPU, no peer traffic)")
 
     def evaluate_logits(self, images: torch.Tensor, layer_stack_index: int = 0):
         """images: CUDA float32 [B, H, W, 3] -- the raw buffer the engine would be handed, read as HWC
         (callers holding CHW tensors pass `chw.contiguous().view(B, H, W, 3)`, the byte
         reinterpretation evaluate.py:154-168 performs).  Returns (logits [B, NC], density [B])."""
-        self._require()
+        self._require(images)
         if images.dim() != 4 or images.shape[-1] != 3:
             raise ValueError(f"expected images [B,H,W,3], got {tuple(images.shape)}")
         B, H, W, _ = images.shape
-        logits = torch.empty((B, self.num_classes), dtype=torch.float32, device=images.device)
-        density = torch.empty((B,), dtype=torch.float32, device=images.device)
-        check(_lib.lib().nnue_q_infer(self._h, dptr(images, torch.float32), B, H, W, int(layer_stack_index),
-                                      dptr(logits), dptr(density), stream_ptr()))
+        with _lib.on_device_of(images):
+            logits = torch.empty((B, self.num_classes), dtype=torch.float32, device=images.device)
+            density = torch.empty((B,), dtype=torch.float32, device=images.device)
+            # scratch of the large-batch (tensor-core) form comes from the caller: nothing is allocated or mutated
+            # inside the C call, so several streams may share one evaluator's tables
+            ws_bytes = int(_lib.lib().nnue_q_workspace_bytes(self._h, B))
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=images.device) if ws_bytes else None
+            check(_lib.lib().nnue_q_infer_ws(self._h, dptr(images, torch.float32), B, H, W, int(layer_stack_index),
+                                             dptr(logits), dptr(density), dptr(ws), ws_bytes, stream_ptr()))
         return logits, density
 
     def evaluate_logits_host(self, images: np.ndarray, layer_stack_index: int = 0):
@@ -107,7 +117,7 @@ class NNUEEvaluator:
         return torch.from_numpy(off).to(device), torch.from_numpy(idx).to(device)
 
     def _device(self):
-        return torch.device("cuda", torch.cuda.current_device())
+        return self.device  # the device the tables were loaded on
 
     def refresh_accumulator(self, features):
         """acc = (int16)bias + sum of the listed rows, for every stream (nnue_engine.cpp:804-815)."""
@@ -118,7 +128,8 @@ class NNUEEvaluator:
         if self._acc is None or self._acc.shape[0] != S or self._acc.device != dev:
             self._acc = torch.empty((S, self.l1_size), dtype=torch.int16, device=dev)
         off, idx = self._csr(lists, dev)
-        check(_lib.lib().nnue_q_acc_apply(self._h, S, 1, dptr(off), dptr(idx), None, None, dptr(self._acc), stream_ptr()))
+        with torch.cuda.device(dev):
+            check(_lib.lib().nnue_q_acc_apply(self._h, S, 1, dptr(off), dptr(idx), None, None, dptr(self._acc), stream_ptr()))
 
     def update_features(self, added, removed):
         """acc -= rows(removed); acc += rows(added) with int16 wrap-around (nnue_engine.cpp:818-821)."""
@@ -133,7 +144,8 @@ class NNUEEvaluator:
         dev = self._acc.device
         ao, ai = self._csr(la, dev)
         ro, ri = self._csr(lr, dev)
-        check(_lib.lib().nnue_q_acc_apply(self._h, S, 0, dptr(ao), dptr(ai), dptr(ro), dptr(ri), dptr(self._acc), stream_ptr()))
+        with torch.cuda.device(dev):
+            check(_lib.lib().nnue_q_acc_apply(self._h, S, 0, dptr(ao), dptr(ai), dptr(ro), dptr(ri), dptr(self._acc), stream_ptr()))
 
     def evaluate_incremental(self, current_features, layer_stack_index: int = 0):
         """The engine's chess-style entry point (nnue_engine.cpp:739-787): refresh when dirty / disabled, otherwise
@@ -156,7 +168,8 @@ class NNUEEvaluator:
                 self._last_features = cur
         S = self._acc.shape[0]
         score = torch.empty((S,), dtype=torch.float32, device=self._acc.device)
-        check(_lib.lib().nnue_q_acc_score(self._h, S, dptr(self._acc), int(layer_stack_index), dptr(score), stream_ptr()))
+        with torch.cuda.device(self._acc.device):
+            check(_lib.lib().nnue_q_acc_score(self._h, S, dptr(self._acc), int(layer_stack_index), dptr(score), stream_ptr()))
         return float(score[0]) if single else score
 
     def save_accumulator(self):

@@ -14,6 +14,7 @@ fallback: CPU tensors raise.
 """
 import ctypes
 import os
+import weakref
 from dataclasses import dataclass
 from typing import Optional
 
@@ -100,8 +101,9 @@ class _FTIndexed(torch.autograd.Function):
         F, L1 = weight.shape
         out = _empty((B, L1), torch.float32, weight)
         w, b = weight.detach().contiguous(), bias.detach().contiguous()
-        check(_lib.lib().nnue_ft_fwd_indexed(B, K, F, L1, dptr(idx), dptr(val), dptr(w), dptr(b), dptr(out),
-                                             stream_ptr()))
+        with _lib.on_device_of(weight):
+            check(_lib.lib().nnue_ft_fwd_indexed(B, K, F, L1, dptr(idx), dptr(val), dptr(w), dptr(b), dptr(out),
+                                                 stream_ptr()))
         ctx.save_for_backward(idx, val, w)
         return out
 
@@ -124,9 +126,10 @@ class _FTIndexed(torch.autograd.Function):
         g_w = _empty((F, L1), torch.float32, w)
         g_b = _empty((L1,), torch.float32, w)
         g_val = _empty((B, K), torch.float32, w) if ctx.needs_input_grad[1] else None
-        check(_lib.lib().nnue_ft_bwd_indexed(B, K, F, L1, dptr(idx), dptr(w), dptr(g_out), n, dptr(rows) if n else None,
-                                             dptr(samples) if n else None, dptr(vals) if n else None, dptr(g_w),
-                                             dptr(g_b), dptr(g_val), stream_ptr()))
+        with _lib.on_device_of(w):
+            check(_lib.lib().nnue_ft_bwd_indexed(B, K, F, L1, dptr(idx), dptr(w), dptr(g_out), n, dptr(rows) if n else None,
+                                                 dptr(samples) if n else None, dptr(vals) if n else None, dptr(g_w),
+                                                 dptr(g_b), dptr(g_val), stream_ptr()))
         return None, g_val, g_w, g_b
 
 
@@ -240,7 +243,8 @@ class _NNUEForward(torch.autograd.Function):
         B, _, H, W = images.shape
         shape = _lib.make_shape(B, H, W, C, G, ft_w.shape[1], w1.shape[0], w2.shape[0], w3.shape[0], stride)
         need_bwd = any(ctx.needs_input_grad[4:])
-        logits, bits_s, bits_t, xpad, ft_out, act1, act2 = _run_forward(shape, images, params, need_bwd)
+        with _lib.on_device_of(images):
+            logits, bits_s, bits_t, xpad, ft_out, act1, act2 = _run_forward(shape, images, params, need_bwd)
         if need_bwd:
             sv = _Saved()
             sv.shape, sv.images, sv.bits_s, sv.bits_t, sv.xpad = shape, images, bits_s, bits_t, xpad
@@ -251,8 +255,9 @@ class _NNUEForward(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_logits):
         sv = ctx.sv
-        g = _run_backward(sv.shape, sv.images, sv.params, sv.bits_s, sv.bits_t, sv.xpad, sv.ft_out, sv.act1, sv.act2,
-                          g_logits.contiguous().float())
+        with _lib.on_device_of(sv.images):
+            g = _run_backward(sv.shape, sv.images, sv.params, sv.bits_s, sv.bits_t, sv.xpad, sv.ft_out, sv.act1, sv.act2,
+                              g_logits.contiguous().float())
         return (None, None, None, None) + tuple(g)
 
 
@@ -276,11 +281,16 @@ def _side_stream(device):
     return _SIDE_STREAMS[key]
 
 
-def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_out=None, marks=None):
+def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_out=None, marks=None, exchange=None):
     """One whole training step of the hot path -- forward, mean cross-entropy, every parameter gradient --
     in seven launches: extract, feature transformer, fused head step (forward + loss + backward), the two
     feature-transformer gradients, conv / threshold gradients.  `grads` / `loss_out` may be preallocated
-    (views of a flat data-parallel buffer).  Returns (loss [1], grads in parameter order)."""
+    (views of a flat data-parallel buffer).  Returns (loss [1], grads in parameter order).
+
+    `exchange` (data parallelism, train.DataParallelStep): an object with early() / late() / full() that all-reduces
+    the slices of the flat gradient buffer.  early() -- feature transformer, head, loss -- is issued on the side stream
+    right behind the table gradient, so it travels while the value / conv gradients are still being computed; late()
+    -- conv weights and thresholds, a few hundred floats -- at the end."""
     L = _lib.lib()
     st = stream_ptr()
     thr, conv_w, ft_w, ft_b, w1, b1, w2, b2, w3, b3 = params
@@ -334,9 +344,13 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
             with torch.cuda.stream(side):
                 check(L.nnue_ft_bwd_dw(sp, dptr(bits_s), None, dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(ws), ws_bytes,
                                        ctypes.c_void_p(side.cuda_stream)))
+                if exchange is not None:
+                    exchange.early(ctypes.c_void_p(side.cuda_stream))
         else:
             check(L.nnue_ft_bwd_dw(sp, dptr(bits_s), None, dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(ws), ws_bytes, st))
             _mark(marks, "ft_bwd_dw")
+            if exchange is not None:
+                exchange.early(st)
         gbin = _empty((shape.B, shape.PP), torch.float32, images)
         if tables is not None:
             check(L.nnue_ft_bwd_gbin_tables(sp, dptr(bits_s), dptr(tables), dptr(g_ft), dptr(gbin), dptr(ws), ws_bytes, st))
@@ -348,6 +362,9 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
         _mark(marks, "conv_bwd")
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)  # the step's gradients are complete on the caller's stream
+        if exchange is not None:
+            exchange.late(st)
+            _mark(marks, "exchange")
         return loss_out, grads
     if L.nnue_ft_bwd_is_fused(sp):  # both feature-transformer gradients in one CUDA-core pass over g_ft
         gbin = _empty((shape.B, shape.PP), torch.float32, images)
@@ -357,10 +374,28 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
         check(L.nnue_conv_bwd(sp, dptr(images), dptr(gbin), dptr(xpad), dptr(conv_w), dptr(thr), dptr(g_conv_w), dptr(g_thr),
                               dptr(ws), ws_bytes, st))
         _mark(marks, "conv_bwd")
+        if exchange is not None:
+            exchange.full(st)
+            _mark(marks, "exchange")
         return loss_out, grads
-    check(L.nnue_ft_bwd_dw(sp, dptr(bits_s), dptr(bits_t), dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(ws), ws_bytes,
-                           st))
-    _mark(marks, "ft_bwd_dw")
+    # General shapes (ImageNet-sized images, large tables).  Under data parallelism the table gradient runs on the side
+    # stream with its own scratch and its slice of the exchange (the 268 MB of SURVEY config I) follows it there, while
+    # the value / conv gradients run on the caller's stream.
+    side = _side_stream(images.device) if (exchange is not None and marks is None and OVERLAP_TABLE_GRADIENT) else None
+    if side is not None:
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
+        ws_dw = _empty((ws_bytes,), torch.uint8, images)  # (the general input gradient uses all of `ws`)
+        with torch.cuda.stream(side):
+            sst = ctypes.c_void_p(side.cuda_stream)
+            check(L.nnue_ft_bwd_dw(sp, dptr(bits_s), dptr(bits_t), dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(ws_dw), ws_bytes, sst))
+            exchange.early(sst)
+    else:
+        check(L.nnue_ft_bwd_dw(sp, dptr(bits_s), dptr(bits_t), dptr(g_ft), dptr(g_ft_w), dptr(g_ft_b), dptr(ws), ws_bytes,
+                               st))
+        _mark(marks, "ft_bwd_dw")
+        if exchange is not None:
+            exchange.early(st)
     if L.nnue_input_bwd_is_dense(sp):
         gbin = _empty((shape.B, shape.PP), torch.float32, images)
         check(L.nnue_ft_bwd_gbin(sp, dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(gbin), None, 0, st))
@@ -372,34 +407,74 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
         check(L.nnue_input_bwd_stored(sp, dptr(images), dptr(bits_s), dptr(xpad), dptr(ft_w), dptr(g_ft), dptr(conv_w),
                                       dptr(thr), dptr(g_conv_w), dptr(g_thr), dptr(ws), ws_bytes, st))
         _mark(marks, "input_bwd")
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)
+    if exchange is not None:
+        exchange.late(st)
+        _mark(marks, "exchange")
     return loss_out, grads
+
+
+# The module-level loss (`model.loss`, `train.compute_loss`) replays the step as a CUDA graph once it has seen the same
+# (input buffers, parameter storages, shape) twice -- the same cache DataParallelStep uses; set False to launch eagerly.
+CUDA_GRAPHS = os.environ.get("NNUE_CUDA_GRAPHS", "1") != "0"
+
+
+_GRAPH_RUNNERS = weakref.WeakKeyDictionary()  # model -> its private DataParallelStep (graph cache + static buffers)
+
+
+def _flat_views(flat, shapes):
+    views, off = [], 0
+    for shp in shapes:
+        n = 1
+        for d in shp:
+            n *= d
+        views.append(flat[off:off + n].view(shp))
+        off += n
+    return views, off
 
 
 class _NNUELoss(torch.autograd.Function):
     """images, labels -> mean cross-entropy (train.py:250-254).  The loss is a scalar, so every parameter
     gradient is linear in the upstream gradient: when gradients are wanted the whole step (forward, loss,
-    backward) runs inside `forward` through the fused kernels, and `backward` only scales the stored
-    gradients by the incoming scalar."""
+    backward) runs inside `forward` through the fused kernels -- every gradient lands in ONE flat buffer owned by this
+    autograd node -- and `backward` is one kernel that scales that buffer by the incoming scalar into a fresh one."""
 
     @staticmethod
-    def forward(ctx, images, labels, stride, C, G, inv_count, thr, conv_w, ft_w, ft_b, w1, b1, w2, b2, w3, b3):
+    def forward(ctx, images, labels, stride, C, G, inv_count, runner, thr, conv_w, ft_w, ft_b, w1, b1, w2, b2, w3, b3):
         params = tuple(p.detach().contiguous() for p in (thr, conv_w, ft_w, ft_b, w1, b1, w2, b2, w3, b3))
         B, _, H, W = images.shape
         shape = _lib.make_shape(B, H, W, C, G, ft_w.shape[1], w1.shape[0], w2.shape[0], w3.shape[0], stride)
-        if any(ctx.needs_input_grad[6:]):
-            loss, ctx.grads = _run_train_step(shape, images, labels, params, inv_count)
-            return loss.reshape(())
-        logits = _run_forward(shape, images, params, False)[0]
-        loss = _empty((1,), torch.float32, images)
-        per = _empty((B,), torch.float32, images)
-        check(_lib.lib().nnue_ce_fwd_bwd(B, shape.NC, dptr(logits), dptr(labels), inv_count, None, dptr(loss),
-                                         dptr(per), None, None, 0, stream_ptr()))
+        with _lib.on_device_of(images):
+            if any(ctx.needs_input_grad[7:]):
+                ctx.shapes = [tuple(p.shape) for p in params]
+                if runner is not None:
+                    # graph replay into the runner's static buffer, then ONE copy: this node owns its gradients even if
+                    # the model is stepped again before backward() runs
+                    flat = runner.run_local_flat(images, labels, inv_count).clone()
+                else:
+                    n = sum(p.numel() for p in params)
+                    flat = _empty(((n + 1 + 3) // 4 * 4,), torch.float32, images)
+                    views, n = _flat_views(flat, ctx.shapes)
+                    _run_train_step(shape, images, labels, params, inv_count, grads=views, loss_out=flat[n:n + 1])
+                ctx.flat = flat
+                ctx.n = sum(p.numel() for p in params)
+                return flat[ctx.n].clone()
+            logits = _run_forward(shape, images, params, False)[0]
+            loss = _empty((1,), torch.float32, images)
+            per = _empty((B,), torch.float32, images)
+            check(_lib.lib().nnue_ce_fwd_bwd(B, shape.NC, dptr(logits), dptr(labels), inv_count, None, dptr(loss),
+                                             dptr(per), None, None, 0, stream_ptr()))
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, g_loss):
-        g = g_loss.detach().float()
-        return (None,) * 6 + tuple(gr * g for gr in ctx.grads)
+        flat = ctx.flat
+        g = g_loss.detach().to(device=flat.device, dtype=torch.float32).contiguous()
+        out = torch.empty_like(flat)
+        with _lib.on_device_of(flat):
+            check(_lib.lib().nnue_scale_flat(ctx.n, dptr(flat), dptr(g), dptr(out), stream_ptr()))
+        return (None,) * 7 + tuple(_flat_views(out, ctx.shapes)[0])
 
 
 class NNUE(nn.Module):
@@ -495,9 +570,10 @@ class NNUE(nn.Module):
         shape = _lib.make_shape(B, H, W, fs.num_features_per_square, fs.grid_size, self.l1_size, self.l2_size,
                                 self.l3_size, self.num_classes, self.conv.stride[0])
         bits = _empty((B, shape.NW), torch.int32, images)
-        check(_lib.lib().nnue_extract_fwd(ctypes.byref(shape), dptr(images), dptr(self.conv.weight.detach().contiguous()),
-                                          dptr(self.visual_threshold.detach().contiguous()), dptr(bits), None, None,
-                                          None, None, stream_ptr()))
+        with _lib.on_device_of(images):
+            check(_lib.lib().nnue_extract_fwd(ctypes.byref(shape), dptr(images), dptr(self.conv.weight.detach().contiguous()),
+                                              dptr(self.visual_threshold.detach().contiguous()), dptr(bits), None, None,
+                                              None, None, stream_ptr()))
         return shape, bits
 
     def _to_sparse_features(self, binary_features: torch.Tensor):
@@ -529,5 +605,12 @@ class NNUE(nn.Module):
         fs = self.feature_set
         labels = targets.to(device=images.device, dtype=torch.long).contiguous()
         inv = 1.0 / float(global_batch if global_batch else images.shape[0])
+        runner = None
+        if CUDA_GRAPHS and torch.is_grad_enabled():
+            runner = _GRAPH_RUNNERS.get(self)  # (kept outside the module: attributes, state_dict, deepcopy unchanged)
+            if runner is None or runner.device != images.device:
+                from .train import DataParallelStep
+                runner = DataParallelStep(self, device=images.device, cuda_graphs=True, attach=False, single=True)
+                _GRAPH_RUNNERS[self] = runner
         return _NNUELoss.apply(images, labels, self.conv.stride[0], fs.num_features_per_square, fs.grid_size, inv,
-                               *self._hot_params())
+                               runner, *self._hot_params())

@@ -45,6 +45,11 @@ class FlatGradBuffer:
             self.views.append(self.flat[off:off + n].view(p.shape))
             off += n
         self.loss = self.flat[off:off + 1]
+        # The conv / threshold gradients (the first two tensors) are the last to become final in a step; everything
+        # behind them -- feature transformer, head, loss -- is final earlier.  `split` = first float4-aligned offset
+        # behind the two: [split, end) can be exchanged while the conv gradient is still running, [0, split) at the end.
+        early = sum(n for name, n in zip(self.names, sizes) if name in ("visual_threshold", "conv.weight"))
+        self.split = min(total, (early + 3) // 4 * 4) if self.names[:2] == ["visual_threshold", "conv.weight"] else total
 
     def attach(self):
         for p, v in zip(self.params, self.views):
@@ -115,6 +120,10 @@ class FusedOptimizer:
         return self.sqnorm.sqrt().reshape(())
 
     def step(self):
+        with torch.cuda.device(self.grads.flat.device):  # the C side launches on the current device
+            self._step()
+
+    def _step(self):
         L, d, st = self._lib.lib(), self._lib.dptr, self._lib.stream_ptr()
         g = self.grads.flat[: self.n]
         if self.max_grad_norm > 0:
@@ -130,11 +139,83 @@ class FusedOptimizer:
                                                  self.steps, self.max_grad_norm, d(self.sqnorm), st))
 
 
+class OneShotExchange:
+    """The library's one-shot all-reduce (csrc/allreduce.cu) over two slices of the flat gradient buffer, each with its own
+    symmetric receive area, flags and device-side step counter: `early` = [split, end) (feature transformer, head, loss),
+    `late` = [0, split) (conv weights, thresholds).  No host argument changes from step to step, so both launches can be
+    captured in the step's CUDA graph."""
+
+    def __init__(self, buf: "FlatGradBuffer", world, group, device):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        L = _lib.lib()
+        self._lib, self.world, self.buf = _lib, world, buf
+        group = group if group is not None else dist.group.WORLD
+        self.parts = []
+        for lo, hi in ((buf.split, buf.numel()), (0, buf.split)):
+            n = hi - lo
+            if n <= 0:
+                self.parts.append(None)
+                continue
+            recv = symm.empty(int(L.nnue_allreduce_recv_floats(world, n)), dtype=torch.float32, device=device)
+            flags = symm.empty(int(L.nnue_allreduce_max_world()), dtype=torch.int32, device=device)
+            recv.zero_()
+            flags.zero_()
+            h_recv = symm.rendezvous(recv, group)
+            h_flags = symm.rendezvous(flags, group)
+            self.rank = int(h_recv.rank)
+            self.parts.append(dict(
+                lo=lo, n=n, keep=(recv, flags, h_recv, h_flags),
+                recv=(ctypes.c_void_p * world)(*[int(x) for x in h_recv.buffer_ptrs]),
+                flags=(ctypes.c_void_p * world)(*[int(x) for x in h_flags.buffer_ptrs]),
+                state=torch.zeros(2, dtype=torch.int32, device=device)))
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)  # every rank's flags are zero before anybody publishes an epoch
+
+    def _launch(self, part, stream):
+        if part is None:
+            return
+        _lib = self._lib
+        _lib.check(_lib.lib().nnue_allreduce_oneshot(
+            self.world, self.rank, part["recv"], part["flags"], _lib.dptr(part["state"]), part["n"],
+            _lib.dptr(self.buf.flat[part["lo"]:part["lo"] + part["n"]]), stream))
+
+    def early(self, stream=None):
+        self._launch(self.parts[0], stream if stream is not None else self._lib.stream_ptr())
+
+    def late(self, stream=None):
+        self._launch(self.parts[1], stream if stream is not None else self._lib.stream_ptr())
+
+    def full(self, stream=None):
+        self.early(stream)
+        self.late(stream)
+
+
+class CollectiveExchange:
+    """NCCL all-reduce of the same two slices (large buffers: the 268 MB table gradient of SURVEY config I rides a ring /
+    NVLS reduction while the value and conv gradients are still being computed)."""
+
+    def __init__(self, buf: "FlatGradBuffer", group):
+        self.buf, self.group = buf, group
+
+    def early(self, stream=None):
+        if self.buf.split < self.buf.numel():
+            dist.all_reduce(self.buf.flat[self.buf.split:], op=dist.ReduceOp.SUM, group=self.group)
+
+    def late(self, stream=None):
+        if self.buf.split > 0:
+            dist.all_reduce(self.buf.flat[:self.buf.split], op=dist.ReduceOp.SUM, group=self.group)
+
+    def full(self, stream=None):
+        dist.all_reduce(self.buf.flat, op=dist.ReduceOp.SUM, group=self.group)
+
+
 def _cuda_local_step(model):
     """The B200 hot path: forward, fused CE, backward -- every kernel through the C ABI."""
     from . import _lib, nnue as _nnue
 
-    def run(images, labels, inv_count, buf: FlatGradBuffer, marks=None):
+    def run(images, labels, inv_count, buf: FlatGradBuffer, marks=None, exchange=None):
         images = model._check_images(images)
         labels = labels.to(device=images.device, dtype=torch.long).contiguous()
         fs = model.feature_set
@@ -144,7 +225,7 @@ def _cuda_local_step(model):
                                 model.l3_size, model.num_classes, model.conv.stride[0])
         # gradients land directly in the flat buffer's views, the loss in its trailing slot
         _nnue._run_train_step(shape, images, labels, params, inv_count, grads=buf.views, loss_out=buf.loss,
-                              marks=marks)
+                              marks=marks, exchange=exchange)
 
     return run
 
@@ -161,14 +242,18 @@ class DataParallelStep:
     """
 
     def __init__(self, model, process_group=None, local_step: Optional[Callable] = None, device=None,
-                 cuda_graphs: Optional[bool] = None, max_graphs: int = 8, allreduce: str = "auto"):
+                 cuda_graphs: Optional[bool] = None, max_graphs: int = 8, allreduce: str = "auto", attach: bool = True,
+                 single: bool = False):
         self.model = model
         self.group = process_group
-        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.world = 1 if single else (dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1)
         named = dict(model.named_parameters())
-        device = device if device is not None else named["input.weight"].device
+        device = torch.device(device if device is not None else named["input.weight"].device)
+        self.device = device
         self.buf = FlatGradBuffer(named, device)
-        self.buf.attach()
+        self._attach = bool(attach)  # False: the buffer is private scratch of the module-level loss (nnue.NNUE.loss)
+        if self._attach:
+            self.buf.attach()
         self._local = local_step if local_step is not None else _cuda_local_step(model)
         # The step is ~20 short launches on two streams: replaying it as ONE CUDA graph removes the host launch cost
         # and the gaps between dependent kernels.  A graph is captured per (input buffers, parameter storages, shape)
@@ -178,74 +263,73 @@ class DataParallelStep:
             cuda_graphs = local_step is None and torch.device(device).type == "cuda"
         self.cuda_graphs = bool(cuda_graphs)
         self.max_graphs = int(max_graphs)
-        self._graphs = {}   # key -> [hits, CUDAGraph or None, (images, labels) kept alive]
+        self._graphs = {}   # key -> [hits, CUDAGraph or None, kernels in the graph]
         self._pool = None
-        # Exchange: the library's one-shot all-reduce over NVLink peer memory when the ranks share a node and
-        # symmetric memory is available (in place on the flat buffer), otherwise one NCCL / gloo all-reduce.
+        # Exchange (inside the step, overlapped: see _run_train_step): the library's one-shot all-reduce over NVLink peer
+        # memory for small buffers when the ranks share a node and symmetric memory is available -- it has no per-step
+        # host argument and is captured in the step's CUDA graph -- otherwise NCCL (gloo on CPU) all-reduces of the same
+        # slices, issued eagerly on the step's streams (a step with a 268 MB gradient is not launch-bound).
         self.allreduce = "none" if self.world == 1 else "collective"
-        # measured on 8 x B200 (config D, 216 KB per step): one-shot 233 / 237 us per step at 4 / 8 GPUs against 239 / 253 us
-        # with NCCL; at 2 GPUs NCCL's two-rank path is 4 us ahead, so "auto" keeps the collective there
-        want = allreduce == "oneshot" or (allreduce == "auto" and self.world >= 3)
-        if self.world > 1 and local_step is None and torch.device(device).type == "cuda" and want:
+        self._xchg = None
+        self._inline = local_step is None and device.type == "cuda" and self.world > 1  # the exchange runs inside the step
+        small = self.buf.numel() * 4 <= (4 << 20)
+        want = allreduce == "oneshot" or (allreduce == "auto" and small)
+        if self._inline and want:
             self._setup_oneshot(named, device)
+        if self._inline and self._xchg is None:
+            self._xchg = CollectiveExchange(self.buf, self.group)
+            self.cuda_graphs = False  # (NCCL calls stay outside graph capture)
 
     def _setup_oneshot(self, named, device):
-        import ctypes
         import sys
         from . import _lib
         try:
-            import torch.distributed._symmetric_memory as symm
-            L = _lib.lib()
-            group = self.group if self.group is not None else dist.group.WORLD
-            if self.world > int(L.nnue_allreduce_max_world()):
+            if self.world > int(_lib.lib().nnue_allreduce_max_world()):
                 return
-            n = self.buf.numel()  # (FlatGradBuffer pads its buffer to a multiple of 4 floats)
-            recv = symm.empty(int(L.nnue_allreduce_recv_floats(self.world, n)), dtype=torch.float32, device=device)
-            flags = symm.empty(int(L.nnue_allreduce_max_world()), dtype=torch.int32, device=device)
-            recv.zero_()
-            flags.zero_()
-            h_recv = symm.rendezvous(recv, group)
-            h_flags = symm.rendezvous(flags, group)
-            torch.cuda.synchronize(device)
-            dist.barrier(group=self.group)  # every rank's flags are zero before anybody publishes an epoch
-            self._ar = dict(
-                rank=int(h_recv.rank), n=n, epoch=0, keep=(recv, flags, h_recv, h_flags),
-                recv=(ctypes.c_void_p * self.world)(*[int(x) for x in h_recv.buffer_ptrs]),
-                flags=(ctypes.c_void_p * self.world)(*[int(x) for x in h_flags.buffer_ptrs]),
-                counter=torch.zeros(1, dtype=torch.int32, device=device))
+            self._xchg = OneShotExchange(self.buf, self.world, self.group, device)
             self.allreduce = "oneshot_p2p"
         except Exception as e:  # no peer access / no symmetric memory on this system: the collective stays
             print(f"nnue_vision_b200: one-shot all-reduce unavailable ({type(e).__name__}: {e}); using the collective",
                   file=sys.stderr)
 
     def _exchange(self):
-        if self.allreduce == "oneshot_p2p":
-            from . import _lib
-            a = self._ar
-            a["epoch"] += 1
-            _lib.check(_lib.lib().nnue_allreduce_oneshot(
-                self.world, a["rank"], a["recv"], a["flags"], _lib.dptr(a["counter"]), a["n"], _lib.dptr(self.buf.flat),
-                a["epoch"], _lib.stream_ptr()))
+        """The whole buffer, now, on the current stream (the step itself issues the two slices where they become final)."""
+        if self._xchg is not None:
+            self._xchg.full()
         else:
             dist.all_reduce(self.buf.flat, op=dist.ReduceOp.SUM, group=self.group)
 
     def _graph_key(self, images, labels, inv_count):
+        # Everything the captured launches depend on: buffer addresses, shapes, the scaling, the parameter storages, and
+        # the library / module switches that select kernels.  No tensor is kept alive by the cache: a replay only needs
+        # the addresses to hold the caller's CURRENT inputs, which the key guarantees (when the allocator hands a new
+        # batch the address of a freed one, the graph is simply reused).
+        from . import _lib, nnue as _nnue
         return (images.data_ptr(), labels.data_ptr(), tuple(images.shape), images.dtype, labels.dtype, inv_count,
-                tuple(p.data_ptr() for p in self.model.parameters()))
+                tuple(p.data_ptr() for p in self.model.parameters()), _lib.options_epoch(), _nnue.STORE_ACTIVATIONS,
+                _nnue.PREFORMAT_TABLES, _nnue.OVERLAP_TABLE_GRADIENT)
+
+    def _call_local(self, images, labels, inv_count, marks=None):
+        if self._inline:  # the step issues the exchange itself, slice by slice, where the gradients become final
+            self._local(images, labels, inv_count, self.buf, marks, self._xchg)
+        elif marks is not None:
+            self._local(images, labels, inv_count, self.buf, marks)
+        else:
+            self._local(images, labels, inv_count, self.buf)
 
     def _run_local(self, images, labels, inv_count):
         ok = (self.cuda_graphs and images.is_cuda and labels.is_cuda and images.is_contiguous() and labels.is_contiguous()
               and images.dtype == torch.float32)
         if not ok:
-            self._local(images, labels, inv_count, self.buf)
+            self._call_local(images, labels, inv_count)
             return
         key = self._graph_key(images, labels, inv_count)
         ent = self._graphs.get(key)
         if ent is None:
             if len(self._graphs) >= self.max_graphs:  # drop the least recently used entry
                 self._graphs.pop(next(iter(self._graphs)))
-            self._graphs[key] = [1, None, (images, labels)]
-            self._local(images, labels, inv_count, self.buf)
+            self._graphs[key] = [1, None, 0]
+            self._call_local(images, labels, inv_count)
             return
         self._graphs[key] = self._graphs.pop(key)  # most recently used last
         ent[0] += 1
@@ -258,32 +342,44 @@ class DataParallelStep:
             n0 = int(_lib.lib().nnue_launch_count(0))
             try:
                 with torch.cuda.graph(g, pool=self._pool):
-                    self._local(images, labels, inv_count, self.buf)
+                    self._call_local(images, labels, inv_count)
             except Exception as e:  # a capture that cannot be taken must not cost the step: stay eager for good
                 import sys
                 print(f"nnue_vision_b200: CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
                 self.cuda_graphs = False
                 self._graphs.clear()
                 torch.cuda.synchronize(images.device)
-                self._local(images, labels, inv_count, self.buf)
+                self._call_local(images, labels, inv_count)
                 return
             ent[1] = g
-            ent.append(int(_lib.lib().nnue_launch_count(0)) - n0)  # kernels in the graph
+            ent[2] = int(_lib.lib().nnue_launch_count(0)) - n0  # kernels in the graph
             self._count_add = _lib.lib().nnue_launch_count_add
             g.replay()  # (the capture pass launched nothing but was counted: it stands for this replay)
             return
         ent[1].replay()
-        self._count_add(ent[3])  # keep nnue_launch_count() meaning "kernels launched", replayed or not
+        self._count_add(ent[2])  # keep nnue_launch_count() meaning "kernels launched", replayed or not
+
+    def run_local_flat(self, images, labels, inv_count):
+        """This rank's step (graph replay when possible, no exchange); returns the flat buffer: every gradient in
+        parameter order, then the loss.  Used by the module-level loss, which copies what it needs."""
+        labels = labels.to(device=images.device, dtype=torch.long).contiguous()
+        with torch.cuda.device(self.device):
+            self._run_local(images, labels, inv_count)
+        return self.buf.flat
 
     def step(self, images, labels, global_batch: Optional[int] = None, marks=None):
         if global_batch is None:
             global_batch = images.shape[0] * self.world  # equal shards
-        if marks is not None:
-            self._local(images, labels, 1.0 / float(global_batch), self.buf, marks)
-        else:
-            self._run_local(images, labels, 1.0 / float(global_batch))
-        if self.world > 1:
-            self._exchange()
+        import contextlib
+        guard = torch.cuda.device(self.device) if self.device.type == "cuda" else contextlib.nullcontext()
+        with guard:  # (the C side launches on the current device: a model on cuda:1 must work while cuda:0 is current)
+            if marks is not None:
+                self._call_local(images, labels, 1.0 / float(global_batch), marks)
+            else:
+                self._run_local(images, labels, 1.0 / float(global_batch))
+            if self.world > 1 and not self._inline:
+                self._exchange()
         # optimizer.zero_grad() sets .grad to None by default: make the views the gradients again (ten assignments)
-        self.buf.attach()
+        if self._attach:
+            self.buf.attach()
         return self.buf.loss.reshape(())

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_functions():
         assert hasattr(handle, name), f"{name} declared in nnue_b200.h but not exported"
     assert set(_lib.SIGNATURES) == set(declared_functions()), "python binding table out of sync with the header"
-    assert _lib.lib().nnue_b200_abi_version() == 2
+    assert _lib.lib().nnue_b200_abi_version() == 3
     assert _lib.lib().nnue_error_string(-5) == b"malformed .nnue file"
 
 
@@ -49,6 +49,28 @@ def test_shape_derivation_matches_reference_rules():
         _lib.make_shape(0, 32, 32, 8, 10, 64, 32, 8, 10, 3)
     with pytest.raises(_lib.NnueError):
         _lib.make_shape(4, 32, 32, 8, 10, 63, 32, 8, 10, 3)  # odd L1: torch.split would give 3 chunks
+
+
+def test_truncated_nnue_with_huge_header_sizes_is_refused_without_allocating():
+    """A header that promises gigabytes of payload the file does not hold answers NNUE_ERR_FORMAT (load_model -> false,
+    nnue_engine.cpp:544-657) before anything is allocated for it, and nothing unwinds through the C boundary."""
+    import struct
+    from nnue_vision_b200 import _lib
+    good = (ROOT / "tests" / "golden" / "parity_small.nnue").read_bytes()
+    F, L1, L2, L3 = struct.unpack_from("<4I", good, 8)
+    cases = []
+    huge_table = bytearray(good)                      # F x L1 = 2^31 int16 elements, file ends long before
+    struct.pack_into("<2I", huge_table, 8, 1 << 20, 1 << 11)
+    cases.append(bytes(huge_table))
+    huge_l2 = bytearray(good)                         # an absurd L2
+    struct.pack_into("<I", huge_l2, 16, 0xFFFFFFF0)
+    cases.append(bytes(huge_l2))
+    cases.append(good[: len(good) // 2])              # plain truncation
+    for blob in cases:
+        h = ctypes.c_void_p()
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        rc = _lib.lib().nnue_q_load_memory(ctypes.cast(buf, ctypes.c_void_p), len(blob), ctypes.byref(h))
+        assert rc in (-5, -2) and not h.value, rc
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -140,3 +140,35 @@ def test_step_reattaches_gradients_after_zero_grad():
         assert named[n].grad is not None and named[n].grad.data_ptr() == v.data_ptr()
     opt.step()
     assert not torch.equal(named["input.weight"], before)
+
+
+def _slice_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nnue_vision_b200 import train
+        model = _model()
+        buf = train.FlatGradBuffer(dict(model.named_parameters()), "cpu")
+        g = torch.Generator().manual_seed(100 + rank)
+        vals = torch.randn(buf.numel(), generator=g)
+        whole = vals.clone()
+        dist.all_reduce(whole)
+        buf.flat.copy_(vals)
+        x = train.CollectiveExchange(buf, None)
+        x.early()   # [split, end): feature transformer, head, loss -- final before the conv gradient
+        x.late()    # [0, split): thresholds and conv weights
+        np.savez(os.path.join(out_dir, f"slices{rank}.npz"), got=buf.flat.numpy(), whole=whole.numpy(), split=buf.split)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slice_exchange_equals_whole_buffer_exchange(tmp_path):
+    """The step exchanges the flat buffer as two slices (early / late, train.OneShotExchange / CollectiveExchange); on
+    two gloo ranks the slices together give exactly the whole-buffer all-reduce, and the split falls on a float4
+    boundary behind the conv / threshold gradients."""
+    world = 2
+    mp.spawn(_slice_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(tmp_path / f"slices{k}.npz") for k in range(world)]
+    assert np.array_equal(r[0]["got"], r[0]["whole"]) and np.array_equal(r[1]["got"], r[0]["got"])
+    split = int(r[0]["split"])
+    assert split % 4 == 0 and CFG["C"] * 28 <= split < CFG["C"] * 28 + 4

@@ -86,6 +86,10 @@ CFGS = {
     # wide stacks at a batch where layer 1 runs as the split-bf16 tcgen05 GEMM (gemm_umma.cu)
     "D1k_tensor_head": (dict(grid=10, C=8, L1=1024, L2=128, L3=32, NC=10, model_input=32), 32, 300),
     "wide_head_ragged": (dict(grid=6, C=16, L1=256, L2=48, L3=16, NC=10, model_input=64), 64, 257),
+    # the table gradient (side stream) and the conv gradient's partials (main stream) share one workspace: shapes where
+    # the partials are larger than the value gradient's operands (L1 = 32 / small grids, B >= 148)
+    "L1_32_overlap": (dict(grid=8, C=8, L1=32, L2=8, L3=8, NC=10, model_input=32), 32, 300),
+    "umma_small_grid_overlap": (dict(grid=5, C=32, L1=64, L2=8, L3=8, NC=10, model_input=32), 32, 200),
     # SURVEY config I: the largest grid the integer engine supports (F = 65536 rows x 1024 columns = 268 MB, beyond L2)
     "I_large": (dict(grid=32, C=64, L1=1024, L2=128, L3=32, NC=1000, model_input=224), 224, 6),
 }
@@ -345,6 +349,55 @@ def test_large_batch_properties():
         step_grads = cur if step_grads is None else {k: step_grads[k] + cur[k] for k in cur}
     for k in g1:
         assert_close(g1[k], step_grads[k], "shard additivity " + k, rtol=2e-5)
+
+
+def test_benchmark_batch_against_the_fp64_oracle():
+    """Config D at the BENCHMARK batch (16384): loss and every gradient of the fused step (the 296-CTA split-K weight
+    gradient, the chunked folds) against the vectorised fp64 oracle -- not only against themselves."""
+    cfg, isize, _ = CFGS["D"]
+    torch.manual_seed(1)
+    model = build_model(cfg)
+    g = torch.Generator().manual_seed(9)
+    B = 16384
+    images = torch.randn(B, 3, isize, isize, generator=g)
+    labels = torch.randint(0, cfg["NC"], (B,), generator=g)
+    ref = oracle_step(model, images, labels, dtype=torch.float64)
+    amb = ambiguous_samples(ref["conv_out"].numpy(), model.visual_threshold.detach().cpu().numpy(), eps=2e-6)
+    if amb.any():  # (a handful of the 15.9 M activations lie within rounding of their threshold: drop those samples)
+        keep = torch.as_tensor(~amb)
+        images, labels = images[keep].contiguous(), labels[keep].contiguous()
+        ref = oracle_step(model, images, labels, dtype=torch.float64)
+    assert images.shape[0] > 16000
+    model.zero_grad()
+    loss = model.loss(images.cuda(), labels.cuda())
+    loss.backward()
+    assert_close(loss, ref["loss"], "loss")
+    for k, gr in ref["grads"].items():
+        assert_close(dict(model.named_parameters())[k].grad, gr, "grad " + k)
+
+
+def test_wide_stack_split_k_batch_against_the_fp64_oracle():
+    """The reference's "real" config (L1 = 1024, 128/32 stack) at a batch that engages the split-K weight gradient of
+    gemm_umma.cu and several K chunks of the table gradient."""
+    cfg, isize, _ = CFGS["D1k"]
+    torch.manual_seed(2)
+    model = build_model(cfg)
+    g = torch.Generator().manual_seed(10)
+    B = 4096
+    images = torch.randn(B, 3, isize, isize, generator=g)
+    labels = torch.randint(0, cfg["NC"], (B,), generator=g)
+    ref = oracle_step(model, images, labels, dtype=torch.float64)
+    amb = ambiguous_samples(ref["conv_out"].numpy(), model.visual_threshold.detach().cpu().numpy(), eps=2e-6)
+    if amb.any():
+        keep = torch.as_tensor(~amb)
+        images, labels = images[keep].contiguous(), labels[keep].contiguous()
+        ref = oracle_step(model, images, labels, dtype=torch.float64)
+    model.zero_grad()
+    loss = model.loss(images.cuda(), labels.cuda())
+    loss.backward()
+    assert_close(loss, ref["loss"], "loss")
+    for k, gr in ref["grads"].items():
+        assert_close(dict(model.named_parameters())[k].grad, gr, "grad " + k)
 
 
 def test_preformatted_table_tiles_give_identical_results():

@@ -45,6 +45,50 @@ def test_graph_replay_matches_eager_and_tracks_parameter_updates():
     assert len(dp_g._graphs) == 3
 
 
+def test_module_level_loss_replays_a_graph_and_owns_its_gradients():
+    """model.loss (train.compute_loss): the second sighting of the same buffers is captured, later ones replayed; the
+    result equals the eager launch sequence bit for bit, the upstream factor is applied, and a node's gradients
+    survive another step of the same model before its backward() runs."""
+    from nnue_vision_b200 import nnue as nn_mod
+    torch.manual_seed(3)
+    model_g = build_model(CFG)
+    model_e = copy.deepcopy(model_g)
+    g = torch.Generator().manual_seed(5)
+    xa, ya = torch.randn(300, 3, 32, 32, generator=g).cuda(), torch.randint(0, 10, (300,), generator=g).cuda()
+    xb, yb = torch.randn(300, 3, 32, 32, generator=g).cuda(), torch.randint(0, 10, (300,), generator=g).cuda()
+
+    def grads(model, x, y, scale, graphs):
+        old = nn_mod.CUDA_GRAPHS
+        nn_mod.CUDA_GRAPHS = graphs
+        try:
+            model.zero_grad(set_to_none=True)
+            loss = model.loss(x, y)
+            (loss * scale).backward()
+        finally:
+            nn_mod.CUDA_GRAPHS = old
+        return loss.detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+
+    for it in range(4):
+        lg, gg = grads(model_g, xa, ya, 1.0 + it, True)
+        le, ge = grads(model_e, xa, ya, 1.0 + it, False)
+        assert torch.equal(lg, le)
+        for k in ge:
+            assert torch.equal(gg[k], ge[k]), (it, k)
+    runner = nn_mod._GRAPH_RUNNERS[model_g]
+    assert any(e[1] is not None for e in runner._graphs.values()), "no graph was captured"
+    assert all(p.grad is None or p.grad.data_ptr() != runner.buf.flat.data_ptr() for p in model_g.parameters())
+    # two forwards before any backward: each node keeps its own gradients
+    model_g.zero_grad(set_to_none=True)
+    la = model_g.loss(xa, ya)
+    lb = model_g.loss(xb, yb)
+    la.backward()
+    ga = {k: p.grad.clone() for k, p in model_g.named_parameters() if p.grad is not None}
+    _, ea = grads(model_e, xa, ya, 1.0, False)
+    for k in ea:
+        assert torch.equal(ga[k], ea[k]), k
+    assert copy.deepcopy(model_g) is not None  # the runner lives outside the module
+
+
 def test_graph_cache_is_bounded():
     from nnue_vision_b200 import train
     torch.manual_seed(4)

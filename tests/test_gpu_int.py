@@ -80,16 +80,18 @@ def test_threshold_edges(oracle_built, tmp_path, thr):
 
 
 def test_batch_sweep_is_batch_invariant_and_exact(oracle_built):
-    """BASELINE config: batch sweep 1..65536 on the default model.  The oracle checks the first
-    2048 samples; beyond that, per-sample results must not depend on the batch they ran in."""
+    """BASELINE config: batch sweep 1..65536 on the default model.  EVERY one of the 65536 samples is checked against
+    the compiled reference engine (oracle/_ref; the C restatement when it is absent), and per-sample results must not
+    depend on the batch they ran in."""
     path = GOLDEN / "default_cfg.nnue"
     rng = np.random.default_rng(11)
     full = rng.standard_normal((65536, 32, 32, 3)).astype(np.float32)
     ev = _engine().NNUEEvaluator(path)
     big_l, big_d = gpu_eval(ev, full)
-    ol, od = oracle_built.IntOracle(path).eval_batch(full[:2048], threads=8)
-    np.testing.assert_array_equal(big_l[:2048], ol)
-    np.testing.assert_array_equal(big_d[:2048], od)
+    cpu = oracle_built.RefEngine(path) if oracle_built.RefEngine.available() else oracle_built.IntOracle(path)
+    ol, od = cpu.eval_batch(full, threads=oracle_built.host_threads())
+    np.testing.assert_array_equal(big_l, ol)
+    np.testing.assert_array_equal(big_d, od)
     for B in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 4096, 16384):
         l, d = gpu_eval(ev, full[:B])
         np.testing.assert_array_equal(l, big_l[:B])
