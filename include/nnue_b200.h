@@ -424,6 +424,9 @@ int nnue_q_acc_score(const nnue_qmodel *m, int S, const int16_t *acc_d, int buck
  * into every rank's receive area (posted NVLink stores), publishes the epoch, waits for the peers' and sums its own area.
  */
 int nnue_allreduce_max_world(void);
+/* slices of at most this many floats travel in the flagged 8-byte form (value + epoch in one store, no fence, no flag
+ * round): lower latency at twice the bytes; larger ones (n % 4 == 0, 16-byte aligned) in the fenced bulk form */
+size_t nnue_allreduce_ll_max_floats(void);
 size_t nnue_allreduce_recv_floats(int world, size_t n);
 int nnue_allreduce_oneshot(int world, int rank, void *const *peer_recv_h, void *const *peer_flags_h,
                            void *state_d, size_t n, float *buf_d, void *stream);

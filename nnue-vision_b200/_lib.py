@@ -36,6 +36,7 @@ SIGNATURES = {
     "nnue_launch_count_add": (ctypes.c_ulonglong, [ctypes.c_ulonglong]),
     "nnue_allreduce_max_world": (ctypes.c_int, []),
     "nnue_allreduce_recv_floats": (sz, [ctypes.c_int, sz]),
+    "nnue_allreduce_ll_max_floats": (sz, []),
     "nnue_allreduce_oneshot": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
     "nnue_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),

@@ -83,6 +83,66 @@ allreduce_push_kernel(const ArPeers p, int rank, int world, size_t n4, float4 *_
     }
 }
 
+// ---- small slices: data and flag travel in ONE 8-byte store (the "LL" idea of NCCL's low-latency protocol) ----------
+// Every element is pushed as {value bits, epoch} with one 8-byte system-scope store per peer (8-byte stores are single
+// transactions on NVLink), into slot [epoch parity][source rank][element] of the receiver.  The receiver spins on the
+// element itself until its epoch word matches and sums in rank order.  No fence, no flag round, no inter-CTA dependency:
+// the latency is one kernel start plus one one-way NVLink store (measured: profiles/r2_exchange_latency.json), at twice
+// the bytes -- the right trade below a few hundred KB.  Parity double-buffering as above: a rank reaches epoch e + 2 only
+// after it has received every peer's e + 1, which a peer sends only after it has consumed epoch e.
+__device__ __forceinline__ void st_sys_u2(uint2 *p, uint2 v) {
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ uint2 ld_sys_u2(const uint2 *p) {
+    uint2 v;
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+constexpr int kLlPerThread = 4;  // elements per thread: all pushed before the first poll
+__global__ void __launch_bounds__(256)
+allreduce_ll_kernel(const ArPeers p, int rank, int world, size_t n, float *__restrict__ buf, unsigned *__restrict__ state) {
+    const unsigned epoch = *reinterpret_cast<volatile unsigned *>(state + 1) + 1u;
+    const size_t slot0 = (size_t)(epoch & 1u) * world * n;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * kLlPerThread) {
+        float mine[kLlPerThread];
+#pragma unroll
+        for (int k = 0; k < kLlPerThread; ++k) {
+            const size_t i = i0 + k * stride;
+            if (i < n) {
+                mine[k] = buf[i];
+                const uint2 pk = make_uint2(__float_as_uint(mine[k]), epoch);
+                for (int r = 0; r < world; ++r)
+                    if (r != rank) st_sys_u2(reinterpret_cast<uint2 *>(p.recv[r]) + slot0 + (size_t)rank * n + i, pk);
+            }
+        }
+        const uint2 *in = reinterpret_cast<const uint2 *>(p.recv[rank]) + slot0;
+#pragma unroll
+        for (int k = 0; k < kLlPerThread; ++k) {
+            const size_t i = i0 + k * stride;
+            if (i < n) {
+                float acc = 0.0f;
+                for (int r = 0; r < world; ++r) {  // rank order: bit-identical on every rank
+                    float v = mine[k];
+                    if (r != rank) {
+                        uint2 got;
+                        do { got = ld_sys_u2(in + (size_t)r * n + i); } while (got.y != epoch);
+                        v = __uint_as_float(got.x);
+                    }
+                    acc = r == 0 ? v : acc + v;
+                }
+                buf[i] = acc;
+            }
+        }
+    }
+    // the last CTA to finish advances the device-side epoch (every CTA read it at the top)
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(state, 1u) == gridDim.x - 1) {
+        state[0] = 0u;
+        state[1] = epoch;
+    }
+}
+
 }  // namespace nnue
 
 using namespace nnue;
@@ -91,18 +151,32 @@ extern "C" {
 
 int nnue_allreduce_max_world(void) { return kArMaxWorld; }
 
-size_t nnue_allreduce_recv_floats(int world, size_t n) { return 2 * (size_t)world * ((n + 3) / 4 * 4); }
+// receive area: two parities x world slots of n elements; small slices (the flagged 8-byte form) need 8 bytes per element
+size_t nnue_allreduce_ll_max_floats(void) { return 65536; }
+size_t nnue_allreduce_recv_floats(int world, size_t n) {
+    const size_t per = (n + 3) / 4 * 4;
+    return 2 * (size_t)world * per * (n <= nnue_allreduce_ll_max_floats() ? 2 : 1);
+}
 
 int nnue_allreduce_oneshot(int world, int rank, void *const *peer_recv_h, void *const *peer_flags_h, void *state_d,
                            size_t n, float *buf_d, void *stream) {
     if (world < 1 || world > kArMaxWorld || rank < 0 || rank >= world || !peer_recv_h || !peer_flags_h || !state_d ||
-        !buf_d || n < 1 || (n & 3) || (reinterpret_cast<uintptr_t>(buf_d) & 15))
+        !buf_d || n < 1)
         return NNUE_ERR_INVALID_ARG;
+    const bool ll = n <= nnue_allreduce_ll_max_floats();
+    if (!ll && ((n & 3) || (reinterpret_cast<uintptr_t>(buf_d) & 15))) return NNUE_ERR_INVALID_ARG;
     ArPeers p{};
     for (int r = 0; r < world; ++r) {
         p.recv[r] = static_cast<float *>(peer_recv_h[r]);
         p.flags[r] = static_cast<int *>(peer_flags_h[r]);
         if (!p.recv[r] || !p.flags[r]) return NNUE_ERR_INVALID_ARG;
+    }
+    if (ll) {
+        const size_t want = (n + 256 * kLlPerThread - 1) / (256 * kLlPerThread);
+        const int grid = (int)(want < 1 ? 1 : want > 64 ? 64 : want);
+        allreduce_ll_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, rank, world, n, buf_d, static_cast<unsigned *>(state_d));
+        NNUE_CHECK_LAUNCH("allreduce_ll_kernel");
+        return NNUE_OK;
     }
     // every CTA spins on the flags: few, small CTAs, so that they fit beside a kernel of the step that is still running
     const size_t n4 = n / 4, want = (n4 + 255) / 256;

@@ -8,6 +8,7 @@ local gradients straight into ONE flat fp32 buffer, and a single NCCL all-reduce
 NVLink makes it the global mean gradient.  `clip_grad_norm_`
 (train.py:363-364) must run after `step()` on the reduced buffer.
 """
+import os
 from typing import Callable, Optional
 
 import torch
@@ -151,6 +152,7 @@ class OneShotExchange:
         from . import _lib
         L = _lib.lib()
         self._lib, self.world, self.buf = _lib, world, buf
+        self.overlap = os.environ.get("NNUE_EXCHANGE_OVERLAP", "1") != "0"
         group = group if group is not None else dist.group.WORLD
         self.parts = []
         for lo, hi in ((buf.split, buf.numel()), (0, buf.split)):
@@ -182,14 +184,17 @@ class OneShotExchange:
             _lib.dptr(self.buf.flat[part["lo"]:part["lo"] + part["n"]]), stream))
 
     def early(self, stream=None):
-        self._launch(self.parts[0], stream if stream is not None else self._lib.stream_ptr())
+        if self.overlap:
+            self._launch(self.parts[0], stream if stream is not None else self._lib.stream_ptr())
 
     def late(self, stream=None):
+        if not self.overlap:  # both slices at the end, on the caller's stream
+            self._launch(self.parts[0], stream if stream is not None else self._lib.stream_ptr())
         self._launch(self.parts[1], stream if stream is not None else self._lib.stream_ptr())
 
     def full(self, stream=None):
-        self.early(stream)
-        self.late(stream)
+        self._launch(self.parts[0], stream if stream is not None else self._lib.stream_ptr())
+        self._launch(self.parts[1], stream if stream is not None else self._lib.stream_ptr())
 
 
 class CollectiveExchange:

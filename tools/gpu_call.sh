@@ -1,6 +1,6 @@
-set -x
 cd $GRAFT_REPO_ROOT
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/c9_tests.log 2>&1; echo "tests rc=$?"; tail -5 gpurun_out/c9_tests.log
-timeout 400 python bench.py --steps 20 --warmup 5 > gpurun_out/c9_bench_d.json 2> gpurun_out/c9_bench_d.err; echo "bench rc=$?"; python -c "import json;d=json.load(open('gpurun_out/c9_bench_d.json'));print(d['value'],d['ms_per_step'],d['stages_ms'],d['module_api'],d['e2e']['value'],d['cpu_baseline'])"; tail -3 gpurun_out/c9_bench_d.err
-timeout 400 python bench.py --workload imagenet_large_b4096 --steps 5 --warmup 3 --windows 3 --no-cpu-baseline > gpurun_out/c9_bench_large.json 2> gpurun_out/c9_bench_large.err; echo "bench rc=$?"; python -c "import json;d=json.load(open('gpurun_out/c9_bench_large.json'));print(d['value'],d['ms_per_step'],d['stages_ms'],d['module_api'])"; tail -3 gpurun_out/c9_bench_large.err
-timeout 400 python bench.py --workload imagenet_small_b16384 --steps 5 --warmup 3 --windows 3 --no-cpu-baseline > gpurun_out/c9_bench_small.json 2> gpurun_out/c9_bench_small.err; echo "bench rc=$?"; python -c "import json;d=json.load(open('gpurun_out/c9_bench_small.json'));print(d['value'],d['ms_per_step'],d['stages_ms'],d['module_api'])"; tail -3 gpurun_out/c9_bench_small.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29711 tools/exchange_time.py 2>gpurun_out/c13.err | tail -1 | tee gpurun_out/c13_exchange_n2.json; tail -3 gpurun_out/c13.err
+timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -3
+run2() { timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $1 bench.py --gpus 2 "${@:3}" 2> gpurun_out/$2.err | tail -1 > gpurun_out/$2.json; echo "bench rc=$?"; python -c "import json;d=json.load(open('gpurun_out/$2.json'));print(d['value'],d['ms_per_step'],d['config']['exchange'],d.get('exchange_check'),d['e2e']['value'],d['windows_ms'])"; tail -3 gpurun_out/$2.err; }
+run2 29701 c13_d_n2 --steps 50 --warmup 5 --no-cpu-baseline
+NNUE_EXCHANGE_OVERLAP=0 run2 29702 c13_d_n2_nooverlap --steps 50 --warmup 5 --no-cpu-baseline
