@@ -67,6 +67,7 @@ def parse_args():
     ap.add_argument("--exchange", default="auto", choices=["auto", "oneshot", "nccl"],
                     help="gradient exchange at N > 1: the library's one-shot all-reduce over NVLink peer memory (auto) or NCCL")
     ap.add_argument("--no-int", action="store_true", help="skip the integer-inference side measurement")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (extra scaling lines only)")
     ap.add_argument("--no-module-api", action="store_true", help="skip the compute_loss(model, batch); loss.backward() leg")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="library tuning knob (nnue_set_option), e.g. --opt input_bwd_variant=1")
@@ -398,7 +399,84 @@ def int_inference_leg(w, device, seconds):
         t0 = time.perf_counter()
         cpu.eval_batch(sample[:512], threads=1)
         out["cpu_single_thread"] = {"value": 512 / (time.perf_counter() - t0), "unit": "samples/s", "cores": 1}
+        try:
+            out["incremental"] = incremental_leg(ev, cpu if kind == "reference" else None, device)
+        except Exception as e:
+            out["incremental"] = {"error": repr(e)}
     return out
+
+
+def incremental_leg(ev, ref_engine, device, changed=8):
+    """N3: the engine's incremental accumulator interface (evaluate_incremental: update_features + clipped ReLU + the
+    single-score stack, nnue_engine.cpp:739-821) over S independent streams with device-resident CSR feature lists;
+    every evaluation adds and removes `changed` features per stream.  Next to it the reference engine's own
+    evaluate_incremental on one host thread (benchmark_engine.cpp:68-124 measures the same call)."""
+    import numpy as np
+    res = {"changed_features_per_eval": changed}
+    rng = np.random.default_rng(5)
+    F = ev.num_features
+    for S in (1, 4096):
+        base = [np.sort(rng.choice(F, size=F // 4, replace=False)).astype(np.int32) for _ in range(min(S, 64))]
+        lists = [base[i % len(base)] for i in range(S)]
+        off = np.zeros(S + 1, np.int32)
+        np.cumsum([len(l) for l in lists], out=off[1:])
+        d_off, d_idx = torch.from_numpy(off).to(device), torch.from_numpy(np.concatenate(lists)).to(device)
+        ev.refresh_accumulator_csr(d_off, d_idx)
+        # two alternating update sets: +A -B, then +B -A (the accumulators return to their start every second eval)
+        a = torch.from_numpy(rng.integers(0, F, size=(S, changed)).astype(np.int32)).to(device).reshape(-1)
+        b = torch.from_numpy(rng.integers(0, F, size=(S, changed)).astype(np.int32)).to(device).reshape(-1)
+        uoff = torch.arange(0, (S + 1) * changed, changed, dtype=torch.int32, device=device)
+        score = torch.empty(S, dtype=torch.float32, device=device)
+        def one(i):
+            if i % 2 == 0:
+                ev.update_features_csr(uoff, a, uoff, b)
+            else:
+                ev.update_features_csr(uoff, b, uoff, a)
+            ev.score_accumulators(out=score)
+        for i in range(10):
+            one(i)
+        torch.cuda.synchronize()
+        reps = 200
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(reps):
+            one(i)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        # the same 200 evaluations replayed as one CUDA graph (no host launch cost)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(reps):
+                one(i)
+        g.replay()
+        torch.cuda.synchronize()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        g.replay()
+        e3.record()
+        torch.cuda.synchronize()
+        res[f"streams_{S}"] = {"evals_per_s": S * reps / wall, "us_per_eval_call": 1e6 * wall / reps,
+                               "device_us_per_eval_call": 1e3 * e0.elapsed_time(e1) / reps,
+                               "graph_replay_evals_per_s": S * reps / (e2.elapsed_time(e3) * 1e-3),
+                               "graph_replay_us_per_eval_call": 1e3 * e2.elapsed_time(e3) / reps}
+    if ref_engine is not None:  # the reference engine, one host thread: alternate two feature lists differing in `changed` features
+        base = np.sort(rng.choice(F, size=F // 4, replace=False)).astype(np.int32)
+        other = base.copy()
+        other[:changed] = (other[:changed] + 1) % F
+        ref_engine.mark_dirty()
+        ref_engine.eval_incremental(base)
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < 1.0:
+            for _ in range(500):
+                ref_engine.eval_incremental(other)
+                ref_engine.eval_incremental(base)
+            n += 1000
+        dt = time.perf_counter() - t0
+        res["cpu_reference_one_thread"] = {"evals_per_s": n / dt, "us_per_eval": 1e6 * dt / n, "kind": "reference",
+                                           "note": "oracle/_ref evaluate_incremental through ctypes (the ~1 us ctypes call is included)"}
+    return res
 
 
 def touched_image_bytes(w, shape, B):
@@ -532,6 +610,16 @@ def run_b200(args):
     value = args.steps * global_batch / (ms_total * 1e-3)
     final_loss = float(loss)
 
+    e2e = None
+    if not args.no_e2e:
+        e2e = e2e_leg(args, w, B, world, rank, device, dp, sets, global_batch, img_bytes)
+    clocks.end()
+    clocks.__exit__()
+    return finish_line(args, w, B, world, rank, device, dp, model, sets, global_batch, img_bytes, n_sets, value, ms_total, windows,
+                       launches, final_loss, xcheck, clocks, e2e)
+
+
+def e2e_leg(args, w, B, world, rank, device, dp, sets, global_batch, img_bytes):
     # ---- e2e: the user-facing call with HOST buffers; H2D of the step's inputs and D2H of the loss timed
     n_host = 2 if img_bytes < (1 << 30) else 1
     host_sets = [synthetic_batch(w, B, seed=2000 * rank + i, pin=True) for i in range(n_host)]
@@ -572,10 +660,15 @@ def run_b200(args):
     barrier(world)
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, device)
     e2e_value = e2e_n * global_batch / (e2e_ms * 1e-3)
-    clocks.end()
-    clocks.__exit__()
     h2d = int(host_sets[0][0].numel() * 4 + host_sets[0][1].numel() * 8) * world
-    del host_sets, dev_img, dev_lab
+    return {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * world,
+            "ms_per_step": e2e_ms / e2e_n, "steps": e2e_n,
+            "note": "DataParallelStep.step on pinned host batches, H2D double-buffered against compute, loss read back every step"}
+
+
+def finish_line(args, w, B, world, rank, device, dp, model, sets, global_batch, img_bytes, n_sets, value, ms_total, windows,
+                launches, final_loss, xcheck, clocks, e2e):
+    from nnue_vision_b200 import _lib
 
     # ---- the module API (compute_loss + backward, eager)
     module_api = None
@@ -598,14 +691,14 @@ def run_b200(args):
     mma = bool(L.nnue_ft_uses_mma(sp))
     # algorithmic bytes per launch
     algo = {
-        "extract_fwd": img_algo + B * shape.NW * 4 + (row_bytes if dense_in else 0),  # images -> bitmask (+ stored activations)
+        "extract_fwd": img_algo + B * shape.NW * 4 + row_bytes,  # images -> bitmask + stored activations
         "ft_fwd": nnz_total * L1 * 4 + B * L1 * 4 + nnz_total * 4,        # row reads + out + indices
         "ft_bwd_dw": nnz_total * L1 * 4 + F * L1 * 4,                      # g_ft row per active pair + dW
         "ft_bwd_gbin": nnz_total * L1 * 4 + B * L1 * 4 + row_bytes,       # table row per active pair + g_ft + g_bin
         "ft_bwd": 2 * nnz_total * L1 * 4 + F * L1 * 4 + B * L1 * 4 + row_bytes,
         "conv_bwd": img_algo + 2 * row_bytes,                             # images + g_bin + stored activations
-        # general input gradient: activations recomputed and stored, table rows, g_bin written and read, images twice
-        "input_bwd": nnz_total * L1 * 4 + B * L1 * 4 + 2 * img_algo + 4 * row_bytes,
+        # general input gradient: table rows, g_bin written and read back, stored activations read, touched image rows read
+        "input_bwd": nnz_total * L1 * 4 + B * L1 * 4 + img_algo + 3 * row_bytes,
         "head_train": 2 * B * L1 * 4,
     }
     # tensor-core work actually issued by the bf16-split contractions (2 * M * N * K * number of term products)
@@ -664,9 +757,7 @@ def run_b200(args):
                    "l2_policy": "inputs larger than L2: %d image set(s) x %.0f MB cycled" % (n_sets, img_bytes / 1e6),
                    "loss_after_timed_steps": final_loss},
         "clocks": clocks.summary(),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * world,
-                "ms_per_step": e2e_ms / e2e_n, "steps": e2e_n,
-                "note": "DataParallelStep.step on pinned host batches, H2D double-buffered against compute, loss read back every step"},
+        "e2e": e2e,
         "gpu_launches": launches,
         "stages_ms": stages,
     }

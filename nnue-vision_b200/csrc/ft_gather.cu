@@ -284,7 +284,7 @@ ft_gather_fold_kernel(int L1, int n_ranges, const float *__restrict__ partial, c
 int ft_gather_ranges(const nnue_shape &s, int cs) {
     const long long base = 1LL * s.B * (s.L1 / cs);
     if (base >= kNumSMs) return 1;
-    int r = (int)(3 * kNumSMs / base);    // three units per SM: the active rows are not spread evenly over the words
+    int r = (int)(1LL * get_option(kOptGatherUnits) * kNumSMs / base);  // (units per SM: 1 measured best at one sample -- 36 / 38 / 42 / 44 us for 1 / 2 / 3 / 4: the fold grows with the partials)
     const int max_r = ceil_div(s.NW, 2);  // at least 2 words (64 positions) per range
     if (r > max_r) r = max_r;
     return r < 1 ? 1 : r;

@@ -172,6 +172,34 @@ class NNUEEvaluator:
             check(_lib.lib().nnue_q_acc_score(self._h, S, dptr(self._acc), int(layer_stack_index), dptr(score), stream_ptr()))
         return float(score[0]) if single else score
 
+    # ---- the same three steps on DEVICE-RESIDENT CSR lists (int32 offsets [S + 1], int32 indices [nnz]): no Python list
+    #      handling, no host->device copy per call -- the form a video pipeline that extracts features on the GPU uses ----
+    def refresh_accumulator_csr(self, off: torch.Tensor, idx: torch.Tensor):
+        self._require(off)
+        S = off.numel() - 1
+        if self._acc is None or self._acc.shape[0] != S or self._acc.device != off.device:
+            self._acc = torch.empty((S, self.l1_size), dtype=torch.int16, device=off.device)
+        with torch.cuda.device(off.device):
+            check(_lib.lib().nnue_q_acc_apply(self._h, S, 1, dptr(off, torch.int32), dptr(idx, torch.int32), None, None,
+                                              dptr(self._acc), stream_ptr()))
+
+    def update_features_csr(self, add_off, add_idx, rem_off, rem_idx):
+        self._require(add_off)
+        if self._acc is None or self._acc.shape[0] != add_off.numel() - 1:
+            raise _lib.NnueError("update_features_csr before refresh_accumulator_csr (or a different stream count)")
+        with torch.cuda.device(self._acc.device):
+            check(_lib.lib().nnue_q_acc_apply(self._h, self._acc.shape[0], 0, dptr(add_off, torch.int32), dptr(add_idx, torch.int32),
+                                              dptr(rem_off, torch.int32), dptr(rem_idx, torch.int32), dptr(self._acc), stream_ptr()))
+
+    def score_accumulators(self, layer_stack_index: int = 0, out: torch.Tensor = None):
+        """clipped ReLU + the single-score layer stack over the current accumulators -> CUDA tensor [S]."""
+        self._require()
+        S = self._acc.shape[0]
+        score = out if out is not None else torch.empty((S,), dtype=torch.float32, device=self._acc.device)
+        with torch.cuda.device(self._acc.device):
+            check(_lib.lib().nnue_q_acc_score(self._h, S, dptr(self._acc), int(layer_stack_index), dptr(score), stream_ptr()))
+        return score
+
     def save_accumulator(self):
         if self._acc is not None:
             self._backup = self._acc.clone()

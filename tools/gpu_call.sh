@@ -1,6 +1,7 @@
 cd $GRAFT_REPO_ROOT
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29711 tools/exchange_time.py 2>gpurun_out/c13.err | tail -1 | tee gpurun_out/c13_exchange_n2.json; tail -3 gpurun_out/c13.err
-timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -3
-run2() { timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $1 bench.py --gpus 2 "${@:3}" 2> gpurun_out/$2.err | tail -1 > gpurun_out/$2.json; echo "bench rc=$?"; python -c "import json;d=json.load(open('gpurun_out/$2.json'));print(d['value'],d['ms_per_step'],d['config']['exchange'],d.get('exchange_check'),d['e2e']['value'],d['windows_ms'])"; tail -3 gpurun_out/$2.err; }
-run2 29701 c13_d_n2 --steps 50 --warmup 5 --no-cpu-baseline
-NNUE_EXCHANGE_OVERLAP=0 run2 29702 c13_d_n2_nooverlap --steps 50 --warmup 5 --no-cpu-baseline
+timeout 900 python -m pytest tests/test_gpu_float.py -m gpu -x -q 2>&1 | tail -2
+for U in 1 2 3 4; do timeout 300 python tools/ft_compare.py --workload imagenet_large_b4096 --batch 1 --only fwd --forms gather --reps 15 --opt ft_gather_units=$U 2>/dev/null | python -c "import json,sys;d=json.load(sys.stdin);print('units $U', d['calls']['fwd']['gather'])"; done
+b() { name=$1; shift; timeout 600 python bench.py "$@" 2> gpurun_out/$name.err | tail -1 > gpurun_out/$name.json; python -c "import json;d=json.load(open('gpurun_out/$name.json'));print('$name',d['value'],d['ms_per_step'],d['stages_ms'])" || tail -5 gpurun_out/$name.err; }
+b c16_large --workload imagenet_large_b4096 --steps 5 --warmup 3 --windows 5 --no-cpu-baseline --no-module-api --no-e2e
+b c16_small --workload imagenet_small_b16384 --steps 5 --warmup 3 --windows 5 --no-cpu-baseline --no-module-api --no-e2e
+b c16_d1k --workload real_cifar_l1_1024_b16384 --steps 20 --warmup 5 --no-cpu-baseline --no-module-api --no-e2e
