@@ -13,6 +13,7 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libnnue_b200.so"
+CLI = PKG / "nnue_inference_b200"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -25,7 +26,9 @@ def stale():
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*")) + [ROOT / "include" / "nnue_b200.h", Path(__file__)]
+    if not CLI.exists():
+        return True
+    deps = list(CSRC.glob("*")) + list((PKG / "cli").glob("*")) + [ROOT / "include" / "nnue_b200.h", Path(__file__)]
     return any(d.stat().st_mtime > t for d in deps)
 
 
@@ -38,6 +41,10 @@ def build(force=False, verbose=False):
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
+    # the command-line twin of the reference's nnue_inference (engine/nnue_inference.cpp), host C++ over the C ABI
+    cli = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-Wall", "-I", str(ROOT / "include"),
+           str(PKG / "cli" / "nnue_inference.cpp"), "-o", str(CLI), "-L", str(PKG), "-lnnue_b200", "-Wl,-rpath,$ORIGIN"]
+    subprocess.run(cli, check=True)
     return LIB
 
 

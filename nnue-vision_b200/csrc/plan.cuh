@@ -85,36 +85,43 @@ inline bool dense_shape_ok(const nnue_shape &s) { return s.L1 == 64 || s.L1 == 3
 constexpr int kUmmaNCols = 64;    // forward / weight gradient: table columns per CTA (x 3 terms = UMMA N 192)
 constexpr int kUmmaGbinN = 256;   // value gradient: padded positions per CTA (UMMA N)
 // ---- which formulation of the feature transformer serves a shape ----------------------------------------------------
-// dense : the three contractions as bitmask GEMMs on the tensor cores.  Work is independent of how many positions are
-//         active: 2 B PP L1 flops x (3 + 3 + 6) exact split-bf16 term products per step, plus re-formatting the table
-//         into operand tiles (two passes over it).  The table is re-read once per wave of M tiles, not once per sample.
-// gather: index-driven (nnue.py:686-710): every active (sample, position) pair moves one table row (forward,
-//         value gradient) or one g_ft row (weight gradient): 3 x nnz x L1 x 4 bytes per step, from HBM when the table
-//         is larger than L2 and from L2 otherwise.
-// The model compares the two with rates measured on B200 (profiles/r2_ft_compare_*.json): the tcgen05 kernels sustain
-// ~0.55 of the measured sustained bf16 peak over the three contractions, the gather kernels ~0.65 of the measured HBM
-// copy bandwidth on tables beyond L2 and ~1.2x that bandwidth on L2-resident ones.  With the density the reference
-// model has at initialisation (0.33 - 0.43) the dense form wins at every table size -- a row of L1 floats
+// dense : the three contractions as bitmask GEMMs on the tensor cores (ft_umma.cu).  Work is independent of how many
+//         positions are active: 2 B PP L1 flops x (3 + 3 + 6) exact split-bf16 term products per step, in M tiles of 128
+//         samples, plus re-formatting the table into operand tiles (two passes over it) and a K loop of NW stages whose
+//         latency shows at small batches.  The table is re-read once per wave of M tiles, not once per sample.
+// gather: index-driven (nnue.py:686-710; ft_gather.cu, ft.cu): every active (sample, position) pair moves one
+//         table row (forward, value gradient) or one g_ft row (weight gradient): 3 x nnz x L1 x 4 bytes per step.
+// Measured on B200 at SURVEY config I (F = 65536, L1 = 1024, 0.43 of the positions active; profiles/r2_ft_compare_*):
+//   batch 512: dense 0.62 / 0.46 / 0.68 ms (forward / weight gradient / value gradient), gather 9.5 / 2.7 / 11.8 ms;
+//   batch   1: dense 0.63 /  -   / 0.22 ms,                                              gather 0.036 / - / 0.044 ms;
+// the crossover lies near 16 samples.  The model below reproduces that with the measured rates: the tcgen05 kernels
+// sustain ~0.55 of the measured sustained bf16 peak over the three contractions, a K-loop stage costs ~0.22 us, the
+// formatting passes run at ~0.8 of the HBM copy bandwidth, and the gather kernels move ~0.65 of it.  A row of L1 floats
 // gathered per ACTIVE position costs more than 12 flops per position and column on a 1.4 PFLOP/s pipe as soon as more
-// than ~2 % of the positions are active.  `ft_density_permille` (default 400) tells the model what to expect;
-// `ft_form` forces a formulation (1 dense, 2 gather).
-constexpr double kTensorPeakFlops = 1384.6e12, kHbmPeakBytes = 6464.9e9, kL2Bytes = 126.0e6;
+// than ~2 % of the positions are active, so at the density of the reference model (0.33 - 0.43) the dense
+// form wins for every batch that fills a few M tiles; the gather form serves single-digit batches of large tables and
+// models whose thresholds have trained the density down.  `ft_density_permille` (default 400) tells the model what to
+// expect; `ft_form` forces a formulation (1 dense, 2 gather).  Tables small enough to sit in shared memory / L1 (the
+// CIFAR configs) always take the dense form: there the choice was measured per kernel in round 1.
+constexpr double kTensorPeakFlops = 1384.6e12, kHbmPeakBytes = 6464.9e9;
 struct FtCost {
     double dense_s, gather_s;
 };
 inline FtCost ft_cost(const nnue_shape &s) {
     FtCost c{};
-    const double B = s.B, L1 = s.L1, table = (double)s.F * s.L1 * 4.0;
+    const double B128 = ceil_div(s.B, 128) * 128.0, L1 = s.L1, table = (double)s.F * s.L1 * 4.0;
     const double density = get_option(kOptFtDensity) / 1000.0;
-    c.dense_s = 12.0 * 2.0 * B * (double)s.PP * L1 / (0.55 * kTensorPeakFlops) + 2.0 * (table + 1.5 * table) / (0.8 * kHbmPeakBytes);
-    const double bw = table > 0.75 * kL2Bytes ? 0.65 * kHbmPeakBytes : 1.2 * kHbmPeakBytes;
-    c.gather_s = 3.0 * density * B * (double)s.P * L1 * 4.0 / bw;
+    c.dense_s = 12.0 * 2.0 * B128 * (double)s.PP * L1 / (0.55 * kTensorPeakFlops)   // tensor work, whole M tiles
+                + 2.0 * (table + 1.5 * table) / (0.8 * kHbmPeakBytes)                // two formatting passes: read fp32, write 3 x bf16
+                + 0.22e-6 * s.NW;                                                    // forward K loop: one stage per bitmask word
+    c.gather_s = 3.0 * density * (double)s.B * (double)s.P * L1 * 4.0 / (0.65 * kHbmPeakBytes);
     return c;
 }
 inline bool ft_prefers_dense(const nnue_shape &s) {
     const int form = get_option(kOptFtForm);
     if (form == 1) return true;
     if (form == 2) return false;
+    if ((double)s.F * s.L1 * 4.0 <= 1048576.0) return true;  // small tables: on-chip either way, dense measured faster
     const FtCost c = ft_cost(s);
     return c.dense_s <= c.gather_s;
 }

@@ -240,6 +240,52 @@ def test_backward_kernel_variants_agree(name, options):
         assert_close(dict(model.named_parameters())[k].grad, g, "grad " + k)
 
 
+@pytest.mark.parametrize("form", [1, 2], ids=["dense_tcgen05", "gather_tma"])
+@pytest.mark.parametrize("name", ["I_small", "I_large", "D1k"])
+def test_large_table_formulations_against_oracle(name, form):
+    """Both formulations of the feature transformer (plan.cuh cost model: dense bit-GEMMs on the tensor cores, or the
+    TMA-staged row gather / segment reduction) forced on the large-table shapes, loss and every gradient against the
+    fp64 oracle -- whichever the model would pick at this batch, the other one is covered too."""
+    lib = _lib()
+    cfg, model, images, labels = _make(name)
+    ref = oracle_step(model, images, labels, dtype=torch.float64)
+    amb = ambiguous_samples(ref["conv_out"].numpy(), model.visual_threshold.detach().cpu().numpy())
+    if amb.any():
+        keep = torch.as_tensor(~amb).cuda()
+        images, labels = images[keep].contiguous(), labels[keep].contiguous()
+        ref = oracle_step(model, images, labels, dtype=torch.float64)
+    lib.set_option("ft_form", form)
+    try:
+        shape = shape_of(model, images)
+        assert bool(lib.lib().nnue_ft_uses_umma(ctypes.byref(shape))) == (form == 1)
+        model.zero_grad()
+        loss = model.loss(images, labels)
+        loss.backward()
+        torch.cuda.synchronize()
+    finally:
+        lib.set_option("ft_form", 0)
+    assert_close(loss, ref["loss"], "loss")
+    for k, g in ref["grads"].items():
+        assert_close(dict(model.named_parameters())[k].grad, g, "grad " + k)
+
+
+def test_cost_model_picks_the_measured_winner():
+    """plan.cuh: at SURVEY config I the gather form serves single-digit batches (one sample: 0.04 ms against 0.63 ms),
+    the dense form everything from a few dozen samples up (batch 512: 0.6 ms against 9.5 ms); a density hint of 1 %
+    turns large batches over to the gather form; the CIFAR tables are always dense."""
+    lib = _lib()
+    def dense(B, cfg=(224, 64, 32, 1024, 128, 32, 1000, 7)):
+        H, C, G, L1, L2, L3, NC, s = cfg
+        return bool(lib.lib().nnue_ft_uses_umma(ctypes.byref(lib.make_shape(B, H, H, C, G, L1, L2, L3, NC, s))))
+    assert not dense(1) and not dense(4) and dense(64) and dense(4096)
+    assert dense(1, (32, 8, 10, 64, 32, 8, 10, 3)) and dense(16384, (32, 8, 10, 64, 32, 8, 10, 3))
+    lib.set_option("ft_density_permille", 10)
+    try:
+        assert not dense(4096)
+    finally:
+        lib.set_option("ft_density_permille", 400)
+
+
 def test_feature_transformer_indexed_interface():
     """model.input(idx, val) with repeated / unsorted / out-of-range / -1 indices and float values
     (tests/test_model.py:1026-1064 use this sub-interface), forward and all three gradients."""

@@ -318,3 +318,26 @@ def test_incremental_api_matches_reference_engine_golden(name):
     ev.mark_dirty()
     batch = ev.evaluate_incremental([list(f) for f in g["fresh"]]).cpu().numpy()
     np.testing.assert_array_equal(batch, g["fresh_score"])
+
+
+def test_command_line_twin_prints_the_reference_csv(tmp_path):
+    """nnue_inference_b200 <model> <image.bin> H W (host C++ over the C ABI): the same CSV line the reference's
+    engine/nnue_inference.cpp:56-62 prints -- logits at setprecision(10), then the density -- for a golden model whose
+    expected numbers came from the compiled reference engine."""
+    import subprocess
+    from util import ROOT, load_golden
+    exe = ROOT / "nnue-vision_b200" / "nnue_inference_b200"
+    assert exe.exists(), "build.py builds the CLI next to the library"
+    rec = load_golden("default_cfg")
+    n = int(rec["int.n_images"])
+    chw = np.asarray(rec["images"][:n], np.float32)
+    for i in range(min(n, 3)):
+        img = tmp_path / f"img{i}.bin"
+        chw[i].tofile(img)  # evaluate.py:154-158 dumps the CHW floats; the engine reads the bytes as HWC
+        H, W = chw.shape[2], chw.shape[3]
+        out = subprocess.run([str(exe), str(GOLDEN / "default_cfg.nnue"), str(img), str(H), str(W)], capture_output=True,
+                             text=True, check=True).stdout.strip()
+        expect = ",".join(f"{v:.10f}" for v in list(rec["int.logits"][i]) + [float(rec["int.density"][i])])
+        assert out == expect
+    bad = subprocess.run([str(exe), str(tmp_path / "missing.nnue"), str(img), "32", "32"], capture_output=True, text=True)
+    assert bad.returncode == 1 and "Failed to load model" in bad.stderr
