@@ -89,6 +89,11 @@ unsigned long long nnue_launch_count_add(unsigned long long n);
  *                     contractions for small tables, 0 = CUDA-core kernels only.
  *   "ft_umma"         1 (default) = tcgen05 / TMEM (UMMA) feature-transformer contractions for every L1 that is
  *                     a multiple of 64, 0 = the warp-level MMA / CUDA-core families.
+ *   "input_bwd_onchip" 1 = value + conv + threshold gradients of CIFAR-shaped steps in one kernel with g_bin kept in
+ *                     tensor memory (input_bwd_fused.cu), 0 (default) = the two dense kernels through HBM.  Measured at
+ *                     config D: the one-kernel stage is 8 us shorter (112 vs 120 us) but its 212 KB / 512-column CTAs
+ *                     leave no room for the table gradient's CTAs beside them, which puts ~18 us of that kernel back
+ *                     on the critical path: 226 vs 216 us per step.
  *   "input_bwd_rows"  1 (default) = conv / threshold gradients of large images from row-staged tiles
  *                     (input_bwd_rows.cu), 0 = the direct-gather kernel pair.
  *   "ft_gather"       1 (default) = index-driven forward / value gradient through the TMA-staged row gather of
@@ -310,6 +315,17 @@ int nnue_input_bwd(const nnue_shape *s, const float *images_d, const uint32_t *b
                    const float *ft_w_d, const float *g_ft_d, const float *conv_w_d, const float *thr_d,
                    float *g_conv_w_d, float *g_thr_d, void *workspace_d, size_t workspace_bytes,
                    void *stream);
+/*
+ * The dense pair in ONE kernel for CIFAR-shaped steps (32 x 32 images, 97..128 raster cells, C <= 8, L1 32 / 64, stored
+ * activations): the value gradient is computed on the tensor cores inside the conv-gradient CTA and read by its
+ * consumers straight out of tensor memory -- g_bin [B][PP] is never written.  nnue_input_bwd_fused_ok tells whether
+ * the shape qualifies AND the option "input_bwd_onchip" is on (off by default: see its note); scratch from
+ * nnue_workspace_bytes.
+ */
+int nnue_input_bwd_fused_ok(const nnue_shape *s);
+int nnue_input_bwd_fused(const nnue_shape *s, const float *images_d, const uint32_t *bits_s_d, const float *xpad_d,
+                         const float *ft_w_d, const float *g_ft_d, const float *thr_d, float *g_conv_w_d, float *g_thr_d,
+                         void *workspace_d, size_t workspace_bytes, void *stream);
 /* Same, with the pre-threshold activations the forward stored (xpad_d [B][PP] from nnue_extract_fwd; NULL = recompute
  * them from the images, which is what nnue_input_bwd does).  nnue_input_bwd_wants_activations: 1 when passing them
  * saves a pass over the images for this shape (ImageNet-sized input). */

@@ -68,6 +68,8 @@ SIGNATURES = {
     "nnue_conv_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 8 + [sz, vp]),
     "nnue_input_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 9 + [sz, vp]),
     "nnue_input_bwd_wants_activations": (ctypes.c_int, [SHAPE_P]),
+    "nnue_input_bwd_fused_ok": (ctypes.c_int, [SHAPE_P]),
+    "nnue_input_bwd_fused": (ctypes.c_int, [SHAPE_P] + [vp] * 9 + [sz, vp]),
     "nnue_input_bwd_stored": (ctypes.c_int, [SHAPE_P] + [vp] * 10 + [sz, vp]),
     "nnue_ft_bwd_dval": (ctypes.c_int, [SHAPE_P] + [vp] * 8 + [sz, vp]),
     "nnue_extract_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 5 + [sz, vp]),

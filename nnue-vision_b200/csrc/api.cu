@@ -12,7 +12,7 @@ void note_cuda_error(cudaError_t e, const char *what) {
 }
 static unsigned long long g_launches = 0;
 void note_launch() { __atomic_fetch_add(&g_launches, 1ULL, __ATOMIC_RELAXED); }
-static int g_options[kNumOptions] = {/*ft_fwd_staging=*/1, /*ft_bwd_dw_owner=*/1, /*input_bwd_fused=*/1, /*input_bwd_variant=*/1, /*head_fused=*/1, /*ft_bwd_both=*/1, /*ft_mma=*/1, /*extract_tma=*/0, /*extract_fixed=*/1, /*ft_umma=*/1, /*input_bwd_swizzle=*/1, /*head_umma=*/1, /*q_tc_min_batch=*/2048, /*ft_form=*/0, /*ft_density_permille=*/400, /*ft_gather=*/1, /*ft_gather_slab=*/0, /*input_bwd_rows=*/1, /*ft_gather_units=*/1};
+static int g_options[kNumOptions] = {/*ft_fwd_staging=*/1, /*ft_bwd_dw_owner=*/1, /*input_bwd_fused=*/1, /*input_bwd_variant=*/1, /*head_fused=*/1, /*ft_bwd_both=*/1, /*ft_mma=*/1, /*extract_tma=*/0, /*extract_fixed=*/1, /*ft_umma=*/1, /*input_bwd_swizzle=*/1, /*head_umma=*/1, /*q_tc_min_batch=*/2048, /*ft_form=*/0, /*ft_density_permille=*/400, /*ft_gather=*/1, /*ft_gather_slab=*/0, /*input_bwd_rows=*/1, /*ft_gather_units=*/1, /*input_bwd_onchip=*/0};
 int get_option(int which) { return which >= 0 && which < kNumOptions ? g_options[which] : 0; }
 }  // namespace nnue
 
@@ -22,6 +22,7 @@ int nnue_set_option(const char *key, int value) {
     if (!key) return NNUE_ERR_INVALID_ARG;
     if (!strcmp(key, "ft_form")) { nnue::g_options[nnue::kOptFtForm] = value; return NNUE_OK; }
     if (!strcmp(key, "ft_density_permille")) { nnue::g_options[nnue::kOptFtDensity] = value < 1 ? 1 : (value > 1000 ? 1000 : value); return NNUE_OK; }
+    if (!strcmp(key, "input_bwd_onchip")) { nnue::g_options[nnue::kOptInputFusedGbin] = value; return NNUE_OK; }
     if (!strcmp(key, "ft_gather_units")) { nnue::g_options[nnue::kOptGatherUnits] = value < 1 ? 1 : value; return NNUE_OK; }
     if (!strcmp(key, "input_bwd_rows")) { nnue::g_options[nnue::kOptInputRows] = value; return NNUE_OK; }
     if (!strcmp(key, "ft_gather")) { nnue::g_options[nnue::kOptFtGather] = value; return NNUE_OK; }
@@ -102,6 +103,7 @@ size_t nnue_workspace_bytes(const nnue_shape *s) {
     v = nnue::ws_ft_fwd(*s); if (v > m) m = v;
     v = nnue::ws_ft_gather_fwd(*s); if (v > m) m = v;
     v = nnue::ws_ft_bwd_umma(*s); if (v > m) m = v;
+    v = nnue::plan_input_bwd_fused(*s).ws_bytes; if (v > m) m = v;
     v = nnue::ws_ce(s->B); if (v > m) m = v;
     return m + 256;
 }

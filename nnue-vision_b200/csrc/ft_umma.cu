@@ -459,6 +459,15 @@ int launch_ft_format_tables(const nnue_shape &s, const float *w, void *tables, i
     return NNUE_OK;
 }
 
+// the table as [PP / 128][L1 / 16][3][128 x 16] tiles: the A operand of the one-kernel input gradient (input_bwd_fused.cu)
+int launch_format_table_rows128(const nnue_shape &s, const float *w, unsigned char *out, cudaStream_t st) {
+    const int n_rt = ceil_div(s.PP, kUM);
+    const long long n = 1LL * n_rt * kUM * (s.L1 / 8);
+    umma_format_rows_kernel<true, kUM><<<(int)((n + 255) / 256), 256, 0, st>>>(s, w, s.PP, n_rt, out);
+    NNUE_CHECK_LAUNCH("umma_format_rows_kernel");
+    return NNUE_OK;
+}
+
 // out = bias + bits . W from pre-formatted forward tiles
 int launch_ft_fwd_umma_tiles(const nnue_shape &s, const uint32_t *bits_s, const void *tables, const float *bias, float *out,
                              cudaStream_t st) {

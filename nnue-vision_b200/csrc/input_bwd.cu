@@ -333,6 +333,25 @@ int nnue_conv_bwd(const nnue_shape *s, const float *images_d, const float *gbin_
     return NNUE_OK;
 }
 
+int nnue_input_bwd_fused_ok(const nnue_shape *s) { return s && plan_input_bwd_fused(*s).ok ? 1 : 0; }
+
+int nnue_input_bwd_fused(const nnue_shape *s, const float *images_d, const uint32_t *bits_s_d, const float *xpad_d,
+                         const float *ft_w_d, const float *g_ft_d, const float *thr_d, float *g_conv_w_d, float *g_thr_d,
+                         void *workspace_d, size_t workspace_bytes, void *stream) {
+    if (!s || !images_d || !bits_s_d || !xpad_d || !ft_w_d || !g_ft_d || !thr_d || !g_conv_w_d || !g_thr_d || !workspace_d)
+        return NNUE_ERR_INVALID_ARG;
+    const FusedPlan fp = plan_input_bwd_fused(*s);
+    if (!fp.ok) return NNUE_ERR_UNSUPPORTED;
+    if (workspace_bytes < fp.ws_bytes) return NNUE_ERR_WORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float *partial = nullptr;
+    const int rc = launch_input_bwd_fused(*s, fp, images_d, bits_s_d, xpad_d, ft_w_d, g_ft_d, thr_d, workspace_d, &partial, st);
+    if (rc != NNUE_OK) return rc;
+    input_bwd_fold_kernel<<<ceil_div(s->C * 28, 128), 128, 0, st>>>(s->C, fp.nq, partial, g_conv_w_d, g_thr_d);
+    NNUE_CHECK_LAUNCH("input_bwd_fold_kernel");
+    return NNUE_OK;
+}
+
 int nnue_input_bwd_wants_activations(const nnue_shape *s) {
     if (!s) return 0;
     return plan_input_bwd(*s).fused ? 0 : 1;  // (the dense pair takes them through nnue_conv_bwd)

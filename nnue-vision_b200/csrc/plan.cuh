@@ -164,9 +164,12 @@ inline size_t ws_ft_dw_umma(const nnue_shape &s) {
 // nnue_conv_bwd while the weight gradient may still be running on the side stream): it is sized for the larger of the
 // two, and the weight gradient's region starts behind it.
 inline size_t ws_conv_partials_bound(const nnue_shape &s) { return align_up((size_t)kNumSMs * s.C * 28 * 4, 256); }
+size_t ws_input_bwd_fused(const nnue_shape &s);  // scratch of the one-kernel input gradient (input_bwd_fused.cu), 0 if it does not apply
 inline size_t ws_bwd_front_umma(const nnue_shape &s) {
-    const size_t a = ws_ft_gbin_umma(s), b = ws_conv_partials_bound(s);
-    return a > b ? a : b;
+    size_t a = ws_ft_gbin_umma(s);
+    const size_t b = ws_conv_partials_bound(s), c = align_up(ws_input_bwd_fused(s), 256);
+    if (b > a) a = b;
+    return c > a ? c : a;
 }
 inline size_t ws_ft_bwd_umma(const nnue_shape &s) { return ws_bwd_front_umma(s) + align_up(ws_ft_dw_umma(s), 256); }
 int launch_ft_fwd_umma(const nnue_shape &s, const uint32_t *bits_s, const float *w, const float *bias, float *out,
@@ -402,6 +405,20 @@ inline RowsPlan plan_conv_bwd_rows(const nnue_shape &s) {
 }
 int launch_conv_bwd_rows(const nnue_shape &s, const RowsPlan &pl, const float *images, const uint32_t *bits_s, const float *dval,
                          const float *xpad, const float *thr, float *partial, cudaStream_t st);
+
+// ---- value + conv + threshold gradients in one kernel, g_bin kept in tensor memory (input_bwd_fused.cu) ----
+struct FusedPlan {
+    bool ok;
+    int nq, rounds, ST, n_ks;            // sample streams (= CTAs), 32-sample rounds per stream, ring depth, k steps
+    uint32_t a_bytes, b_bytes;           // one channel's table tiles, one round's g_ft tiles
+    uint32_t a_off, b_off, stage_off;    // shared-memory layout
+    size_t smem;
+    size_t ws_wtiles, ws_gtiles, ws_bytes;  // scratch: table tiles | g_ft tiles | per-CTA partials
+};
+FusedPlan plan_input_bwd_fused(const nnue_shape &s);
+int launch_input_bwd_fused(const nnue_shape &s, const FusedPlan &p, const float *images, const uint32_t *bits_s, const float *xpad,
+                           const float *ft_w, const float *g_ft, const float *thr, void *workspace, float **partial_out,
+                           cudaStream_t st);
 
 // ---- extraction forward, TMA-staged form (extract.cu) -------------------------------------------------
 constexpr int kExtWarps = 8;   // warps per CTA (lane 0 of warp 0 is the TMA producer)

@@ -351,15 +351,21 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
             _mark(marks, "ft_bwd_dw")
             if exchange is not None:
                 exchange.early(st)
-        gbin = _empty((shape.B, shape.PP), torch.float32, images)
-        if tables is not None:
-            check(L.nnue_ft_bwd_gbin_tables(sp, dptr(bits_s), dptr(tables), dptr(g_ft), dptr(gbin), dptr(ws), ws_bytes, st))
+        if xpad is not None and tables is None and L.nnue_input_bwd_fused_ok(sp):
+            # one kernel: the value gradient stays in tensor memory, the conv-gradient consumers read it from there
+            check(L.nnue_input_bwd_fused(sp, dptr(images), dptr(bits_s), dptr(xpad), dptr(ft_w), dptr(g_ft), dptr(thr),
+                                         dptr(g_conv_w), dptr(g_thr), dptr(ws), ws_bytes, st))
+            _mark(marks, "input_bwd_onchip")
         else:
-            check(L.nnue_ft_bwd_gbin(sp, dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(gbin), dptr(ws), ws_bytes, st))
-        _mark(marks, "ft_bwd_gbin")
-        check(L.nnue_conv_bwd(sp, dptr(images), dptr(gbin), dptr(xpad), dptr(conv_w), dptr(thr), dptr(g_conv_w), dptr(g_thr),
-                              dptr(ws), ws_bytes, st))
-        _mark(marks, "conv_bwd")
+            gbin = _empty((shape.B, shape.PP), torch.float32, images)
+            if tables is not None:
+                check(L.nnue_ft_bwd_gbin_tables(sp, dptr(bits_s), dptr(tables), dptr(g_ft), dptr(gbin), dptr(ws), ws_bytes, st))
+            else:
+                check(L.nnue_ft_bwd_gbin(sp, dptr(bits_s), dptr(ft_w), dptr(g_ft), dptr(gbin), dptr(ws), ws_bytes, st))
+            _mark(marks, "ft_bwd_gbin")
+            check(L.nnue_conv_bwd(sp, dptr(images), dptr(gbin), dptr(xpad), dptr(conv_w), dptr(thr), dptr(g_conv_w), dptr(g_thr),
+                                  dptr(ws), ws_bytes, st))
+            _mark(marks, "conv_bwd")
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)  # the step's gradients are complete on the caller's stream
         if exchange is not None:
