@@ -345,17 +345,49 @@ int nnue_head_bwd(const nnue_shape *s, const float *g_logits_d, const float *ft_
     float *g_act1 = carve((size_t)B * L2 * 4);
     float *g_l0 = carve((size_t)B * L1 * 4);
 
-    int rc = wgrad(g_logits_d, NC, act2_d, L3, 0, B, p3, g_w3_d, g_b3_d, st);
-    if (rc < 0) return rc;
+    int rc;
     GemmArgs g{};
     g.b_ones_col = -1;
-    // g_z2 = (g_logits * W3) masked by act2 > 0
-    g.A = g_logits_d; g.sam = NC; g.sak = 1;
-    g.Bm = w3_d; g.sbk = L3; g.sbn = 1;
-    g.M = B; g.N = L3; g.K = NC;
-    g.C = g_act2; g.scm = L3; g.mask = act2_d; g.smm = L3;
-    rc = launch_gemm(g, 1, st);
-    if (rc < 0) return rc;
+    g.sak = 1; g.sbn = 1; g.M = B;  // (common to the layer gradients below)
+    if (head3_umma_ok(*s)) {
+        // many classes: both output-layer gradients as split-bf16 tcgen05 GEMMs (scratch at the END of the workspace, behind
+        // everything the other layers carve)
+        unsigned char *w3s = reinterpret_cast<unsigned char *>(static_cast<char *>(workspace_d) + ws_head_bwd(*s) - ws_head3_umma_bwd(*s));
+        auto carve3 = [&](size_t bytes) { unsigned char *p = w3s; w3s += align_up(bytes, 256); return p; };
+        unsigned char *gl_rows = carve3(ugemm_tile_bytes(B, 128, NC)), *w3_cols = carve3(ugemm_tile_bytes(L3, 128, NC));
+        unsigned char *gl_cols = carve3(ugemm_tile_bytes(NC, 128, B)), *a2_cols = carve3(ugemm_tile_bytes(L3, 128, B));
+        const int splits = head3_umma_wgrad_splits(*s);
+        float *wpart = reinterpret_cast<float *>(carve3((size_t)splits * NC * L3 * 4));
+        float *cpart = reinterpret_cast<float *>(carve3((size_t)ceil_div(B, 256) * NC * 4));
+        // g_w3[o, i] = sum_b g_logits[b, o] act2[b, i]: A = g_logits^T, B = act2^T, K = batch, split-K partials
+        if ((rc = ugemm_format_cols(128, g_logits_d, NC, B, NC, 0, gl_cols, st)) < 0) return rc;
+        if ((rc = ugemm_format_cols(128, act2_d, L3, B, L3, 0, a2_cols, st)) < 0) return rc;
+        const int nz = ugemm_launch(128, NC, L3, B, gl_cols, a2_cols, wpart, L3, nullptr, 0, nullptr, 0, splits, (long long)NC * L3, st);
+        if (nz < 0) return nz;
+        const long long nw = 1LL * NC * L3;
+        head_fold_kernel<<<(int)((nw + 255) / 256), 256, 0, st>>>(nw, nz, nw, wpart, g_w3_d);
+        NNUE_CHECK_LAUNCH("head_fold_kernel");
+        const int nrc = ceil_div(B, 256);
+        head_colsum_partial_kernel<<<dim3(ceil_div(NC, 128), nrc), 128, 0, st>>>(B, NC, g_logits_d, cpart);
+        NNUE_CHECK_LAUNCH("head_colsum_partial_kernel");
+        head_fold_kernel<<<ceil_div(NC, 256), 256, 0, st>>>(NC, nrc, NC, cpart, g_b3_d);
+        NNUE_CHECK_LAUNCH("head_fold_kernel");
+        // g_z2 = (g_logits W3) masked by act2 > 0: A = g_logits, B = W3^T (rows = the L3 inputs, K = classes)
+        if ((rc = ugemm_format_rows(128, g_logits_d, NC, B, NC, 0, gl_rows, st)) < 0) return rc;
+        if ((rc = ugemm_format_cols(128, w3_d, L3, NC, L3, 0, w3_cols, st)) < 0) return rc;
+        rc = ugemm_launch(128, B, L3, NC, gl_rows, w3_cols, g_act2, L3, nullptr, 0, act2_d, L3, 1, 0, st);
+        if (rc < 0) return rc;
+    } else {
+        rc = wgrad(g_logits_d, NC, act2_d, L3, 0, B, p3, g_w3_d, g_b3_d, st);
+        if (rc < 0) return rc;
+        // g_z2 = (g_logits * W3) masked by act2 > 0
+        g.A = g_logits_d; g.sam = NC; g.sak = 1;
+        g.Bm = w3_d; g.sbk = L3; g.sbn = 1;
+        g.M = B; g.N = L3; g.K = NC;
+        g.C = g_act2; g.scm = L3; g.mask = act2_d; g.smm = L3;
+        rc = launch_gemm(g, 1, st);
+        if (rc < 0) return rc;
+    }
     rc = wgrad(g_act2, L3, act1_d, L2, 0, B, p2, g_w2_d, g_b2_d, st);
     if (rc < 0) return rc;
     // g_z1 = (g_z2 * W2) masked by act1 > 0

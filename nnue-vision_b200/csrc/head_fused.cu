@@ -372,18 +372,26 @@ __global__ void head_train_fold_kernel(int nblk, const float *__restrict__ parti
                                        float inv_count, float *g_w1, float *g_b1, float *g_w2, float *g_b2, float *g_w3,
                                        float *g_b3, float *loss) {
     using Lay = HeadLayout<L1P, L2P, L3P, NCP>;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e > Lay::pLoss) return;
+    // 256 threads = 32 elements x 8 slices of the CTA list (slice q: CTAs q, q + 8, ...): every thread has all its loads
+    // in flight at once (the fold is pure latency); slices are combined in slice order -- a fixed order per shape
+    __shared__ float red[8][32];
+    const int e = blockIdx.x * 32 + (threadIdx.x & 31), q = threadIdx.x >> 5;
     float v = 0.0f;
-    int k = 0;
-    for (; k + 16 <= nblk; k += 16) {  // loads batched sixteen deep (the loop is latency-bound); same summation order
-        float t[16];
+    if (e <= Lay::pLoss) {
+        float t[20];
+        int k = q;
+        while (k < nblk) {
 #pragma unroll
-        for (int u = 0; u < 16; ++u) t[u] = __ldg(partial + (size_t)(k + u) * Lay::pTotal + e);
+            for (int u = 0; u < 20; ++u) t[u] = k + 8 * u < nblk ? __ldg(partial + (size_t)(k + 8 * u) * Lay::pTotal + e) : 0.0f;
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v += t[u];
+            for (int u = 0; u < 20; ++u) v += t[u];
+            k += 160;
+        }
     }
-    for (; k < nblk; ++k) v += __ldg(partial + (size_t)k * Lay::pTotal + e);
+    red[q][threadIdx.x & 31] = v;
+    __syncthreads();
+    if (q != 0 || e > Lay::pLoss) return;
+    for (int s2 = 1; s2 < 8; ++s2) v += red[s2][threadIdx.x & 31];
     const int h = L1 / 2;
     if (e < Lay::pB1) {
         const int o = e / L1P, sl = e % L1P;
@@ -441,7 +449,7 @@ int nnue_head_train(const nnue_shape *s, const float *ft_out_d, const int64_t *l
         NNUE_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, kHeadTile, smem, st>>>(a);
         NNUE_CHECK_LAUNCH("head_train_kernel");
-        head_train_fold_kernel<64, 32, 8, 16><<<ceil_div(Lay::pLoss + 1, 128), 128, 0, st>>>(
+        head_train_fold_kernel<64, 32, 8, 16><<<ceil_div(Lay::pLoss + 1, 32), 256, 0, st>>>(
             grid, a.partial, s->L1, s->L2, s->L3, s->NC, inv_count, g_w1_d, g_b1_d, g_w2_d, g_b2_d, g_w3_d, g_b3_d,
             loss_d);
         NNUE_CHECK_LAUNCH("head_train_fold_kernel");

@@ -216,24 +216,34 @@ conv_bwd_kernel(const nnue_shape s, const float *__restrict__ images, const floa
     }
 }
 
-// g_conv_w[c][t] and g_thr[c] = sum over CTAs (in CTA order) of partial[cta][c][28]
-__global__ void input_bwd_fold_kernel(int C, int nblk, const float *__restrict__ partial, float *__restrict__ g_conv_w,
-                                      float *__restrict__ g_thr) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= C * 28) return;
+// g_conv_w[c][t] and g_thr[c] = sum over CTAs of partial[cta][c][28].  The fold is pure latency (148 dependent-free loads
+// per element): a CTA of 256 threads takes 32 elements and eight slices of the CTA list (slice q: CTAs q, q + 8, ...),
+// so every thread has its ~19 loads in flight at once; slices are combined in slice order -- a fixed order per shape.
+__global__ void __launch_bounds__(256)
+input_bwd_fold_kernel(int C, int nblk, const float *__restrict__ partial, float *__restrict__ g_conv_w,
+                      float *__restrict__ g_thr) {
+    __shared__ float red[8][32];
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31), q = threadIdx.x >> 5;
     float v = 0.0f;
-    int k = 0;
-    for (; k + 16 <= nblk; k += 16) {  // loads batched sixteen deep (the loop is latency-bound); same summation order
-        float t[16];
+    if (i < C * 28) {
+        float t[20];
+        int k = q;
+        while (k < nblk) {
 #pragma unroll
-        for (int u = 0; u < 16; ++u) t[u] = __ldg(partial + (size_t)(k + u) * C * 28 + i);
+            for (int u = 0; u < 20; ++u) t[u] = k + 8 * u < nblk ? __ldg(partial + (size_t)(k + 8 * u) * C * 28 + i) : 0.0f;
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v += t[u];
+            for (int u = 0; u < 20; ++u) v += t[u];
+            k += 160;
+        }
     }
-    for (; k < nblk; ++k) v += __ldg(partial + (size_t)k * C * 28 + i);
-    const int c = i / 28, t = i % 28;
-    if (t < 27) g_conv_w[c * 27 + t] = v;
-    else if (g_thr) g_thr[c] = v;
+    red[q][threadIdx.x & 31] = v;
+    __syncthreads();
+    if (q == 0 && i < C * 28) {
+        for (int s2 = 1; s2 < 8; ++s2) v += red[s2][threadIdx.x & 31];
+        const int c = i / 28, t = i % 28;
+        if (t < 27) g_conv_w[c * 27 + t] = v;
+        else if (g_thr) g_thr[c] = v;
+    }
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
@@ -328,7 +338,7 @@ int nnue_conv_bwd(const nnue_shape *s, const float *images_d, const float *gbin_
     if (pl.CH == 2) rc = launch_conv_bwd<2, 16>(*s, pl, images_d, gbin_d, xpad_d, conv_w_d, thr_d, partial, st);
     else rc = launch_conv_bwd<4, 8>(*s, pl, images_d, gbin_d, xpad_d, conv_w_d, thr_d, partial, st);
     if (rc != NNUE_OK) return rc;
-    input_bwd_fold_kernel<<<ceil_div(s->C * 28, 128), 128, 0, st>>>(s->C, pl.grid, partial, g_conv_w_d, g_thr_d);
+    input_bwd_fold_kernel<<<ceil_div(s->C * 28, 32), 256, 0, st>>>(s->C, pl.grid, partial, g_conv_w_d, g_thr_d);
     NNUE_CHECK_LAUNCH("input_bwd_fold_kernel");
     return NNUE_OK;
 }
@@ -347,7 +357,7 @@ int nnue_input_bwd_fused(const nnue_shape *s, const float *images_d, const uint3
     float *partial = nullptr;
     const int rc = launch_input_bwd_fused(*s, fp, images_d, bits_s_d, xpad_d, ft_w_d, g_ft_d, thr_d, workspace_d, &partial, st);
     if (rc != NNUE_OK) return rc;
-    input_bwd_fold_kernel<<<ceil_div(s->C * 28, 128), 128, 0, st>>>(s->C, fp.nq, partial, g_conv_w_d, g_thr_d);
+    input_bwd_fold_kernel<<<ceil_div(s->C * 28, 32), 256, 0, st>>>(s->C, fp.nq, partial, g_conv_w_d, g_thr_d);
     NNUE_CHECK_LAUNCH("input_bwd_fold_kernel");
     return NNUE_OK;
 }
@@ -405,7 +415,7 @@ int nnue_input_bwd_stored(const nnue_shape *s, const float *images_d, const uint
         float *partial = reinterpret_cast<float *>(rest);
         rc = launch_conv_bwd_rows(*s, rp, images_d, bits_s_d, dval, xpad, thr_d, partial, st);
         if (rc != NNUE_OK) return rc;
-        input_bwd_fold_kernel<<<ceil_div(s->C * 28, 128), 128, 0, st>>>(s->C, rp.grid, partial, g_conv_w_d, g_thr_d);
+        input_bwd_fold_kernel<<<ceil_div(s->C * 28, 32), 256, 0, st>>>(s->C, rp.grid, partial, g_conv_w_d, g_thr_d);
         NNUE_CHECK_LAUNCH("input_bwd_fold_kernel");
         return NNUE_OK;
     }
@@ -415,7 +425,7 @@ int nnue_input_bwd_stored(const nnue_shape *s, const float *images_d, const uint
         float *partial = reinterpret_cast<float *>(rest);
         rc = launch_conv_bwd_rows(*s, rp, images_d, bits_s_d, dval, xpad, thr_d, partial, st);
         if (rc != NNUE_OK) return rc;
-        input_bwd_fold_kernel<<<ceil_div(s->C * 28, 128), 128, 0, st>>>(s->C, rp.grid, partial, g_conv_w_d, nullptr);
+        input_bwd_fold_kernel<<<ceil_div(s->C * 28, 32), 256, 0, st>>>(s->C, rp.grid, partial, g_conv_w_d, nullptr);
         NNUE_CHECK_LAUNCH("input_bwd_fold_kernel");
         return NNUE_OK;
     }

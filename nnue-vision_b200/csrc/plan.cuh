@@ -473,6 +473,24 @@ inline int head_umma_wgrad_splits(const nnue_shape &s) {
     if (want > n_ks / 8) want = n_ks / 8;  // at least 8 k-steps per split
     return want < 1 ? 1 : want;
 }
+// ---- the output layer of many-class heads (1000 classes at the ImageNet-shaped configs) ----------------------------
+// Its two backward contractions -- g_w3 = g_logits^T act2 (K = batch) and g_z2 = g_logits W3 (K = classes) -- are skinny
+// (32 columns) and ran at 4 - 8 TFLOP/s on the fp32 FMA GEMM kernel: 252 + 139 us of the 2.4 ms I-s step.  As split-bf16
+// tcgen05 GEMMs (gemm_umma.cu, exact products, fp32 accumulation) they are bound by formatting g_logits twice.
+inline bool head3_umma_ok(const nnue_shape &s) { return get_option(kOptHeadUmma) && s.NC >= 128 && s.B >= 256 && s.L3 <= 128; }
+inline int head3_umma_wgrad_splits(const nnue_shape &s) {
+    int want = ceil_div(2 * kNumSMs, ceil_div(s.NC, 128));
+    const int n_ks = ceil_div(s.B, 16);
+    if (want > n_ks / 8) want = n_ks / 8;  // at least 8 k-steps per split
+    return want < 1 ? 1 : want;
+}
+// g_logits rows | W3 cols | g_logits cols | act2 cols | split-K partials [splits][NC][L3] | colsum partials
+inline size_t ws_head3_umma_bwd(const nnue_shape &s) {
+    if (!head3_umma_ok(s)) return 0;
+    return align_up(ugemm_tile_bytes(s.B, 128, s.NC), 256) + align_up(ugemm_tile_bytes(s.L3, 128, s.NC), 256) +
+           align_up(ugemm_tile_bytes(s.NC, 128, s.B), 256) + align_up(ugemm_tile_bytes(s.L3, 128, s.B), 256) +
+           align_up((size_t)head3_umma_wgrad_splits(s) * s.NC * s.L3 * 4, 256) + align_up((size_t)ceil_div(s.B, 256) * s.NC * 4, 256);
+}
 // forward scratch: l0 rows tiles | W1 rows tiles
 inline size_t ws_head_umma_fwd(const nnue_shape &s) {
     if (!head_umma_ok(s)) return 0;
@@ -505,7 +523,7 @@ inline size_t ws_head_bwd(const nnue_shape &s) {
     bytes += align_up((size_t)gemm_splits(s.L3, s.L2 + 1, s.B, 64, 64) * s.L3 * (s.L2 + 1) * 4, 256);
     bytes += align_up((size_t)gemm_splits(s.L2, s.L1 + 1, s.B, 64, 64) * s.L2 * (s.L1 + 1) * 4, 256);
     bytes += align_up(B * s.L3 * 4, 256) + align_up(B * s.L2 * 4, 256) + align_up(B * s.L1 * 4, 256);
-    return bytes + ws_head_umma_bwd(s);
+    return bytes + ws_head_umma_bwd(s) + ws_head3_umma_bwd(s);
 }
 inline size_t ws_input_bwd(const nnue_shape &s) {
     const InPlan p = plan_input_bwd(s);

@@ -86,6 +86,9 @@ CFGS = {
     # wide stacks at a batch where layer 1 runs as the split-bf16 tcgen05 GEMM (gemm_umma.cu)
     "D1k_tensor_head": (dict(grid=10, C=8, L1=1024, L2=128, L3=32, NC=10, model_input=32), 32, 300),
     "wide_head_ragged": (dict(grid=6, C=16, L1=256, L2=48, L3=16, NC=10, model_input=64), 64, 257),
+    # 1000 classes at a batch where the output layer's two gradients run as split-bf16 tcgen05 GEMMs (head.cu / gemm_umma.cu)
+    "many_classes_tensor_head": (dict(grid=6, C=16, L1=128, L2=16, L3=32, NC=1000, model_input=64), 64, 300),
+    "many_classes_ragged": (dict(grid=6, C=8, L1=64, L2=24, L3=20, NC=333, model_input=32), 32, 515),
     # the table gradient (side stream) and the conv gradient's partials (main stream) share one workspace: shapes where
     # the partials are larger than the value gradient's operands (L1 = 32 / small grids, B >= 148)
     "L1_32_overlap": (dict(grid=8, C=8, L1=32, L2=8, L3=8, NC=10, model_input=32), 32, 300),
