@@ -134,12 +134,17 @@ __device__ __forceinline__ uint4 bits8_to_bf16x8(uint32_t byte) {
 // MODE 2 (integer inference, qinfer.cu): same as the forward but the B operand is the int16 table as TWO exact bf16
 // terms (high byte, signed; low byte, unsigned: UMMA 128 x 128 x 16), bias is int32 [L1] and out is int16 [B][L1]:
 // out = (int16)(bias + 256 * sum_hi + sum_lo), the engine's wrap-around accumulate (simd_scalar.cpp:78-95).
+// MODE 3: MODE 2 with L1 = 64 (one N tile holds the whole accumulator row) and the rest of the integer path in the epilogue:
+// clipped ReLU, pairwise, the three dense layers (dp4a), logits / 64 -- `out` is unused, qa.logits is written.
+// MODE 2 / 3 walk only the bitmask words that can hold a bit (qa: the words of a channel past the conv raster are skipped
+// when the threshold is not negative): stage jj = word (jj / cw_used) * cw_all + jj % cw_used.
 template <int MODE>
 __global__ void __launch_bounds__(kBgThreads, 2)
 ft_bitgemm_umma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const unsigned char *__restrict__ btiles,
-                       const float *__restrict__ bias, float *__restrict__ out, int chunk_blocks) {
+                       const float *__restrict__ bias, float *__restrict__ out, int chunk_blocks, const QAccArgs qa) {
     constexpr bool DW = MODE == 1;
-    constexpr uint32_t NR = MODE == 2 ? kBgNRowsInt : kBgNRows, BTile = NR * 32, BBytes = 2 * BTile;
+    constexpr bool INT = MODE >= 2;
+    constexpr uint32_t NR = INT ? kBgNRowsInt : kBgNRows, BTile = NR * 32, BBytes = 2 * BTile;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t *full_a = reinterpret_cast<uint64_t *>(smem_raw);     // [ST] producer warps -> issuer
     uint64_t *full_b = full_a + kBgStages;                         // [ST] TMA -> issuer
@@ -157,9 +162,10 @@ ft_bitgemm_umma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, 
         n_ks_total = 2 * s.BW;
     } else {
         first = 0;
-        n_stage = s.NW;
+        n_stage = INT ? qa.n_words_used : s.NW;
         n_ks_total = 2 * s.NW;
     }
+    auto word_of = [&](int jj) -> int { return INT ? (jj / qa.cw_used) * qa.cw_all + jj % qa.cw_used : jj; };
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kBgStages; ++i) {
@@ -183,7 +189,7 @@ ft_bitgemm_umma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, 
                 const int st = j % kBgStages;
                 if (j >= kBgStages) mbar_wait(&empty[st], ((j / kBgStages) - 1) & 1);
                 mbar_arrive_expect_tx(&full_b[st], BBytes);
-                tma_bulk_g2s(sb + (uint32_t)st * BBytes, src + (size_t)j * BBytes, BBytes, &full_b[st]);
+                tma_bulk_g2s(sb + (uint32_t)st * BBytes, src + (size_t)word_of(j) * BBytes, BBytes, &full_b[st]);
             }
         }
     } else if (warp == 1) {
@@ -218,7 +224,7 @@ ft_bitgemm_umma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, 
                 return (wi < s.NW && b < s.B) ? __ldg(bits_s + (size_t)b * s.NW + wi) : 0u;
             }
             const int b = mt * kUM + row;
-            return b < s.B ? __ldg(bits_s + (size_t)b * s.NW + j) : 0u;
+            return b < s.B ? __ldg(bits_s + (size_t)b * s.NW + word_of(j)) : 0u;
         };
         unsigned char *dst0 = sa + (uint32_t)row * 16;
         uint32_t pre[4];
@@ -265,7 +271,82 @@ ft_bitgemm_umma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, 
             const int b = mt * kUM + row;
             if (b < s.B) orow = out + (size_t)b * s.L1 + nt * kUmmaNCols;
         }
-        if (MODE == 2) {
+        if (MODE == 3) {
+            // ---- the layer stack on the accumulator row (nnue_engine.cpp:726-729, 490-533).  The two column groups of a
+            // row meet through shared memory (the A ring is idle: every UMMA has completed); per row 65 words (odd pitch:
+            // the 32 rows of a warp hit 32 banks): clipped int16 x 64 | pairwise int8 x 64 | layer-1 out | layer-2 out
+            constexpr int kPitch = 65, oPw = 32, oH1 = 48, oH2 = 56;
+            uint32_t *srow = reinterpret_cast<uint32_t *>(sa) + row * kPitch;
+            const int b = mt * kUM + row;
+            const int32_t *bias32 = reinterpret_cast<const int32_t *>(bias);
+            auto qbar = []() { asm volatile("bar.sync 1, 256;" ::: "memory"); };  // the eight epilogue warps
+#pragma unroll
+            for (int cc = 0; cc < kUmmaNCols / 2; cc += 16) {
+                const int c0 = grp * (kUmmaNCols / 2) + cc;
+                float hi[16], lo[16];
+                tmem_ld16(tbase + (uint32_t)c0, hi);
+                tmem_ld16(tbase + (uint32_t)(kUmmaNCols + c0), lo);
+                tmem_ld_wait();
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int v0 = __ldg(bias32 + c0 + 2 * u) + 256 * __float2int_rn(hi[2 * u]) + __float2int_rn(lo[2 * u]);
+                    const int v1 = __ldg(bias32 + c0 + 2 * u + 1) + 256 * __float2int_rn(hi[2 * u + 1]) + __float2int_rn(lo[2 * u + 1]);
+                    const int x0 = max(0, min(qa.qone, (int)(int16_t)v0)), x1 = max(0, min(qa.qone, (int)(int16_t)v1));  // int16 wrap, clipped ReLU
+                    srow[(c0 >> 1) + u] = (uint32_t)x0 | ((uint32_t)x1 << 16);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) srow[(grp ? oH2 : oH1) + k] = 0u;  // zero padding of the dense layers' inputs
+            qbar();
+            {   // pairwise words: group 0 the 32 products, group 1 the 32 clipped first-half values
+                const int16_t *c16 = reinterpret_cast<const int16_t *>(srow);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    uint32_t wd = 0u;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i = 4 * k + e;
+                        const int x = c16[i];
+                        const int v = grp == 0 ? max(0, min(127, (x * (int)c16[i + 32]) / 128)) : min(127, x);
+                        wd |= (uint32_t)v << (8 * e);
+                    }
+                    srow[oPw + 8 * grp + k] = wd;
+                }
+            }
+            qbar();
+            {   // layer 1: float divide then truncate (simd_scalar.cpp:131-133), clamp 0..127; each group half of the outputs
+                int pw[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) pw[k] = (int)srow[oPw + k];
+                const int hn = (qa.L2 + 1) / 2, o1 = min(qa.L2, (grp + 1) * hn);
+                int8_t *h1 = reinterpret_cast<int8_t *>(srow + oH1);
+                for (int o = grp * hn; o < o1; ++o) {
+                    int a = __ldg(qa.b1 + o);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) a = __dp4a(pw[k], __ldg(qa.w1 + k * qa.L2 + o), a);
+                    h1[o] = (int8_t)max(0, min(127, __float2int_rz(__fdiv_rn(__int2float_rn(a), qa.l1_scale))));
+                }
+            }
+            qbar();
+            {   // layer 2: integer divide (truncating), clamp +-127, ReLU (nnue_engine.cpp:512-523)
+                const int hn = (qa.L3 + 1) / 2, o1 = min(qa.L3, (grp + 1) * hn);
+                int8_t *h2 = reinterpret_cast<int8_t *>(srow + oH2);
+                for (int o = grp * hn; o < o1; ++o) {
+                    int a = __ldg(qa.b2 + o);
+                    for (int k = 0; k < qa.K2; ++k) a = __dp4a((int)srow[oH1 + k], __ldg(qa.w2 + k * qa.L3 + o), a);
+                    h2[o] = (int8_t)max(0, max(-127, min(127, a / qa.l2_iscale)));
+                }
+            }
+            qbar();
+            {   // output: (float)acc / output_scale (nnue_engine.cpp:526-533)
+                const int hn = (qa.NC + 1) / 2, c1 = min(qa.NC, (grp + 1) * hn);
+                for (int c = grp * hn; c < c1; ++c) {
+                    int a = __ldg(qa.bo + c);
+                    for (int k = 0; k < qa.K3; ++k) a = __dp4a((int)srow[oH2 + k], __ldg(qa.wo + k * qa.NC + c), a);
+                    if (b < s.B) qa.logits[(size_t)b * qa.NC + c] = __fdiv_rn(__int2float_rn(a), qa.out_scale);
+                }
+            }
+        } else if (MODE == 2) {
             const int b = mt * kUM + row;
             int16_t *orow16 = reinterpret_cast<int16_t *>(out) + (size_t)min(b, s.B - 1) * s.L1 + nt * kUmmaNCols;
             const int32_t *bias32 = reinterpret_cast<const int32_t *>(bias) + nt * kUmmaNCols;
@@ -473,7 +554,7 @@ int launch_ft_fwd_umma_tiles(const nnue_shape &s, const uint32_t *bits_s, const 
                              cudaStream_t st) {
     NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_bitgemm_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmem));
     ft_bitgemm_umma_kernel<0><<<dim3(ceil_div(s.B, kUM), s.L1 / kUmmaNCols, 1), kBgThreads, kBgSmem, st>>>(
-        s, bits_s, static_cast<const unsigned char *>(tables), bias, out, 0);
+        s, bits_s, static_cast<const unsigned char *>(tables), bias, out, 0, QAccArgs{});
     NNUE_CHECK_LAUNCH("ft_bitgemm_umma_kernel");
     return NNUE_OK;
 }
@@ -553,7 +634,7 @@ int launch_ft_bwd_dw_umma(const nnue_shape &s, const uint32_t *bits_s, const flo
     NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_bitgemm_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmem));
     const int m_rows = umma_bias_pp(s) + 1 > s.PP ? s.PP + 1 : s.PP;  // the all-ones row may need one more M tile
     ft_bitgemm_umma_kernel<1><<<dim3(ceil_div(m_rows, kUM), s.L1 / kUmmaNCols, p.n_chunks), kBgThreads, kBgSmem, st>>>(
-        s, bits_s, gt, nullptr, partial, p.chunk_blocks);
+        s, bits_s, gt, nullptr, partial, p.chunk_blocks, QAccArgs{});
     NNUE_CHECK_LAUNCH("ft_bitgemm_umma_kernel");
     n = 1LL * ((s.P > s.F - 1 ? s.P : s.F - 1) + 1) * (s.L1 / 4);
     umma_dw_fold_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(s, p.n_chunks, partial, g_w, g_b, alias);
@@ -564,15 +645,24 @@ int launch_ft_bwd_dw_umma(const nnue_shape &s, const uint32_t *bits_s, const flo
 }
 
 // Integer accumulate of qinfer.cu: acc16[b] = (int16)(bias + sum over set bits of the int16 table rows).
-// bits [B][NW] (word w = 32 k-indices), tiles [L1 / 64][2 NW][128 x 16] (high / low byte terms, built at load time)
+// bits [B][NW] (word w = 32 k-indices), tiles [L1 / 64][2 NW][128 x 16] (high / low byte terms, built at load time).
+// qa: which bitmask words are walked and, with qa.logits set (L1 = 64, small stacks: q_stack_fused_ok), the layer stack
+// in the epilogue -- acc16 is then unused.
 int launch_q_accumulate_umma(int B, int NW, int L1, const uint32_t *bits, const unsigned char *tiles, const int32_t *bias,
-                             int16_t *acc16, cudaStream_t st) {
+                             int16_t *acc16, const QAccArgs &qa, cudaStream_t st) {
     nnue_shape s{};
     s.B = B; s.NW = NW; s.L1 = L1; s.PP = 32 * NW; s.BW = ceil_div(B, 32);
     constexpr size_t smem = 1024 + (size_t)kBgStages * (kBgABytes + 2 * kBgNRowsInt * 32);
-    NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_bitgemm_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ft_bitgemm_umma_kernel<2><<<dim3(ceil_div(B, kUM), L1 / kUmmaNCols, 1), kBgThreads, smem, st>>>(
-        s, bits, tiles, reinterpret_cast<const float *>(bias), reinterpret_cast<float *>(acc16), 0);
+    if (qa.logits) {
+        if (L1 != kUmmaNCols) return NNUE_ERR_UNSUPPORTED;
+        NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_bitgemm_umma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ft_bitgemm_umma_kernel<3><<<dim3(ceil_div(B, kUM), 1, 1), kBgThreads, smem, st>>>(
+            s, bits, tiles, reinterpret_cast<const float *>(bias), nullptr, 0, qa);
+    } else {
+        NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_bitgemm_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ft_bitgemm_umma_kernel<2><<<dim3(ceil_div(B, kUM), L1 / kUmmaNCols, 1), kBgThreads, smem, st>>>(
+            s, bits, tiles, reinterpret_cast<const float *>(bias), reinterpret_cast<float *>(acc16), 0, qa);
+    }
     NNUE_CHECK_LAUNCH("ft_bitgemm_umma_kernel");
     return NNUE_OK;
 }

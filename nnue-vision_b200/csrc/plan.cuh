@@ -176,8 +176,19 @@ int launch_ft_fwd_umma(const nnue_shape &s, const uint32_t *bits_s, const float 
                        void *workspace, cudaStream_t st);
 int launch_ft_bwd_dw_umma(const nnue_shape &s, const uint32_t *bits_s, const float *g_ft, void *ws, float *g_w, float *g_b,
                           cudaStream_t st);
+// integer accumulate (qinfer.cu): which bitmask words of a channel are walked (stage jj = word (jj / cw_used) * cw_all +
+// jj % cw_used, n_words_used stages) and, when `logits` is set, the layer stack run in the kernel's epilogue
+struct QAccArgs {
+    int cw_all, cw_used, n_words_used;
+    const int32_t *w1, *b1, *w2, *b2, *wo, *bo;  // dp4a words [K][n_out] and biases of the three dense layers
+    int L2, L3, NC, K2, K3, qone, l2_iscale;
+    float l1_scale, out_scale;
+    float *logits;                               // [B][NC]; null: the int16 accumulators are written instead
+};
+// the stack fits the epilogue's per-row scratch: L1 = 64 (one N tile), at most 32 / 32 / 64 outputs per layer
+inline bool q_stack_fused_ok(int L1, int L2, int L3, int NC) { return L1 == 64 && L2 <= 32 && L3 <= 32 && NC <= 64; }
 int launch_q_accumulate_umma(int B, int NW, int L1, const uint32_t *bits, const unsigned char *tiles, const int32_t *bias,
-                             int16_t *acc16, cudaStream_t st);
+                             int16_t *acc16, const QAccArgs &qa, cudaStream_t st);
 int launch_ft_bwd_gbin_umma(const nnue_shape &s, const uint32_t *bits_s, const float *w, const float *g_ft, void *workspace,
                             float *gbin, cudaStream_t st, const void *table_tiles = nullptr);
 // both tile orders of the table in one buffer (forward tiles | value-gradient tiles); which: bit 0 forward, bit 1 value gradient

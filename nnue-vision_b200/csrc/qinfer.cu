@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "plan.cuh"
+#include "qinfer.cuh"
 
 struct nnue_qmodel {
     int F, L1, L2, L3, NC, OC, G, n_buckets;
@@ -23,6 +24,7 @@ struct nnue_qmodel {
     // device blobs
     int32_t *conv_w;   // [OC][28] taps in the engine's [kh][kw][ic] order, widened to int32
     int32_t *conv_b;   // [OC]
+    int32_t *conv_taps = nullptr;  // [OC][28] taps with the bias in entry 27 (the fixed-shape conv kernel's constant-bank image)
     int16_t *ft_w;     // [F][L1p]
     int16_t *ft_b;     // [L1p]  bias truncated to int16 (simd_scalar.cpp:82-84)
     int32_t *ft_b32 = nullptr;  // [L1] the same bias as stored (the tensor-core accumulate wraps at the end)
@@ -147,7 +149,10 @@ static int parse_and_upload(const unsigned char *bytes, size_t n, nnue_qmodel *m
     std::vector<int16_t> fwp((size_t)F * m->L1p, 0), fbp((size_t)m->L1p, 0);
     for (uint32_t f = 0; f < F; ++f) memcpy(&fwp[(size_t)f * m->L1p], &fw[(size_t)f * L1], (size_t)L1 * 2);
     for (uint32_t i = 0; i < L1; ++i) fbp[i] = (int16_t)fb[i];
+    std::vector<int32_t> taps28 = cw32;
+    for (uint32_t oc = 0; oc < OC; ++oc) taps28[(size_t)oc * 28 + 27] = cb[oc];
     int rc;
+    if ((rc = upload(m, taps28, &m->conv_taps))) return rc;
     if ((rc = upload(m, cw32, &m->conv_w)) || (rc = upload(m, cb, &m->conv_b)) || (rc = upload(m, fwp, &m->ft_w)) ||
         (rc = upload(m, fbp, &m->ft_b)) || (rc = upload(m, fb, &m->ft_b32)))
         return rc;
@@ -236,25 +241,6 @@ static int parse_and_upload(const unsigned char *bytes, size_t n, nnue_qmodel *m
     }
     return NNUE_OK;
 }
-
-struct QParams {
-    int B, H, W, stride, oh, ow;
-    int F, L1, L2, L3, NC, OC, L1p, K1, K2, K3;
-    float threshold, conv_scale;
-    int conv_iscale, qone, l2_iscale;
-    float l1_scale, out_scale;
-    const int32_t *conv_w, *conv_b;
-    const int16_t *ft_w, *ft_b;
-    const int32_t *w1, *b1, *w2, *b2, *wo, *bo;
-    const float *images;
-    float *logits, *density;
-    // split form (MODE 1 / 2 of the kernel)
-    int G2, CWq;              // cells of the whole feature buffer (F / OC), bitmask words per channel
-    uint32_t *bits_out;       // MODE 1: [B][OC][CWq]
-    const int16_t *acc_in;    // MODE 2: [B][L1]
-};
-
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return max(lo, min(hi, v)); }
 
 constexpr int kQWarps = 8;
 
@@ -466,6 +452,7 @@ static int fill_params(const nnue_qmodel *m, int B, int H, int W, int bucket, QP
     if (q->conv_iscale == 0 || q->l2_iscale == 0) return NNUE_ERR_FORMAT;
     q->conv_w = m->conv_w; q->conv_b = m->conv_b; q->ft_w = m->ft_w; q->ft_b = m->ft_b;
     q->w1 = st.w1; q->b1 = st.b1; q->w2 = st.w2; q->b2 = st.b2; q->wo = st.wo; q->bo = st.bo;
+    q->G2 = m->F / m->OC; q->CWq = (q->G2 + 31) / 32;  // the whole G x G buffer as bitmask words per channel
     return NNUE_OK;
 }
 
@@ -575,13 +562,33 @@ int nnue_q_infer_ws(const nnue_qmodel *m, const float *images_d, int B, int H, i
         // large batches: bitmask -> tcgen05 accumulate -> layer stack (three launches, same integers) on the caller's scratch
         uint32_t *s_bits = static_cast<uint32_t *>(workspace_d);
         int16_t *s_acc = reinterpret_cast<int16_t *>(static_cast<char *>(workspace_d) + align_up((size_t)B * m->OC * m->CWq * 4, 256));
-        q.G2 = m->F / m->OC; q.CWq = m->CWq; q.bits_out = s_bits; q.acc_in = s_acc;
-        int rc2 = launch_q_infer(q, 1, st);
+        q.bits_out = s_bits; q.acc_in = s_acc;
+        int rc2 = (get_option(kOptQConvFixed) && q_conv_bits32_ok(q)) ? launch_q_conv_bits32(q, m->conv_taps, st)
+                                                                      : launch_q_infer(q, 1, st);
         if (rc2 != NNUE_OK) return rc2;
+        // the accumulate walks only the words that can hold a bit: a non-negative threshold leaves the cells past the conv
+        // raster inactive (nnue_engine.cpp:720); small stacks on a 64-wide accumulator finish in the same kernel
+        QAccArgs qa{};
+        qa.cw_all = m->CWq;
+        qa.cw_used = (0.0f > q.threshold) ? m->CWq : min(m->CWq, (q.oh * q.ow + 31) / 32);
+        qa.n_words_used = m->OC * qa.cw_used;
+        // (option q_stack_fused = the smallest batch that takes the one-kernel form, 0 = never: with few 128-sample tiles the
+        // serial epilogue of a CTA costs more than the extra launch -- measured 24.0 vs 22.3 us at 2048, 64.6 vs 70.0 at 16384)
+        const int fuse_min = get_option(kOptQStackFused);
+        const bool fused = fuse_min > 0 && B >= fuse_min && q_stack_fused_ok(m->L1, m->L2, m->L3, m->NC);
+        if (fused) {
+            qa.w1 = q.w1; qa.b1 = q.b1; qa.w2 = q.w2; qa.b2 = q.b2; qa.wo = q.wo; qa.bo = q.bo;
+            qa.L2 = q.L2; qa.L3 = q.L3; qa.NC = q.NC; qa.K2 = q.K2; qa.K3 = q.K3; qa.qone = q.qone; qa.l2_iscale = q.l2_iscale;
+            qa.l1_scale = q.l1_scale; qa.out_scale = q.out_scale; qa.logits = logits_d;
+        }
         rc2 = launch_q_accumulate_umma(B, m->OC * m->CWq, m->L1, s_bits, m->tc_tiles,
-                                       reinterpret_cast<const int32_t *>(m->ft_b32), s_acc, st);
-        if (rc2 != NNUE_OK) return rc2;
+                                       reinterpret_cast<const int32_t *>(m->ft_b32), s_acc, qa, st);
+        if (rc2 != NNUE_OK || fused) return rc2;
         return launch_q_infer(q, 2, st);
+    }
+    if (B <= get_option(kOptQCtaMaxBatch)) {  // small batches: a CTA per sample (falls through when its scratch does not fit)
+        const int rc2 = launch_q_infer_cta(q, st);
+        if (rc2 != NNUE_ERR_UNSUPPORTED) return rc2;
     }
     return launch_q_infer(q, 0, st);
 }

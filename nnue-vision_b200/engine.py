@@ -26,6 +26,7 @@ class NNUEEvaluator:
         self._acc = self._backup = None
         self._last_features = None
         self._dirty, self._incremental = True, True
+        self._ws_bytes = {}  # scratch size of the large-batch form per batch size
         if path is not None and not self.load_model(path):
             raise _lib.NnueError(f"cannot load {path}")
 
@@ -56,6 +57,7 @@ class NNUEEvaluator:
         self.visual_threshold = float(thr.value)
         self._acc = self._backup = self._last_features = None
         self._dirty = True
+        self._ws_bytes = {}
         return True
 
     def _require(self, t=None):
@@ -65,23 +67,42 @@ class NNUEEvaluator:
             raise _lib.NnueError(f"the model was loaded on {self.device} but the input lives on {t.device}: load one "
                                  "evaluator per device (inference runs per GPU, no peer traffic)")
 
-    def evaluate_logits(self, images: torch.Tensor, layer_stack_index: int = 0):
+    def evaluate_logits(self, images: torch.Tensor, layer_stack_index: int = 0, out=None):
         """images: CUDA float32 [B, H, W, 3] -- the raw buffer the engine would be handed, read as HWC
         (callers holding CHW tensors pass `chw.contiguous().view(B, H, W, 3)`, the byte
-        reinterpretation evaluate.py:154-168 performs).  Returns (logits [B, NC], density [B])."""
+        reinterpretation evaluate.py:154-168 performs).  Returns (logits [B, NC], density [B]).
+        `out=(logits, density)` reuses the caller's result tensors (a latency-bound loop over single images
+        then allocates nothing per call)."""
         self._require(images)
         if images.dim() != 4 or images.shape[-1] != 3:
             raise ValueError(f"expected images [B,H,W,3], got {tuple(images.shape)}")
         B, H, W, _ = images.shape
-        with _lib.on_device_of(images):
-            logits = torch.empty((B, self.num_classes), dtype=torch.float32, device=images.device)
-            density = torch.empty((B,), dtype=torch.float32, device=images.device)
+        dev = images.device
+        guard = None
+        if dev.index != torch.cuda.current_device():
+            guard = _lib.on_device_of(images)
+            guard.__enter__()
+        try:
+            if out is None:
+                logits = torch.empty((B, self.num_classes), dtype=torch.float32, device=dev)
+                density = torch.empty((B,), dtype=torch.float32, device=dev)
+            else:
+                logits, density = out
+                if tuple(logits.shape) != (B, self.num_classes) or tuple(density.shape) != (B,) or logits.device != dev \
+                        or density.device != dev:
+                    raise ValueError("out=(logits [B, NC], density [B]) on the images' device")
             # scratch of the large-batch (tensor-core) form comes from the caller: nothing is allocated or mutated
             # inside the C call, so several streams may share one evaluator's tables
-            ws_bytes = int(_lib.lib().nnue_q_workspace_bytes(self._h, B))
-            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=images.device) if ws_bytes else None
+            ws_bytes = self._ws_bytes.get(B)
+            if ws_bytes is None:
+                ws_bytes = self._ws_bytes[B] = int(_lib.lib().nnue_q_workspace_bytes(self._h, B))
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
             check(_lib.lib().nnue_q_infer_ws(self._h, dptr(images, torch.float32), B, H, W, int(layer_stack_index),
-                                             dptr(logits), dptr(density), dptr(ws), ws_bytes, stream_ptr()))
+                                             dptr(logits, torch.float32), dptr(density, torch.float32), dptr(ws), ws_bytes,
+                                             stream_ptr()))
+        finally:
+            if guard is not None:
+                guard.__exit__(None, None, None)
         return logits, density
 
     def evaluate_logits_host(self, images: np.ndarray, layer_stack_index: int = 0):

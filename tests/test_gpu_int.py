@@ -45,9 +45,12 @@ def test_matches_reference_engine_golden(name):
 
 @pytest.mark.parametrize("arch", INT_ARCHS, ids=lambda a: "x".join(map(str, a)))
 @pytest.mark.parametrize("wild", [False, True])
-def test_random_models_match_oracle(oracle_built, tmp_path, arch, wild):
+@pytest.mark.parametrize("form", ["cta", "warp"])
+def test_random_models_match_oracle(oracle_built, tmp_path, arch, wild, form):
     """Random .nnue payloads over the format's full integer ranges: int16 wraparound, every clamp,
-    negative thresholds (zero-filled tail of the conv buffer becomes active), > 64 channels."""
+    negative thresholds (zero-filled tail of the conv buffer becomes active), > 64 channels.
+    Both one-kernel forms: a CTA per sample (the default up to 1024 samples) and a warp per sample."""
+    from nnue_vision_b200 import _lib
     G, C, L1, L2, L3, NC, H = arch
     rng = np.random.default_rng(abs(hash(arch)) % (2**32) + 17 * wild)
     path = tmp_path / "m.nnue"
@@ -58,7 +61,11 @@ def test_random_models_match_oracle(oracle_built, tmp_path, arch, wild):
     orc = oracle_built.IntOracle(path)
     ol, od = orc.eval_batch(imgs, threads=4)
     ev = _engine().NNUEEvaluator(path)
-    gl, gd = gpu_eval(ev, imgs)
+    _lib.set_option("q_cta_max_batch", 1024 if form == "cta" else 0)
+    try:
+        gl, gd = gpu_eval(ev, imgs)
+    finally:
+        _lib.set_option("q_cta_max_batch", 1024)
     np.testing.assert_array_equal(gl, ol)
     np.testing.assert_array_equal(gd, od)
     if oracle_built.RefEngine.available():
@@ -231,15 +238,58 @@ def test_tensor_core_accumulate_matches_oracle(oracle_built, tmp_path, arch, wil
     ev = _engine().NNUEEvaluator(path)
     fl, fd = gpu_eval(ev, imgs)  # fused kernel (batch below the switch-over)
     _lib.set_option("q_tc_min_batch", 1)
+    _lib.set_option("q_stack_fused", 1)
     try:
-        tl, td = gpu_eval(ev, imgs)
+        tl, td = gpu_eval(ev, imgs)  # (L1 = 64 with a small stack: the layer stack runs in the accumulate kernel's epilogue)
         tl1, td1 = gpu_eval(ev, imgs[:1])
+        _lib.set_option("q_stack_fused", 0)
+        sl, sd = gpu_eval(ev, imgs)  # three launches: bitmask, accumulate to int16, layer stack
     finally:
         _lib.set_option("q_tc_min_batch", 2048)
+        _lib.set_option("q_stack_fused", 8192)
     np.testing.assert_array_equal(fl, ol)
     np.testing.assert_array_equal(tl, ol)
     np.testing.assert_array_equal(td, od)
     np.testing.assert_array_equal(tl1, ol[:1])
+    np.testing.assert_array_equal(sl, ol)
+    np.testing.assert_array_equal(sd, od)
+
+
+# 32 x 32 images at conv stride 4 (grids of 9..11 squares): the shapes q_conv_bits32_kernel serves, every channel count it is built for
+FIXED_CONV_ARCHS = [(10, 8, 64, 32, 8, 10, 32), (9, 4, 64, 8, 8, 10, 32), (11, 16, 64, 16, 8, 10, 32), (10, 32, 128, 16, 16, 10, 32)]
+
+
+@pytest.mark.parametrize("arch", FIXED_CONV_ARCHS, ids=lambda a: "x".join(map(str, a)))
+@pytest.mark.parametrize("thr", [-127.5, -127.0, -126.5, -1.0, -0.5, 0.0, 0.5, 1.0, 63.0, 126.5, 127.0])
+def test_fixed_conv_bitmask_matches_oracle(oracle_built, tmp_path, arch, thr):
+    """The TMA-staged conv + bitmask kernel of the large-batch form replaces the engine's truncating divide, clamp and
+    float compare by one integer compare against a host-computed bound: every threshold regime (never, always, the
+    truncation asymmetry around zero, the clamp ends) against the oracle and against the general conv kernel, on
+    saturating inputs, with a ragged batch (persistent CTAs, 14 consumer warps, two half-sample stages per sample)."""
+    from nnue_vision_b200 import _lib
+    G, C, L1, L2, L3, NC, H = arch
+    rng = np.random.default_rng(abs(hash((arch, thr))) % (2**32))
+    path = tmp_path / "m.nnue"
+    write_random_nnue(path, rng, G, C, L1, L2, L3, NC, wild=True, threshold=thr)
+    B = 2500
+    imgs = (rng.standard_normal((B, H, H, 3)) * rng.choice([0.05, 0.5, 3.0], size=(B, 1, 1, 1))).astype(np.float32)
+    imgs[0] = 0.0
+    ol, od = oracle_built.IntOracle(path).eval_batch(imgs, threads=oracle_built.host_threads())
+    ev = _engine().NNUEEvaluator(path)
+    _lib.set_option("q_stack_fused", 1)
+    try:
+        tl, td = gpu_eval(ev, imgs)                  # batch >= 2048: the tensor-core form with the fixed conv kernel
+        _lib.set_option("q_conv_fixed", 0)
+        _lib.set_option("q_stack_fused", 0)
+        gl, gd = gpu_eval(ev, imgs)                  # the general conv kernel, accumulate and layer stack as separate launches
+    finally:
+        _lib.set_option("q_conv_fixed", 1)
+        _lib.set_option("q_stack_fused", 8192)
+    np.testing.assert_array_equal(td, od)
+    np.testing.assert_array_equal(tl, ol)
+    np.testing.assert_array_equal(gd, od)
+    np.testing.assert_array_equal(gl, ol)
+    assert 0.0 < float(od.mean()) < 1.0 or thr in (-127.5, -127.0, 127.0)  # (the middle thresholds do exercise both outcomes)
 
 
 @pytest.mark.parametrize("arch", [(8, 4, 64, 4, 8, 10), (10, 8, 64, 32, 8, 10), (5, 3, 30, 5, 7, 3), (6, 16, 128, 16, 32, 1000)],

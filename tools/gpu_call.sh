@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests/test_gpu_float.py -m gpu -x -q 2>&1 | tail -3
-b() { name=$1; shift; timeout 600 python bench.py "$@" 2> gpurun_out/$name.err | tail -1 > gpurun_out/$name.json; python -c "import json;d=json.load(open('gpurun_out/$name.json'));print('$name',d['value'],d['ms_per_step'],d['stages_ms'])" || tail -5 gpurun_out/$name.err; }
-b c21_small --workload imagenet_small_b16384 --steps 5 --warmup 3 --windows 5 --no-cpu-baseline --no-module-api --no-e2e
-b c21_large --workload imagenet_large_b4096 --steps 5 --warmup 3 --windows 5 --no-cpu-baseline --no-module-api --no-e2e
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_int.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/s2_int_tests.log
+timeout 300 python tools/int_time.py 2>&1 | tee gpurun_out/s2_int_time.log | grep "^B="
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"q_conv|ft_bitgemm|q_infer" -c 6 -o gpurun_out/s2_int_b16384 -f python tools/int_time.py --profile 16384 > gpurun_out/s2_ncu.log 2>&1; tail -3 gpurun_out/s2_ncu.log
