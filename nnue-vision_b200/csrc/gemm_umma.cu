@@ -32,6 +32,11 @@ struct UGemmArgs {
     const float *mask; long long ldm;    // C *= (mask[m * ldm + n] > 0), or null
     int ks_per_split;                    // k-steps per blockIdx.z slice
     long long c_split_stride;            // elements between consecutive split-K partials of C
+    // pairwise-backward epilogue (NT = 256, B operand formatted with pair_perm = h): the tile's first 128 columns are
+    // g_l0[:, i], the last 128 g_l0[:, h + i] for i = 128 nt ..; C is g_ft [M][2 h] and is written as
+    //   g_ft[:, i] = g_l0[:, i] * ft[:, h + i] + g_l0[:, h + i],   g_ft[:, h + i] = g_l0[:, i] * ft[:, i]     (nnue.py:660-666 backward)
+    const float *pair_ft;                // ft_out [M][2 h] (ldc), or null
+    int pair_h;
 };
 
 // value of operand element (r, k) read from a row-major fp32 source; pair_half > 0 applies the pairwise transform
@@ -85,18 +90,26 @@ __global__ void ugemm_format_rows_kernel(const float *__restrict__ src, long lon
 // "cols": operand row n = source column n, k = source row (K = number of source rows).  One thread = 8 consecutive
 // k (source rows) of one column; neighbouring threads take neighbouring columns (coalesced reads).
 // pair_half > 0: the source row is x[2h] and the operand column n is l0[n].
+// pair_perm = h > 0 (RT = 256, ncols = 2 h, h a multiple of 128): operand row n of tile t holds source column
+// 128 t + n % 256 for the first 128 rows of the tile and h + 128 t + n % 256 - 128 for the last 128, so that one N tile
+// carries both members of every pairwise pair (the GEMM's pairwise-backward epilogue).
 template <int RT>
 __global__ void ugemm_format_cols_kernel(const float *__restrict__ src, long long ld, int K, int ncols, int pair_half,
-                                         int n_rt, int n_ks, unsigned char *__restrict__ out) {
+                                         int pair_perm, int n_rt, int n_ks, unsigned char *__restrict__ out) {
     const long long i = 1LL * blockIdx.x * blockDim.x + threadIdx.x;
     const int NR = n_rt * RT;
     if (i >= 1LL * NR * n_ks * 2) return;
     const int n = (int)(i % NR), kc = (int)(i / NR);
+    int col = n;
+    if (pair_perm > 0) {
+        const int t = n / 256, r = n % 256;
+        col = r < 128 ? 128 * t + r : pair_perm + 128 * t + r - 128;
+    }
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int k = kc * 8 + j;
-        v[j] = (n < ncols && k < K) ? pair_load(src + (size_t)k * ld, n, pair_half) : 0.0f;
+        v[j] = (n < ncols && k < K) ? pair_load(src + (size_t)k * ld, col, pair_half) : 0.0f;
     }
     uint4 o[3];
     split3x8(v, o);
@@ -184,6 +197,31 @@ ugemm_kernel(const UGemmArgs g) {
         const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16);
         float *crow = g.C + (size_t)split * g.c_split_stride + (size_t)min(m, g.M - 1) * g.ldc;
         const float *mrow = g.mask ? g.mask + (size_t)min(m, g.M - 1) * g.ldm : nullptr;
+        if (NT == 256 && g.pair_ft) {
+            // pairwise backward on the accumulator row: columns c (product slot) and 128 + c (pass-through slot) of this tile
+            const float *frow = g.pair_ft + (size_t)min(m, g.M - 1) * g.ldc;
+            const int h = g.pair_h;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += 16) {
+                const int i0 = nt * 128 + c0;
+                float gp[16], ga[16];
+                tmem_ld16(tbase + (uint32_t)c0, gp);
+                tmem_ld16(tbase + (uint32_t)(128 + c0), ga);
+                tmem_ld_wait();
+                if (m < g.M) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 fa = __ldg(reinterpret_cast<const float4 *>(frow + i0) + u);
+                        const float4 fb = __ldg(reinterpret_cast<const float4 *>(frow + h + i0) + u);
+                        reinterpret_cast<float4 *>(crow + i0)[u] =
+                            make_float4(fmaf(gp[4 * u], fb.x, ga[4 * u]), fmaf(gp[4 * u + 1], fb.y, ga[4 * u + 1]),
+                                        fmaf(gp[4 * u + 2], fb.z, ga[4 * u + 2]), fmaf(gp[4 * u + 3], fb.w, ga[4 * u + 3]));
+                        reinterpret_cast<float4 *>(crow + h + i0)[u] =
+                            make_float4(gp[4 * u] * fa.x, gp[4 * u + 1] * fa.y, gp[4 * u + 2] * fa.z, gp[4 * u + 3] * fa.w);
+                    }
+                }
+            }
+        } else
 #pragma unroll 2
         for (int c0 = 0; c0 < NT; c0 += 16) {
             const int n0 = nt * NT + c0;
@@ -231,12 +269,13 @@ int ugemm_format_rows(int RT, const float *src, long long ld, int nrows, int K, 
     return NNUE_OK;
 }
 int ugemm_format_cols(int RT, const float *src, long long ld, int K, int ncols, int pair_half, unsigned char *out,
-                      cudaStream_t st) {
+                      cudaStream_t st, int pair_perm) {
     const int n_rt = ceil_div(ncols, RT), n_ks = ceil_div(K, 16);
     const long long n = 1LL * n_rt * RT * n_ks * 2;
     const int grid = (int)((n + 255) / 256);
-    if (RT == 128) ugemm_format_cols_kernel<128><<<grid, 256, 0, st>>>(src, ld, K, ncols, pair_half, n_rt, n_ks, out);
-    else ugemm_format_cols_kernel<256><<<grid, 256, 0, st>>>(src, ld, K, ncols, pair_half, n_rt, n_ks, out);
+    if (pair_perm > 0 && (RT != 256 || pair_perm % 128 || ncols != 2 * pair_perm)) return NNUE_ERR_INVALID_ARG;
+    if (RT == 128) ugemm_format_cols_kernel<128><<<grid, 256, 0, st>>>(src, ld, K, ncols, pair_half, 0, n_rt, n_ks, out);
+    else ugemm_format_cols_kernel<256><<<grid, 256, 0, st>>>(src, ld, K, ncols, pair_half, pair_perm, n_rt, n_ks, out);
     NNUE_CHECK_LAUNCH("ugemm_format_cols_kernel");
     return NNUE_OK;
 }
@@ -245,8 +284,10 @@ int ugemm_format_cols(int RT, const float *src, long long ld, int K, int ncols, 
 // C + z * c_split_stride).  Returns the number of splits actually used (every split non-empty), or < 0.
 int ugemm_launch(int NT, int M, int N, int K, const unsigned char *at, const unsigned char *bt, float *C, long long ldc,
                  const float *bias, int relu, const float *mask, long long ldm, int splits, long long c_split_stride,
-                 cudaStream_t st) {
+                 cudaStream_t st, const float *pair_ft, int pair_h) {
     UGemmArgs g{};
+    if (pair_ft && (NT != 256 || splits > 1 || N != 2 * pair_h || pair_h % 128 || (ldc & 3))) return NNUE_ERR_INVALID_ARG;
+    g.pair_ft = pair_ft; g.pair_h = pair_h;
     g.M = M; g.N = N; g.n_ks = ceil_div(K, 16);
     g.at = at; g.bt = bt; g.C = C; g.ldc = ldc; g.bias = bias; g.relu = relu; g.mask = mask; g.ldm = ldm;
     if (splits < 1) splits = 1;

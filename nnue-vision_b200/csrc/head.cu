@@ -251,31 +251,39 @@ __global__ void head_fold_kernel(long long n, int nparts, long long stride, cons
     out[i] = acc;
 }
 
-// forward with optional scratch: layer 1 on the tensor cores when the shape is wide and the scratch is there
-int head_fwd_ws(const nnue_shape *s, const float *ft_out_d, const float *w1_d, const float *b1_d, const float *w2_d,
-                const float *b2_d, const float *w3_d, const float *b3_d, float *act1_d, float *act2_d, float *logits_d,
-                void *workspace_d, size_t workspace_bytes, cudaStream_t st) {
-    GemmArgs g{};
-    g.b_ones_col = -1;
+// layer 1 alone: act1 = relu(l0 W1^T + b1), l0 = the pairwise transform of ft_out; on the tensor cores when the shape is wide
+// and the scratch (ws_head_umma_fwd bytes) is there
+int head_layer1_fwd(const nnue_shape *s, const float *ft_out_d, const float *w1_d, const float *b1_d, float *act1_d,
+                    void *workspace_d, size_t workspace_bytes, cudaStream_t st) {
     int rc;
     if (head_umma_ok(*s) && workspace_d && workspace_bytes >= ws_head_umma_fwd(*s)) {
-        // act1 = relu(l0 W1^T + b1): A = l0 (pairwise transform fused into the formatter), B = W1, both K-major
+        // A = l0 (pairwise transform fused into the formatter), B = W1, both K-major
         const int NT = head_umma_nt(*s);
         unsigned char *at = static_cast<unsigned char *>(workspace_d);
         unsigned char *bt = at + align_up(ugemm_tile_bytes(s->B, 128, s->L1), 256);
         if ((rc = ugemm_format_rows(128, ft_out_d, s->L1, s->B, s->L1, s->L1 / 2, at, st)) < 0) return rc;
         if ((rc = ugemm_format_rows(NT, w1_d, s->L1, s->L2, s->L1, 0, bt, st)) < 0) return rc;
         rc = ugemm_launch(NT, s->B, s->L2, s->L1, at, bt, act1_d, s->L2, b1_d, 1, nullptr, 0, 1, 0, st);
-        if (rc < 0) return rc;
-    } else {
-        // layer 1: act1 = relu(l0 * W1^T + b1), l0 built on the fly from ft_out
-        g.A = ft_out_d; g.sam = s->L1; g.sak = 1; g.a_pair_half = s->L1 / 2;
-        g.Bm = w1_d; g.sbk = 1; g.sbn = s->L1;
-        g.M = s->B; g.N = s->L2; g.K = s->L1;
-        g.C = act1_d; g.scm = s->L2; g.bias = b1_d; g.relu = 1;
-        rc = launch_gemm(g, 1, st);
-        if (rc < 0) return rc;
+        return rc < 0 ? rc : NNUE_OK;
     }
+    GemmArgs g{};
+    g.b_ones_col = -1;
+    g.A = ft_out_d; g.sam = s->L1; g.sak = 1; g.a_pair_half = s->L1 / 2;  // l0 built on the fly from ft_out
+    g.Bm = w1_d; g.sbk = 1; g.sbn = s->L1;
+    g.M = s->B; g.N = s->L2; g.K = s->L1;
+    g.C = act1_d; g.scm = s->L2; g.bias = b1_d; g.relu = 1;
+    rc = launch_gemm(g, 1, st);
+    return rc < 0 ? rc : NNUE_OK;
+}
+
+// forward with optional scratch: layer 1 on the tensor cores when the shape is wide and the scratch is there
+int head_fwd_ws(const nnue_shape *s, const float *ft_out_d, const float *w1_d, const float *b1_d, const float *w2_d,
+                const float *b2_d, const float *w3_d, const float *b3_d, float *act1_d, float *act2_d, float *logits_d,
+                void *workspace_d, size_t workspace_bytes, cudaStream_t st) {
+    GemmArgs g{};
+    g.b_ones_col = -1;
+    int rc = head_layer1_fwd(s, ft_out_d, w1_d, b1_d, act1_d, workspace_d, workspace_bytes, st);
+    if (rc != NNUE_OK) return rc;
     // layer 2
     g.A = act1_d; g.sam = s->L2; g.sak = 1; g.a_pair_half = 0;
     g.Bm = w2_d; g.sbk = 1; g.sbn = s->L2;
@@ -290,6 +298,82 @@ int head_fwd_ws(const nnue_shape *s, const float *ft_out_d, const float *w1_d, c
     g.C = logits_d; g.scm = s->NC; g.bias = b3_d; g.relu = 0;
     rc = launch_gemm(g, 1, st);
     return rc < 0 ? rc : NNUE_OK;
+}
+
+// scratch of nnue_head_bwd: split-K partials of the three weight(+bias) gradients, g_act2, g_act1 (= g_z1), g_l0, then
+// the tensor-core scratch of layer 1 (ws_head_umma_bwd); the many-class scratch sits at the END (ws_head3_umma_bwd)
+HeadBwdWs carve_head_bwd(const nnue_shape &s, void *workspace_d) {
+    char *ws = static_cast<char *>(workspace_d);
+    auto carve = [&](size_t bytes) { float *p = reinterpret_cast<float *>(ws); ws += align_up(bytes, 256); return p; };
+    HeadBwdWs w{};
+    w.p3 = carve((size_t)gemm_splits(s.NC, s.L3 + 1, s.B, 64, 64) * s.NC * (s.L3 + 1) * 4);
+    w.p2 = carve((size_t)gemm_splits(s.L3, s.L2 + 1, s.B, 64, 64) * s.L3 * (s.L2 + 1) * 4);
+    w.p1 = carve((size_t)gemm_splits(s.L2, s.L1 + 1, s.B, 64, 64) * s.L2 * (s.L1 + 1) * 4);
+    w.g_act2 = carve((size_t)s.B * s.L3 * 4);
+    w.g_act1 = carve((size_t)s.B * s.L2 * 4);
+    w.g_l0 = carve((size_t)s.B * s.L1 * 4);
+    w.rest = ws;
+    return w;
+}
+
+// layer 1 backward from g_z1 (bw.g_act1, already masked by act1 > 0): g_w1, g_b1, g_l0 and the pairwise backward -> g_ft
+int head_bwd_layer1(const nnue_shape *s, const HeadBwdWs &bw, const float *ft_out_d, const float *w1_d, float *g_w1_d,
+                    float *g_b1_d, float *g_ft_d, cudaStream_t st) {
+    const int B = s->B, L1 = s->L1, L2 = s->L2;
+    float *g_act1 = bw.g_act1, *g_l0 = bw.g_l0, *p1 = bw.p1;
+    char *ws = bw.rest;
+    int rc;
+    GemmArgs g{};
+    g.b_ones_col = -1;
+    g.sak = 1; g.sbn = 1; g.M = B;
+    if (head_umma_ok(*s)) {
+        // both layer-1 gradients as split-bf16 tcgen05 GEMMs (scratch carved behind g_l0)
+        auto carve_b = [&](size_t bytes) { unsigned char *p = reinterpret_cast<unsigned char *>(ws); ws += align_up(bytes, 256); return p; };
+        unsigned char *g1_rows = carve_b(ugemm_tile_bytes(B, 128, L2)), *w1_cols = carve_b(ugemm_tile_bytes(L1, 256, L2));
+        unsigned char *g1_cols = carve_b(ugemm_tile_bytes(L2, 128, B)), *l0_cols = carve_b(ugemm_tile_bytes(L1, 256, B));
+        const int splits = head_umma_wgrad_splits(*s);
+        float *wpart = reinterpret_cast<float *>(carve_b((size_t)splits * L2 * L1 * 4));
+        float *cpart = reinterpret_cast<float *>(carve_b((size_t)ceil_div(B, 256) * L2 * 4));
+        // g_w1[o, i] = sum_b g_z1[b, o] l0[b, i]: A = g_z1^T, B = l0^T (pairwise fused), K = batch, split-K partials
+        if ((rc = ugemm_format_cols(128, g_act1, L2, B, L2, 0, g1_cols, st)) < 0) return rc;
+        if ((rc = ugemm_format_cols(256, ft_out_d, L1, B, L1, L1 / 2, l0_cols, st)) < 0) return rc;
+        const int nz = ugemm_launch(256, L2, L1, B, g1_cols, l0_cols, wpart, L1, nullptr, 0, nullptr, 0, splits, (long long)L2 * L1, st);
+        if (nz < 0) return nz;
+        const long long nw = 1LL * L2 * L1;
+        head_fold_kernel<<<(int)((nw + 255) / 256), 256, 0, st>>>(nw, nz, nw, wpart, g_w1_d);
+        NNUE_CHECK_LAUNCH("head_fold_kernel");
+        const int nrc = ceil_div(B, 256);
+        head_colsum_partial_kernel<<<dim3(ceil_div(L2, 128), nrc), 128, 0, st>>>(B, L2, g_act1, cpart);
+        NNUE_CHECK_LAUNCH("head_colsum_partial_kernel");
+        head_fold_kernel<<<ceil_div(L2, 256), 256, 0, st>>>(L2, nrc, L2, cpart, g_b1_d);
+        NNUE_CHECK_LAUNCH("head_fold_kernel");
+        // g_l0 = g_z1 W1: A = g_z1, B = W1^T
+        if ((rc = ugemm_format_rows(128, g_act1, L2, B, L2, 0, g1_rows, st)) < 0) return rc;
+        if (head_pair_epilogue_ok(*s)) {
+            // W1's columns permuted so that an N tile holds g_l0[:, i] and g_l0[:, h + i]: the epilogue writes g_ft itself
+            // (no g_l0 round trip, no pairwise kernel: 37 us of the 0.96 ms step at L1 = 1024, batch 16384)
+            if ((rc = ugemm_format_cols(256, w1_d, L1, L2, L1, 0, w1_cols, st, L1 / 2)) < 0) return rc;
+            rc = ugemm_launch(256, B, L1, L2, g1_rows, w1_cols, g_ft_d, L1, nullptr, 0, nullptr, 0, 1, 0, st, ft_out_d, L1 / 2);
+            return rc < 0 ? rc : NNUE_OK;
+        }
+        if ((rc = ugemm_format_cols(256, w1_d, L1, L2, L1, 0, w1_cols, st)) < 0) return rc;
+        rc = ugemm_launch(256, B, L1, L2, g1_rows, w1_cols, g_l0, L1, nullptr, 0, nullptr, 0, 1, 0, st);
+        if (rc < 0) return rc;
+    } else {
+        rc = wgrad(g_act1, L2, ft_out_d, L1, L1 / 2, B, p1, g_w1_d, g_b1_d, st);
+        if (rc < 0) return rc;
+        // g_l0 = g_z1 * W1, then the pairwise backward
+        g.A = g_act1; g.sam = L2;
+        g.Bm = w1_d; g.sbk = L1;
+        g.N = L1; g.K = L2;
+        g.C = g_l0; g.scm = L1; g.mask = nullptr;
+        rc = launch_gemm(g, 1, st);
+        if (rc < 0) return rc;
+    }
+    const long long n = 1LL * B * (L1 / 2);
+    pairwise_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(n, L1 / 2, g_l0, ft_out_d, g_ft_d);
+    NNUE_CHECK_LAUNCH("pairwise_bwd_kernel");
+    return NNUE_OK;
 }
 
 }  // namespace nnue
@@ -335,16 +419,9 @@ int nnue_head_bwd(const nnue_shape *s, const float *g_logits_d, const float *ft_
         return NNUE_ERR_INVALID_ARG;
     if (workspace_bytes < ws_head_bwd(*s)) return NNUE_ERR_WORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int B = s->B, L1 = s->L1, L2 = s->L2, L3 = s->L3, NC = s->NC;
-    char *ws = static_cast<char *>(workspace_d);
-    auto carve = [&](size_t bytes) { float *p = reinterpret_cast<float *>(ws); ws += align_up(bytes, 256); return p; };
-    float *p3 = carve((size_t)gemm_splits(NC, L3 + 1, B, 64, 64) * NC * (L3 + 1) * 4);
-    float *p2 = carve((size_t)gemm_splits(L3, L2 + 1, B, 64, 64) * L3 * (L2 + 1) * 4);
-    float *p1 = carve((size_t)gemm_splits(L2, L1 + 1, B, 64, 64) * L2 * (L1 + 1) * 4);
-    float *g_act2 = carve((size_t)B * L3 * 4);
-    float *g_act1 = carve((size_t)B * L2 * 4);
-    float *g_l0 = carve((size_t)B * L1 * 4);
-
+    const int B = s->B, L2 = s->L2, L3 = s->L3, NC = s->NC;
+    const HeadBwdWs bw = carve_head_bwd(*s, workspace_d);
+    float *p3 = bw.p3, *p2 = bw.p2, *g_act2 = bw.g_act2, *g_act1 = bw.g_act1;
     int rc;
     GemmArgs g{};
     g.b_ones_col = -1;
@@ -397,47 +474,7 @@ int nnue_head_bwd(const nnue_shape *s, const float *g_logits_d, const float *ft_
     g.C = g_act1; g.scm = L2; g.mask = act1_d; g.smm = L2;
     rc = launch_gemm(g, 1, st);
     if (rc < 0) return rc;
-    if (head_umma_ok(*s)) {
-        // both layer-1 gradients as split-bf16 tcgen05 GEMMs (scratch carved behind g_l0)
-        auto carve_b = [&](size_t bytes) { unsigned char *p = reinterpret_cast<unsigned char *>(ws); ws += align_up(bytes, 256); return p; };
-        unsigned char *g1_rows = carve_b(ugemm_tile_bytes(B, 128, L2)), *w1_cols = carve_b(ugemm_tile_bytes(L1, 256, L2));
-        unsigned char *g1_cols = carve_b(ugemm_tile_bytes(L2, 128, B)), *l0_cols = carve_b(ugemm_tile_bytes(L1, 256, B));
-        const int splits = head_umma_wgrad_splits(*s);
-        float *wpart = reinterpret_cast<float *>(carve_b((size_t)splits * L2 * L1 * 4));
-        float *cpart = reinterpret_cast<float *>(carve_b((size_t)ceil_div(B, 256) * L2 * 4));
-        // g_w1[o, i] = sum_b g_z1[b, o] l0[b, i]: A = g_z1^T, B = l0^T (pairwise fused), K = batch, split-K partials
-        if ((rc = ugemm_format_cols(128, g_act1, L2, B, L2, 0, g1_cols, st)) < 0) return rc;
-        if ((rc = ugemm_format_cols(256, ft_out_d, L1, B, L1, L1 / 2, l0_cols, st)) < 0) return rc;
-        const int nz = ugemm_launch(256, L2, L1, B, g1_cols, l0_cols, wpart, L1, nullptr, 0, nullptr, 0, splits, (long long)L2 * L1, st);
-        if (nz < 0) return nz;
-        const long long nw = 1LL * L2 * L1;
-        head_fold_kernel<<<(int)((nw + 255) / 256), 256, 0, st>>>(nw, nz, nw, wpart, g_w1_d);
-        NNUE_CHECK_LAUNCH("head_fold_kernel");
-        const int nrc = ceil_div(B, 256);
-        head_colsum_partial_kernel<<<dim3(ceil_div(L2, 128), nrc), 128, 0, st>>>(B, L2, g_act1, cpart);
-        NNUE_CHECK_LAUNCH("head_colsum_partial_kernel");
-        head_fold_kernel<<<ceil_div(L2, 256), 256, 0, st>>>(L2, nrc, L2, cpart, g_b1_d);
-        NNUE_CHECK_LAUNCH("head_fold_kernel");
-        // g_l0 = g_z1 W1: A = g_z1, B = W1^T
-        if ((rc = ugemm_format_rows(128, g_act1, L2, B, L2, 0, g1_rows, st)) < 0) return rc;
-        if ((rc = ugemm_format_cols(256, w1_d, L1, L2, L1, 0, w1_cols, st)) < 0) return rc;
-        rc = ugemm_launch(256, B, L1, L2, g1_rows, w1_cols, g_l0, L1, nullptr, 0, nullptr, 0, 1, 0, st);
-        if (rc < 0) return rc;
-    } else {
-        rc = wgrad(g_act1, L2, ft_out_d, L1, L1 / 2, B, p1, g_w1_d, g_b1_d, st);
-        if (rc < 0) return rc;
-        // g_l0 = g_z1 * W1, then the pairwise backward
-        g.A = g_act1; g.sam = L2;
-        g.Bm = w1_d; g.sbk = L1;
-        g.N = L1; g.K = L2;
-        g.C = g_l0; g.scm = L1; g.mask = nullptr;
-        rc = launch_gemm(g, 1, st);
-        if (rc < 0) return rc;
-    }
-    const long long n = 1LL * B * (L1 / 2);
-    pairwise_bwd_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(n, L1 / 2, g_l0, ft_out_d, g_ft_d);
-    NNUE_CHECK_LAUNCH("pairwise_bwd_kernel");
-    return NNUE_OK;
+    return head_bwd_layer1(s, bw, ft_out_d, w1_d, g_w1_d, g_b1_d, g_ft_d, st);
 }
 
 }  // extern "C"

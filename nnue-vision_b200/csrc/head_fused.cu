@@ -455,10 +455,26 @@ int nnue_head_train(const nnue_shape *s, const float *ft_out_d, const int64_t *l
         NNUE_CHECK_LAUNCH("head_train_fold_kernel");
         return NNUE_OK;
     }
-    // larger stacks: the layer kernels of head.cu, with the activations in scratch
     char *ws = static_cast<char *>(workspace_d);
     auto carve = [&](size_t bytes) { float *p = reinterpret_cast<float *>(ws); ws += align_up(bytes, 256); return p; };
     const size_t B = s->B;
+    if (head_mid_ok(*s)) {
+        // wide first layer, small tail: layer 1 forward (tensor cores when wide), then ONE kernel for layers 2 - 3, the
+        // loss and their gradients (head_mid.cu), then layer 1 backward.  act1 | per-CTA partials | backward scratch | forward scratch
+        float *act1 = carve(B * s->L2 * 4);
+        float *midp = carve((size_t)head_mid_grid(*s) * kHeadMidPartial * 4);
+        const size_t rest = workspace_bytes - (size_t)(ws - static_cast<char *>(workspace_d));
+        const size_t fwd_ws = ws_head_umma_fwd(*s);
+        void *fwd_scratch = fwd_ws && rest >= ws_head_bwd(*s) + fwd_ws ? ws + align_up(ws_head_bwd(*s), 256) : nullptr;
+        int rc = head_layer1_fwd(s, ft_out_d, w1_d, b1_d, act1, fwd_scratch, fwd_scratch ? fwd_ws : 0, st);
+        if (rc != NNUE_OK) return rc;
+        const HeadBwdWs bw = carve_head_bwd(*s, ws);
+        rc = launch_head_mid(*s, act1, labels_d, inv_count, w2_d, b2_d, w3_d, b3_d, loss_d, bw.g_act1, g_w2_d, g_b2_d, g_w3_d,
+                             g_b3_d, midp, st);
+        if (rc != NNUE_OK) return rc;
+        return head_bwd_layer1(s, bw, ft_out_d, w1_d, g_w1_d, g_b1_d, g_ft_d, st);
+    }
+    // other stacks: the layer kernels of head.cu, with the activations in scratch
     float *act1 = carve(B * s->L2 * 4), *act2 = carve(B * s->L3 * 4), *logits = carve(B * s->NC * 4);
     float *g_logits = carve(B * s->NC * 4), *per = carve(B * 4);
     const size_t rest = workspace_bytes - (size_t)(ws - static_cast<char *>(workspace_d));

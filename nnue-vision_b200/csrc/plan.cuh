@@ -517,10 +517,13 @@ inline size_t ws_head_umma_bwd(const nnue_shape &s) {
 int ugemm_format_rows(int RT, const float *src, long long ld, int nrows, int K, int pair_half, unsigned char *out,
                       cudaStream_t st);
 int ugemm_format_cols(int RT, const float *src, long long ld, int K, int ncols, int pair_half, unsigned char *out,
-                      cudaStream_t st);
+                      cudaStream_t st, int pair_perm = 0);
+// pair_ft != null (NT = 256, B operand formatted with pair_perm = pair_h): the pairwise backward runs in the epilogue and C is g_ft
 int ugemm_launch(int NT, int M, int N, int K, const unsigned char *at, const unsigned char *bt, float *C, long long ldc,
                  const float *bias, int relu, const float *mask, long long ldm, int splits, long long c_split_stride,
-                 cudaStream_t st);
+                 cudaStream_t st, const float *pair_ft = nullptr, int pair_h = 0);
+// the input gradient of layer 1 with the pairwise backward in the GEMM's epilogue: both members of a pair in one N tile
+inline bool head_pair_epilogue_ok(const nnue_shape &s) { return get_option(kOptHeadPairEpi) && head_umma_ok(s) && (s.L1 / 2) % 128 == 0; }
 // forward of the stack with optional scratch (head.cu): with ws_head_umma_fwd bytes layer 1 runs on the tensor cores
 int head_fwd_ws(const nnue_shape *s, const float *ft_out_d, const float *w1_d, const float *b1_d, const float *w2_d,
                 const float *b2_d, const float *w3_d, const float *b3_d, float *act1_d, float *act2_d, float *logits_d,
@@ -619,11 +622,31 @@ inline int head_train_grid(const nnue_shape &s) {
     const int ntiles = ceil_div(s.B, kHeadTile);
     return ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs;
 }
+// ---- layers 2 - 3 + cross-entropy + their backward in one kernel (head_mid.cu) for wide stacks with a small tail ----
+constexpr int kHeadMidPartial = 4660;  // floats per per-CTA gradient block (MidLayout::pTotal)
+inline bool head_mid_ok(const nnue_shape &s) {
+    return get_option(kOptHeadMid) && !head_train_fused_ok(s) && s.L2 % 4 == 0 && s.L2 <= 128 && s.L3 <= 32 && s.NC <= 16;
+}
+inline int head_mid_grid(const nnue_shape &s) {  // persistent CTAs over 128-sample tiles (option head_mid > 1 caps the grid: tests)
+    const int t = ceil_div(s.B, 128), cap = get_option(kOptHeadMid) > 1 ? get_option(kOptHeadMid) : kNumSMs;
+    return t < cap ? t : (cap < kNumSMs ? cap : kNumSMs);
+}
+int launch_head_mid(const nnue_shape &s, const float *act1, const int64_t *labels, float inv_count, const float *w2, const float *b2,
+                    const float *w3, const float *b3, float *loss, float *g_z1, float *g_w2, float *g_b2, float *g_w3, float *g_b3,
+                    float *partial, cudaStream_t st);
+// pieces of head.cu shared with nnue_head_train
+struct HeadBwdWs { float *p3, *p2, *p1, *g_act2, *g_act1, *g_l0; char *rest; };
+HeadBwdWs carve_head_bwd(const nnue_shape &s, void *workspace_d);
+int head_layer1_fwd(const nnue_shape *s, const float *ft_out_d, const float *w1_d, const float *b1_d, float *act1_d,
+                    void *workspace_d, size_t workspace_bytes, cudaStream_t st);
+int head_bwd_layer1(const nnue_shape *s, const HeadBwdWs &bw, const float *ft_out_d, const float *w1_d, float *g_w1_d,
+                    float *g_b1_d, float *g_ft_d, cudaStream_t st);
+
 inline size_t ws_head_train(const nnue_shape &s) {
     if (head_train_fused_ok(s)) return (size_t)head_train_grid(s) * kHeadPartial * 4;
     const size_t B = s.B;
     return align_up(B * s.L2 * 4, 256) + align_up(B * s.L3 * 4, 256) + 2 * align_up(B * s.NC * 4, 256) +
-           align_up(B * 4, 256) + ws_head_bwd(s) + ws_head_umma_fwd(s);
+           align_up(B * 4, 256) + ws_head_bwd(s) + ws_head_umma_fwd(s) + align_up((size_t)kNumSMs * kHeadMidPartial * 4, 256);
 }
 inline size_t ws_ce(int B) { return align_up((size_t)B * 4, 256); }
 

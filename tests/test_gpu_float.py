@@ -213,7 +213,7 @@ OPTION_DEFAULTS = {"extract_tma": 0, "ft_form": 0, "input_bwd_onchip": 0}
 
 @pytest.mark.parametrize("options", [dict(extract_tma=1), dict(extract_fixed=0), dict(ft_umma=0), dict(ft_umma=0, ft_mma=0),
                                      dict(ft_umma=0, ft_mma=0, ft_bwd_both=0), dict(ft_umma=0, ft_mma=0, ft_bwd_dw_owner=0),
-                                     dict(ft_umma=0, ft_mma=0, input_bwd_fused=0), dict(input_bwd_fused=0), dict(input_bwd_onchip=1), dict(ft_form=2), dict(ft_form=2, input_bwd_fused=0), dict(input_bwd_variant=0), dict(input_bwd_swizzle=0), dict(input_bwd_swizzle=0, input_bwd_variant=0), dict(head_fused=0), dict(head_umma=0),
+                                     dict(ft_umma=0, ft_mma=0, input_bwd_fused=0), dict(input_bwd_fused=0), dict(input_bwd_onchip=1), dict(ft_form=2), dict(ft_form=2, input_bwd_fused=0), dict(input_bwd_variant=0), dict(input_bwd_swizzle=0), dict(input_bwd_swizzle=0, input_bwd_variant=0), dict(head_fused=0), dict(head_umma=0), dict(head_mid=0), dict(head_mid=0, head_umma=0), dict(head_mid=2), dict(head_pair_epilogue=0),
                                      dict(ft_umma=0, ft_mma=0, ft_bwd_dw_owner=0, input_bwd_fused=0, head_fused=0)],
                          ids=str)
 @pytest.mark.parametrize("name", ["D", "T", "big_into_small", "D1k_tensor_head"])
