@@ -353,24 +353,52 @@ def int_inference_leg(w, device, seconds):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         out["device"] = {"value": B / (ms * 1e-3), "unit": "samples/s", "batch": B, "ms": ms}
-        # BASELINE config "batch sweep 1..65536": device-resident throughput per batch size (images [Bs,32,32,3] views
-        # of one buffer; small batches run the fused kernel, >= 2048 the bitmask -> tcgen05 accumulate -> stack form)
-        sweep = {}
+        # BASELINE config "batch sweep 1..65536": device-resident throughput per batch size (images [Bs,32,32,3] views of
+        # one buffer; <= 592 samples: a CTA per sample, < 2048: a warp per sample, >= 2048: conv + bitmask -> tcgen05
+        # accumulate (+ the layer stack in its epilogue from 8192 up)).  Two numbers per size: the Python call loop
+        # (evaluate_logits with reused result tensors; small batches are bound by ~19 us of host time per call) and the
+        # same calls replayed as one CUDA graph = device time per call
+        sweep, sweep_dev, call_us, dev_us = {}, {}, {}, {}
         big = torch.randn(65536, w["image"], w["image"], 3, generator=torch.Generator().manual_seed(4)).to(device) \
             if w["image"] <= 64 else None
         if big is not None:
             for Bs in (1, 16, 256, 4096, 16384, 65536):
                 x = big[:Bs]
+                res = (torch.empty(Bs, ev.num_classes, device=device), torch.empty(Bs, device=device))
                 for _ in range(3):
-                    ev.evaluate_logits(x)
+                    ev.evaluate_logits(x, out=res)
                 n_rep = 50
                 e0.record()
                 for _ in range(n_rep):
-                    ev.evaluate_logits(x)
+                    ev.evaluate_logits(x, out=res)
                 e1.record()
                 torch.cuda.synchronize()
+                call_us[str(Bs)] = 1e3 * e0.elapsed_time(e1) / n_rep
                 sweep[str(Bs)] = Bs / (e0.elapsed_time(e1) / n_rep * 1e-3)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for _ in range(n_rep):
+                        ev.evaluate_logits(x, out=res)
+                g.replay()
+                torch.cuda.synchronize()
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                dev_us[str(Bs)] = 1e3 * e0.elapsed_time(e1) / n_rep
+                sweep_dev[str(Bs)] = Bs / (e0.elapsed_time(e1) / n_rep * 1e-3)
+                del g
             out["device_sweep_samples_per_s"] = sweep
+            out["device_sweep_graph_replay_samples_per_s"] = sweep_dev
+            out["us_per_call"] = {"python_loop": call_us, "graph_replay": dev_us}
+            # the conv + bitmask kernel is the dominant launch of the large-batch form: its image-stream roofline
+            # (algorithmic bytes = the 23 of 32 image rows the stride-4 conv touches; ncu: dram bytes equal them)
+            if w["image"] == 32 and w["grid"] in (9, 10, 11):
+                algo = 65536 * 23 * 32 * 3 * 4
+                out["roofline_b65536"] = {"bound": "hbm", "kernel": "q_conv_bits32_kernel", "algorithmic_bytes": algo,
+                                          "whole_call_us": dev_us["65536"], "whole_call_gbs": algo / (dev_us["65536"] * 1e-6) / 1e9,
+                                          "note": "whole call = conv + bitmask, tcgen05 accumulate + layer stack; the conv kernel "
+                                                  "alone: profiles/r2_ncu_int_path_summary.txt"}
             del big
         # end to end through host buffers (pinned), copies inside the C call
         pinned = imgs.pin_memory().numpy()

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NNUE_B200_ABI_VERSION 3
+#define NNUE_B200_ABI_VERSION 4
 
 enum {
     NNUE_OK = 0,
@@ -232,6 +232,21 @@ int nnue_head_train(const nnue_shape *s, const float *ft_out_d, const int64_t *l
                     const float *w3_d, const float *b3_d, float *loss_d, float *g_ft_d, float *g_w1_d,
                     float *g_b1_d, float *g_w2_d, float *g_b2_d, float *g_w3_d, float *g_b3_d,
                     void *workspace_d, size_t workspace_bytes, void *stream);
+/*
+ * The same with a second stream: wide stacks whose first layer runs on the tensor cores (nnue_head_uses_umma) hand the
+ * layer-1 weight-gradient chain (operand formatting, split-K GEMM, fold: independent of g_ft and of every later stage of
+ * the step) to `side_stream`, behind an event recorded on `stream`; its scratch and the g_z1 rows it reads come from
+ * `side_workspace_d` (nnue_head_side_workspace_bytes(s) bytes; 0 = this shape has no side chain), which must stay
+ * untouched until the side stream has been joined.  g_w1_d is complete on `side_stream`, everything else on `stream`.
+ * Null side arguments = nnue_head_train.  autograd has no counterpart: it runs the reference's nodes one after another.
+ */
+size_t nnue_head_side_workspace_bytes(const nnue_shape *s);
+int nnue_head_train_overlapped(const nnue_shape *s, const float *ft_out_d, const int64_t *labels_d, float inv_count,
+                               const float *w1_d, const float *b1_d, const float *w2_d, const float *b2_d,
+                               const float *w3_d, const float *b3_d, float *loss_d, float *g_ft_d, float *g_w1_d,
+                               float *g_b1_d, float *g_w2_d, float *g_b2_d, float *g_w3_d, float *g_b3_d,
+                               void *workspace_d, size_t workspace_bytes, void *stream, void *side_workspace_d,
+                               size_t side_workspace_bytes, void *side_stream);
 
 /*
  * Feature-transformer weight/bias gradient: a segment reduction over (feature, sample)

@@ -15,7 +15,7 @@ i32, i64, f32 = ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 vp, sz = ctypes.c_void_p, ctypes.c_size_t
 
 
-ABI_VERSION = 3  # NNUE_B200_ABI_VERSION of include/nnue_b200.h
+ABI_VERSION = 4  # NNUE_B200_ABI_VERSION of include/nnue_b200.h
 
 
 class NnueShape(ctypes.Structure):
@@ -53,6 +53,8 @@ SIGNATURES = {
     "nnue_head_is_fused": (ctypes.c_int, [SHAPE_P]),
     "nnue_head_uses_umma": (ctypes.c_int, [SHAPE_P]),
     "nnue_head_train": (ctypes.c_int, [SHAPE_P, vp, vp, f32] + [vp] * 14 + [vp, sz, vp]),
+    "nnue_head_train_overlapped": (ctypes.c_int, [SHAPE_P, vp, vp, f32] + [vp] * 14 + [vp, sz, vp, vp, sz, vp]),
+    "nnue_head_side_workspace_bytes": (sz, [SHAPE_P]),
     "nnue_ft_bwd_is_fused": (ctypes.c_int, [SHAPE_P]),
     "nnue_ft_bwd": (ctypes.c_int, [SHAPE_P] + [vp] * 7 + [sz, vp]),
     "nnue_wants_transposed_bits": (ctypes.c_int, [SHAPE_P]),

@@ -198,28 +198,61 @@ ugemm_kernel(const UGemmArgs g) {
         float *crow = g.C + (size_t)split * g.c_split_stride + (size_t)min(m, g.M - 1) * g.ldc;
         const float *mrow = g.mask ? g.mask + (size_t)min(m, g.M - 1) * g.ldm : nullptr;
         if (NT == 256 && g.pair_ft) {
-            // pairwise backward on the accumulator row: columns c (product slot) and 128 + c (pass-through slot) of this tile
-            const float *frow = g.pair_ft + (size_t)min(m, g.M - 1) * g.ldc;
+            // Pairwise backward on the accumulator rows: columns c (product slot) and 128 + c (pass-through slot) of this tile.
+            // A thread owns one ROW of the accumulator, but global memory wants a warp on one row at a time (the first
+            // version read ft and wrote g_ft 64 bytes per thread and row: 8 KB in flight per SM, 79 us for 134 MB).  So each
+            // warp transposes its 32 rows through the (by now idle) operand ring, 64 pair columns at a time, and then walks
+            // them row by row: 128-byte loads of ft / stores of g_ft per instruction, eight rows in flight.
+            constexpr int kPitch = 129;  // odd: lane r writing row r and lane c reading column c are both conflict-free
+            float *S = reinterpret_cast<float *>(sa) + (size_t)q * 32 * kPitch;
             const int h = g.pair_h;
+            const int m0 = mt * kGuM + q * 32;
 #pragma unroll 1
-            for (int c0 = 0; c0 < 128; c0 += 16) {
-                const int i0 = nt * 128 + c0;
-                float gp[16], ga[16];
-                tmem_ld16(tbase + (uint32_t)c0, gp);
-                tmem_ld16(tbase + (uint32_t)(128 + c0), ga);
-                tmem_ld_wait();
-                if (m < g.M) {
+            for (int cb = 0; cb < 2; ++cb) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float4 fa = __ldg(reinterpret_cast<const float4 *>(frow + i0) + u);
-                        const float4 fb = __ldg(reinterpret_cast<const float4 *>(frow + h + i0) + u);
-                        reinterpret_cast<float4 *>(crow + i0)[u] =
-                            make_float4(fmaf(gp[4 * u], fb.x, ga[4 * u]), fmaf(gp[4 * u + 1], fb.y, ga[4 * u + 1]),
-                                        fmaf(gp[4 * u + 2], fb.z, ga[4 * u + 2]), fmaf(gp[4 * u + 3], fb.w, ga[4 * u + 3]));
-                        reinterpret_cast<float4 *>(crow + h + i0)[u] =
-                            make_float4(gp[4 * u] * fa.x, gp[4 * u + 1] * fa.y, gp[4 * u + 2] * fa.z, gp[4 * u + 3] * fa.w);
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+                    float gp[16], ga[16];
+                    tmem_ld16(tbase + (uint32_t)(cb * 64 + c0), gp);
+                    tmem_ld16(tbase + (uint32_t)(128 + cb * 64 + c0), ga);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        S[lane * kPitch + c0 + u] = gp[u];
+                        S[lane * kPitch + 64 + c0 + u] = ga[u];
                     }
                 }
+                __syncwarp();
+                const int i0 = nt * 128 + cb * 64;
+#pragma unroll 1
+                for (int r0 = 0; r0 < 32; r0 += 8) {
+                    // eight rows' loads first (row index clamped, not branched on: a branch per row keeps the compiler from
+                    // batching them and the loop then pays one DRAM latency per row), then the arithmetic and the stores
+                    float fa[8][2], fb[8][2];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float *frow = g.pair_ft + (size_t)min(m0 + r0 + u, g.M - 1) * g.ldc + i0;
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            fa[u][hh] = __ldg(frow + lane + 32 * hh);
+                            fb[u][hh] = __ldg(frow + h + lane + 32 * hh);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int rr = r0 + u;
+                        if (m0 + rr < g.M) {  // warp-uniform
+                            float *orow = g.C + (size_t)(m0 + rr) * g.ldc + i0;
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const int c = lane + 32 * hh;
+                                const float p_ = S[rr * kPitch + c], a_ = S[rr * kPitch + 64 + c];
+                                orow[c] = fmaf(p_, fb[u][hh], a_);
+                                orow[h + c] = p_ * fa[u][hh];
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
             }
         } else
 #pragma unroll 2

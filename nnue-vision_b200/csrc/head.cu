@@ -316,9 +316,12 @@ HeadBwdWs carve_head_bwd(const nnue_shape &s, void *workspace_d) {
     return w;
 }
 
-// layer 1 backward from g_z1 (bw.g_act1, already masked by act1 > 0): g_w1, g_b1, g_l0 and the pairwise backward -> g_ft
+// layer 1 backward from g_z1 (bw.g_act1, already masked by act1 > 0): g_w1, g_b1, g_l0 and the pairwise backward -> g_ft.
+// `side` (tensor-core form only): the weight-gradient chain (two operand formatters, split-K GEMM, fold -- independent of
+// the input-gradient chain and of everything downstream) runs on side->stream out of side->ws, behind an event recorded on
+// `st`; bw.g_act1 must then live where the later stages of `st` do not write (the caller carves it from the side scratch).
 int head_bwd_layer1(const nnue_shape *s, const HeadBwdWs &bw, const float *ft_out_d, const float *w1_d, float *g_w1_d,
-                    float *g_b1_d, float *g_ft_d, cudaStream_t st) {
+                    float *g_b1_d, float *g_ft_d, cudaStream_t st, const HeadSide *side) {
     const int B = s->B, L1 = s->L1, L2 = s->L2;
     float *g_act1 = bw.g_act1, *g_l0 = bw.g_l0, *p1 = bw.p1;
     char *ws = bw.rest;
@@ -335,18 +338,31 @@ int head_bwd_layer1(const nnue_shape *s, const HeadBwdWs &bw, const float *ft_ou
         float *wpart = reinterpret_cast<float *>(carve_b((size_t)splits * L2 * L1 * 4));
         float *cpart = reinterpret_cast<float *>(carve_b((size_t)ceil_div(B, 256) * L2 * 4));
         // g_w1[o, i] = sum_b g_z1[b, o] l0[b, i]: A = g_z1^T, B = l0^T (pairwise fused), K = batch, split-K partials
-        if ((rc = ugemm_format_cols(128, g_act1, L2, B, L2, 0, g1_cols, st)) < 0) return rc;
-        if ((rc = ugemm_format_cols(256, ft_out_d, L1, B, L1, L1 / 2, l0_cols, st)) < 0) return rc;
-        const int nz = ugemm_launch(256, L2, L1, B, g1_cols, l0_cols, wpart, L1, nullptr, 0, nullptr, 0, splits, (long long)L2 * L1, st);
+        cudaStream_t wst = st;
+        if (side) {  // the chain's scratch comes from the side workspace, its launches go to the side stream
+            unsigned char *sp = static_cast<unsigned char *>(side->ws);
+            auto carve_s = [&](size_t bytes) { unsigned char *p = sp; sp += align_up(bytes, 256); return p; };
+            g1_cols = carve_s(ugemm_tile_bytes(L2, 128, B)); l0_cols = carve_s(ugemm_tile_bytes(L1, 256, B));
+            wpart = reinterpret_cast<float *>(carve_s((size_t)splits * L2 * L1 * 4));
+            cpart = reinterpret_cast<float *>(carve_s((size_t)ceil_div(B, 256) * L2 * 4));
+            NNUE_CUDA_TRY(cudaEventRecord(side->ready, st));
+            NNUE_CUDA_TRY(cudaStreamWaitEvent(side->stream, side->ready, 0));
+            wst = side->stream;
+        }
+        if ((rc = ugemm_format_cols(128, g_act1, L2, B, L2, 0, g1_cols, wst)) < 0) return rc;
+        if ((rc = ugemm_format_cols(256, ft_out_d, L1, B, L1, L1 / 2, l0_cols, wst)) < 0) return rc;
+        const int nz = ugemm_launch(256, L2, L1, B, g1_cols, l0_cols, wpart, L1, nullptr, 0, nullptr, 0, splits, (long long)L2 * L1, wst);
         if (nz < 0) return nz;
         const long long nw = 1LL * L2 * L1;
-        head_fold_kernel<<<(int)((nw + 255) / 256), 256, 0, st>>>(nw, nz, nw, wpart, g_w1_d);
+        head_fold_kernel<<<(int)((nw + 255) / 256), 256, 0, wst>>>(nw, nz, nw, wpart, g_w1_d);
         NNUE_CHECK_LAUNCH("head_fold_kernel");
-        const int nrc = ceil_div(B, 256);
-        head_colsum_partial_kernel<<<dim3(ceil_div(L2, 128), nrc), 128, 0, st>>>(B, L2, g_act1, cpart);
-        NNUE_CHECK_LAUNCH("head_colsum_partial_kernel");
-        head_fold_kernel<<<ceil_div(L2, 256), 256, 0, st>>>(L2, nrc, L2, cpart, g_b1_d);
-        NNUE_CHECK_LAUNCH("head_fold_kernel");
+        if (g_b1_d) {
+            const int nrc = ceil_div(B, 256);
+            head_colsum_partial_kernel<<<dim3(ceil_div(L2, 128), nrc), 128, 0, wst>>>(B, L2, g_act1, cpart);
+            NNUE_CHECK_LAUNCH("head_colsum_partial_kernel");
+            head_fold_kernel<<<ceil_div(L2, 256), 256, 0, wst>>>(L2, nrc, L2, cpart, g_b1_d);
+            NNUE_CHECK_LAUNCH("head_fold_kernel");
+        }
         // g_l0 = g_z1 W1: A = g_z1, B = W1^T
         if ((rc = ugemm_format_rows(128, g_act1, L2, B, L2, 0, g1_rows, st)) < 0) return rc;
         if (head_pair_epilogue_ok(*s)) {
@@ -474,7 +490,7 @@ int nnue_head_bwd(const nnue_shape *s, const float *g_logits_d, const float *ft_
     g.C = g_act1; g.scm = L2; g.mask = act1_d; g.smm = L2;
     rc = launch_gemm(g, 1, st);
     if (rc < 0) return rc;
-    return head_bwd_layer1(s, bw, ft_out_d, w1_d, g_w1_d, g_b1_d, g_ft_d, st);
+    return head_bwd_layer1(s, bw, ft_out_d, w1_d, g_w1_d, g_b1_d, g_ft_d, st, nullptr);
 }
 
 }  // extern "C"

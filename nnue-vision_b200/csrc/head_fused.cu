@@ -423,11 +423,23 @@ extern "C" {
 int nnue_head_is_fused(const nnue_shape *s) { return s && head_train_fused_ok(*s) ? 1 : 0; }
 int nnue_head_uses_umma(const nnue_shape *s) { return s && !head_train_fused_ok(*s) && head_umma_ok(*s) ? 1 : 0; }
 
+size_t nnue_head_side_workspace_bytes(const nnue_shape *s) { return s ? ws_head_side(*s) : 0; }
+
 int nnue_head_train(const nnue_shape *s, const float *ft_out_d, const int64_t *labels_d, float inv_count,
                     const float *w1_d, const float *b1_d, const float *w2_d, const float *b2_d, const float *w3_d,
                     const float *b3_d, float *loss_d, float *g_ft_d, float *g_w1_d, float *g_b1_d, float *g_w2_d,
                     float *g_b2_d, float *g_w3_d, float *g_b3_d, void *workspace_d, size_t workspace_bytes,
                     void *stream) {
+    return nnue_head_train_overlapped(s, ft_out_d, labels_d, inv_count, w1_d, b1_d, w2_d, b2_d, w3_d, b3_d, loss_d, g_ft_d,
+                                      g_w1_d, g_b1_d, g_w2_d, g_b2_d, g_w3_d, g_b3_d, workspace_d, workspace_bytes, stream,
+                                      nullptr, 0, nullptr);
+}
+
+int nnue_head_train_overlapped(const nnue_shape *s, const float *ft_out_d, const int64_t *labels_d, float inv_count,
+                               const float *w1_d, const float *b1_d, const float *w2_d, const float *b2_d, const float *w3_d,
+                               const float *b3_d, float *loss_d, float *g_ft_d, float *g_w1_d, float *g_b1_d, float *g_w2_d,
+                               float *g_b2_d, float *g_w3_d, float *g_b3_d, void *workspace_d, size_t workspace_bytes,
+                               void *stream, void *side_workspace_d, size_t side_workspace_bytes, void *side_stream) {
     if (!s || !ft_out_d || !labels_d || !w1_d || !b1_d || !w2_d || !b2_d || !w3_d || !b3_d || !loss_d || !g_ft_d ||
         !g_w1_d || !g_b1_d || !g_w2_d || !g_b2_d || !g_w3_d || !g_b3_d || !workspace_d)
         return NNUE_ERR_INVALID_ARG;
@@ -468,11 +480,29 @@ int nnue_head_train(const nnue_shape *s, const float *ft_out_d, const int64_t *l
         void *fwd_scratch = fwd_ws && rest >= ws_head_bwd(*s) + fwd_ws ? ws + align_up(ws_head_bwd(*s), 256) : nullptr;
         int rc = head_layer1_fwd(s, ft_out_d, w1_d, b1_d, act1, fwd_scratch, fwd_scratch ? fwd_ws : 0, st);
         if (rc != NNUE_OK) return rc;
-        const HeadBwdWs bw = carve_head_bwd(*s, ws);
+        HeadBwdWs bw = carve_head_bwd(*s, ws);
+        // with a side stream (and enough side scratch) the layer-1 weight-gradient chain leaves the caller's stream: g_z1
+        // then lives in the side scratch, which no later stage of the caller's stream writes
+        HeadSide side{};
+        const bool use_side = side_stream && side_workspace_d && ws_head_side(*s) > 0 && side_workspace_bytes >= ws_head_side(*s);
+        if (use_side) {
+            static thread_local cudaEvent_t ev[16] = {};  // one per device, reused by every call (a record replaces the last)
+            int dev = 0;
+            NNUE_CUDA_TRY(cudaGetDevice(&dev));
+            if (dev < 0 || dev >= 16) return NNUE_ERR_UNSUPPORTED;
+            if (!ev[dev]) NNUE_CUDA_TRY(cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming));
+            side.stream = static_cast<cudaStream_t>(side_stream);
+            side.ready = ev[dev];
+            bw.g_act1 = static_cast<float *>(side_workspace_d);
+            side.ws = static_cast<char *>(side_workspace_d) + align_up(B * s->L2 * 4, 256);
+            side.ws_bytes = side_workspace_bytes - align_up(B * s->L2 * 4, 256);
+        }
         rc = launch_head_mid(*s, act1, labels_d, inv_count, w2_d, b2_d, w3_d, b3_d, loss_d, bw.g_act1, g_w2_d, g_b2_d, g_w3_d,
-                             g_b3_d, midp, st);
+                             g_b3_d, g_b1_d, midp, st);
         if (rc != NNUE_OK) return rc;
-        return head_bwd_layer1(s, bw, ft_out_d, w1_d, g_w1_d, g_b1_d, g_ft_d, st);
+        // (the tensor-core form takes g_b1 from head_mid; the FMA form's weight-gradient GEMM produces it alongside g_w1)
+        return head_bwd_layer1(s, bw, ft_out_d, w1_d, g_w1_d, head_umma_ok(*s) ? nullptr : g_b1_d, g_ft_d, st,
+                               use_side ? &side : nullptr);
     }
     // other stacks: the layer kernels of head.cu, with the activations in scratch
     float *act1 = carve(B * s->L2 * 4), *act2 = carve(B * s->L3 * 4), *logits = carve(B * s->NC * 4);

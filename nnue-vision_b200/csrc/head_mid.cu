@@ -8,7 +8,7 @@
 // launch tails and re-reading [B][32] / [B][10] activations.  Here a persistent CTA takes 128 samples at a time:
 //
 //   act1 tile -> shared memory -> z2 = act1 W2^T + b2 -> ReLU -> logits -> softmax / loss / g_logits
-//             -> g_W3, g_b3, g_z2 -> g_W2, g_b2 -> g_z1 = (g_z2 W2) * (act1 > 0) -> global
+//             -> g_W3, g_b3, g_z2 -> g_W2, g_b2 -> g_z1 = (g_z2 W2) * (act1 > 0) -> global (+ its column sums = g_b1)
 //
 // with register-tiled fp32 FMA contractions over shared-memory tiles (row strides chosen so that every LDS.128 of a
 // quarter warp covers distinct banks).  Parameter gradients accumulate in shared memory across the CTA's tiles (every
@@ -34,7 +34,7 @@ struct MidLayout {
                          oGL = oGZ + kMidTB * kMidSZ, oAcc = (oGL + kMidTB * kMidSG + 3) / 4 * 4;
     // per-CTA partial block
     static constexpr int pW2 = 0, pB2 = pW2 + kMidL3P * kMidL2P, pW3 = pB2 + kMidL3P, pB3 = pW3 + kMidNCP * kMidL3P,
-                         pLoss = pB3 + kMidNCP, pTotal = (pLoss + 1 + 3) / 4 * 4;
+                         pB1 = pB3 + kMidNCP, pLoss = pB1 + kMidL2P, pTotal = (pLoss + 1 + 3) / 4 * 4;
     static constexpr int total = oAcc + pTotal;
 };
 static_assert(MidLayout::pTotal == kHeadMidPartial, "plan.cuh kHeadMidPartial must match the partial block layout");
@@ -58,13 +58,31 @@ head_mid_kernel(const HeadMidArgs a) {
     const int tid = threadIdx.x;
 
     // ---- weights, zero padded ----
-    for (int e = tid; e < kMidL3P * kMidSA; e += kMidThreads) {
-        const int o = e / kMidSA, k = e % kMidSA;
-        W2s[e] = (o < a.L3 && k < a.L2) ? __ldg(a.w2 + (size_t)o * a.L2 + k) : 0.0f;
-    }
-    for (int e = tid; e < kMidNCP * kMidSZ; e += kMidThreads) {
-        const int c = e / kMidSZ, k = e % kMidSZ;
-        W3s[e] = (c < a.NC && k < a.L3) ? __ldg(a.w3 + (size_t)c * a.L3 + k) : 0.0f;
+    // (loads of a batch are issued together, then stored: a load -> store loop pays one memory latency per iteration)
+    {
+        float4 v[4];  // W2 [L3][L2] as float4 (L2 % 4 == 0): 32 rows x 32 chunks = 4 per thread; the 4 pad floats of a row stay unread
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + u * kMidThreads, o = e / (kMidL2P / 4), c4 = e % (kMidL2P / 4);
+            v[u] = (o < a.L3 && 4 * c4 < a.L2) ? __ldg(reinterpret_cast<const float4 *>(a.w2 + (size_t)o * a.L2) + c4)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = tid + u * kMidThreads, o = e / (kMidL2P / 4), c4 = e % (kMidL2P / 4);
+            *reinterpret_cast<float4 *>(W2s + o * kMidSA + 4 * c4) = v[u];
+        }
+        float w[3];   // W3 [NC][L3]: 16 x 33 padded slots = 528 <= 3 per thread
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int e = tid + u * kMidThreads, c = e / kMidSZ, k = e % kMidSZ;
+            w[u] = (e < kMidNCP * kMidSZ && c < a.NC && k < a.L3) ? __ldg(a.w3 + (size_t)c * a.L3 + k) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int e = tid + u * kMidThreads;
+            if (e < kMidNCP * kMidSZ) W3s[e] = w[u];
+        }
     }
     if (tid < kMidL3P) b2s[tid] = tid < a.L3 ? __ldg(a.b2 + tid) : 0.0f;
     if (tid < kMidNCP) b3s[tid] = tid < a.NC ? __ldg(a.b3 + tid) : 0.0f;
@@ -77,11 +95,20 @@ head_mid_kernel(const HeadMidArgs a) {
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int b0 = tile * kMidTB;
         // ---- act1 tile (rows past the batch and columns past L2 are zero) ----
-        for (int e = tid; e < kMidTB * (kMidL2P / 4); e += kMidThreads) {
-            const int r = e / (kMidL2P / 4), c4 = e % (kMidL2P / 4);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (b0 + r < a.B && 4 * c4 < a.L2) v = __ldg(reinterpret_cast<const float4 *>(a.act1 + (size_t)(b0 + r) * a.L2) + c4);
-            *reinterpret_cast<float4 *>(A1 + r * kMidSA + 4 * c4) = v;
+#pragma unroll
+        for (int e0 = 0; e0 < kMidTB * (kMidL2P / 4); e0 += 8 * kMidThreads) {  // sixteen 16-byte chunks per thread, eight in flight
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * kMidThreads + tid, r = e / (kMidL2P / 4), c4 = e % (kMidL2P / 4);
+                v[u] = (b0 + r < a.B && 4 * c4 < a.L2) ? __ldg(reinterpret_cast<const float4 *>(a.act1 + (size_t)(b0 + r) * a.L2) + c4)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * kMidThreads + tid, r = e / (kMidL2P / 4), c4 = e % (kMidL2P / 4);
+                *reinterpret_cast<float4 *>(A1 + r * kMidSA + 4 * c4) = v[u];
+            }
         }
         __syncthreads();
 
@@ -241,6 +268,9 @@ head_mid_kernel(const HeadMidArgs a) {
                         g1[i][j].w = fmaf(gz[i], wv[j].w, g1[i][j].w);
                     }
             }
+            float4 cs[4];  // column sums of this thread's four samples (the bias gradient of layer 1)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int s = sg + 32 * i;
@@ -254,12 +284,22 @@ head_mid_kernel(const HeadMidArgs a) {
                             v.x = av.x > 0.0f ? v.x : 0.0f; v.y = av.y > 0.0f ? v.y : 0.0f;
                             v.z = av.z > 0.0f ? v.z : 0.0f; v.w = av.w > 0.0f ? v.w : 0.0f;
                             *reinterpret_cast<float4 *>(a.g_z1 + (size_t)(b0 + s) * a.L2 + k) = v;
+                            cs[j] = f4_add(cs[j], v);
                         }
                     }
                 }
             }
+            // (the act2 tile is dead since the g_z2 phase: it carries the 32 sample groups' column sums to their owners)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<float4 *>(Z2 + sg * kMidL2P + 4 * (oc + 8 * j)) = cs[j];
         }
-        __syncthreads();  // the next tile overwrites A1 / Z2 / GZ / GL
+        __syncthreads();  // the next tile overwrites A1 / GZ / GL (and, after its own barrier, Z2)
+        if (tid < kMidL2P) {
+            float v = 0.0f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) v += Z2[r * kMidL2P + tid];
+            acc[Lay::pB1 + tid] += v;
+        }
     }
 
     // ---- the CTA's partial block; the loss in thread order (fixed) ----
@@ -279,7 +319,7 @@ head_mid_kernel(const HeadMidArgs a) {
 // every element of the partial block summed over the CTAs in CTA order, then scattered to the parameter gradients
 __global__ void __launch_bounds__(256)
 head_mid_fold_kernel(int nblk, const float *__restrict__ partial, int L2, int L3, int NC, float inv_count, float *__restrict__ g_w2,
-                     float *__restrict__ g_b2, float *__restrict__ g_w3, float *__restrict__ g_b3, float *__restrict__ loss) {
+                     float *__restrict__ g_b2, float *__restrict__ g_w3, float *__restrict__ g_b3, float *__restrict__ g_b1, float *__restrict__ loss) {
     using Lay = MidLayout;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e > Lay::pLoss) return;
@@ -301,17 +341,20 @@ head_mid_fold_kernel(int nblk, const float *__restrict__ partial, int L2, int L3
     } else if (e < Lay::pB3) {
         const int c = (e - Lay::pW3) / kMidL3P, i = (e - Lay::pW3) % kMidL3P;
         if (c < NC && i < L3) g_w3[(size_t)c * L3 + i] = v;
-    } else if (e < Lay::pLoss) {
+    } else if (e < Lay::pB1) {
         if (e - Lay::pB3 < NC) g_b3[e - Lay::pB3] = v;
+    } else if (e < Lay::pLoss) {
+        if (e - Lay::pB1 < L2) g_b1[e - Lay::pB1] = v;
     } else if (loss) {
         loss[0] = v * inv_count;
     }
 }
 
-// act1 [B][L2] -> loss, g_z1 [B][L2], g_w2, g_b2, g_w3, g_b3;  partial: head_mid_grid(s) * kHeadMidPartial floats
+// act1 [B][L2] -> loss, g_z1 [B][L2], g_w2, g_b2, g_w3, g_b3 and g_b1 (= column sums of g_z1);
+// partial: head_mid_grid(s) * kHeadMidPartial floats
 int launch_head_mid(const nnue_shape &s, const float *act1, const int64_t *labels, float inv_count, const float *w2, const float *b2,
                     const float *w3, const float *b3, float *loss, float *g_z1, float *g_w2, float *g_b2, float *g_w3, float *g_b3,
-                    float *partial, cudaStream_t st) {
+                    float *g_b1, float *partial, cudaStream_t st) {
     if (!head_mid_ok(s)) return NNUE_ERR_UNSUPPORTED;
     HeadMidArgs a{};
     a.B = s.B; a.L2 = s.L2; a.L3 = s.L3; a.NC = s.NC;
@@ -323,7 +366,7 @@ int launch_head_mid(const nnue_shape &s, const float *act1, const int64_t *label
     head_mid_kernel<<<grid, kMidThreads, smem, st>>>(a);
     NNUE_CHECK_LAUNCH("head_mid_kernel");
     head_mid_fold_kernel<<<ceil_div(MidLayout::pLoss + 1, 256), 256, 0, st>>>(grid, partial, s.L2, s.L3, s.NC, inv_count, g_w2, g_b2,
-                                                                             g_w3, g_b3, loss);
+                                                                             g_w3, g_b3, g_b1, loss);
     NNUE_CHECK_LAUNCH("head_mid_fold_kernel");
     return NNUE_OK;
 }

@@ -623,7 +623,7 @@ inline int head_train_grid(const nnue_shape &s) {
     return ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs;
 }
 // ---- layers 2 - 3 + cross-entropy + their backward in one kernel (head_mid.cu) for wide stacks with a small tail ----
-constexpr int kHeadMidPartial = 4660;  // floats per per-CTA gradient block (MidLayout::pTotal)
+constexpr int kHeadMidPartial = 4788;  // floats per per-CTA gradient block (MidLayout::pTotal)
 inline bool head_mid_ok(const nnue_shape &s) {
     return get_option(kOptHeadMid) && !head_train_fused_ok(s) && s.L2 % 4 == 0 && s.L2 <= 128 && s.L3 <= 32 && s.NC <= 16;
 }
@@ -633,14 +633,24 @@ inline int head_mid_grid(const nnue_shape &s) {  // persistent CTAs over 128-sam
 }
 int launch_head_mid(const nnue_shape &s, const float *act1, const int64_t *labels, float inv_count, const float *w2, const float *b2,
                     const float *w3, const float *b3, float *loss, float *g_z1, float *g_w2, float *g_b2, float *g_w3, float *g_b3,
-                    float *partial, cudaStream_t st);
+                    float *g_b1, float *partial, cudaStream_t st);
 // pieces of head.cu shared with nnue_head_train
 struct HeadBwdWs { float *p3, *p2, *p1, *g_act2, *g_act1, *g_l0; char *rest; };
 HeadBwdWs carve_head_bwd(const nnue_shape &s, void *workspace_d);
 int head_layer1_fwd(const nnue_shape *s, const float *ft_out_d, const float *w1_d, const float *b1_d, float *act1_d,
                     void *workspace_d, size_t workspace_bytes, cudaStream_t st);
+// a second stream with its own scratch for the layer-1 weight-gradient chain (nnue_head_train_overlapped)
+struct HeadSide { cudaStream_t stream; void *ws; size_t ws_bytes; cudaEvent_t ready; };
+// side scratch: g_z1 [B][L2] | g_z1^T tiles | l0^T tiles | split-K partials | column-sum partials
+inline size_t ws_head_side(const nnue_shape &s) {
+    if (!head_umma_ok(s) || !head_mid_ok(s)) return 0;
+    return align_up((size_t)s.B * s.L2 * 4, 256) + align_up(ugemm_tile_bytes(s.L2, 128, s.B), 256) +
+           align_up(ugemm_tile_bytes(s.L1, 256, s.B), 256) + align_up((size_t)head_umma_wgrad_splits(s) * s.L2 * s.L1 * 4, 256) +
+           align_up((size_t)ceil_div(s.B, 256) * s.L2 * 4, 256);
+}
+// (g_b1_d null: the bias gradient has been produced already, by head_mid)
 int head_bwd_layer1(const nnue_shape *s, const HeadBwdWs &bw, const float *ft_out_d, const float *w1_d, float *g_w1_d,
-                    float *g_b1_d, float *g_ft_d, cudaStream_t st);
+                    float *g_b1_d, float *g_ft_d, cudaStream_t st, const HeadSide *side = nullptr);
 
 inline size_t ws_head_train(const nnue_shape &s) {
     if (head_train_fused_ok(s)) return (size_t)head_train_grid(s) * kHeadPartial * 4;

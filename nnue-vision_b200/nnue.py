@@ -267,6 +267,10 @@ STORE_ACTIVATIONS = os.environ.get("NNUE_STORE_ACTIVATIONS", "1") != "0"
 
 
 OVERLAP_TABLE_GRADIENT = True
+# wide stacks: the layer-1 weight-gradient chain of the head on the side stream (nnue_head_train_overlapped)
+# -- measured at L1 = 1024, batch 16384 on one B200: 0.814 ms per step with, 0.795 ms without (the chain then competes with
+# the value-gradient GEMM for the tensor pipe and delays the table gradient behind it on the same side stream): off by default
+HEAD_SIDE_STREAM = os.environ.get("NNUE_HEAD_SIDE_STREAM", "0") == "1"
 # Format the table tiles on the side stream while the images are extracted (tcgen05 shapes).  Off by default: at
 # config D the two 4 us formatting kernels running beside the extraction cost more than they save (measured on one
 # box, 200 steps each: 227 us per step with, 216 us without -- the extraction is issue-bound and shares its SMs).
@@ -329,9 +333,21 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
         check(L.nnue_ft_fwd(sp, dptr(bits_s), dptr(ft_w), dptr(ft_b), dptr(ft_out), dptr(ws), ws_bytes, st))
     _mark(marks, "ft_fwd")
     g_ft = _empty((shape.B, shape.L1), torch.float32, images)
-    check(L.nnue_head_train(sp, dptr(ft_out), dptr(labels), inv_count, dptr(w1), dptr(b1), dptr(w2), dptr(b2),
-                            dptr(w3), dptr(b3), dptr(loss_out), dptr(g_ft), dptr(g_w1), dptr(g_b1), dptr(g_w2),
-                            dptr(g_b2), dptr(g_w3), dptr(g_b3), dptr(ws), ws_bytes, st))
+    # wide stacks on the tensor cores: the layer-1 weight-gradient chain (independent of g_ft and of everything after it)
+    # goes to the side stream with its own scratch; the side stream is joined at the end of the step
+    head_side = (marks is None and OVERLAP_TABLE_GRADIENT and HEAD_SIDE_STREAM and L.nnue_ft_uses_mma(sp)
+                 and L.nnue_input_bwd_is_dense(sp))
+    side_bytes = int(L.nnue_head_side_workspace_bytes(sp)) if head_side else 0
+    if side_bytes:
+        side_ws = _empty((side_bytes,), torch.uint8, images)
+        check(L.nnue_head_train_overlapped(sp, dptr(ft_out), dptr(labels), inv_count, dptr(w1), dptr(b1), dptr(w2), dptr(b2),
+                                           dptr(w3), dptr(b3), dptr(loss_out), dptr(g_ft), dptr(g_w1), dptr(g_b1), dptr(g_w2),
+                                           dptr(g_b2), dptr(g_w3), dptr(g_b3), dptr(ws), ws_bytes, st, dptr(side_ws), side_bytes,
+                                           ctypes.c_void_p(_side_stream(images.device).cuda_stream)))
+    else:
+        check(L.nnue_head_train(sp, dptr(ft_out), dptr(labels), inv_count, dptr(w1), dptr(b1), dptr(w2), dptr(b2),
+                                dptr(w3), dptr(b3), dptr(loss_out), dptr(g_ft), dptr(g_w1), dptr(g_b1), dptr(g_w2),
+                                dptr(g_b2), dptr(g_w3), dptr(g_b3), dptr(ws), ws_bytes, st))
     _mark(marks, "head_train")
     if L.nnue_ft_uses_mma(sp) and L.nnue_input_bwd_is_dense(sp):  # small tables: tensor-core contractions
         # The table gradient depends only on g_ft and nothing downstream depends on it, while the value gradient

@@ -312,7 +312,7 @@ class DataParallelStep:
         from . import _lib, nnue as _nnue
         return (images.data_ptr(), labels.data_ptr(), tuple(images.shape), images.dtype, labels.dtype, inv_count,
                 tuple(p.data_ptr() for p in self.model.parameters()), _lib.options_epoch(), _nnue.STORE_ACTIVATIONS,
-                _nnue.PREFORMAT_TABLES, _nnue.OVERLAP_TABLE_GRADIENT)
+                _nnue.PREFORMAT_TABLES, _nnue.OVERLAP_TABLE_GRADIENT, _nnue.HEAD_SIDE_STREAM)
 
     def _call_local(self, images, labels, inv_count, marks=None):
         if self._inline:  # the step issues the exchange itself, slice by slice, where the gradients become final

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_functions():
         assert hasattr(handle, name), f"{name} declared in nnue_b200.h but not exported"
     assert set(_lib.SIGNATURES) == set(declared_functions()), "python binding table out of sync with the header"
-    assert _lib.lib().nnue_b200_abi_version() == 3
+    assert _lib.lib().nnue_b200_abi_version() == 4
     assert _lib.lib().nnue_error_string(-5) == b"malformed .nnue file"
 
 

@@ -449,6 +449,37 @@ def test_wide_stack_split_k_batch_against_the_fp64_oracle():
         assert_close(dict(model.named_parameters())[k].grad, gr, "grad " + k)
 
 
+@pytest.mark.parametrize("name", ["D1k_tensor_head", "wide_head_ragged"])
+def test_head_side_stream_chain_is_bit_identical(name):
+    """Wide stacks hand the layer-1 weight-gradient chain to the side stream (nnue_head_train_overlapped): the same
+    kernels on the same data, so loss and every gradient must be bit-identical to the one-stream step, eager and replayed
+    as a CUDA graph (the event fork / join is captured)."""
+    from nnue_vision_b200 import nnue as _n
+    lib = _lib()
+    cfg, model, images, labels = _make(name)
+    shape = shape_of(model, images)
+    assert int(lib.lib().nnue_head_side_workspace_bytes(ctypes.byref(shape))) > 0
+    out = {}
+    for flag in (True, False):
+        _n.HEAD_SIDE_STREAM = flag
+        try:
+            runs = []
+            for _ in range(3):  # third call: replayed graph
+                model.zero_grad()
+                loss = model.loss(images, labels)
+                loss.backward()
+                torch.cuda.synchronize()
+                runs.append([loss.detach().clone()] + [p.grad.detach().clone() for p in model.parameters() if p.grad is not None])
+            for r in runs[1:]:
+                for a, b in zip(runs[0], r):
+                    assert torch.equal(a, b)
+            out[flag] = runs[0]
+        finally:
+            _n.HEAD_SIDE_STREAM = False
+    for a, b in zip(out[True], out[False]):
+        assert torch.equal(a, b)
+
+
 def test_preformatted_table_tiles_give_identical_results():
     """nnue_ft_format_tables + the *_tables entry points (table tiles formatted once, on the side stream) run the same
     kernels on the same tiles as the per-call formatting: bit-identical loss and gradients."""
