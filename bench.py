@@ -64,8 +64,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: the workload's batch is the GLOBAL batch, split evenly over the GPUs (default: weak)")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "oneshot", "nccl"],
-                    help="gradient exchange at N > 1: the library's one-shot all-reduce over NVLink peer memory (auto) or NCCL")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "oneshot", "nccl", "none"],
+                    help="gradient exchange at N > 1: the library's one-shot all-reduce over NVLink peer memory (auto) or NCCL; "
+                         "`none` is a DIAGNOSTIC (every rank steps on its shard without exchanging gradients: not a training "
+                         "step, it separates the exchange's cost from what running N GPUs at once costs each of them)")
     ap.add_argument("--no-int", action="store_true", help="skip the integer-inference side measurement")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (extra scaling lines only)")
     ap.add_argument("--no-module-api", action="store_true", help="skip the compute_loss(model, batch); loss.backward() leg")
@@ -192,6 +194,18 @@ def max_over_ranks(ms, world, device):
     t = torch.tensor([ms], dtype=torch.float64, device=device)
     torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     return float(t.item())
+
+
+RANK_MS = None
+
+
+def per_rank(v, world, device):
+    if world == 1:
+        return [v]
+    t = torch.zeros(world, dtype=torch.float64, device=device)
+    t[torch.distributed.get_rank()] = v
+    torch.distributed.all_reduce(t)
+    return [float(x) for x in t.tolist()]
 
 
 def barrier(world):
@@ -601,7 +615,7 @@ def run_b200(args):
         key, val = kv.split("=")
         _lib.set_option(key, int(val))
     model = build_model(w, device)
-    dp = train.DataParallelStep(model, allreduce=args.exchange)
+    dp = train.DataParallelStep(model, single=True) if args.exchange == "none" else train.DataParallelStep(model, allreduce=args.exchange)
     if world > 1:  # identical replicas
         for p in model.parameters():
             torch.distributed.broadcast(p.data, src=0)
@@ -618,11 +632,11 @@ def run_b200(args):
     for _ in range(2):
         for imgs, labs in sets:
             dp.step(imgs, labs, global_batch=global_batch)
-    xcheck = exchange_check(dp, world, device)
+    xcheck = exchange_check(dp, world, device) if args.exchange != "none" else None
     clocks.begin()
     for i in range(max(args.warmup, 3)):
         dp.step(*sets[i % n_sets], global_batch=global_batch)
-    windows, launches = [], 0
+    windows, launches, own = [], 0, []
     for wdw in range(max(1, args.windows)):
         barrier(world)
         _lib.lib().nnue_launch_count(1)
@@ -633,8 +647,11 @@ def run_b200(args):
         e1.record()
         barrier(world)
         launches = int(_lib.lib().nnue_launch_count(0))
+        own.append(e0.elapsed_time(e1))
         windows.append(max_over_ranks(e0.elapsed_time(e1), world, device))
     ms_total = sorted(windows)[len(windows) // 2]
+    global RANK_MS
+    RANK_MS = per_rank(sorted(own)[len(own) // 2] / args.steps, world, device)  # every rank's own median step time
     value = args.steps * global_batch / (ms_total * 1e-3)
     final_loss = float(loss)
 
@@ -791,6 +808,10 @@ def finish_line(args, w, B, world, rank, device, dp, model, sets, global_batch, 
     }
     if xcheck is not None:
         line["exchange_check"] = xcheck
+    if world > 1 and RANK_MS is not None:
+        line["ms_per_step_by_rank"] = RANK_MS  # each rank's own device time per step (median window): the spread is the skew
+    if args.exchange == "none" and world > 1:
+        line["diagnostic"] = "no gradient exchange (--exchange none): NOT a training step; compare ms_per_step with the exchanging run"
     if module_api is not None:
         line["module_api"] = module_api
     if dominant:

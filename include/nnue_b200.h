@@ -171,6 +171,18 @@ int nnue_ft_fwd(const nnue_shape *s, const uint32_t *bits_s_d, const float *ft_w
 int nnue_ft_fwd_indexed(int B, int K, int F, int L1, const int64_t *idx_d, const float *val_d,
                         const float *ft_w_d, const float *ft_b_d, float *ft_out_d, void *stream);
 /*
+ * The (row, sample, value) triples nnue_ft_bwd_indexed consumes, sorted by table row on the device: a chunked stable
+ * counting sort of the B * K pairs of (idx, val) -- key min(idx, F - 1) (the clamp of nnue.py:701), pairs with idx < 0
+ * sort behind every row as key F with value 0 -- that keeps (sample, slot) order inside a row, so the segment reduction
+ * that follows is deterministic.  Always B * K triples come out: nothing is read back to the host.  Replaces the
+ * argsort a reference maintainer would otherwise write in torch around nnue.py:702-708.
+ *   idx_d [B,K] i64; val_d [B,K] f32; row_out_d / sample_out_d [B*K] i32; pval_out_d [B*K] f32
+ */
+size_t nnue_ft_sort_pairs_workspace_bytes(int B, int K, int F);
+int nnue_ft_sort_pairs(int B, int K, int F, const int64_t *idx_d, const float *val_d, int32_t *row_out_d,
+                       int32_t *sample_out_d, float *pval_out_d, void *workspace_d, size_t workspace_bytes, void *stream);
+
+/*
  * Backward of the indexed form.  The weight gradient is a SORTED SEGMENT REDUCTION: the
  * caller passes the (row, sample, value) triples sorted by row (rows already clamped,
  * -1 entries removed); one warp sums each row's segment, no atomics.
@@ -461,6 +473,26 @@ size_t nnue_allreduce_ll_max_floats(void);
 size_t nnue_allreduce_recv_floats(int world, size_t n);
 int nnue_allreduce_oneshot(int world, int rank, void *const *peer_recv_h, void *const *peer_flags_h,
                            void *state_d, size_t n, float *buf_d, void *stream);
+
+/*
+ * The flagged form (n <= nnue_allreduce_ll_max_floats()) over one or two slices in ONE launch, each slice in a phase:
+ *   0  push + collect (= nnue_allreduce_oneshot),  1  push only (waits for nobody),  2  collect only (poll the peers'
+ *   values, sum in rank order, advance the slice's epoch).
+ * A slice pushed by one call must be collected by a later call on a stream ordered behind it, before it is pushed again.
+ * The data-parallel step pushes the slice that is final early (feature transformer, head) from the side stream and
+ * collects it at the end of the step in the same launch that exchanges the last slice (conv weights, thresholds): one
+ * point per step where ranks wait for each other.
+ */
+typedef struct nnue_allreduce_slice {
+    void *const *peer_recv_h;   /* as nnue_allreduce_oneshot */
+    void *const *peer_flags_h;
+    void *state_d;
+    size_t n;
+    float *buf_d;
+    int phase;
+} nnue_allreduce_slice;
+int nnue_allreduce_oneshot_slices(int world, int rank, const nnue_allreduce_slice *slices, int n_slices, void *stream);
+
 
 #ifdef __cplusplus
 }

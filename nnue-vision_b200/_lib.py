@@ -18,6 +18,12 @@ vp, sz = ctypes.c_void_p, ctypes.c_size_t
 ABI_VERSION = 4  # NNUE_B200_ABI_VERSION of include/nnue_b200.h
 
 
+class AllreduceSlice(ctypes.Structure):
+    """struct nnue_allreduce_slice (include/nnue_b200.h)."""
+    _fields_ = [("peer_recv_h", ctypes.c_void_p), ("peer_flags_h", ctypes.c_void_p), ("state_d", ctypes.c_void_p),
+                ("n", ctypes.c_size_t), ("buf_d", ctypes.c_void_p), ("phase", ctypes.c_int)]
+
+
 class NnueShape(ctypes.Structure):
     """struct nnue_shape (include/nnue_b200.h)."""
     _fields_ = [(n, i32) for n in (
@@ -39,6 +45,8 @@ SIGNATURES = {
     "nnue_allreduce_ll_max_floats": (sz, []),
     "nnue_allreduce_oneshot": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
+    "nnue_allreduce_oneshot_slices": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(AllreduceSlice), ctypes.c_int,
+                                                      ctypes.c_void_p]),
     "nnue_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "nnue_shape_init": (ctypes.c_int, [SHAPE_P] + [ctypes.c_int] * 10),
     "nnue_workspace_bytes": (sz, [SHAPE_P]),
@@ -46,6 +54,8 @@ SIGNATURES = {
     "nnue_sparse_from_bits": (ctypes.c_int, [SHAPE_P, vp, ctypes.c_int, vp, vp, vp]),
     "nnue_ft_fwd": (ctypes.c_int, [SHAPE_P, vp, vp, vp, vp, vp, sz, vp]),
     "nnue_ft_fwd_indexed": (ctypes.c_int, [ctypes.c_int] * 4 + [vp] * 6),
+    "nnue_ft_sort_pairs_workspace_bytes": (sz, [ctypes.c_int] * 3),
+    "nnue_ft_sort_pairs": (ctypes.c_int, [ctypes.c_int] * 3 + [vp] * 6 + [sz, vp]),
     "nnue_ft_bwd_indexed": (ctypes.c_int, [ctypes.c_int] * 4 + [vp, vp, vp, ctypes.c_int] + [vp] * 7),
     "nnue_head_fwd": (ctypes.c_int, [SHAPE_P] + [vp] * 11),
     "nnue_ce_fwd_bwd": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, vp, f32, vp, vp, vp, vp, vp, sz, vp]),

@@ -99,48 +99,119 @@ __device__ __forceinline__ uint2 ld_sys_u2(const uint2 *p) {
     return v;
 }
 constexpr int kLlPerThread = 4;  // elements per thread: all pushed before the first poll
-__global__ void __launch_bounds__(256)
-allreduce_ll_kernel(const ArPeers p, int rank, int world, size_t n, float *__restrict__ buf, unsigned *__restrict__ state) {
+// W = upper bound of `world` the instance is unrolled for (2, 4, 8 or 16).  The polls of a round -- up to 16 (element, peer)
+// pairs; more would cost registers, and the kernel must stay small enough to fit beside the conv-gradient kernel that is
+// still running -- are issued TOGETHER and only the pairs whose epoch has not arrived are polled again: the first version
+// polled pair after pair (28 dependent system-scope loads per thread at 8 ranks: 16 us for 55 K floats, of which one
+// load latency was the wire and the rest the loop).
+// One launch serves up to two slices (CTAs [0, a.grid) take slice a, the rest slice b), each in one of three phases:
+//   0 push + collect (the whole exchange),  1 push only,  2 collect only (poll + rank-order sum; advances the epoch).
+// The data-parallel step pushes the early slice (feature transformer, head) on the side stream as soon as the table
+// gradient is final -- a push waits for nobody -- and collects it at the END of the step in the same launch that
+// exchanges the last few hundred floats: by then the peers' values have long arrived, so the step has ONE point where
+// ranks wait for each other instead of two, and the early slice costs its local sum (measured at 8 GPUs: both slices as
+// whole exchanges 18 us per step, of which the early one -- nominally overlapped -- 8.7).
+struct LlSlice {
+    ArPeers p;
+    size_t n;
+    float *buf;
+    unsigned *state;
+    int phase, grid;
+};
+template <int W>
+__global__ void __launch_bounds__(256, 3)
+allreduce_ll_kernel(const LlSlice sa, const LlSlice sb, int rank, int world) {
+    constexpr int KR = 16 / W < kLlPerThread ? 16 / W : kLlPerThread;  // elements polled per round
+    const bool second = (int)blockIdx.x >= sa.grid;
+    const LlSlice &sl = second ? sb : sa;
+    const int bid = second ? (int)blockIdx.x - sa.grid : (int)blockIdx.x;
+    const size_t n = sl.n;
+    float *__restrict__ buf = sl.buf;
+    unsigned *state = sl.state;
+    const bool push = sl.phase != 2, collect = sl.phase != 1;
     const unsigned epoch = *reinterpret_cast<volatile unsigned *>(state + 1) + 1u;
     const size_t slot0 = (size_t)(epoch & 1u) * world * n;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * kLlPerThread) {
+    const size_t stride = (size_t)sl.grid * blockDim.x;
+    for (size_t i0 = (size_t)bid * blockDim.x + threadIdx.x; i0 < n; i0 += stride * kLlPerThread) {
         float mine[kLlPerThread];
 #pragma unroll
         for (int k = 0; k < kLlPerThread; ++k) {
             const size_t i = i0 + k * stride;
             if (i < n) {
                 mine[k] = buf[i];
-                const uint2 pk = make_uint2(__float_as_uint(mine[k]), epoch);
-                for (int r = 0; r < world; ++r)
-                    if (r != rank) st_sys_u2(reinterpret_cast<uint2 *>(p.recv[r]) + slot0 + (size_t)rank * n + i, pk);
+                if (push) {
+                    const uint2 pk = make_uint2(__float_as_uint(mine[k]), epoch);
+                    for (int r = 0; r < world; ++r)
+                        if (r != rank) st_sys_u2(reinterpret_cast<uint2 *>(sl.p.recv[r]) + slot0 + (size_t)rank * n + i, pk);
+                }
             }
         }
-        const uint2 *in = reinterpret_cast<const uint2 *>(p.recv[rank]) + slot0;
+        if (!collect) continue;
+        const uint2 *in = reinterpret_cast<const uint2 *>(sl.p.recv[rank]) + slot0;
 #pragma unroll
-        for (int k = 0; k < kLlPerThread; ++k) {
-            const size_t i = i0 + k * stride;
-            if (i < n) {
-                float acc = 0.0f;
-                for (int r = 0; r < world; ++r) {  // rank order: bit-identical on every rank
-                    float v = mine[k];
-                    if (r != rank) {
-                        uint2 got;
-                        do { got = ld_sys_u2(in + (size_t)r * n + i); } while (got.y != epoch);
-                        v = __uint_as_float(got.x);
-                    }
-                    acc = r == 0 ? v : acc + v;
+        for (int k0 = 0; k0 < kLlPerThread; k0 += KR) {
+            float v[KR][W];
+            unsigned pending = 0u;  // bit kk * W + r: the value of element k0 + kk from rank r has not arrived yet
+#pragma unroll
+            for (int kk = 0; kk < KR; ++kk)
+#pragma unroll
+                for (int r = 0; r < W; ++r) {
+                    v[kk][r] = 0.0f;
+                    if (i0 + (size_t)(k0 + kk) * stride < n && r < world && r != rank) pending |= 1u << (kk * W + r);
                 }
-                buf[i] = acc;
+            while (pending) {
+                uint2 got[KR][W];
+#pragma unroll
+                for (int kk = 0; kk < KR; ++kk)
+#pragma unroll
+                    for (int r = 0; r < W; ++r)
+                        if (pending >> (kk * W + r) & 1u) got[kk][r] = ld_sys_u2(in + (size_t)r * n + i0 + (size_t)(k0 + kk) * stride);
+#pragma unroll
+                for (int kk = 0; kk < KR; ++kk)
+#pragma unroll
+                    for (int r = 0; r < W; ++r)
+                        if ((pending >> (kk * W + r) & 1u) && got[kk][r].y == epoch) {
+                            v[kk][r] = __uint_as_float(got[kk][r].x);
+                            pending &= ~(1u << (kk * W + r));
+                        }
+            }
+#pragma unroll
+            for (int kk = 0; kk < KR; ++kk) {
+                const size_t i = i0 + (size_t)(k0 + kk) * stride;
+                if (i < n) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int r = 0; r < W; ++r)  // rank order: bit-identical on every rank
+                        if (r < world) {
+                            const float x = r == rank ? mine[k0 + kk] : v[kk][r];
+                            acc = r == 0 ? x : acc + x;
+                        }
+                    buf[i] = acc;
+                }
             }
         }
     }
-    // the last CTA to finish advances the device-side epoch (every CTA read it at the top)
+    // the last CTA of a slice to finish its collect advances the slice's device-side epoch (every CTA read it at the top;
+    // a push-only launch leaves it alone: the collect that follows computes the same epoch)
     __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(state, 1u) == gridDim.x - 1) {
+    if (collect && threadIdx.x == 0 && atomicAdd(state, 1u) == (unsigned)sl.grid - 1) {
         state[0] = 0u;
         state[1] = epoch;
     }
+}
+
+static int ll_grid(size_t n) {
+    const size_t want = (n + 256 * kLlPerThread - 1) / (256 * kLlPerThread);
+    return (int)(want < 1 ? 1 : want > 64 ? 64 : want);
+}
+static int launch_ll(const LlSlice &a, const LlSlice &b, int rank, int world, cudaStream_t st) {
+    const int grid = a.grid + b.grid;
+    if (world <= 2) allreduce_ll_kernel<2><<<grid, 256, 0, st>>>(a, b, rank, world);
+    else if (world <= 4) allreduce_ll_kernel<4><<<grid, 256, 0, st>>>(a, b, rank, world);
+    else if (world <= 8) allreduce_ll_kernel<8><<<grid, 256, 0, st>>>(a, b, rank, world);
+    else allreduce_ll_kernel<16><<<grid, 256, 0, st>>>(a, b, rank, world);
+    NNUE_CHECK_LAUNCH("allreduce_ll_kernel");
+    return NNUE_OK;
 }
 
 }  // namespace nnue
@@ -172,11 +243,9 @@ int nnue_allreduce_oneshot(int world, int rank, void *const *peer_recv_h, void *
         if (!p.recv[r] || !p.flags[r]) return NNUE_ERR_INVALID_ARG;
     }
     if (ll) {
-        const size_t want = (n + 256 * kLlPerThread - 1) / (256 * kLlPerThread);
-        const int grid = (int)(want < 1 ? 1 : want > 64 ? 64 : want);
-        allreduce_ll_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, rank, world, n, buf_d, static_cast<unsigned *>(state_d));
-        NNUE_CHECK_LAUNCH("allreduce_ll_kernel");
-        return NNUE_OK;
+        LlSlice a{}, none{};
+        a.p = p; a.n = n; a.buf = buf_d; a.state = static_cast<unsigned *>(state_d); a.phase = 0; a.grid = ll_grid(n);
+        return launch_ll(a, none, rank, world, static_cast<cudaStream_t>(stream));
     }
     // every CTA spins on the flags: few, small CTAs, so that they fit beside a kernel of the step that is still running
     const size_t n4 = n / 4, want = (n4 + 255) / 256;
@@ -185,6 +254,27 @@ int nnue_allreduce_oneshot(int world, int rank, void *const *peer_recv_h, void *
         p, rank, world, n4, reinterpret_cast<float4 *>(buf_d), static_cast<unsigned *>(state_d));
     NNUE_CHECK_LAUNCH("allreduce_push_kernel");
     return NNUE_OK;
+}
+
+
+int nnue_allreduce_oneshot_slices(int world, int rank, const nnue_allreduce_slice *slices, int n_slices, void *stream) {
+    if (world < 1 || world > kArMaxWorld || rank < 0 || rank >= world || !slices || n_slices < 1 || n_slices > 2)
+        return NNUE_ERR_INVALID_ARG;
+    LlSlice sl[2] = {};
+    for (int k = 0; k < n_slices; ++k) {
+        const nnue_allreduce_slice &in = slices[k];
+        if (!in.peer_recv_h || !in.peer_flags_h || !in.state_d || !in.buf_d || in.n < 1 || in.phase < 0 || in.phase > 2)
+            return NNUE_ERR_INVALID_ARG;
+        if (in.n > nnue_allreduce_ll_max_floats()) return NNUE_ERR_UNSUPPORTED;  // phases exist for the flagged form only
+        for (int r = 0; r < world; ++r) {
+            sl[k].p.recv[r] = static_cast<float *>(in.peer_recv_h[r]);
+            sl[k].p.flags[r] = static_cast<int *>(in.peer_flags_h[r]);
+            if (!sl[k].p.recv[r]) return NNUE_ERR_INVALID_ARG;
+        }
+        sl[k].n = in.n; sl[k].buf = in.buf_d; sl[k].state = static_cast<unsigned *>(in.state_d); sl[k].phase = in.phase;
+        sl[k].grid = ll_grid(in.n);
+    }
+    return launch_ll(sl[0], sl[1], rank, world, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

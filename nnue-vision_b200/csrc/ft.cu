@@ -1090,6 +1090,99 @@ int launch_ft_bwd_dval_dense(const nnue_shape &s, const uint32_t *bits_s, const 
     return NNUE_OK;
 }
 
+
+// ---- (row, sample, value) triples of the indexed interface sorted by row: a chunked stable counting sort ------------
+// The weight gradient of FeatureTransformer.forward(idx, val) (nnue.py:702-708: autograd's index_put accumulates in
+// whatever order its atomics land) is a segment reduction over the pairs sorted by table row, in (sample, slot) order
+// inside a row -- deterministic.  Keys are min(idx, F - 1) (the clamp of nnue.py:701), idx < 0 sorts behind everything as
+// key F with value 0, so the pair count is always B * K and nothing is read back to the host.
+//   pass A  a warp per chunk of pairs counts its keys (match.any aggregates equal keys of a 32-pair group)
+//   pass B  per key, the counts become exclusive prefixes over the chunks; one CTA scans the per-key totals
+//   pass C  the warps walk their chunks again and place every pair at base[key] + prefix[chunk][key] + rank in group
+constexpr int kSortChunkPairs = 2048, kSortMaxChunks = 256;
+__host__ __device__ inline int sort_chunks(long long n) {
+    long long c = (n + kSortChunkPairs - 1) / kSortChunkPairs;
+    return (int)(c < 1 ? 1 : (c > kSortMaxChunks ? kSortMaxChunks : c));
+}
+__device__ __forceinline__ int sort_key(long long v, int F) { return v < 0 ? F : (int)(v < F ? v : F - 1); }
+
+__global__ void __launch_bounds__(128)
+ft_sort_count_kernel(long long n, int F, int C, const int64_t *__restrict__ idx, unsigned *__restrict__ hist) {
+    const int lane = threadIdx.x & 31, c = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (c >= C) return;
+    const int NK = F + 1;
+    unsigned *h = hist + (size_t)c * NK;
+    for (int f = lane; f < NK; f += 32) h[f] = 0u;
+    __syncwarp();
+    const long long per = (n + C - 1) / C, i0 = (long long)c * per, i1 = i0 + per < n ? i0 + per : n;
+    for (long long i = i0; i < i1; i += 32) {
+        const bool on = i + lane < i1;
+        const int key = on ? sort_key(__ldg(idx + i + lane), F) : -1 - lane;  // idle lanes get unique keys
+        const unsigned peers = __match_any_sync(kFull, key);
+        if (on && lane == __ffs(peers) - 1) h[key] += __popc(peers);
+        __syncwarp();
+    }
+}
+// hist[c][f] -> exclusive prefix over c; tot[f] = total of key f
+__global__ void ft_sort_prefix_kernel(int NK, int C, unsigned *__restrict__ hist, unsigned *__restrict__ tot) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= NK) return;
+    unsigned run = 0u;
+    for (int c = 0; c < C; ++c) {
+        const unsigned v = hist[(size_t)c * NK + f];
+        hist[(size_t)c * NK + f] = run;
+        run += v;
+    }
+    tot[f] = run;
+}
+// exclusive scan of tot[0 .. NK) into base, one CTA
+__global__ void __launch_bounds__(1024)
+ft_sort_scan_kernel(int NK, const unsigned *__restrict__ tot, unsigned *__restrict__ base) {
+    __shared__ unsigned part[1024];
+    const int per = (NK + 1023) / 1024, f0 = threadIdx.x * per, f1 = min(NK, f0 + per);
+    unsigned sum = 0u;
+    for (int f = f0; f < f1; ++f) sum += tot[f];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan
+        const unsigned v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned run = part[threadIdx.x] - sum;
+    for (int f = f0; f < f1; ++f) {
+        base[f] = run;
+        run += tot[f];
+    }
+}
+__global__ void __launch_bounds__(128)
+ft_sort_place_kernel(long long n, int K, int F, int C, const int64_t *__restrict__ idx, const float *__restrict__ val,
+                     unsigned *__restrict__ hist, const unsigned *__restrict__ base, int32_t *__restrict__ row_out,
+                     int32_t *__restrict__ sample_out, float *__restrict__ pval_out) {
+    const int lane = threadIdx.x & 31, c = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (c >= C) return;
+    const int NK = F + 1;
+    unsigned *h = hist + (size_t)c * NK;  // running cursor of this chunk per key (starts at the prefix over earlier chunks)
+    const long long per = (n + C - 1) / C, i0 = (long long)c * per, i1 = i0 + per < n ? i0 + per : n;
+    for (long long i = i0; i < i1; i += 32) {
+        const bool on = i + lane < i1;
+        const long long raw = on ? __ldg(idx + i + lane) : 0;
+        const int key = on ? sort_key(raw, F) : -1 - lane;
+        const unsigned peers = __match_any_sync(kFull, key);
+        const unsigned cur = on ? h[key] : 0u;
+        __syncwarp();
+        if (on && lane == __ffs(peers) - 1) h[key] = cur + __popc(peers);
+        __syncwarp();
+        if (on) {
+            const unsigned pos = __ldg(base + key) + cur + __popc(peers & ((1u << lane) - 1u));
+            row_out[pos] = key;
+            sample_out[pos] = (int32_t)((i + lane) / K);
+            pval_out[pos] = raw < 0 ? 0.0f : __ldg(val + i + lane);
+        }
+    }
+}
+
 }  // namespace nnue
 
 using namespace nnue;
@@ -1160,6 +1253,32 @@ int nnue_ft_fwd_indexed(int B, int K, int F, int L1, const int64_t *idx_d, const
     ft_fwd_indexed_kernel<<<ceil_div(B, kFtThreads / 32), kFtThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         B, K, F, L1, idx_d, val_d, ft_w_d, ft_b_d, ft_out_d);
     NNUE_CHECK_LAUNCH("ft_fwd_indexed_kernel");
+    return NNUE_OK;
+}
+
+size_t nnue_ft_sort_pairs_workspace_bytes(int B, int K, int F) {
+    if (B < 1 || K < 1 || F < 1) return 0;
+    return ((size_t)sort_chunks(1LL * B * K) * (F + 1) + 2 * (size_t)(F + 1)) * 4 + 256;
+}
+
+int nnue_ft_sort_pairs(int B, int K, int F, const int64_t *idx_d, const float *val_d, int32_t *row_out_d, int32_t *sample_out_d,
+                       float *pval_out_d, void *workspace_d, size_t workspace_bytes, void *stream) {
+    if (B < 1 || K < 1 || F < 1 || !idx_d || !val_d || !row_out_d || !sample_out_d || !pval_out_d || !workspace_d)
+        return NNUE_ERR_INVALID_ARG;
+    if (workspace_bytes < nnue_ft_sort_pairs_workspace_bytes(B, K, F)) return NNUE_ERR_WORKSPACE;
+    if (1LL * B * K > 2147483647LL) return NNUE_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long n = 1LL * B * K;
+    const int C = sort_chunks(n), NK = F + 1;
+    unsigned *hist = static_cast<unsigned *>(workspace_d), *tot = hist + (size_t)C * NK, *base = tot + NK;
+    ft_sort_count_kernel<<<ceil_div(C, 4), 128, 0, st>>>(n, F, C, idx_d, hist);
+    NNUE_CHECK_LAUNCH("ft_sort_count_kernel");
+    ft_sort_prefix_kernel<<<ceil_div(NK, 256), 256, 0, st>>>(NK, C, hist, tot);
+    NNUE_CHECK_LAUNCH("ft_sort_prefix_kernel");
+    ft_sort_scan_kernel<<<1, 1024, 0, st>>>(NK, tot, base);
+    NNUE_CHECK_LAUNCH("ft_sort_scan_kernel");
+    ft_sort_place_kernel<<<ceil_div(C, 4), 128, 0, st>>>(n, K, F, C, idx_d, val_d, hist, base, row_out_d, sample_out_d, pval_out_d);
+    NNUE_CHECK_LAUNCH("ft_sort_place_kernel");
     return NNUE_OK;
 }
 

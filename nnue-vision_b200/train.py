@@ -153,6 +153,7 @@ class OneShotExchange:
         L = _lib.lib()
         self._lib, self.world, self.buf = _lib, world, buf
         self.overlap = os.environ.get("NNUE_EXCHANGE_OVERLAP", "1") != "0"
+        self.split_phases = os.environ.get("NNUE_EXCHANGE_SPLIT", "1") != "0"  # push early, collect at the end (one wait point)
         group = group if group is not None else dist.group.WORLD
         self.parts = []
         for lo, hi in ((buf.split, buf.numel()), (0, buf.split)):
@@ -183,14 +184,41 @@ class OneShotExchange:
             self.world, self.rank, part["recv"], part["flags"], _lib.dptr(part["state"]), part["n"],
             _lib.dptr(self.buf.flat[part["lo"]:part["lo"] + part["n"]]), stream))
 
+    def _slices(self, jobs, stream):
+        """One launch over (part, phase) jobs of the flagged form: phase 0 = whole exchange, 1 = push, 2 = collect."""
+        import ctypes
+        _lib = self._lib
+        arr = (_lib.AllreduceSlice * len(jobs))()
+        for a, (part, phase) in zip(arr, jobs):
+            a.peer_recv_h = ctypes.cast(part["recv"], ctypes.c_void_p)
+            a.peer_flags_h = ctypes.cast(part["flags"], ctypes.c_void_p)
+            a.state_d = part["state"].data_ptr()
+            a.n = part["n"]
+            a.buf_d = self.buf.flat[part["lo"]:part["lo"] + part["n"]].data_ptr()
+            a.phase = phase
+        _lib.check(_lib.lib().nnue_allreduce_oneshot_slices(self.world, self.rank, arr, len(jobs), stream))
+
+    def _split_ok(self):
+        # the early slice is pushed where it becomes final and collected at the end of the step together with the late
+        # slice's whole exchange (csrc/allreduce.cu): needs the flagged form for both
+        ll = int(self._lib.lib().nnue_allreduce_ll_max_floats())
+        return (self.overlap and self.split_phases and all(p is not None and p["n"] <= ll for p in self.parts))
+
     def early(self, stream=None):
-        if self.overlap:
-            self._launch(self.parts[0], stream if stream is not None else self._lib.stream_ptr())
+        stream = stream if stream is not None else self._lib.stream_ptr()
+        if self._split_ok():
+            self._slices([(self.parts[0], 1)], stream)
+        elif self.overlap:
+            self._launch(self.parts[0], stream)
 
     def late(self, stream=None):
+        stream = stream if stream is not None else self._lib.stream_ptr()
+        if self._split_ok():
+            self._slices([(self.parts[1], 0), (self.parts[0], 2)], stream)
+            return
         if not self.overlap:  # both slices at the end, on the caller's stream
-            self._launch(self.parts[0], stream if stream is not None else self._lib.stream_ptr())
-        self._launch(self.parts[1], stream if stream is not None else self._lib.stream_ptr())
+            self._launch(self.parts[0], stream)
+        self._launch(self.parts[1], stream)
 
     def full(self, stream=None):
         self._launch(self.parts[0], stream if stream is not None else self._lib.stream_ptr())

@@ -311,6 +311,31 @@ def test_feature_transformer_indexed_interface():
     assert_close(val.grad, gv, "ft indexed dval")
 
 
+@pytest.mark.parametrize("B,K,F", [(300, 40, 97), (7, 5, 3), (1, 1, 1), (513, 129, 70000)])
+def test_sort_pairs_is_the_stable_sort_by_row(B, K, F):
+    """nnue_ft_sort_pairs (the chunked counting sort in front of the indexed weight gradient) against torch's stable sort:
+    keys min(idx, F - 1), negative indices behind every row with value 0, (sample, slot) order kept inside a row; several
+    chunks of pairs, keys that repeat inside a 32-pair group, tables larger than the pair count."""
+    lib = _lib()
+    g = torch.Generator().manual_seed(B * 1000 + K)
+    idx = torch.randint(-3, F + 10, (B, K), generator=g).cuda()
+    val = torch.randn(B, K, generator=g).cuda()
+    n = B * K
+    rows = torch.empty(n, dtype=torch.int32, device="cuda")
+    samples = torch.empty(n, dtype=torch.int32, device="cuda")
+    vals = torch.empty(n, dtype=torch.float32, device="cuda")
+    nb = int(lib.lib().nnue_ft_sort_pairs_workspace_bytes(B, K, F))
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    lib.check(lib.lib().nnue_ft_sort_pairs(B, K, F, lib.dptr(idx), lib.dptr(val), lib.dptr(rows), lib.dptr(samples), lib.dptr(vals),
+                                           lib.dptr(ws), nb, lib.stream_ptr()))
+    torch.cuda.synchronize()
+    key = torch.where(idx < 0, torch.full_like(idx, F), idx.clamp(max=F - 1)).reshape(-1)
+    order = torch.sort(key, stable=True).indices
+    assert torch.equal(rows.long(), key[order])
+    assert torch.equal(samples.long(), (order // K))
+    assert torch.equal(vals, torch.where(idx < 0, torch.zeros_like(val), val).reshape(-1)[order])
+
+
 def test_sparse_feature_values_keep_autograd_edge():
     cfg, model, images, _ = _make("T")
     x = model.conv(images)

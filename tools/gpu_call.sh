@@ -1,6 +1,5 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-( timeout 1500 python -m pytest tests/test_gpu_float.py tests/test_gpu_graph.py -m gpu -x -q 2>&1 | tail -3 ) 2>&1 | tee gpurun_out/s8_tests.log
-b() { name=$1; shift; timeout 600 python bench.py "$@" 2> gpurun_out/$name.err | tail -1 > gpurun_out/$name.json; python -c "import json;d=json.load(open('gpurun_out/$name.json'));print('$name',d['value'],d['ms_per_step'],d.get('stages_ms'))" || tail -5 gpurun_out/$name.err; }
-b s8_l1k --workload real_cifar_l1_1024_b16384 --steps 20 --warmup 5 --no-cpu-baseline --no-module-api --no-e2e --no-int
-NNUE_HEAD_SIDE_STREAM=0 b s8_l1k_noside --workload real_cifar_l1_1024_b16384 --steps 20 --warmup 5 --no-cpu-baseline --no-module-api --no-e2e --no-int
+N=8
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 tools/exchange_parts.py 2> gpurun_out/s15_parts_n$N.err | tee gpurun_out/s15_parts_n$N.log | tail -1
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 30 --warmup 5 --no-cpu-baseline --no-int --no-e2e --no-module-api 2> gpurun_out/s15_d_n8.err | tail -1 > gpurun_out/s15_d_n8.json; python -c "import json;d=json.load(open('gpurun_out/s15_d_n8.json'));print(d['value'],d['ms_per_step'],d.get('exchange_check'))"
