@@ -277,18 +277,19 @@ HEAD_SIDE_STREAM = os.environ.get("NNUE_HEAD_SIDE_STREAM", "0") == "1"
 # config D the two 4 us formatting kernels running beside the extraction cost more than they save (measured on one
 # box, 200 steps each: 227 us per step with, 216 us without -- the extraction is issue-bound and shares its SMs).
 PREFORMAT_TABLES = os.environ.get("NNUE_PREFORMAT_TABLES", "0") == "1"
+
+
+# Under data parallelism the side stream runs at high priority: the table gradient and the push of the exchange behind it
+# get their SMs first (2 GPUs, config D: 218.3 vs 220.3 us per step).  Without an exchange it stays at normal priority: at
+# L1 = 1024 the 200 us table gradient in front of everything else costs the step 0.817 vs 0.795 ms.
+SIDE_STREAM_PRIORITY = int(os.environ.get("NNUE_SIDE_PRIORITY", "-1"))
 _SIDE_STREAMS = {}
 
 
-# -1 = scheduled ahead of the caller's stream: the table gradient and the slice of the exchange behind it get their SMs
-# first (2 GPUs, config D: 218.3 vs 220.3 us per step)
-SIDE_STREAM_PRIORITY = int(os.environ.get("NNUE_SIDE_PRIORITY", "-1"))
-
-
-def _side_stream(device):
-    key = (device.type, device.index)
+def _side_stream(device, high=False):
+    key = (device.type, device.index, bool(high))
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device, priority=SIDE_STREAM_PRIORITY)
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device, priority=SIDE_STREAM_PRIORITY if high else 0)
     return _SIDE_STREAMS[key]
 
 
@@ -350,7 +351,7 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
         check(L.nnue_head_train_overlapped(sp, dptr(ft_out), dptr(labels), inv_count, dptr(w1), dptr(b1), dptr(w2), dptr(b2),
                                            dptr(w3), dptr(b3), dptr(loss_out), dptr(g_ft), dptr(g_w1), dptr(g_b1), dptr(g_w2),
                                            dptr(g_b2), dptr(g_w3), dptr(g_b3), dptr(ws), ws_bytes, st, dptr(side_ws), side_bytes,
-                                           ctypes.c_void_p(_side_stream(images.device).cuda_stream)))
+                                           ctypes.c_void_p(_side_stream(images.device, high=exchange is not None).cuda_stream)))
     else:
         check(L.nnue_head_train(sp, dptr(ft_out), dptr(labels), inv_count, dptr(w1), dptr(b1), dptr(w2), dptr(b2),
                                 dptr(w3), dptr(b3), dptr(loss_out), dptr(g_ft), dptr(g_w1), dptr(g_b1), dptr(g_w2),
@@ -360,7 +361,7 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
         # The table gradient depends only on g_ft and nothing downstream depends on it, while the value gradient
         # and the conv gradient that follow are latency-bound and leave issue slots free: outside the per-stage
         # timing mode it runs on a side stream next to them (it uses its own part of the workspace).
-        side = _side_stream(images.device) if (marks is None and OVERLAP_TABLE_GRADIENT) else None
+        side = _side_stream(images.device, high=exchange is not None) if (marks is None and OVERLAP_TABLE_GRADIENT) else None
         if side is not None:
             main = torch.cuda.current_stream()
             side.wait_stream(main)
@@ -410,7 +411,7 @@ def _run_train_step(shape, images, labels, params, inv_count, grads=None, loss_o
     # General shapes (ImageNet-sized images, large tables).  Under data parallelism the table gradient runs on the side
     # stream with its own scratch and its slice of the exchange (the 268 MB of SURVEY config I) follows it there, while
     # the value / conv gradients run on the caller's stream.
-    side = _side_stream(images.device) if (exchange is not None and marks is None and OVERLAP_TABLE_GRADIENT) else None
+    side = _side_stream(images.device, high=True) if (exchange is not None and marks is None and OVERLAP_TABLE_GRADIENT) else None
     if side is not None:
         main = torch.cuda.current_stream()
         side.wait_stream(main)
