@@ -399,7 +399,7 @@ ft_bitgemm_umma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, 
 // g_ft tile (12 KB) and of the table tile (24 KB); six UMMAs (128 x 256 x 16) per stage.
 __global__ void __launch_bounds__(kGbThreads, 2)
 ft_gbin_umma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, const unsigned char *__restrict__ atiles,
-                    const unsigned char *__restrict__ btiles, float *__restrict__ gbin) {
+                    const unsigned char *__restrict__ btiles, float *__restrict__ gbin, const float *__restrict__ g_ft_src) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
     uint64_t *empty = full + kGbStages;
@@ -423,9 +423,12 @@ ft_gbin_umma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, con
         nt = (lid % group) / gm;
     }
 
+    // g_ft_src != null: the A operand (g_ft as three bf16 terms) is built in the kernel by the epilogue warps from the fp32
+    // rows (umma.cuh: row_chunk_*) instead of arriving as pre-formatted tiles
+    const bool a_inline = g_ft_src != nullptr;
     if (threadIdx.x == 0) {
         for (int i = 0; i < kGbStages; ++i) {
-            mbar_init(&full[i], 1);
+            mbar_init(&full[i], a_inline ? 5 : 1);
             mbar_init(&empty[i], 1);
         }
         mbar_init(done, 1);
@@ -443,8 +446,8 @@ ft_gbin_umma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, con
             for (int j = 0; j < n_ks; ++j) {
                 const int st = j % kGbStages;
                 if (j >= kGbStages) mbar_wait(&empty[st], ((j / kGbStages) - 1) & 1);
-                mbar_arrive_expect_tx(&full[st], kGbABytes + kGbBBytes);
-                tma_bulk_g2s(sa + (uint32_t)st * kGbABytes, asrc + (size_t)j * kGbABytes, kGbABytes, &full[st]);
+                mbar_arrive_expect_tx(&full[st], a_inline ? kGbBBytes : kGbABytes + kGbBBytes);
+                if (!a_inline) tma_bulk_g2s(sa + (uint32_t)st * kGbABytes, asrc + (size_t)j * kGbABytes, kGbABytes, &full[st]);
                 tma_bulk_g2s(sb + (uint32_t)st * kGbBBytes, bsrc + (size_t)j * kGbBBytes, kGbBBytes, &full[st]);
             }
         }
@@ -471,6 +474,23 @@ ft_gbin_umma_kernel(const nnue_shape s, const uint32_t *__restrict__ bits_s, con
         // ---- epilogue: mask with the sample's bits, transpose through shared memory (the operand ring is idle
         //      once `done` fires) so that every global store instruction writes 512 contiguous bytes of one row ----
         const int q = warp & 3, b = mt * kUM + q * 32 + lane;
+        if (a_inline) {  // A producers (thread = tile row): k-step j + 1 is loading while k-step j is split and stored
+            const bool live = b < s.B;
+            const float *row = g_ft_src + (size_t)min(b, s.B - 1) * s.L1;
+            unsigned char *dst0 = sa + (uint32_t)(q * 32 + lane) * 16;
+            RowChunk nxt;
+            row_chunk_load(nxt, row, 0, 0, live);
+            for (int j = 0; j < n_ks; ++j) {
+                const int st = j % kGbStages;
+                const RowChunk cur = nxt;
+                if (j + 1 < n_ks) row_chunk_load(nxt, row, (j + 1) * 16, 0, live);
+                if (j >= kGbStages) mbar_wait(&empty[st], ((j / kGbStages) - 1) & 1);
+                row_chunk_store(cur, false, dst0 + (uint32_t)st * kGbABytes, kGbATile);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[st]);
+            }
+        }
         uint32_t mw[kUmmaGbinN / 32];
 #pragma unroll
         for (int i = 0; i < kUmmaGbinN / 32; ++i) {
@@ -675,8 +695,13 @@ int launch_ft_bwd_gbin_umma(const nnue_shape &s, const uint32_t *bits_s, const f
     unsigned char *at = static_cast<unsigned char *>(workspace);
     unsigned char *bt = at + align_up((size_t)n_mt * kUM * s.L1 * 6, 256);
     long long n = 1LL * n_mt * kUM * (s.L1 / 8);
-    umma_format_rows_kernel<false, kUM><<<(int)((n + 255) / 256), 256, 0, st>>>(s, g_ft, s.B, n_mt, at);
-    NNUE_CHECK_LAUNCH("umma_format_rows_kernel");
+    // wide tables: the kernel's epilogue warps split g_ft themselves (64 k-steps give them time; at L1 = 64 the four
+    // k-steps do not, and the 5 us formatter stays)
+    const bool a_inline = get_option(kOptInlineA) && s.L1 >= 256 && (reinterpret_cast<uintptr_t>(g_ft) & 15) == 0;
+    if (!a_inline) {
+        umma_format_rows_kernel<false, kUM><<<(int)((n + 255) / 256), 256, 0, st>>>(s, g_ft, s.B, n_mt, at);
+        NNUE_CHECK_LAUNCH("umma_format_rows_kernel");
+    }
     if (table_tiles) {
         bt = const_cast<unsigned char *>(static_cast<const unsigned char *>(table_tiles)) + align_up(umma_kt_bytes((size_t)s.PP, s), 256);
     } else {
@@ -685,7 +710,7 @@ int launch_ft_bwd_gbin_umma(const nnue_shape &s, const uint32_t *bits_s, const f
         NNUE_CHECK_LAUNCH("umma_format_rows_kernel");
     }
     NNUE_CUDA_TRY(cudaFuncSetAttribute(ft_gbin_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGbSmem));
-    ft_gbin_umma_kernel<<<dim3(n_nt, n_mt), kGbThreads, kGbSmem, st>>>(s, bits_s, at, bt, gbin);
+    ft_gbin_umma_kernel<<<dim3(n_nt, n_mt), kGbThreads, kGbSmem, st>>>(s, bits_s, at, bt, gbin, a_inline ? g_ft : nullptr);
     NNUE_CHECK_LAUNCH("ft_gbin_umma_kernel");
     return NNUE_OK;
 }

@@ -37,6 +37,9 @@ struct UGemmArgs {
     //   g_ft[:, i] = g_l0[:, i] * ft[:, h + i] + g_l0[:, h + i],   g_ft[:, h + i] = g_l0[:, i] * ft[:, i]     (nnue.py:660-666 backward)
     const float *pair_ft;                // ft_out [M][2 h] (ldc), or null
     int pair_h;
+    // A operand produced in the kernel from a row-major fp32 source (umma.cuh: row_chunk_*), or null = pre-formatted tiles
+    const float *a_src; long long a_ld;  // A(m, k) = a_src[m * a_ld + k] through the pairwise transform when a_pair_half > 0
+    int a_pair_half;
 };
 
 // value of operand element (r, k) read from a row-major fp32 source; pair_half > 0 applies the pairwise transform
@@ -146,9 +149,10 @@ ugemm_kernel(const UGemmArgs g) {
     const int nt = blockIdx.x, mt = blockIdx.y, split = blockIdx.z;
     const int ks0 = split * g.ks_per_split, ks1 = min(g.n_ks, ks0 + g.ks_per_split), n_stage = ks1 - ks0;
 
+    const bool a_inline = g.a_src != nullptr;
     if (threadIdx.x == 0) {
         for (int i = 0; i < ST; ++i) {
-            mbar_init(&full[i], 1);
+            mbar_init(&full[i], a_inline ? 5 : 1);  // the TMA thread (+ the four producer warps of an in-kernel A operand)
             mbar_init(&empty[i], 1);
         }
         mbar_init(done, 1);
@@ -167,8 +171,9 @@ ugemm_kernel(const UGemmArgs g) {
             for (int j = 0; j < n_stage; ++j) {
                 const int st = j % ST;
                 if (j >= ST) mbar_wait(&empty[st], ((j / ST) - 1) & 1);
-                mbar_arrive_expect_tx(&full[st], Cfg::kABytes + Cfg::kBBytes);
-                tma_bulk_g2s(sa + (uint32_t)st * Cfg::kABytes, asrc + (size_t)j * Cfg::kABytes, Cfg::kABytes, &full[st]);
+                mbar_arrive_expect_tx(&full[st], a_inline ? Cfg::kBBytes : Cfg::kABytes + Cfg::kBBytes);
+                if (!a_inline)
+                    tma_bulk_g2s(sa + (uint32_t)st * Cfg::kABytes, asrc + (size_t)j * Cfg::kABytes, Cfg::kABytes, &full[st]);
                 tma_bulk_g2s(sb + (uint32_t)st * Cfg::kBBytes, bsrc + (size_t)j * Cfg::kBBytes, Cfg::kBBytes, &full[st]);
             }
         }
@@ -192,6 +197,26 @@ ugemm_kernel(const UGemmArgs g) {
         }
     } else {
         const int q = warp & 3, m = mt * kGuM + q * 32 + lane;
+        if (a_inline) {
+            // ---- A producers: the four epilogue warps build the stage's A tiles from the fp32 rows while the main loop
+            // runs (thread = tile row; the loads of k-step j + 1 are in flight while k-step j is split and stored) ----
+            const bool live = m < g.M;
+            const float *row = g.a_src + (size_t)min(m, g.M - 1) * g.a_ld;
+            const int h = g.a_pair_half;
+            unsigned char *dst0 = sa + (uint32_t)(q * 32 + lane) * 16;
+            RowChunk nxt;
+            row_chunk_load(nxt, row, ks0 * 16, h, live);
+            for (int j = 0; j < n_stage; ++j) {
+                const int st = j % ST, k0 = (ks0 + j) * 16;
+                const RowChunk cur = nxt;
+                if (j + 1 < n_stage) row_chunk_load(nxt, row, k0 + 16, h, live);
+                if (j >= ST) mbar_wait(&empty[st], ((j / ST) - 1) & 1);
+                row_chunk_store(cur, h > 0 && k0 < h, dst0 + (uint32_t)st * Cfg::kABytes, Cfg::kATile);
+                fence_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[st]);
+            }
+        }
         mbar_wait(done, 0);
         tcgen05_fence_after();
         const uint32_t tbase = tmem_acc + ((uint32_t)(q * 32) << 16);
@@ -317,8 +342,10 @@ int ugemm_format_cols(int RT, const float *src, long long ld, int K, int ncols, 
 // C + z * c_split_stride).  Returns the number of splits actually used (every split non-empty), or < 0.
 int ugemm_launch(int NT, int M, int N, int K, const unsigned char *at, const unsigned char *bt, float *C, long long ldc,
                  const float *bias, int relu, const float *mask, long long ldm, int splits, long long c_split_stride,
-                 cudaStream_t st, const float *pair_ft, int pair_h) {
+                 cudaStream_t st, const float *pair_ft, int pair_h, const float *a_src, long long a_ld, int a_pair_half) {
     UGemmArgs g{};
+    if (a_src && (K % 16 || (a_ld & 3) || a_pair_half % 16 || (reinterpret_cast<uintptr_t>(a_src) & 15))) return NNUE_ERR_INVALID_ARG;
+    g.a_src = a_src; g.a_ld = a_ld; g.a_pair_half = a_pair_half;
     if (pair_ft && (NT != 256 || splits > 1 || N != 2 * pair_h || pair_h % 128 || (ldc & 3))) return NNUE_ERR_INVALID_ARG;
     g.pair_ft = pair_ft; g.pair_h = pair_h;
     g.M = M; g.N = N; g.n_ks = ceil_div(K, 16);

@@ -261,8 +261,15 @@ int head_layer1_fwd(const nnue_shape *s, const float *ft_out_d, const float *w1_
         const int NT = head_umma_nt(*s);
         unsigned char *at = static_cast<unsigned char *>(workspace_d);
         unsigned char *bt = at + align_up(ugemm_tile_bytes(s->B, 128, s->L1), 256);
-        if ((rc = ugemm_format_rows(128, ft_out_d, s->L1, s->B, s->L1, s->L1 / 2, at, st)) < 0) return rc;
         if ((rc = ugemm_format_rows(NT, w1_d, s->L1, s->L2, s->L1, 0, bt, st)) < 0) return rc;
+        if (gemm_inline_a_ok(s->L1, s->L1 / 2)) {
+            // l0 never exists in HBM: the GEMM's epilogue warps build its split-bf16 tiles from ft_out while the main loop runs
+            // (the formatter wrote 100 MB and the GEMM read them back: 34 + 37 us at L1 = 1024, batch 16384)
+            rc = ugemm_launch(NT, s->B, s->L2, s->L1, nullptr, bt, act1_d, s->L2, b1_d, 1, nullptr, 0, 1, 0, st, nullptr, 0, ft_out_d,
+                              s->L1, s->L1 / 2);
+            return rc < 0 ? rc : NNUE_OK;
+        }
+        if ((rc = ugemm_format_rows(128, ft_out_d, s->L1, s->B, s->L1, s->L1 / 2, at, st)) < 0) return rc;
         rc = ugemm_launch(NT, s->B, s->L2, s->L1, at, bt, act1_d, s->L2, b1_d, 1, nullptr, 0, 1, 0, st);
         return rc < 0 ? rc : NNUE_OK;
     }

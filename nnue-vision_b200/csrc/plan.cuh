@@ -521,7 +521,10 @@ int ugemm_format_cols(int RT, const float *src, long long ld, int K, int ncols, 
 // pair_ft != null (NT = 256, B operand formatted with pair_perm = pair_h): the pairwise backward runs in the epilogue and C is g_ft
 int ugemm_launch(int NT, int M, int N, int K, const unsigned char *at, const unsigned char *bt, float *C, long long ldc,
                  const float *bias, int relu, const float *mask, long long ldm, int splits, long long c_split_stride,
-                 cudaStream_t st, const float *pair_ft = nullptr, int pair_h = 0);
+                 cudaStream_t st, const float *pair_ft = nullptr, int pair_h = 0, const float *a_src = nullptr, long long a_ld = 0,
+                 int a_pair_half = 0);
+// a_src != null: the A operand is built inside the kernel from the row-major fp32 source (K % 16 == 0; `at` is unused)
+inline bool gemm_inline_a_ok(int K, int pair_half) { return get_option(kOptInlineA) && K % 16 == 0 && K >= 256 && pair_half % 16 == 0; }
 // the input gradient of layer 1 with the pairwise backward in the GEMM's epilogue: both members of a pair in one N tile
 inline bool head_pair_epilogue_ok(const nnue_shape &s) { return get_option(kOptHeadPairEpi) && head_umma_ok(s) && (s.L1 / 2) % 128 == 0; }
 // forward of the stack with optional scratch (head.cu): with ws_head_umma_fwd bytes layer 1 runs on the tensor cores

@@ -70,4 +70,38 @@ __device__ __forceinline__ void split3x8(const float (&v)[8], uint4 (&o)[3]) {
         o[t] = make_uint4(h[t][0] | (h[t][1] << 16), h[t][2] | (h[t][3] << 16), h[t][4] | (h[t][5] << 16), h[t][6] | (h[t][7] << 16));
 }
 
+// ---- an A operand produced inside the GEMM kernel ------------------------------------------------------------------
+// The [128 rows x 16 k] x 3-term stage of a K-major operand built straight from a row-major fp32 source by the kernel's
+// (otherwise idle) epilogue warps, instead of by a formatting kernel that writes 6 bytes per element to HBM for the
+// GEMM to read back: thread r owns tile row r, reads its 16 consecutive k (64 bytes), splits them exactly and stores the
+// six 16-byte chunks (canonical no-swizzle layout: chunk (k / 8) at (k / 8) * 2048 + r * 16, terms 4096 bytes apart).
+// pair_half = h > 0: the source row is x[2 h] and the operand is l0[k] = k < h ? x[k] * x[k + h] : x[k - h]
+// (nnue.py:660-666; h % 16 == 0 so that a k-step never straddles the halves).
+struct RowChunk { float4 a[4], b[4]; };  // 16 floats of the row (+ the partner half's 16 for a product k-step)
+__device__ __forceinline__ void row_chunk_load(RowChunk &c, const float *row, int k0, int h, bool live) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 *p = reinterpret_cast<const float4 *>(row + (h > 0 && k0 >= h ? k0 - h : k0));
+    const float4 *q = reinterpret_cast<const float4 *>(row + k0 + h);
+    const bool prod = h > 0 && k0 < h;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        c.a[i] = live ? __ldg(p + i) : z;
+        c.b[i] = (live && prod) ? __ldg(q + i) : z;
+    }
+}
+__device__ __forceinline__ void row_chunk_store(const RowChunk &c, bool prod, unsigned char *stage_row, uint32_t term_bytes) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const float4 x0 = c.a[2 * half], x1 = c.a[2 * half + 1], y0 = c.b[2 * half], y1 = c.b[2 * half + 1];
+        float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        if (prod) {
+            v[0] *= y0.x; v[1] *= y0.y; v[2] *= y0.z; v[3] *= y0.w; v[4] *= y1.x; v[5] *= y1.y; v[6] *= y1.z; v[7] *= y1.w;
+        }
+        uint4 o[3];
+        split3x8(v, o);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) *reinterpret_cast<uint4 *>(stage_row + (uint32_t)t * term_bytes + (uint32_t)half * 2048u) = o[t];
+    }
+}
+
 }  // namespace nnue

@@ -213,7 +213,7 @@ OPTION_DEFAULTS = {"extract_tma": 0, "ft_form": 0, "input_bwd_onchip": 0}
 
 @pytest.mark.parametrize("options", [dict(extract_tma=1), dict(extract_fixed=0), dict(ft_umma=0), dict(ft_umma=0, ft_mma=0),
                                      dict(ft_umma=0, ft_mma=0, ft_bwd_both=0), dict(ft_umma=0, ft_mma=0, ft_bwd_dw_owner=0),
-                                     dict(ft_umma=0, ft_mma=0, input_bwd_fused=0), dict(input_bwd_fused=0), dict(input_bwd_onchip=1), dict(ft_form=2), dict(ft_form=2, input_bwd_fused=0), dict(input_bwd_variant=0), dict(input_bwd_swizzle=0), dict(input_bwd_swizzle=0, input_bwd_variant=0), dict(head_fused=0), dict(head_umma=0), dict(head_mid=0), dict(head_mid=0, head_umma=0), dict(head_mid=2), dict(head_pair_epilogue=0),
+                                     dict(ft_umma=0, ft_mma=0, input_bwd_fused=0), dict(input_bwd_fused=0), dict(input_bwd_onchip=1), dict(ft_form=2), dict(ft_form=2, input_bwd_fused=0), dict(input_bwd_variant=0), dict(input_bwd_swizzle=0), dict(input_bwd_swizzle=0, input_bwd_variant=0), dict(head_fused=0), dict(head_umma=0), dict(head_mid=0), dict(head_mid=0, head_umma=0), dict(head_mid=2), dict(head_pair_epilogue=0), dict(gemm_inline_a=1),
                                      dict(ft_umma=0, ft_mma=0, ft_bwd_dw_owner=0, input_bwd_fused=0, head_fused=0)],
                          ids=str)
 @pytest.mark.parametrize("name", ["D", "T", "big_into_small", "D1k_tensor_head"])
@@ -502,6 +502,30 @@ def test_head_side_stream_chain_is_bit_identical(name):
         finally:
             _n.HEAD_SIDE_STREAM = False
     for a, b in zip(out[True], out[False]):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["D1k_tensor_head", "wide_head_ragged", "I_small", "D1k"])
+def test_in_kernel_operand_split_is_bit_identical(name):
+    """Option gemm_inline_a (measured no faster, off by default): wide shapes build the A operand of the layer-1 forward GEMM
+    (l0, pairwise transform included) and of the value-gradient GEMM (g_ft) inside the kernel, by the epilogue warps, instead
+    of reading tiles a formatting kernel wrote: the same exact
+    split feeds the same UMMAs in the same order, so loss and every gradient are bit-identical to the formatter path
+    (ragged batches: rows past the batch are zero in both)."""
+    lib = _lib()
+    cfg, model, images, labels = _make(name)
+    out = {}
+    for flag in (1, 0):
+        lib.set_option("gemm_inline_a", flag)
+        try:
+            model.zero_grad()
+            loss = model.loss(images, labels)
+            loss.backward()
+            torch.cuda.synchronize()
+            out[flag] = [loss.detach().clone()] + [p.grad.detach().clone() for p in model.parameters() if p.grad is not None]
+        finally:
+            lib.set_option("gemm_inline_a", 0)
+    for a, b in zip(out[1], out[0]):
         assert torch.equal(a, b)
 
 
