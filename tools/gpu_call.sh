@@ -1,7 +1,6 @@
-cd $GRAFT_REPO_ROOT
+# One validation pass on a GPU box (run through gpurun): the parity suite, the headline bench line, the integer timing table.
+cd ${GRAFT_REPO_ROOT:-.}
 mkdir -p gpurun_out
-N=${NGPU:-2}
-timeout 300 python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -2 | tee gpurun_out/f4_multi_n$N.log
-for W in default_cifar_b16384; do
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --workload $W --steps 30 --warmup 5 --no-cpu-baseline --no-int --no-e2e --no-module-api 2> gpurun_out/f4_${W}_n$N.err | tail -1 > gpurun_out/f4_${W}_n$N.json; python -c "import json;d=json.load(open('gpurun_out/f4_${W}_n$N.json'));print('$W',d['n_gpus'],d['value'],d['ms_per_step'],d.get('exchange_check',{}).get('identical_on_all_ranks'))" || tail -3 gpurun_out/f4_${W}_n$N.err
-done
+( timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 ) 2>&1 | tee gpurun_out/final_tests.log
+timeout 900 python bench.py > gpurun_out/final_bench_d_n1.json 2> gpurun_out/final_bench_d_n1.err
+python -c "import json;d=json.loads(open('gpurun_out/final_bench_d_n1.json').read().strip().splitlines()[-1]);print('D',d['value'],d['ms_per_step'],d['e2e']['value'],d['roofline']['frac'],d['cpu_baseline']['value'],d['int_inference']['device_sweep_graph_replay_samples_per_s'])" || tail -5 gpurun_out/final_bench_d_n1.err
