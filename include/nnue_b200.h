@@ -424,6 +424,12 @@ int nnue_q_infer(const nnue_qmodel *m, const float *images_d, int B, int H, int 
  * may serve several streams at once as long as each call has its own scratch; nnue_q_infer (no scratch) always runs
  * the one-kernel form.
  */
+/*
+ * Host-only: the integer bound the fixed-shape conv kernel compares against instead of dividing.  The engine fires a
+ * feature iff (float)clamp(a / conv_scale, -127, 127) > threshold (C++ truncating division; nnue_engine.cpp:93-103, 199).
+ * Returns 0 with *a_min set (fires iff a >= *a_min), 1 = never fires, 2 = always fires, or a negative NNUE_ERR_*.
+ */
+int nnue_q_conv_bound(float threshold, int conv_scale, int32_t *a_min);
 size_t nnue_q_workspace_bytes(const nnue_qmodel *m, int B);
 int nnue_q_infer_ws(const nnue_qmodel *m, const float *images_d, int B, int H, int W, int bucket,
                     float *logits_d, float *density_d, void *workspace_d, size_t workspace_bytes, void *stream);

@@ -96,6 +96,7 @@ SIGNATURES = {
     "nnue_q_free": (None, [vp]),
     "nnue_q_dims": (ctypes.c_int, [vp, vp, ctypes.POINTER(f32)]),
     "nnue_q_infer": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp]),
+    "nnue_q_conv_bound": (ctypes.c_int, [f32, ctypes.c_int, vp]),
     "nnue_q_workspace_bytes": (sz, [vp, ctypes.c_int]),
     "nnue_q_infer_ws": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, sz, vp]),
     "nnue_q_acc_apply": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]),

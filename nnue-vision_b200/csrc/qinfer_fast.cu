@@ -432,3 +432,11 @@ int launch_q_conv_bits32(const QParams &q, const int32_t *taps_d, cudaStream_t s
 }
 
 }  // namespace nnue
+
+extern "C" int nnue_q_conv_bound(float threshold, int conv_scale, int32_t *a_min) {
+    if (!a_min || conv_scale < 1) return NNUE_ERR_INVALID_ARG;
+    int bound = 0;
+    const int mode = nnue::conv_bound(threshold, conv_scale, &bound);
+    *a_min = bound;
+    return mode;
+}

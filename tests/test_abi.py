@@ -80,3 +80,43 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "nope.so")
     with pytest.raises(_lib.NnueError, match="no CPU or PyTorch fallback"):
         _lib.lib()
+
+
+def test_conv_bound_is_the_engine_threshold_rule():
+    """The fixed-shape integer conv kernel fires a feature iff `a >= a_min` instead of computing
+    `(float)clamp(a / scale, -127, 127) > threshold` (C++ truncating division; nnue_engine.cpp:93-103, 199).  The host-side
+    bound (nnue_q_conv_bound, no GPU involved) is checked against that rule exhaustively around every boundary: thresholds
+    on and between integers, negative (truncation toward zero makes the two sides of zero asymmetric), at and beyond the
+    clamp ends, NaN; several scales."""
+    import numpy as np
+    from nnue_vision_b200 import _lib
+    L = _lib.lib()
+    thresholds = [-200.0, -127.5, -127.0, -126.99, -126.5, -2.0, -1.5, -1.0, -0.5, -0.0, 0.0, 0.25, 0.5, 1.0, 1.5, 63.0,
+                  126.0, 126.5, 126.999, 127.0, 300.0, float("nan")]
+    for scale in (1, 3, 64, 1000):
+        a = np.arange(-130 * scale - 5, 130 * scale + 6, dtype=np.int64)
+        q = np.where(a >= 0, a // scale, -((-a) // scale))          # truncation toward zero
+        v = np.clip(q, -127, 127).astype(np.float32)
+        for thr in thresholds:
+            want = v > np.float32(thr)                               # NaN compares false
+            a_min = ctypes.c_int32(0)
+            mode = L.nnue_q_conv_bound(ctypes.c_float(thr), scale, ctypes.byref(a_min))
+            assert mode in (0, 1, 2)
+            got = (a >= a_min.value) if mode == 0 else np.full(a.shape, mode == 2)
+            assert np.array_equal(got, want), (scale, thr, mode, a_min.value)
+    assert L.nnue_q_conv_bound(ctypes.c_float(0.0), 0, ctypes.byref(ctypes.c_int32(0))) < 0
+
+
+def test_scratch_size_queries_answer_without_a_gpu():
+    """Pure host arithmetic: the sizes a caller must allocate before the calls that need them."""
+    from nnue_vision_b200 import _lib
+    L = _lib.lib()
+    wide = _lib.make_shape(16384, 32, 32, 8, 10, 1024, 128, 32, 10, 3)   # the reference's "real" stack: has a side chain
+    small = _lib.make_shape(16384, 32, 32, 8, 10, 64, 32, 8, 10, 3)      # config D: the one-kernel head, no side chain
+    assert int(L.nnue_head_side_workspace_bytes(ctypes.byref(wide))) > 16384 * 128 * 4
+    assert int(L.nnue_head_side_workspace_bytes(ctypes.byref(small))) == 0
+    assert int(L.nnue_head_is_fused(ctypes.byref(small))) == 1 and int(L.nnue_head_uses_umma(ctypes.byref(wide))) == 1
+    # counting sort in front of the indexed weight gradient: chunks x (F + 1) counters + two (F + 1) arrays
+    assert int(L.nnue_ft_sort_pairs_workspace_bytes(9, 23, 800)) >= (1 + 2) * 801 * 4
+    assert int(L.nnue_ft_sort_pairs_workspace_bytes(0, 23, 800)) == 0
+    assert int(L.nnue_allreduce_ll_max_floats()) == 65536 and int(L.nnue_allreduce_recv_floats(8, 256)) == 2 * 8 * 256 * 2
