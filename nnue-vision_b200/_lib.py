@@ -128,6 +128,13 @@ def lib():
         if handle.nnue_b200_abi_version() != ABI_VERSION:
             raise NnueError("libnnue_b200.so ABI version mismatch; rebuild it")
         _lib = handle
+        # NNUE_OPTIONS="key=value,key=value": nnue_set_option knobs applied at load (to run a whole test file or bench
+        # under another kernel choice without touching the code)
+        import os
+        for kv in filter(None, os.environ.get("NNUE_OPTIONS", "").split(",")):
+            key, _, val = kv.partition("=")
+            if handle.nnue_set_option(key.strip().encode(), int(val)) != 0:
+                raise NnueError(f"NNUE_OPTIONS: unknown option {key!r}")
     return _lib
 
 

@@ -12,7 +12,7 @@ void note_cuda_error(cudaError_t e, const char *what) {
 }
 static unsigned long long g_launches = 0;
 void note_launch() { __atomic_fetch_add(&g_launches, 1ULL, __ATOMIC_RELAXED); }
-static int g_options[kNumOptions] = {/*ft_fwd_staging=*/1, /*ft_bwd_dw_owner=*/1, /*input_bwd_fused=*/1, /*input_bwd_variant=*/1, /*head_fused=*/1, /*ft_bwd_both=*/1, /*ft_mma=*/1, /*extract_tma=*/0, /*extract_fixed=*/1, /*ft_umma=*/1, /*input_bwd_swizzle=*/1, /*head_umma=*/1, /*q_tc_min_batch=*/2048, /*ft_form=*/0, /*ft_density_permille=*/400, /*ft_gather=*/1, /*ft_gather_slab=*/0, /*input_bwd_rows=*/1, /*ft_gather_units=*/1, /*input_bwd_onchip=*/0, /*q_cta_max_batch=*/592, /*q_conv_fixed=*/1, /*q_stack_fused=*/8192, /*head_mid=*/1, /*head_pair_epilogue=*/1, /*gemm_inline_a=*/0};
+static int g_options[kNumOptions] = {/*ft_fwd_staging=*/1, /*ft_bwd_dw_owner=*/1, /*input_bwd_fused=*/1, /*input_bwd_variant=*/1, /*head_fused=*/1, /*ft_bwd_both=*/1, /*ft_mma=*/1, /*extract_tma=*/0, /*extract_fixed=*/1, /*ft_umma=*/1, /*input_bwd_swizzle=*/1, /*head_umma=*/1, /*q_tc_min_batch=*/2048, /*ft_form=*/0, /*ft_density_permille=*/400, /*ft_gather=*/1, /*ft_gather_slab=*/0, /*input_bwd_rows=*/1, /*ft_gather_units=*/1, /*input_bwd_onchip=*/0, /*q_cta_max_batch=*/592, /*q_conv_fixed=*/1, /*q_stack_fused=*/8192, /*head_mid=*/1, /*head_pair_epilogue=*/1, /*gemm_inline_a=*/0, /*conv_bwd_packed=*/1};
 int get_option(int which) { return which >= 0 && which < kNumOptions ? g_options[which] : 0; }
 }  // namespace nnue
 
@@ -37,6 +37,7 @@ int nnue_set_option(const char *key, int value) {
     if (!strcmp(key, "head_mid")) { nnue::g_options[nnue::kOptHeadMid] = value; return NNUE_OK; }
     if (!strcmp(key, "head_pair_epilogue")) { nnue::g_options[nnue::kOptHeadPairEpi] = value; return NNUE_OK; }
     if (!strcmp(key, "gemm_inline_a")) { nnue::g_options[nnue::kOptInlineA] = value; return NNUE_OK; }
+    if (!strcmp(key, "conv_bwd_packed")) { nnue::g_options[nnue::kOptConvBwdPacked] = value; return NNUE_OK; }
     if (!strcmp(key, "head_umma")) { nnue::g_options[nnue::kOptHeadUmma] = value; return NNUE_OK; }
     if (!strcmp(key, "input_bwd_swizzle")) { nnue::g_options[nnue::kOptInputSwizzle] = value; return NNUE_OK; }
     if (!strcmp(key, "ft_umma")) { nnue::g_options[nnue::kOptFtUmma] = value; return NNUE_OK; }

@@ -40,7 +40,7 @@ void note_launch();
     } while (0)
 
 // Tuning knobs settable through nnue_set_option (api.cu); every value has a working default.
-enum Option { kOptFtFwdStaging = 0, kOptDwOwner, kOptInputFused, kOptInputVariant, kOptHeadFused, kOptFtBwdBoth, kOptFtMma, kOptExtractTma, kOptExtractFixed, kOptFtUmma, kOptInputSwizzle, kOptHeadUmma, kOptQTcMinBatch, kOptFtForm, kOptFtDensity, kOptFtGather, kOptFtGatherVariant, kOptInputRows, kOptGatherUnits, kOptInputFusedGbin, kOptQCtaMaxBatch, kOptQConvFixed, kOptQStackFused, kOptHeadMid, kOptHeadPairEpi, kOptInlineA, kNumOptions };
+enum Option { kOptFtFwdStaging = 0, kOptDwOwner, kOptInputFused, kOptInputVariant, kOptHeadFused, kOptFtBwdBoth, kOptFtMma, kOptExtractTma, kOptExtractFixed, kOptFtUmma, kOptInputSwizzle, kOptHeadUmma, kOptQTcMinBatch, kOptFtForm, kOptFtDensity, kOptFtGather, kOptFtGatherVariant, kOptInputRows, kOptGatherUnits, kOptInputFusedGbin, kOptQCtaMaxBatch, kOptQConvFixed, kOptQStackFused, kOptHeadMid, kOptHeadPairEpi, kOptInlineA, kOptConvBwdPacked, kNumOptions };
 int get_option(int which);
 
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -45,7 +45,9 @@ __device__ __forceinline__ void tma_tensor3d_g2s(void *smem_dst, const CUtensorM
 // HWT: H*W when known at compile time (plane offsets become LDS immediates), 0 = read it from the shape
 // XS: the forward stored the pre-threshold activations (xpad, staged next to g_bin) -- otherwise they are
 //     recomputed from the taps and the conv weights
-template <int CH, int WARPS, int HWT, bool XS, bool SWZ>
+// P2: the conv-gradient accumulators as pairs of taps updated by the packed fp32 FMA of sm_100 (fma.rn.f32x2 -> FFMA2:
+//     two IEEE FMAs per instruction, so the results are bit-identical to the scalar form); needs XS
+template <int CH, int WARPS, int HWT, bool XS, bool SWZ, bool P2 = false>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 conv_bwd_kernel(const nnue_shape s, const float *__restrict__ images, const float *__restrict__ dval,
                 const float *__restrict__ xpad, const float *__restrict__ conv_w, const float *__restrict__ thr,
@@ -136,6 +138,7 @@ conv_bwd_kernel(const nnue_shape s, const float *__restrict__ images, const floa
             }
     }
     float acc[CH][27], dth[CH], thr_c[CH];
+    float2 acc2[CH][14];  // P2: taps 2 u, 2 u + 1 (entry 13: tap 26 and nothing)
     const float *cwk[CH];
     int goff[CH];  // my g_bin element inside the staged dval row
     bool chan_ok[CH];
@@ -149,6 +152,8 @@ conv_bwd_kernel(const nnue_shape s, const float *__restrict__ images, const floa
         dth[k] = 0.0f;
 #pragma unroll
         for (int t = 0; t < 27; ++t) acc[k][t] = 0.0f;
+#pragma unroll
+        for (int u = 0; u < 14; ++u) acc2[k][u] = make_float2(0.0f, 0.0f);
     }
 
     int st = 0;
@@ -167,6 +172,22 @@ conv_bwd_kernel(const nnue_shape s, const float *__restrict__ images, const floa
                 x[k][0] = (XS && chan_ok[k]) ? stg[goff[k] + s.PP] : 0.0f;
                 x[k][1] = x[k][2] = 0.0f;
             }
+            if (P2 && XS) {
+                // the 27 taps two at a time: 13 packed FMAs + one scalar per channel instead of 27 scalar ones
+                float2 g2[CH];
+#pragma unroll
+                for (int k = 0; k < CH; ++k) g2[k] = make_float2(gk[k], gk[k]);
+#pragma unroll
+                for (int u = 0; u < 13; ++u) {
+                    const int ta = 2 * u, tb = 2 * u + 1;
+                    const float2 pp = make_float2(stg[(ta / 9) * HWp + off9[ta % 9]], stg[(tb / 9) * HWp + off9[tb % 9]]);
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) acc2[k][u] = __ffma2_rn(g2[k], pp, acc2[k][u]);
+                }
+                const float p26 = stg[2 * HWp + off9[8]];
+#pragma unroll
+                for (int k = 0; k < CH; ++k) acc2[k][13].x = fmaf(gk[k], p26, acc2[k][13].x);
+            } else
             // one pass over the 27 taps: accumulate the conv weight gradient (and, without stored
             // activations, recompute the conv: one chain per input plane)
 #pragma unroll
@@ -191,6 +212,17 @@ conv_bwd_kernel(const nnue_shape s, const float *__restrict__ images, const floa
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
         if (++st == pl.ST) { st = 0; ph ^= 1u; }
+    }
+    if (P2 && XS) {
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+#pragma unroll
+            for (int u = 0; u < 13; ++u) {
+                acc[k][2 * u] = acc2[k][u].x;
+                acc[k][2 * u + 1] = acc2[k][u].y;
+            }
+            acc[k][26] = acc2[k][13].x;
+        }
     }
     // warp reduction of the per-lane accumulators
 #pragma unroll
@@ -288,7 +320,9 @@ static int launch_conv_bwd(const nnue_shape &s, const InPlan &pl, const float *i
         if (ST >= 3) {
             p2.ST = ST;
             p2.smem = (size_t)p2.stage_off + (size_t)ST * p2.stage_floats * 4;
-            auto k = xpad ? conv_bwd_kernel<CH, WARPS, 1024, true, true> : conv_bwd_kernel<CH, WARPS, 1024, false, true>;
+            auto k = xpad ? (get_option(kOptConvBwdPacked) ? conv_bwd_kernel<CH, WARPS, 1024, true, true, true>
+                                                           : conv_bwd_kernel<CH, WARPS, 1024, true, true, false>)
+                          : conv_bwd_kernel<CH, WARPS, 1024, false, true, false>;
             NNUE_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p2.smem));
             k<<<p2.grid, WARPS * 32, p2.smem, st>>>(s, images, dval, xpad, conv_w, thr, partial, p2, tm);
             NNUE_CHECK_LAUNCH("conv_bwd_kernel");

@@ -208,12 +208,12 @@ def test_ft_forward_staging_modes_agree(mode):
     assert_close(out[torch.as_tensor(~amb).cuda()], ref["ft_out"][torch.as_tensor(~amb)], "ft_out")
 
 
-OPTION_DEFAULTS = {"extract_tma": 0, "ft_form": 0, "input_bwd_onchip": 0}
+OPTION_DEFAULTS = {"extract_tma": 0, "ft_form": 0, "input_bwd_onchip": 0, "gemm_inline_a": 0}
 
 
 @pytest.mark.parametrize("options", [dict(extract_tma=1), dict(extract_fixed=0), dict(ft_umma=0), dict(ft_umma=0, ft_mma=0),
                                      dict(ft_umma=0, ft_mma=0, ft_bwd_both=0), dict(ft_umma=0, ft_mma=0, ft_bwd_dw_owner=0),
-                                     dict(ft_umma=0, ft_mma=0, input_bwd_fused=0), dict(input_bwd_fused=0), dict(input_bwd_onchip=1), dict(ft_form=2), dict(ft_form=2, input_bwd_fused=0), dict(input_bwd_variant=0), dict(input_bwd_swizzle=0), dict(input_bwd_swizzle=0, input_bwd_variant=0), dict(head_fused=0), dict(head_umma=0), dict(head_mid=0), dict(head_mid=0, head_umma=0), dict(head_mid=2), dict(head_pair_epilogue=0), dict(gemm_inline_a=1),
+                                     dict(ft_umma=0, ft_mma=0, input_bwd_fused=0), dict(input_bwd_fused=0), dict(input_bwd_onchip=1), dict(ft_form=2), dict(ft_form=2, input_bwd_fused=0), dict(input_bwd_variant=0), dict(input_bwd_swizzle=0), dict(input_bwd_swizzle=0, input_bwd_variant=0), dict(head_fused=0), dict(head_umma=0), dict(head_mid=0), dict(head_mid=0, head_umma=0), dict(head_mid=2), dict(head_pair_epilogue=0), dict(gemm_inline_a=1), dict(conv_bwd_packed=0),
                                      dict(ft_umma=0, ft_mma=0, ft_bwd_dw_owner=0, input_bwd_fused=0, head_fused=0)],
                          ids=str)
 @pytest.mark.parametrize("name", ["D", "T", "big_into_small", "D1k_tensor_head"])
