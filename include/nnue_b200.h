@@ -110,6 +110,21 @@ unsigned long long nnue_launch_count_add(unsigned long long n);
  *   "head_umma"       1 (default) = layer 1 of wide stacks (L1 >= 256, 16 <= L2 <= 256) as a split-bf16 tcgen05 GEMM
  *                     (fp32-exact products) wherever scratch is passed, 0 = fp32 FMA GEMM kernels.
  *   "head_fused"      1 (default) = one-kernel head training step for small stacks, 0 = layer kernels.
+ *   "head_mid"        1 (default) = layers 2 - 3 + cross-entropy + their backward of wide stacks (L2 <= 128, L3 <= 32,
+ *                     NC <= 16) in one persistent kernel (head_mid.cu), 0 = the layer kernels; N > 1 caps its grid at N CTAs.
+ *   "head_pair_epilogue" 1 (default) = the pairwise backward in the epilogue of the layer-1 input-gradient GEMM
+ *                     (tensor-core form, L1 / 2 a multiple of 128), 0 = g_l0 through HBM and a separate kernel.
+ *   "gemm_inline_a"   1 = the A operands of the layer-1 forward GEMM and of the wide value-gradient GEMM are split into
+ *                     bf16 terms inside the kernels (bit-identical), 0 (default) = formatting kernels.  Measured no faster.
+ *   "conv_bwd_packed" 1 (default) = the conv-gradient accumulators of 32 x 32 images updated two taps at a time by the
+ *                     packed fp32 FMA (fma.rn.f32x2; bit-identical), 0 = scalar FMAs.
+ *   "q_cta_max_batch" integer inference: batches of at most this many samples (default 592) run a CTA per sample, larger
+ *                     ones (below q_tc_min_batch) a warp per sample.
+ *   "q_conv_fixed"    1 (default) = 32 x 32 images at conv stride 4 take the TMA-staged conv + bitmask kernel in the
+ *                     large-batch form, 0 = the general conv kernel.
+ *   "q_stack_fused"   the smallest batch (default 8192; 0 = never) whose layer stack runs in the epilogue of the tcgen05
+ *                     accumulate (L1 = 64, stack <= 32 / 32 / 64) instead of a third launch.
+ * The Python binding applies NNUE_OPTIONS="key=value,..." from the environment when the library is loaded.
  */
 int nnue_set_option(const char *key, int value);
 
